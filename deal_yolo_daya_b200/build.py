@@ -1,0 +1,59 @@
+"""Build libdyd.so (the CUDA hot path + its C ABI) for sm_100a, in-tree.
+
+    python -m deal_yolo_daya_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU.  ``-fmad=false`` keeps every fp64 multiply and add
+separately rounded (the reference's arithmetic is CPython float arithmetic: no FMA).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+OUT = PKG / "libdyd.so"
+SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "synth.cu", "host_pipeline.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (looked at $NVCC, /usr/local/cuda/bin/nvcc, PATH)")
+
+
+def sources():
+    return [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+
+
+def needs_build() -> bool:
+    if not OUT.exists():
+        return True
+    t = OUT.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dyd.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return OUT
+    cmd = [nvcc_path(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-fmad=false", "--shared",
+           "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", str(OUT)] + [str(s) for s in sources()]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libdyd.so")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,288 @@
+// K1 (polygon -> corner points), K2 (box count + any-pair IoU) and the fused K1+K2 path.
+//
+// Direct-load variant ("v1"): warps read the vertex stream with 128-bit non-allocating loads,
+// an 8-lane group per polygon, four polygons per warp step.  The fused kernel keeps each
+// image's boxes in shared memory for the pair test, so boxes are written to HBM once and
+// never re-read.  Images with more than WARP_BOX_CAP objects are appended to a worklist and
+// finished by a block-per-image kernel (shared-memory SoA tile, circular half-range pairing).
+#include "bbox_core.cuh"
+
+namespace dyd {
+
+constexpr int CTA_THREADS = 256;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
+constexpr int CROWD_SMEM_BOXES = 1024;
+
+struct CrowdList {
+    unsigned long long count;   // number of deferred images
+    unsigned long long pad;
+    // int32 image ids follow
+};
+__device__ __forceinline__ int* crowd_ids(void* ws) { return reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + sizeof(CrowdList)); }
+
+__device__ __forceinline__ void store_corner(double* pts, int64_t p, const Corner& c) {
+    double2* o = reinterpret_cast<double2*>(pts + 4 * p);
+    stg_stream_f64x2(o, make_double2(c.mnx, c.mny));
+    stg_stream_f64x2(o + 1, make_double2(c.mxx, c.mxy));
+}
+
+// One group folds polygon [a, a+V) of the global vertex array.  Result in the group's lane 0.
+template <bool ARG>
+__device__ __forceinline__ Corner fold_polygon(const double2* __restrict__ xy2, int64_t a, int V, int gl,
+                                               unsigned gmask, CornerIdx& ci) {
+    auto load = [&](int k) { return ldg_stream_f64x2(xy2 + a + k); };
+    if (ARG || V > 4 * GROUP) return group_bbox_indexed(load, V, gl, gmask, ci);
+    return group_bbox_fast(load, V, gl, gmask);
+}
+
+// ------------------------------------------------------------------------------- K1
+template <bool ARG>
+__global__ void __launch_bounds__(CTA_THREADS)
+bbox_kernel(const int64_t* __restrict__ poly_off, const double2* __restrict__ xy2, int64_t n_poly,
+            double* __restrict__ pts, uint8_t* __restrict__ valid, int32_t* __restrict__ arg) {
+    const int lane = threadIdx.x & 31, gl = lane & (GROUP - 1), g = lane / GROUP;
+    const unsigned gmask = 0xffu << (g * GROUP);
+    const int64_t warp = (blockIdx.x * (int64_t)CTA_THREADS + threadIdx.x) >> 5;
+    const int64_t p = warp * GROUPS_PER_WARP + g;
+    if (p >= n_poly) return;                       // whole group leaves together
+    const int64_t a = __ldg(poly_off + p), b = __ldg(poly_off + p + 1);
+    const int64_t Vl = b - a;
+    const int V = Vl > 0x7fffffff ? 0x7fffffff : (int)Vl;
+    Corner c{0.0, 0.0, 0.0, 0.0};
+    CornerIdx ci{-1, -1, -1, -1};
+    if (V > 0) c = fold_polygon<ARG>(xy2, a, V, gl, gmask, ci);
+    if (gl == 0) {
+        store_corner(pts, p, c);
+        valid[p] = V > 0 ? 1 : 0;
+        if (ARG) *reinterpret_cast<int4*>(arg + 4 * p) = make_int4(ci.mnx, ci.mny, ci.mxx, ci.mxy);
+    }
+}
+
+// ------------------------------------------------------------------------------- K2 (warp per image)
+__global__ void __launch_bounds__(CTA_THREADS)
+iou_warp_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
+                int64_t n_img, int64_t min_boxes, double thr, uint8_t* __restrict__ high,
+                int32_t* __restrict__ count, void* ws) {
+    __shared__ __align__(16) double sbox[CTA_WARPS][WARP_BOX_CAP * 4];
+    __shared__ unsigned short lut[PAIR_LUT_N];
+    fill_pair_lut(lut, threadIdx.x, CTA_THREADS);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t img = blockIdx.x * (int64_t)CTA_WARPS + w;
+    if (img >= n_img) return;
+    const bool zero_hits = 0.0 >= thr;
+    const int64_t q0 = __ldg(img_off + img), q1 = __ldg(img_off + img + 1);
+    const int64_t n = q1 - q0;
+    // effective boxes = prefix before the first null bbox
+    int64_t n_eff = n;
+    if (valid != nullptr) {
+        for (int64_t base = 0; base < n; base += 32) {
+            int64_t j = base + lane;
+            bool bad = j < n && valid[q0 + j] == 0;
+            unsigned m = __ballot_sync(FULL, bad);
+            if (m) { n_eff = base + (__ffs(m) - 1); break; }
+        }
+    }
+    if (lane == 0) count[img] = (int32_t)(n_eff > 0x7fffffff ? 0x7fffffff : n_eff);
+    bool hit = false, deferred = false;
+    if (n_eff >= min_boxes && n_eff >= 2) {
+        if (n_eff <= WARP_BOX_CAP) {
+            const double2* src = reinterpret_cast<const double2*>(pts + 4 * q0);
+            for (int j = lane; j < (int)n_eff; j += 32) {
+                double2 p1 = ldg_stream_f64x2(src + 2 * j), p2 = ldg_stream_f64x2(src + 2 * j + 1);
+                Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
+                double2* d = reinterpret_cast<double2*>(&sbox[w][4 * j]);
+                d[0] = make_double2(bx.x1, bx.y1); d[1] = make_double2(bx.x2, bx.y2);
+            }
+            __syncwarp();
+            hit = warp_any_pair(sbox[w], (int)n_eff, thr, zero_hits, lut, lane);
+        } else {
+            deferred = true;
+            if (lane == 0) {
+                unsigned long long slot = atomicAdd(&reinterpret_cast<CrowdList*>(ws)->count, 1ULL);
+                crowd_ids(ws)[slot] = (int)img;
+            }
+        }
+    }
+    if (lane == 0 && !deferred) high[img] = hit ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------- K2 (block per crowded image)
+__global__ void __launch_bounds__(CTA_THREADS)
+iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const int32_t* __restrict__ count,
+                 double thr, uint8_t* __restrict__ high, void* ws) {
+    __shared__ double sx1[CROWD_SMEM_BOXES], sy1[CROWD_SMEM_BOXES], sx2[CROWD_SMEM_BOXES], sy2[CROWD_SMEM_BOXES];
+    __shared__ int found;
+    const unsigned long long n_list = reinterpret_cast<CrowdList*>(ws)->count;
+    const int* ids = crowd_ids(ws);
+    const bool zero_hits = 0.0 >= thr;
+    for (unsigned long long e = blockIdx.x; e < n_list; e += gridDim.x) {
+        const int64_t img = ids[e];
+        const int64_t q0 = img_off[img];
+        const int n = count[img];
+        const double2* src = reinterpret_cast<const double2*>(pts + 4 * q0);
+        const bool in_smem = n <= CROWD_SMEM_BOXES;
+        __syncthreads();                              // previous image fully consumed
+        if (threadIdx.x == 0) found = 0;
+        if (in_smem) {
+            for (int j = threadIdx.x; j < n; j += CTA_THREADS) {
+                double2 p1 = ldg_stream_f64x2(src + 2 * j), p2 = ldg_stream_f64x2(src + 2 * j + 1);
+                Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
+                sx1[j] = bx.x1; sy1[j] = bx.y1; sx2[j] = bx.x2; sy2[j] = bx.y2;
+            }
+        }
+        __syncthreads();
+        // circular half-range pairing: box s meets s+1 .. s+(n-1)/2 (mod n); for even n the
+        // antipodal pair is taken by the lower half only.  Covers every unordered pair once.
+        const int half = (n - 1) / 2;
+        const bool even = (n & 1) == 0;
+        for (int s = threadIdx.x; s < n; s += CTA_THREADS) {
+            Box a;
+            if (in_smem) a = Box{sx1[s], sy1[s], sx2[s], sy2[s]};
+            else { double2 p1 = ldg_f64x2(src + 2 * s), p2 = ldg_f64x2(src + 2 * s + 1); a = box_from_points(p1.x, p1.y, p2.x, p2.y); }
+            const int dmax = half + ((even && s < n / 2) ? 1 : 0);
+            bool mine = false;
+            for (int d = 1; d <= dmax && !mine; ++d) {
+                int t = s + d; if (t >= n) t -= n;
+                Box b;
+                if (in_smem) b = Box{sx1[t], sy1[t], sx2[t], sy2[t]};
+                else { double2 p1 = ldg_f64x2(src + 2 * t), p2 = ldg_f64x2(src + 2 * t + 1); b = box_from_points(p1.x, p1.y, p2.x, p2.y); }
+                mine = iou_hits(a, b, thr, zero_hits);
+                if ((d & 15) == 0 && *(volatile int*)&found) break;
+            }
+            if (mine) found = 1;
+            if (*(volatile int*)&found) break;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) high[img] = found ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------- fused K1 + K2
+template <bool ARG>
+__global__ void __launch_bounds__(CTA_THREADS)
+fused_warp_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off,
+                  const double2* __restrict__ xy2, int64_t n_img, int64_t min_boxes, double thr,
+                  double* __restrict__ pts, uint8_t* __restrict__ valid, int32_t* __restrict__ arg,
+                  uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
+    __shared__ __align__(16) double sbox[CTA_WARPS][WARP_BOX_CAP * 4];
+    __shared__ unsigned short lut[PAIR_LUT_N];
+    fill_pair_lut(lut, threadIdx.x, CTA_THREADS);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gl = lane & (GROUP - 1), g = lane / GROUP;
+    const unsigned gmask = 0xffu << (g * GROUP);
+    const int64_t img = blockIdx.x * (int64_t)CTA_WARPS + w;
+    if (img >= n_img) return;
+    const bool zero_hits = 0.0 >= thr;
+    const int64_t q0 = __ldg(img_off + img), q1 = __ldg(img_off + img + 1);
+    const int64_t n = q1 - q0;
+    int64_t n_eff = n;
+    for (int64_t base = 0; base < n; base += GROUPS_PER_WARP) {
+        const int64_t j = base + g;
+        const bool active = j < n;
+        int V = 1;
+        if (active) {
+            const int64_t p = q0 + j;
+            const int64_t a = __ldg(poly_off + p), b = __ldg(poly_off + p + 1);
+            const int64_t Vl = b - a;
+            V = Vl > 0x7fffffff ? 0x7fffffff : (int)Vl;
+            Corner c{0.0, 0.0, 0.0, 0.0};
+            CornerIdx ci{-1, -1, -1, -1};
+            if (V > 0) c = fold_polygon<ARG>(xy2, a, V, gl, gmask, ci);
+            if (gl == 0) {
+                store_corner(pts, p, c);
+                valid[p] = V > 0 ? 1 : 0;
+                if (ARG) *reinterpret_cast<int4*>(arg + 4 * p) = make_int4(ci.mnx, ci.mny, ci.mxx, ci.mxy);
+                if (j < WARP_BOX_CAP) {
+                    Box bx = box_from_points(c.mnx, c.mny, c.mxx, c.mxy);
+                    double2* d = reinterpret_cast<double2*>(&sbox[w][4 * j]);
+                    d[0] = make_double2(bx.x1, bx.y1); d[1] = make_double2(bx.x2, bx.y2);
+                }
+            }
+        }
+        const unsigned bad = __ballot_sync(FULL, active && gl == 0 && V <= 0);
+        if (bad && n_eff == n) n_eff = base + (__ffs(bad) - 1) / GROUP;
+    }
+    __syncwarp();
+    if (lane == 0) count[img] = (int32_t)(n_eff > 0x7fffffff ? 0x7fffffff : n_eff);
+    bool hit = false, deferred = false;
+    if (n_eff >= min_boxes && n_eff >= 2) {
+        if (n_eff <= WARP_BOX_CAP) {
+            hit = warp_any_pair(sbox[w], (int)n_eff, thr, zero_hits, lut, lane);
+        } else {
+            deferred = true;
+            if (lane == 0) {
+                __threadfence();                       // boxes visible to the crowd kernel's loads
+                unsigned long long slot = atomicAdd(&reinterpret_cast<CrowdList*>(ws)->count, 1ULL);
+                crowd_ids(ws)[slot] = (int)img;
+            }
+        }
+    }
+    if (lane == 0 && !deferred) high[img] = hit ? 1 : 0;
+}
+
+static inline int crowd_grid() { return NUM_SMS * 4; }
+
+}  // namespace dyd
+
+using namespace dyd;
+
+extern "C" size_t dyd_iou_workspace_bytes(int64_t n_img) {
+    if (n_img < 0) n_img = 0;
+    return sizeof(CrowdList) + sizeof(int) * (size_t)n_img + 16;
+}
+
+extern "C" int dyd_bbox_minmax(const int64_t* d_poly_off, const double* d_xy, int64_t n_poly,
+                               double* d_pts, uint8_t* d_valid, int32_t* d_arg, void* stream) {
+    DYD_REQUIRE(n_poly >= 0, DYD_E_ARG, "negative count");
+    if (n_poly == 0) return 0;
+    DYD_REQUIRE(d_poly_off && d_pts && d_valid, DYD_E_ARG, "null pointer");
+    DYD_REQUIRE(((uintptr_t)d_xy & 15) == 0 && ((uintptr_t)d_pts & 15) == 0 && ((uintptr_t)d_arg & 15) == 0,
+                DYD_E_ALIGN, "xy / pts / arg must be 16-byte aligned");
+    const int64_t warps = (n_poly + GROUPS_PER_WARP - 1) / GROUPS_PER_WARP;
+    const int64_t grid = (warps + CTA_WARPS - 1) / CTA_WARPS;
+    DYD_REQUIRE(grid <= 0x7fffffff, DYD_E_ARG, "too many polygons for one launch");
+    const double2* xy2 = reinterpret_cast<const double2*>(d_xy);
+    if (d_arg) bbox_kernel<true><<<(unsigned)grid, CTA_THREADS, 0, as_stream(stream)>>>(d_poly_off, xy2, n_poly, d_pts, d_valid, d_arg);
+    else bbox_kernel<false><<<(unsigned)grid, CTA_THREADS, 0, as_stream(stream)>>>(d_poly_off, xy2, n_poly, d_pts, d_valid, nullptr);
+    return launch_check("bbox_kernel");
+}
+
+extern "C" int dyd_iou_filter(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid,
+                              int64_t n_img, int64_t min_boxes, double thr, uint8_t* d_high, int32_t* d_count,
+                              void* d_workspace, size_t workspace_bytes, void* stream) {
+    DYD_REQUIRE(n_img >= 0 && n_img <= 0x7fffffff, DYD_E_ARG, "bad image count");
+    if (n_img == 0) return 0;
+    DYD_REQUIRE(d_img_off && d_high && d_count && d_workspace, DYD_E_ARG, "null pointer");
+    DYD_REQUIRE(((uintptr_t)d_pts & 15) == 0 && ((uintptr_t)d_workspace & 15) == 0, DYD_E_ALIGN, "pts / workspace must be 16-byte aligned");
+    DYD_REQUIRE(workspace_bytes >= dyd_iou_workspace_bytes(n_img), DYD_E_WORKSPACE, "workspace too small");
+    cudaStream_t s = as_stream(stream);
+    DYD_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(CrowdList), s));
+    const int64_t grid = (n_img + CTA_WARPS - 1) / CTA_WARPS;
+    iou_warp_kernel<<<(unsigned)grid, CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, n_img, min_boxes, thr, d_high, d_count, d_workspace);
+    if (int rc = launch_check("iou_warp_kernel")) return rc;
+    iou_crowd_kernel<<<crowd_grid(), CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_count, thr, d_high, d_workspace);
+    return launch_check("iou_crowd_kernel");
+}
+
+extern "C" int dyd_bbox_iou_fused(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
+                                  int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
+                                  double* d_pts, uint8_t* d_valid, int32_t* d_arg, uint8_t* d_high, int32_t* d_count,
+                                  void* d_workspace, size_t workspace_bytes, void* stream) {
+    DYD_REQUIRE(n_img >= 0 && n_img <= 0x7fffffff && n_poly >= 0, DYD_E_ARG, "bad count");
+    if (n_img == 0) return 0;
+    DYD_REQUIRE(d_img_off && d_poly_off && d_pts && d_valid && d_high && d_count && d_workspace, DYD_E_ARG, "null pointer");
+    DYD_REQUIRE(((uintptr_t)d_xy & 15) == 0 && ((uintptr_t)d_pts & 15) == 0 && ((uintptr_t)d_arg & 15) == 0 &&
+                    ((uintptr_t)d_workspace & 15) == 0, DYD_E_ALIGN, "xy / pts / arg / workspace must be 16-byte aligned");
+    DYD_REQUIRE(workspace_bytes >= dyd_iou_workspace_bytes(n_img), DYD_E_WORKSPACE, "workspace too small");
+    cudaStream_t s = as_stream(stream);
+    DYD_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(CrowdList), s));
+    const int64_t grid = (n_img + CTA_WARPS - 1) / CTA_WARPS;
+    const double2* xy2 = reinterpret_cast<const double2*>(d_xy);
+    if (d_arg) fused_warp_kernel<true><<<(unsigned)grid, CTA_THREADS, 0, s>>>(d_img_off, d_poly_off, xy2, n_img, min_boxes, thr, d_pts, d_valid, d_arg, d_high, d_count, d_workspace);
+    else fused_warp_kernel<false><<<(unsigned)grid, CTA_THREADS, 0, s>>>(d_img_off, d_poly_off, xy2, n_img, min_boxes, thr, d_pts, d_valid, nullptr, d_high, d_count, d_workspace);
+    if (int rc = launch_check("fused_warp_kernel")) return rc;
+    iou_crowd_kernel<<<crowd_grid(), CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_count, thr, d_high, d_workspace);
+    return launch_check("iou_crowd_kernel");
+}

@@ -1,0 +1,243 @@
+// K0 string hash, K4 first/last-occurrence dedup, K5 anti-join -- device hash tables.
+//
+// Table: open addressing, linear probing, 16-byte slots {key, row}, capacity = 2^k >= 2n.
+// One cudaMemset(0xFF) makes every key EMPTY and every row "no row yet" for both orders
+// (UINT64_MAX under atomicMin, -1 under signed atomicMax).  A key equal to the EMPTY sentinel
+// is folded onto EMPTY-1; like any 64-bit collision it is caught by the host's string check of
+// dropped rows (d_rep / d_ref_row exist for that).
+#include "common.cuh"
+
+namespace dyd {
+
+constexpr unsigned long long EMPTY = 0xFFFFFFFFFFFFFFFFULL;
+constexpr int HT_THREADS = 256;
+
+struct Slot {
+    unsigned long long key;
+    unsigned long long row;
+};
+struct TableHeader {                 // 64 bytes in front of the slots
+    unsigned long long null_first;   // min row among null cells (UINT64_MAX if none)
+    long long null_last;             // max row among null cells (-1 if none)
+    unsigned long long null_count;
+    unsigned long long pad[5];
+};
+
+static inline uint64_t table_capacity(int64_t n) {
+    uint64_t cap = 1024;
+    while (cap < (uint64_t)(n > 0 ? n : 0) * 2) cap <<= 1;
+    return cap;
+}
+static inline int log2u(uint64_t v) { int k = 0; while ((1ULL << k) < v) ++k; return k; }
+
+__device__ __forceinline__ unsigned long long norm_key(unsigned long long k) { return k == EMPTY ? EMPTY - 1 : k; }
+__device__ __forceinline__ uint64_t home_slot(unsigned long long k, int shift) { return (k * 0x9E3779B97F4A7C15ULL) >> shift; }
+
+// ------------------------------------------------------------------------------- K0
+// MurmurHash64A-style: 8-byte little-endian words, multiply-xorshift mixing.
+constexpr unsigned long long HM = 0xC6A4A7935BD1E995ULL;
+constexpr unsigned long long HSEED = 0x8445D61A4E774912ULL;
+
+__global__ void __launch_bounds__(HT_THREADS)
+hash_strings_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__ bytes, int64_t n,
+                    uint64_t* __restrict__ out) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= n) return;
+    const int64_t a = off[r], len = off[r + 1] - a;
+    unsigned long long h = HSEED ^ ((unsigned long long)len * HM);
+    const int64_t nblk = len >> 3;
+    const uint8_t* p = bytes + a;
+    const unsigned sh = ((uintptr_t)p & 7) * 8;
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>((uintptr_t)p & ~(uintptr_t)7);
+    if (nblk > 0) {
+        unsigned long long lo = __ldg(w);
+        for (int64_t i = 0; i < nblk; ++i) {
+            unsigned long long k;
+            if (sh == 0) { k = lo; lo = (i + 1 < nblk) ? __ldg(w + i + 1) : 0ULL; }
+            else { unsigned long long hi = __ldg(w + i + 1); k = (lo >> sh) | (hi << (64 - sh)); lo = hi; }
+            k *= HM; k ^= k >> 47; k *= HM;
+            h ^= k; h *= HM;
+        }
+    }
+    const int rem = (int)(len & 7);
+    if (rem) {
+        unsigned long long t = 0;
+        const uint8_t* q = p + (nblk << 3);
+        for (int i = 0; i < rem; ++i) t |= (unsigned long long)__ldg(q + i) << (8 * i);
+        h ^= t; h *= HM;
+    }
+    h ^= h >> 47; h *= HM; h ^= h >> 47;
+    out[r] = h;
+}
+
+// ------------------------------------------------------------------------------- K4
+template <bool IDS>
+__global__ void __launch_bounds__(HT_THREADS)
+dedup_insert_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
+                    const int64_t* __restrict__ row_id, int64_t n, int keep_mode,
+                    TableHeader* hdr, Slot* tab, unsigned* cnt, int shift, uint64_t mask) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    const bool live = r < n;
+    const bool isnull = live && !IDS && null != nullptr && null[r] != 0;
+    const unsigned nm = __ballot_sync(FULL, isnull);
+    if (nm) {                                          // rows ascend with the lane: aggregate per warp
+        const int lane = threadIdx.x & 31;
+        if (lane == __ffs(nm) - 1) { atomicMin(&hdr->null_first, (unsigned long long)r); atomicAdd(&hdr->null_count, (unsigned long long)__popc(nm)); }
+        if (lane == 31 - __clz(nm)) atomicMax(&hdr->null_last, (long long)r);
+    }
+    if (!live || isnull) return;
+    const unsigned long long key = norm_key(keys[r]);
+    const unsigned long long rid = IDS ? (unsigned long long)row_id[r] : (unsigned long long)r;
+    uint64_t s = home_slot(key, shift);
+    for (;;) {
+        unsigned long long prev = atomicCAS(&tab[s].key, EMPTY, key);
+        if (prev == EMPTY || prev == key) {
+            if (keep_mode == 1) atomicMax(reinterpret_cast<long long*>(&tab[s].row), (long long)rid);
+            else atomicMin(&tab[s].row, rid);
+            if (keep_mode == 2) atomicAdd(&cnt[s], 1u);
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+}
+
+template <bool IDS>
+__global__ void __launch_bounds__(HT_THREADS)
+dedup_lookup_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
+                    const int64_t* __restrict__ row_id, int64_t n, int keep_mode,
+                    const TableHeader* __restrict__ hdr, const Slot* __restrict__ tab,
+                    const unsigned* __restrict__ cnt, int shift, uint64_t mask,
+                    uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= n) return;
+    const long long rid = IDS ? row_id[r] : r;
+    if (!IDS && null != nullptr && null[r] != 0) {
+        const long long rp = keep_mode == 1 ? hdr->null_last : (long long)hdr->null_first;
+        rep[r] = rp;
+        keep[r] = keep_mode == 2 ? (hdr->null_count == 1) : (rp == rid);
+        return;
+    }
+    const unsigned long long key = norm_key(keys[r]);
+    uint64_t s = home_slot(key, shift);
+    while (tab[s].key != key) s = (s + 1) & mask;      // the key was inserted by the previous kernel
+    const long long rp = (long long)tab[s].row;
+    rep[r] = rp;
+    keep[r] = keep_mode == 2 ? (cnt[s] == 1u) : (rp == rid);
+}
+
+// ------------------------------------------------------------------------------- K5
+__global__ void __launch_bounds__(HT_THREADS)
+antijoin_build_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t n,
+                      Slot* tab, int shift, uint64_t mask) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= n || (null != nullptr && null[r] != 0)) return;      // ref.dropna()
+    const unsigned long long key = norm_key(keys[r]);
+    uint64_t s = home_slot(key, shift);
+    for (;;) {
+        unsigned long long prev = atomicCAS(&tab[s].key, EMPTY, key);
+        if (prev == EMPTY || prev == key) { atomicMin(&tab[s].row, (unsigned long long)r); return; }
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(HT_THREADS)
+antijoin_probe_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t n,
+                      const Slot* __restrict__ tab, int shift, uint64_t mask,
+                      uint8_t* __restrict__ keep, int64_t* __restrict__ ref_row) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= n) return;
+    uint8_t k = 1; long long rr = -1;
+    if (null == nullptr || null[r] == 0) {             // a NaN main cell never matches
+        const unsigned long long key = norm_key(keys[r]);
+        uint64_t s = home_slot(key, shift);
+        for (;;) {
+            const unsigned long long cur = tab[s].key;
+            if (cur == key) { k = 0; rr = (long long)tab[s].row; break; }
+            if (cur == EMPTY) break;
+            s = (s + 1) & mask;
+        }
+    }
+    keep[r] = k; ref_row[r] = rr;
+}
+
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + HT_THREADS - 1) / HT_THREADS); }
+
+template <bool IDS>
+static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64_t* d_row_id, int64_t n, int keep_mode,
+                      uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
+    DYD_REQUIRE(n >= 0 && n < (1LL << 40), DYD_E_ARG, "bad row count");
+    DYD_REQUIRE(keep_mode >= 0 && keep_mode <= 2, DYD_E_ARG, "keep_mode must be 0 (first), 1 (last) or 2 (False)");
+    if (n == 0) return 0;
+    DYD_REQUIRE(d_keys && d_keep && d_rep && ws && (!IDS || d_row_id), DYD_E_ARG, "null pointer");
+    DYD_REQUIRE(((uintptr_t)ws & 15) == 0, DYD_E_ALIGN, "workspace must be 16-byte aligned");
+    DYD_REQUIRE(ws_bytes >= dyd_dedup_workspace_bytes(n), DYD_E_WORKSPACE, "workspace too small");
+    const uint64_t cap = table_capacity(n);
+    const int shift = 64 - log2u(cap);
+    cudaStream_t s = as_stream(stream);
+    TableHeader* hdr = reinterpret_cast<TableHeader*>(ws);
+    Slot* tab = reinterpret_cast<Slot*>(hdr + 1);
+    unsigned* cnt = reinterpret_cast<unsigned*>(tab + cap);
+    DYD_CUDA(cudaMemsetAsync(ws, 0xFF, sizeof(TableHeader) + cap * sizeof(Slot), s));
+    DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
+    if (keep_mode == 2) DYD_CUDA(cudaMemsetAsync(cnt, 0, cap * sizeof(unsigned), s));
+    dedup_insert_kernel<IDS><<<grid_for(n), HT_THREADS, 0, s>>>(
+        reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1);
+    if (int rc = launch_check("dedup_insert_kernel")) return rc;
+    dedup_lookup_kernel<IDS><<<grid_for(n), HT_THREADS, 0, s>>>(
+        reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1, d_keep, d_rep);
+    return launch_check("dedup_lookup_kernel");
+}
+
+}  // namespace dyd
+
+using namespace dyd;
+
+extern "C" int dyd_hash_strings(const int64_t* d_off, const uint8_t* d_bytes, int64_t n, uint64_t* d_hash, void* stream) {
+    DYD_REQUIRE(n >= 0, DYD_E_ARG, "negative count");
+    if (n == 0) return 0;
+    DYD_REQUIRE(d_off && d_hash, DYD_E_ARG, "null pointer");
+    hash_strings_kernel<<<grid_for(n), HT_THREADS, 0, as_stream(stream)>>>(d_off, d_bytes, n, d_hash);
+    return launch_check("hash_strings_kernel");
+}
+
+extern "C" size_t dyd_dedup_workspace_bytes(int64_t n) {
+    const uint64_t cap = table_capacity(n);
+    return sizeof(TableHeader) + cap * sizeof(Slot) + cap * sizeof(unsigned);
+}
+
+extern "C" int dyd_dedup(const uint64_t* d_keys, const uint8_t* d_null, int64_t n, int keep_mode,
+                         uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
+    return dedup_impl<false>(d_keys, d_null, nullptr, n, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
+}
+
+extern "C" int dyd_dedup_ids(const uint64_t* d_keys, const int64_t* d_row_id, int64_t n, int keep_mode,
+                             uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
+    return dedup_impl<true>(d_keys, nullptr, d_row_id, n, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
+}
+
+extern "C" size_t dyd_antijoin_workspace_bytes(int64_t n_ref) {
+    return table_capacity(n_ref) * sizeof(Slot);
+}
+
+extern "C" int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
+                            const uint64_t* d_ref_keys, const uint8_t* d_ref_null, int64_t n_ref,
+                            uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, void* stream) {
+    DYD_REQUIRE(n_main >= 0 && n_ref >= 0, DYD_E_ARG, "negative count");
+    if (n_main == 0) return 0;
+    DYD_REQUIRE(d_main_keys && d_keep && d_ref_row && ws && (n_ref == 0 || d_ref_keys), DYD_E_ARG, "null pointer");
+    DYD_REQUIRE(((uintptr_t)ws & 15) == 0, DYD_E_ALIGN, "workspace must be 16-byte aligned");
+    DYD_REQUIRE(ws_bytes >= dyd_antijoin_workspace_bytes(n_ref), DYD_E_WORKSPACE, "workspace too small");
+    const uint64_t cap = table_capacity(n_ref);
+    const int shift = 64 - log2u(cap);
+    cudaStream_t s = as_stream(stream);
+    Slot* tab = reinterpret_cast<Slot*>(ws);
+    DYD_CUDA(cudaMemsetAsync(ws, 0xFF, cap * sizeof(Slot), s));
+    if (n_ref > 0) {
+        antijoin_build_kernel<<<grid_for(n_ref), HT_THREADS, 0, s>>>(
+            reinterpret_cast<const unsigned long long*>(d_ref_keys), d_ref_null, n_ref, tab, shift, cap - 1);
+        if (int rc = launch_check("antijoin_build_kernel")) return rc;
+    }
+    antijoin_probe_kernel<<<grid_for(n_main), HT_THREADS, 0, s>>>(
+        reinterpret_cast<const unsigned long long*>(d_main_keys), d_main_null, n_main, tab, shift, cap - 1, d_keep, d_ref_row);
+    return launch_check("antijoin_probe_kernel");
+}

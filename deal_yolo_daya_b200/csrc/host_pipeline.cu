@@ -1,0 +1,143 @@
+// Host-buffer entry points: the calls the Python drop-in makes for tables that live in host
+// memory.  The image range is cut into chunks that are pushed through H2D -> fused K1+K2 ->
+// D2H on three internal streams, so the copy engines and the SMs work on different chunks at
+// the same time.  Transient device buffers come from the CUDA default memory pool
+// (cudaMallocAsync, released before returning); nothing is retained between calls.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dyd {
+
+constexpr int NSLOT = 3;
+
+struct Slot3 {
+    cudaStream_t stream = nullptr;
+    int64_t* img_off = nullptr;
+    int64_t* poly_off = nullptr;
+    double* xy = nullptr;
+    double* pts = nullptr;
+    uint8_t* valid = nullptr;
+    int32_t* arg = nullptr;
+    uint8_t* high = nullptr;
+    int32_t* count = nullptr;
+    void* ws = nullptr;
+};
+
+struct SlotGuard {
+    Slot3 s[NSLOT];
+    ~SlotGuard() {
+        for (auto& x : s) {
+            if (!x.stream) continue;
+            void* bufs[] = {x.img_off, x.poly_off, x.xy, x.pts, x.valid, x.arg, x.high, x.count, x.ws};
+            for (void* b : bufs) if (b) cudaFreeAsync(b, x.stream);
+            cudaStreamSynchronize(x.stream);
+            cudaStreamDestroy(x.stream);
+        }
+    }
+};
+
+}  // namespace dyd
+
+using namespace dyd;
+
+extern "C" int dyd_bbox_iou_host(const int64_t* h_img_off, const int64_t* h_poly_off, const double* h_xy,
+                                 int64_t n_img, int64_t min_boxes, double thr,
+                                 double* h_pts, uint8_t* h_valid, int32_t* h_arg,
+                                 uint8_t* h_high, int32_t* h_count, int64_t chunk_images) {
+    DYD_REQUIRE(n_img >= 0, DYD_E_ARG, "negative count");
+    if (n_img == 0) return 0;
+    DYD_REQUIRE(h_img_off && h_poly_off && h_high && h_count, DYD_E_ARG, "null pointer");
+    if (chunk_images <= 0) chunk_images = 16384;
+    const int64_t n_chunks = (n_img + chunk_images - 1) / chunk_images;
+    int64_t max_img = 0, max_poly = 0, max_vert = 0;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t i0 = c * chunk_images, i1 = std::min(n_img, i0 + chunk_images);
+        const int64_t q0 = h_img_off[i0], q1 = h_img_off[i1];
+        DYD_REQUIRE(q1 >= q0, DYD_E_ARG, "img_off not monotone");
+        const int64_t v0 = h_poly_off[q0], v1 = h_poly_off[q1];
+        DYD_REQUIRE(v1 >= v0, DYD_E_ARG, "poly_off not monotone");
+        max_img = std::max(max_img, i1 - i0); max_poly = std::max(max_poly, q1 - q0); max_vert = std::max(max_vert, v1 - v0);
+    }
+    DYD_REQUIRE(max_vert == 0 || h_xy, DYD_E_ARG, "null pointer");
+    SlotGuard guard;
+    const size_t ws_bytes = dyd_iou_workspace_bytes(max_img);
+    const int nslot = (int)std::min<int64_t>(NSLOT, n_chunks);
+    for (int k = 0; k < nslot; ++k) {
+        Slot3& s = guard.s[k];
+        DYD_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        DYD_CUDA(cudaMallocAsync((void**)&s.img_off, sizeof(int64_t) * (max_img + 1), s.stream));
+        DYD_CUDA(cudaMallocAsync((void**)&s.poly_off, sizeof(int64_t) * (max_poly + 1), s.stream));
+        DYD_CUDA(cudaMallocAsync((void**)&s.xy, sizeof(double) * 2 * std::max<int64_t>(max_vert, 1), s.stream));
+        DYD_CUDA(cudaMallocAsync((void**)&s.pts, sizeof(double) * 4 * std::max<int64_t>(max_poly, 1), s.stream));
+        DYD_CUDA(cudaMallocAsync((void**)&s.valid, std::max<int64_t>(max_poly, 1), s.stream));
+        if (h_arg) DYD_CUDA(cudaMallocAsync((void**)&s.arg, sizeof(int32_t) * 4 * std::max<int64_t>(max_poly, 1), s.stream));
+        DYD_CUDA(cudaMallocAsync((void**)&s.high, max_img, s.stream));
+        DYD_CUDA(cudaMallocAsync((void**)&s.count, sizeof(int32_t) * max_img, s.stream));
+        DYD_CUDA(cudaMallocAsync(&s.ws, ws_bytes, s.stream));
+    }
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        Slot3& s = guard.s[c % nslot];
+        const int64_t i0 = c * chunk_images, i1 = std::min(n_img, i0 + chunk_images), ni = i1 - i0;
+        const int64_t q0 = h_img_off[i0], q1 = h_img_off[i1], nq = q1 - q0;
+        const int64_t v0 = h_poly_off[q0], v1 = h_poly_off[q1], nv = v1 - v0;
+        DYD_CUDA(cudaMemcpyAsync(s.img_off, h_img_off + i0, sizeof(int64_t) * (ni + 1), cudaMemcpyHostToDevice, s.stream));
+        DYD_CUDA(cudaMemcpyAsync(s.poly_off, h_poly_off + q0, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, s.stream));
+        if (nv) DYD_CUDA(cudaMemcpyAsync(s.xy, h_xy + 2 * v0, sizeof(double) * 2 * nv, cudaMemcpyHostToDevice, s.stream));
+        // the kernels index with the table's global object / vertex numbers: rebase the chunk buffers
+        int rc = dyd_bbox_iou_fused(s.img_off, s.poly_off - q0, s.xy - 2 * v0, ni, nq, min_boxes, thr,
+                                    s.pts - 4 * q0, s.valid - q0, s.arg ? s.arg - 4 * q0 : nullptr,
+                                    s.high, s.count, s.ws, ws_bytes, s.stream);
+        if (rc) return rc;
+        if (nq) {
+            if (h_pts) DYD_CUDA(cudaMemcpyAsync(h_pts + 4 * q0, s.pts, sizeof(double) * 4 * nq, cudaMemcpyDeviceToHost, s.stream));
+            if (h_valid) DYD_CUDA(cudaMemcpyAsync(h_valid + q0, s.valid, nq, cudaMemcpyDeviceToHost, s.stream));
+            if (h_arg) DYD_CUDA(cudaMemcpyAsync(h_arg + 4 * q0, s.arg, sizeof(int32_t) * 4 * nq, cudaMemcpyDeviceToHost, s.stream));
+        }
+        DYD_CUDA(cudaMemcpyAsync(h_high + i0, s.high, ni, cudaMemcpyDeviceToHost, s.stream));
+        DYD_CUDA(cudaMemcpyAsync(h_count + i0, s.count, sizeof(int32_t) * ni, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (int k = 0; k < nslot; ++k) DYD_CUDA(cudaStreamSynchronize(guard.s[k].stream));
+    return 0;
+}
+
+extern "C" int dyd_dedup_host(const int64_t* h_off, const uint8_t* h_bytes, const uint8_t* h_null, int64_t n,
+                              int keep_mode, uint8_t* h_keep, int64_t* h_rep) {
+    DYD_REQUIRE(n >= 0, DYD_E_ARG, "negative count");
+    if (n == 0) return 0;
+    DYD_REQUIRE(h_off && h_keep && h_rep, DYD_E_ARG, "null pointer");
+    const int64_t nbytes = h_off[n] - h_off[0];
+    DYD_REQUIRE(nbytes >= 0 && (nbytes == 0 || h_bytes), DYD_E_ARG, "bad string buffer");
+    cudaStream_t st;
+    DYD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int64_t* d_off = nullptr; uint8_t* d_bytes = nullptr; uint8_t* d_null = nullptr; uint64_t* d_hash = nullptr;
+    uint8_t* d_keep = nullptr; int64_t* d_rep = nullptr; void* d_ws = nullptr;
+    const size_t ws_bytes = dyd_dedup_workspace_bytes(n);
+    int rc = 0;
+    auto body = [&]() -> int {
+        DYD_CUDA(cudaMallocAsync((void**)&d_off, sizeof(int64_t) * (n + 1), st));
+        DYD_CUDA(cudaMallocAsync((void**)&d_bytes, std::max<int64_t>(nbytes, 1) + 8, st));
+        if (h_null) DYD_CUDA(cudaMallocAsync((void**)&d_null, n, st));
+        DYD_CUDA(cudaMallocAsync((void**)&d_hash, sizeof(uint64_t) * n, st));
+        DYD_CUDA(cudaMallocAsync((void**)&d_keep, n, st));
+        DYD_CUDA(cudaMallocAsync((void**)&d_rep, sizeof(int64_t) * n, st));
+        DYD_CUDA(cudaMallocAsync(&d_ws, ws_bytes, st));
+        DYD_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+        if (nbytes) DYD_CUDA(cudaMemcpyAsync(d_bytes, h_bytes + h_off[0], nbytes, cudaMemcpyHostToDevice, st));
+        if (h_null) DYD_CUDA(cudaMemcpyAsync(d_null, h_null, n, cudaMemcpyHostToDevice, st));
+        // offsets are relative to h_bytes; the device copy starts at h_off[0]
+        if (int r = dyd_hash_strings(d_off, d_bytes - h_off[0], n, d_hash, st)) return r;
+        if (int r = dyd_dedup(d_hash, d_null, n, keep_mode, d_keep, d_rep, d_ws, ws_bytes, st)) return r;
+        DYD_CUDA(cudaMemcpyAsync(h_keep, d_keep, n, cudaMemcpyDeviceToHost, st));
+        DYD_CUDA(cudaMemcpyAsync(h_rep, d_rep, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+        DYD_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    };
+    rc = body();
+    void* bufs[] = {d_off, d_bytes, d_null, d_hash, d_keep, d_rep, d_ws};
+    for (void* b : bufs) if (b) cudaFreeAsync(b, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}

@@ -1,0 +1,314 @@
+"""Python wrappers over the C ABI (include/dyd.h).
+
+PyTorch is used for device memory and streams only: every function takes / returns
+``torch.Tensor`` buffers on a CUDA device (or numpy arrays for the ``*_host`` calls) and
+forwards raw pointers to libdyd.so.  No computation happens in torch or numpy here, and
+there is no CPU path: without a GPU these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+KEEP_MODES = {"first": 0, "last": 1, False: 2}
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not (isinstance(t, torch.Tensor) and t.is_cuda):
+            raise _lib.DydError("deal_yolo_daya_b200.ops works on CUDA tensors only (no CPU fallback)")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _ws(nbytes, dev):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+
+
+# ------------------------------------------------------------------ K1
+def bbox_minmax(poly_off, xy, want_arg=False):
+    """Polygon -> two corner points (processor.py:252-260).  Returns (pts, valid, arg|None)."""
+    _need_cuda(poly_off, xy)
+    lib = _lib.load()
+    poly_off = _chk(poly_off, torch.int64, "poly_off"); xy = _chk(xy, torch.float64, "xy")
+    dev = poly_off.device
+    n = poly_off.numel() - 1
+    pts = torch.empty(4 * n, dtype=torch.float64, device=dev)
+    valid = torch.empty(n, dtype=torch.uint8, device=dev)
+    arg = torch.empty(4 * n, dtype=torch.int32, device=dev) if want_arg else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_bbox_minmax(_ptr(poly_off), _ptr(xy), n, _ptr(pts), _ptr(valid), _ptr(arg), _stream(dev)),
+                   "dyd_bbox_minmax")
+    return pts, valid, arg
+
+
+# ------------------------------------------------------------------ K2
+def iou_filter(img_off, pts, valid, min_boxes=2, thr=0.98, workspace=None):
+    """Box-count + any-pair IoU flag per image (processor.py:328-376).  Returns (high, count)."""
+    _need_cuda(img_off, pts, valid)
+    lib = _lib.load()
+    img_off = _chk(img_off, torch.int64, "img_off"); pts = _chk(pts, torch.float64, "pts")
+    valid = _chk(valid, torch.uint8, "valid")
+    dev = img_off.device
+    n = img_off.numel() - 1
+    high = torch.empty(n, dtype=torch.uint8, device=dev)
+    count = torch.empty(n, dtype=torch.int32, device=dev)
+    need = lib.dyd_iou_workspace_bytes(n)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_iou_filter(_ptr(img_off), _ptr(pts), _ptr(valid), n, int(min_boxes), float(thr),
+                                      _ptr(high), _ptr(count), _ptr(ws), ws.numel(), _stream(dev)), "dyd_iou_filter")
+    return high, count
+
+
+# ------------------------------------------------------------------ K1+K2
+class FusedBuffers:
+    """Reusable outputs + workspace of the fused call (allocation kept out of timed loops)."""
+
+    def __init__(self, n_img, n_poly, device, want_arg=False):
+        lib = _lib.load()
+        self.pts = torch.empty(4 * n_poly, dtype=torch.float64, device=device)
+        self.valid = torch.empty(n_poly, dtype=torch.uint8, device=device)
+        self.arg = torch.empty(4 * n_poly, dtype=torch.int32, device=device) if want_arg else None
+        self.high = torch.empty(n_img, dtype=torch.uint8, device=device)
+        self.count = torch.empty(n_img, dtype=torch.int32, device=device)
+        self.ws = _ws(lib.dyd_iou_workspace_bytes(n_img), device)
+
+
+def bbox_iou_fused(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_arg=False, out: FusedBuffers | None = None):
+    """Fused K1+K2 over a device-resident CSR table.  Returns a FusedBuffers."""
+    _need_cuda(img_off, poly_off, xy)
+    lib = _lib.load()
+    img_off = _chk(img_off, torch.int64, "img_off"); poly_off = _chk(poly_off, torch.int64, "poly_off")
+    xy = _chk(xy, torch.float64, "xy")
+    dev = img_off.device
+    n_img = img_off.numel() - 1
+    n_poly = poly_off.numel() - 1
+    if out is None:
+        out = FusedBuffers(n_img, n_poly, dev, want_arg)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_bbox_iou_fused(_ptr(img_off), _ptr(poly_off), _ptr(xy), n_img, n_poly, int(min_boxes),
+                                          float(thr), _ptr(out.pts), _ptr(out.valid), _ptr(out.arg), _ptr(out.high),
+                                          _ptr(out.count), _ptr(out.ws), out.ws.numel(), _stream(dev)),
+                   "dyd_bbox_iou_fused")
+    return out
+
+
+# ------------------------------------------------------------------ K0 / K4 / K5
+def hash_strings(off, data):
+    _need_cuda(off, data)
+    lib = _lib.load()
+    off = _chk(off, torch.int64, "off"); data = _chk(data, torch.uint8, "data")
+    dev = off.device
+    n = off.numel() - 1
+    out = torch.empty(n, dtype=torch.uint64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_hash_strings(_ptr(off), _ptr(data), n, _ptr(out), _stream(dev)), "dyd_hash_strings")
+    return out
+
+
+def dedup(keys, null=None, keep="first", row_id=None, workspace=None):
+    """drop_duplicates keep-mask (processor.py:140-144).  Returns (keep uint8, rep int64)."""
+    _need_cuda(keys, null, row_id)
+    lib = _lib.load()
+    keys = _chk(keys, torch.uint64, "keys"); null = _chk(null, torch.uint8, "null")
+    row_id = _chk(row_id, torch.int64, "row_id")
+    dev = keys.device
+    n = keys.numel()
+    km = torch.empty(n, dtype=torch.uint8, device=dev)
+    rep = torch.empty(n, dtype=torch.int64, device=dev)
+    need = lib.dyd_dedup_workspace_bytes(n)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
+    mode = KEEP_MODES[keep]
+    with torch.cuda.device(dev):
+        if row_id is None:
+            rc = lib.dyd_dedup(_ptr(keys), _ptr(null), n, mode, _ptr(km), _ptr(rep), _ptr(ws), ws.numel(), _stream(dev))
+        else:
+            if null is not None:
+                raise ValueError("null cells are resolved by the caller in the sharded (row_id) form")
+            rc = lib.dyd_dedup_ids(_ptr(keys), _ptr(row_id), n, mode, _ptr(km), _ptr(rep), _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(rc, "dyd_dedup")
+    return km, rep
+
+
+def antijoin(main_keys, main_null, ref_keys, ref_null, workspace=None):
+    """~main.isin(set(ref.dropna())) (processor.py:194-199).  Returns (keep uint8, ref_row int64)."""
+    _need_cuda(main_keys, main_null, ref_keys, ref_null)
+    lib = _lib.load()
+    main_keys = _chk(main_keys, torch.uint64, "main_keys"); ref_keys = _chk(ref_keys, torch.uint64, "ref_keys")
+    main_null = _chk(main_null, torch.uint8, "main_null"); ref_null = _chk(ref_null, torch.uint8, "ref_null")
+    dev = main_keys.device
+    n, nr = main_keys.numel(), ref_keys.numel()
+    km = torch.empty(n, dtype=torch.uint8, device=dev)
+    rr = torch.empty(n, dtype=torch.int64, device=dev)
+    need = lib.dyd_antijoin_workspace_bytes(nr)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_antijoin(_ptr(main_keys), _ptr(main_null), n, _ptr(ref_keys), _ptr(ref_null), nr,
+                                    _ptr(km), _ptr(rr), _ptr(ws), ws.numel(), _stream(dev)), "dyd_antijoin")
+    return km, rr
+
+
+# ------------------------------------------------------------------ K3 / K6 / YOLO
+COUNTER_NAMES = ("total_objects", "missing_name_objects", "total_labels", "replaced_labels",
+                 "replaced_objects", "replaced_rows")
+
+
+def label_lut(img_off, label_id, lut_new, lut_ntok, lut_nrep):
+    """Name rewrite through LUTs (processor.py:582-602).  Returns (new_id, row_replaced, counters tensor[6])."""
+    _need_cuda(img_off, label_id, lut_new, lut_ntok, lut_nrep)
+    lib = _lib.load()
+    dev = img_off.device
+    n_img = img_off.numel() - 1
+    n_box = label_id.numel()
+    new_id = torch.empty(n_box, dtype=torch.int32, device=dev)
+    row_rep = torch.empty(n_img, dtype=torch.uint8, device=dev)
+    counters = torch.empty(6, dtype=torch.uint64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_label_lut(_ptr(_chk(img_off, torch.int64, "img_off")), _ptr(_chk(label_id, torch.int32, "label_id")),
+                                     n_img, n_box, _ptr(_chk(lut_new, torch.int32, "lut_new")),
+                                     _ptr(_chk(lut_ntok, torch.int32, "lut_ntok")), _ptr(_chk(lut_nrep, torch.int32, "lut_nrep")),
+                                     lut_new.numel(), _ptr(new_id), _ptr(row_rep), _ptr(counters), _stream(dev)),
+                   "dyd_label_lut")
+    return new_id, row_rep, counters
+
+
+def split_expand(img_off, label_id, cat_of_label, n_cat):
+    """Category expansion (processor.py:751-775).  Returns (exp_img, exp_box, exp_cat, cat_off)."""
+    _need_cuda(img_off, label_id, cat_of_label)
+    lib = _lib.load()
+    dev = img_off.device
+    n_img = img_off.numel() - 1
+    n_vocab = cat_of_label.numel()
+    cat_off = torch.empty(n_cat + 1, dtype=torch.int64, device=dev)
+    ws = _ws(lib.dyd_split_workspace_bytes(n_img, n_cat), dev)
+    a = (_ptr(_chk(img_off, torch.int64, "img_off")), n_img, _ptr(_chk(label_id, torch.int32, "label_id")),
+         _ptr(_chk(cat_of_label, torch.int32, "cat_of_label")), n_vocab, n_cat)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_split_count(*a, _ptr(cat_off), _ptr(ws), ws.numel(), _stream(dev)), "dyd_split_count")
+        n_exp = int(cat_off[-1].item())          # the one host read the API needs (sizes the outputs)
+        exp_img = torch.empty(n_exp, dtype=torch.int64, device=dev)
+        exp_box = torch.empty(n_exp, dtype=torch.int64, device=dev)
+        exp_cat = torch.empty(n_exp, dtype=torch.int32, device=dev)
+        if n_exp:
+            _lib.check(lib.dyd_split_fill(*a, _ptr(cat_off), _ptr(exp_img), _ptr(exp_box), _ptr(exp_cat),
+                                          _ptr(ws), ws.numel(), _stream(dev)), "dyd_split_fill")
+    return exp_img, exp_box, exp_cat, cat_off
+
+
+def split_assign(cat_off, perm, n_train, n_val):
+    """Split id + shuffled position per expanded row from the host permutation (processor.py:800-806)."""
+    _need_cuda(cat_off, perm, n_train, n_val)
+    lib = _lib.load()
+    dev = cat_off.device
+    n_cat = cat_off.numel() - 1
+    n_exp = perm.numel()
+    split = torch.empty(n_exp, dtype=torch.uint8, device=dev)
+    pos = torch.empty(n_exp, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_split_assign(_ptr(_chk(cat_off, torch.int64, "cat_off")), n_cat, _ptr(_chk(perm, torch.int64, "perm")),
+                                        n_exp, _ptr(_chk(n_train, torch.int64, "n_train")), _ptr(_chk(n_val, torch.int64, "n_val")),
+                                        _ptr(split), _ptr(pos), _stream(dev)), "dyd_split_assign")
+    return split, pos
+
+
+def yolo_normalise(img_off, pts, valid, img_wh):
+    """cx, cy, w, h per box (processor.py:1045-1052).  Returns (cxcywh float64[4*n_box], ok uint8)."""
+    _need_cuda(img_off, pts, valid, img_wh)
+    lib = _lib.load()
+    dev = img_off.device
+    n_img = img_off.numel() - 1
+    n_box = pts.numel() // 4
+    out = torch.empty(4 * n_box, dtype=torch.float64, device=dev)
+    ok = torch.empty(n_box, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_yolo_normalise(_ptr(_chk(img_off, torch.int64, "img_off")), _ptr(_chk(pts, torch.float64, "pts")),
+                                          _ptr(_chk(valid, torch.uint8, "valid")), _ptr(_chk(img_wh, torch.float64, "img_wh")),
+                                          n_img, n_box, _ptr(out), _ptr(ok), _stream(dev)), "dyd_yolo_normalise")
+    return out, ok
+
+
+# ------------------------------------------------------------------ host-buffer entry points
+def _np(a, dtype, name):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda:
+            raise ValueError(f"{name}: host entry points take host buffers")
+        a = a.numpy()
+    a = np.asarray(a)
+    if a.dtype != dtype or not a.flags.c_contiguous:
+        raise TypeError(f"{name} must be a C-contiguous {np.dtype(dtype).name} array")
+    return a
+
+
+def _hp(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def bbox_iou_host(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_pts=True, want_arg=False,
+                  chunk_images=0, out=None, device=0):
+    """Host CSR in -> host results out, H2D / kernels / D2H pipelined inside the library.
+
+    Returns dict(pts, valid, arg, high, count) of numpy arrays (pinned if ``out`` supplies them).
+    """
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.DydError("no CUDA device: the hot path has no CPU fallback")
+    img_off = _np(img_off, np.int64, "img_off"); poly_off = _np(poly_off, np.int64, "poly_off")
+    xy = _np(xy, np.float64, "xy")
+    n_img = len(img_off) - 1
+    n_poly = len(poly_off) - 1
+    out = dict(out or {})
+    if want_pts and out.get("pts") is None:
+        out["pts"] = np.empty(4 * n_poly, np.float64)
+    if out.get("valid") is None:
+        out["valid"] = np.empty(n_poly, np.uint8)
+    if want_arg and out.get("arg") is None:
+        out["arg"] = np.empty(4 * n_poly, np.int32)
+    if out.get("high") is None:
+        out["high"] = np.empty(n_img, np.uint8)
+    if out.get("count") is None:
+        out["count"] = np.empty(n_img, np.int32)
+    pts = _np(out.get("pts"), np.float64, "pts") if want_pts else None
+    arg = _np(out.get("arg"), np.int32, "arg") if want_arg else None
+    with torch.cuda.device(device):
+        _lib.check(lib.dyd_bbox_iou_host(_hp(img_off), _hp(poly_off), _hp(xy), n_img, int(min_boxes), float(thr),
+                                         _hp(pts), _hp(_np(out["valid"], np.uint8, "valid")), _hp(arg),
+                                         _hp(_np(out["high"], np.uint8, "high")), _hp(_np(out["count"], np.int32, "count")),
+                                         int(chunk_images)), "dyd_bbox_iou_host")
+    return out
+
+
+def dedup_host(off, data, null=None, keep="first", device=0):
+    """Host Arrow string buffers in -> (keep uint8, rep int64) numpy arrays out."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.DydError("no CUDA device: the hot path has no CPU fallback")
+    off = _np(off, np.int64, "off"); data = _np(data, np.uint8, "data"); null = _np(null, np.uint8, "null")
+    n = len(off) - 1
+    km = np.empty(n, np.uint8); rep = np.empty(n, np.int64)
+    with torch.cuda.device(device):
+        _lib.check(lib.dyd_dedup_host(_hp(off), _hp(data), _hp(null), n, KEEP_MODES[keep], _hp(km), _hp(rep)),
+                   "dyd_dedup_host")
+    return km, rep

@@ -1,0 +1,197 @@
+/* dyd.h -- C ABI of libdyd.so, the B200 (sm_100a) hot path of Deal-Yolo-Daya's
+ * data-processing pipeline.
+ *
+ * The reference (/root/reference/src/deal_yolo_data/core/processor.py) has no FFI:
+ * its boundary is the Python step-function surface imported by the Streamlit page
+ * (ui/pages/processing.py:25-38).  The Python drop-in (deal_yolo_daya_b200/
+ * processor.py) keeps those signatures and calls the entry points below through
+ * ctypes; each entry point states which reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers + int64 counts; no torch / C++ types in any signature;
+ *   - "d_" pointers are DEVICE pointers on the current CUDA device, "h_" pointers
+ *     are HOST pointers (pinned gives full PCIe speed, pageable is accepted);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     device entry points are stream-ordered and never synchronise the host;
+ *   - the library owns no memory: scratch comes from the caller as a workspace
+ *     sized by the matching dyd_*_workspace_bytes() query;
+ *   - return value: 0 ok; <0 invalid argument (DYD_E_*); >0 a cudaError_t.
+ *     dyd_last_error() gives the thread-local message of the last failure;
+ *   - re-entrant: no mutable globals, callable from any host thread.
+ *
+ * Data layout: a ragged CSR annotation table
+ *   img_off  int64[n_img+1]   object range of each image (row)
+ *   poly_off int64[n_poly+1]  vertex range of each object's polygon
+ *   xy       double[2*n_vert] interleaved x,y of the VALID points only, 16-byte aligned
+ *   pts      double[4*n_poly] per object (p1.x, p1.y, p2.x, p2.y) = (min_x, min_y, max_x, max_y)
+ *   valid    uint8[n_poly]    0 = null bbox ({x: None, y: None} twice in the reference)
+ */
+#ifndef DYD_H_
+#define DYD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYD_VERSION 100          /* 0.1.0 */
+#define DYD_E_ARG (-1)           /* null pointer / negative count / bad enum */
+#define DYD_E_ALIGN (-2)         /* pointer not aligned as required */
+#define DYD_E_WORKSPACE (-3)     /* workspace too small */
+
+int dyd_version(void);
+/* Copies the calling thread's last error message (NUL terminated) into buf. */
+size_t dyd_last_error(char* buf, size_t cap);
+
+/* ---------------------------------------------------------------- K1 ------
+ * polygon -> two corner points.  Replaces get_bbox_points, processor.py:252-260:
+ * four independent builtin min()/max() scans over the valid points, i.e. left
+ * folds that replace the running value only on a strict comparison (first of
+ * equal values -- and of 0.0 / -0.0 -- wins; a NaN survives only from position 0).
+ * Outputs: pts (above), valid, and optionally arg int32[4*n_poly] = the vertex
+ * index inside the polygon that supplied each of the four values (lets the host
+ * re-emit the original JSON number, `10` vs `10.0`).  d_arg may be NULL.        */
+int dyd_bbox_minmax(const int64_t* d_poly_off, const double* d_xy, int64_t n_poly,
+                    double* d_pts, uint8_t* d_valid, int32_t* d_arg, void* stream);
+
+/* ---------------------------------------------------------------- K2 ------
+ * box-count + any-pair IoU quality flag per image.  Replaces extract_boxes /
+ * calculate_iou / meet_conditions, processor.py:328-376:
+ *   boxes = objects of the image up to (not including) the first one whose
+ *           valid flag is 0 (the TypeError a null bbox raises ends the scan);
+ *           each box = (min(p1x,p2x), min(p1y,p2y), max(p1x,p2x), max(p1y,p2y));
+ *   high  = len(boxes) >= min_boxes and any i<j: iou(boxes[i], boxes[j]) >= thr
+ *   iou   = fp64, separately rounded: inter = max(0,dx)*max(0,dy); 0.0 if inter==0;
+ *           union = (area1 + area2) - inter; inter/union, or 0.0 if union == 0.
+ * d_valid may be NULL (all valid).  d_count receives len(boxes).
+ * Workspace: dyd_iou_workspace_bytes(n_img) (worklist of crowded images).       */
+size_t dyd_iou_workspace_bytes(int64_t n_img);
+int dyd_iou_filter(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid,
+                   int64_t n_img, int64_t min_boxes, double thr,
+                   uint8_t* d_high, int32_t* d_count,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------- K1+K2 ------
+ * Fused polygon->bbox + IoU flag (processor.py:252-260 then :328-376 without the
+ * CSV/JSON round trip between the two steps): one pass over the vertices, boxes
+ * written once and not re-read.  Same outputs as the two calls above.           */
+int dyd_bbox_iou_fused(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
+                       int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
+                       double* d_pts, uint8_t* d_valid, int32_t* d_arg,
+                       uint8_t* d_high, int32_t* d_count,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K0 ------
+ * 64-bit hash of each string of an Arrow-style (offsets, bytes) column; the
+ * `source` URLs of processor.py:140 / :194.  Definition in DESIGN.md §4.K0.     */
+int dyd_hash_strings(const int64_t* d_off, const uint8_t* d_bytes, int64_t n,
+                     uint64_t* d_hash, void* stream);
+
+/* ---------------------------------------------------------------- K4 ------
+ * Row keep-mask of df.drop_duplicates(subset=["source"], keep=...), processor.py:
+ * 140-144.  keep_mode 0 = "first", 1 = "last", 2 = False (drop all members of a
+ * repeated group).  d_null may be NULL; all null (NaN) rows form ONE group.
+ * d_rep[r] = row representing r's group (first, or last for mode 1) so the host
+ * can verify every dropped row's string against it (64-bit hash collisions).     */
+size_t dyd_dedup_workspace_bytes(int64_t n);
+int dyd_dedup(const uint64_t* d_keys, const uint8_t* d_null, int64_t n, int keep_mode,
+              uint8_t* d_keep, int64_t* d_rep,
+              void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Sharded form used after the NCCL all-to-all: rows carry explicit global ids. */
+int dyd_dedup_ids(const uint64_t* d_keys, const int64_t* d_row_id, int64_t n, int keep_mode,
+                  uint8_t* d_keep, int64_t* d_rep,
+                  void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K5 ------
+ * Anti-join of processor.py:194-199: keep[r] = main value not in
+ * set(ref.dropna()); null main rows are always kept.  d_ref_row[r] = first
+ * reference row holding the key (-1 when kept), for collision verification.     */
+size_t dyd_antijoin_workspace_bytes(int64_t n_ref);
+int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
+                 const uint64_t* d_ref_keys, const uint8_t* d_ref_null, int64_t n_ref,
+                 uint8_t* d_keep, int64_t* d_ref_row,
+                 void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K3 ------
+ * Object-name rewrite through a lookup table, processor.py:582-602 with the
+ * string rules of utils.py:659-679 folded into three per-vocabulary tables built
+ * on the host: lut_new (id of the rewritten name), lut_ntok (#tokens), lut_nrep
+ * (#tokens found in the mapping).  label_id < 0 = object without a name.
+ * d_counters uint64[6] = total_objects, missing_name_objects, total_labels,
+ * replaced_labels, replaced_objects, replaced_rows (zeroed by the call).        */
+int dyd_label_lut(const int64_t* d_img_off, const int32_t* d_label_id, int64_t n_img, int64_t n_box,
+                  const int32_t* d_lut_new, const int32_t* d_lut_ntok, const int32_t* d_lut_nrep,
+                  int32_t n_vocab, int32_t* d_new_id, uint8_t* d_row_replaced,
+                  uint64_t* d_counters, void* stream);
+
+/* ---------------------------------------------------------------- K6 ------
+ * label -> category expansion of processor.py:751-775: one expanded row per
+ * object whose label has a category, stably grouped by category (encounter
+ * order inside a category).  Two calls: _count fills d_cat_off int64[n_cat+1]
+ * (the caller reads d_cat_off[n_cat] to size the outputs) and leaves per-chunk
+ * offsets in the workspace; _fill (same workspace, untouched in between) scatters
+ * (image, object, category) triples.  n_cat <= 256.
+ * Workspace: dyd_split_workspace_bytes(n_img, n_cat).                            */
+size_t dyd_split_workspace_bytes(int64_t n_img, int32_t n_cat);
+int dyd_split_count(const int64_t* d_img_off, int64_t n_img, const int32_t* d_label_id,
+                    const int32_t* d_cat_of_label, int32_t n_vocab, int32_t n_cat, int64_t* d_cat_off,
+                    void* d_workspace, size_t workspace_bytes, void* stream);
+int dyd_split_fill(const int64_t* d_img_off, int64_t n_img, const int32_t* d_label_id,
+                   const int32_t* d_cat_of_label, int32_t n_vocab, int32_t n_cat, const int64_t* d_cat_off,
+                   int64_t* d_exp_img, int64_t* d_exp_box, int32_t* d_exp_cat,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+/* Split id (0 train / 1 val / 2 test) and shuffled position of every expanded row.
+ * d_perm holds, category after category, np.random.RandomState(seed).permutation(n_c)
+ * computed on the host (what DataFrame.sample(frac=1, random_state=seed) applies,
+ * processor.py:800): shuffled position r takes original row perm[r]; positions
+ * < n_train[c] are train, the next n_val[c] val, the rest test (:801-806).        */
+int dyd_split_assign(const int64_t* d_cat_off, int32_t n_cat, const int64_t* d_perm, int64_t n_exp,
+                     const int64_t* d_n_train, const int64_t* d_n_val,
+                     uint8_t* d_split, int64_t* d_pos, void* stream);
+
+/* ------------------------------------------------------------ YOLO (f-3) ---
+ * cx, cy, w, h of processor.py:1045-1052 for every box: ((x1+x2)/2)/W etc., fp64,
+ * same operation order; ok[q] = 0 where bw <= 0 or bh <= 0 or the box is invalid. */
+int dyd_yolo_normalise(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid,
+                       const double* d_img_wh, int64_t n_img, int64_t n_box,
+                       double* d_cxcywh, uint8_t* d_ok, void* stream);
+
+/* ------------------------------------------------------ host-buffer entry ---
+ * The call the Python drop-in makes for a table that lives in HOST memory: the
+ * image range is cut into chunks; each chunk's CSR slice is copied H2D, run
+ * through the fused K1+K2 kernel and its results copied D2H, with copies and
+ * kernels of consecutive chunks overlapped on internal streams.  Blocks until
+ * the results are in the h_ outputs.  h_arg / h_pts may be NULL (not wanted).
+ * `chunk_images` <= 0 picks a default.                                          */
+int dyd_bbox_iou_host(const int64_t* h_img_off, const int64_t* h_poly_off, const double* h_xy,
+                      int64_t n_img, int64_t min_boxes, double thr,
+                      double* h_pts, uint8_t* h_valid, int32_t* h_arg,
+                      uint8_t* h_high, int32_t* h_count, int64_t chunk_images);
+
+/* Same idea for the URL column: hash + dedup (+ anti-join when n_ref > 0) from host
+ * Arrow buffers to host masks.  h_ref_* may be NULL when n_ref == 0.              */
+int dyd_dedup_host(const int64_t* h_off, const uint8_t* h_bytes, const uint8_t* h_null, int64_t n,
+                   int keep_mode, uint8_t* h_keep, int64_t* h_rep);
+
+/* ------------------------------------------------ synthetic tables (§8d) ---
+ * Device-side twin of deal_yolo_daya_b200/synth.py (bit-identical output).       */
+int dyd_synth_counts(uint64_t seed, int64_t first_img, int64_t n_img, const uint64_t* d_pois_thr,
+                     int32_t n_thr, int64_t* d_npoly /* [n_img] */, void* stream);
+int dyd_synth_nvert(uint64_t seed, int64_t first_img, int64_t n_img, const int64_t* d_img_off,
+                    int64_t* d_nvert /* [n_poly] */, void* stream);
+int dyd_synth_fill(uint64_t seed, int64_t first_img, int64_t n_img, const int64_t* d_img_off,
+                   const int64_t* d_poly_off, double* d_xy, int32_t* d_label_id, void* stream);
+int dyd_synth_urls(uint64_t seed, int64_t first_row, int64_t n, int64_t n_main_for_ref /* <0: main table */,
+                   int64_t* d_url_id, int64_t* d_len /* [n] byte length of each URL */, void* stream);
+int dyd_synth_url_bytes(const int64_t* d_url_id, const int64_t* d_off, int64_t n, uint8_t* d_bytes, void* stream);
+int dyd_synth_crowd(uint64_t seed, int64_t first_img, int64_t n_img, int32_t lo, int32_t hi,
+                    const int64_t* d_img_off /* NULL: write counts to d_nbox */, int64_t* d_nbox,
+                    double* d_pts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYD_H_ */
