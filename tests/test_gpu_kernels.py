@@ -1,0 +1,304 @@
+"""CUDA kernels (through the C ABI) against the CPU oracle -- bit-exact.
+
+Every comparison is on raw bytes for doubles (signed zeros and NaN payloads included) and
+exact equality for masks / indices.  Sizes are chosen so the C oracle finishes in seconds;
+the full-size properties live in test_gpu_scale.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from deal_yolo_daya_b200 import ops, synth, synth_device
+from oracle import oracle_c, oracle_np
+from tests import tables
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, d):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(d)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def assert_bits(a, b, what=""):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.tobytes() != b.tobytes():
+        bad = np.where(a.view(np.uint64) != b.view(np.uint64))[0] if a.dtype == np.float64 else np.where(a != b)[0]
+        raise AssertionError(f"{what}: {len(bad)} mismatches, first at {bad[:8]}: got {a[bad[:8]]} want {b[bad[:8]]}")
+
+
+def check_bbox(poly_off, xy, d):
+    want_pts, want_valid, want_arg = oracle_c.bbox_fold(poly_off, xy)
+    for want_arg_flag in (False, True):
+        pts, valid, arg = ops.bbox_minmax(dev(poly_off, d), dev(xy, d), want_arg=want_arg_flag)
+        assert_bits(host(pts), want_pts, f"pts(arg={want_arg_flag})")
+        assert_bits(host(valid), want_valid, "valid")
+        if want_arg_flag:
+            assert_bits(host(arg), want_arg, "arg")
+    return want_pts, want_valid
+
+
+def check_fused(img_off, poly_off, xy, d, params=((2, 0.7), (2, 0.98), (1, 0.0), (3, 0.5))):
+    want_pts, want_valid, want_arg = oracle_c.bbox_fold(poly_off, xy)
+    for mb, thr in params:
+        want_high, want_count = oracle_c.iou_filter(img_off, want_pts, want_valid, mb, thr)
+        for flag in (False, True):
+            out = ops.bbox_iou_fused(dev(img_off, d), dev(poly_off, d), dev(xy, d), mb, thr, want_arg=flag)
+            assert_bits(host(out.pts), want_pts, "fused pts")
+            assert_bits(host(out.valid), want_valid, "fused valid")
+            assert_bits(host(out.high), want_high, f"fused high mb={mb} thr={thr}")
+            assert_bits(host(out.count), want_count, "fused count")
+            if flag:
+                assert_bits(host(out.arg), want_arg, "fused arg")
+        high, count = ops.iou_filter(dev(img_off, d), dev(want_pts, d), dev(want_valid, d), mb, thr)
+        assert_bits(host(high), want_high, f"k2 high mb={mb} thr={thr}")
+        assert_bits(host(count), want_count, "k2 count")
+
+
+def test_edge_polygons(cuda_device):
+    img_off, poly_off, xy = tables.edge_polygon_table()
+    check_bbox(poly_off, xy, cuda_device)
+    check_fused(img_off, poly_off, xy, cuda_device)
+    # the small table is also checked by the pure-Python oracle (CPython semantics, not C)
+    pts, valid, arg = ops.bbox_minmax(dev(poly_off, cuda_device), dev(xy, cuda_device), want_arg=True)
+    p, v, a = oracle_np.bbox_fold(poly_off, xy)
+    assert_bits(host(pts), p); assert_bits(host(valid), v); assert_bits(host(arg), a)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_polygons_with_specials(cuda_device, seed):
+    img_off, poly_off, xy = tables.random_polygon_table(seed, 400, max_polys=14, max_verts=70)
+    check_bbox(poly_off, xy, cuda_device)
+    check_fused(img_off, poly_off, xy, cuda_device)
+
+
+def test_empty_and_tiny(cuda_device):
+    d = cuda_device
+    z = np.zeros(1, np.int64)
+    pts, valid, arg = ops.bbox_minmax(dev(z, d), dev(np.zeros(0), d), want_arg=True)
+    assert pts.numel() == 0 and valid.numel() == 0
+    out = ops.bbox_iou_fused(dev(z, d), dev(z, d), dev(np.zeros(0), d))
+    assert out.high.numel() == 0
+    img_off, poly_off, xy = tables.csr_from_polygons([[], [], [[(1.0, 1.0)]]])
+    check_fused(img_off, poly_off, xy, d)
+
+
+@pytest.mark.parametrize("seed,n", [(0, 20000), (5, 3000)])
+def test_synth_table_device_equals_numpy_and_oracle(cuda_device, seed, n):
+    d = cuda_device
+    t = synth.make_table(seed, 1000, n)
+    g = synth_device.make_table(seed, 1000, n, d)
+    assert_bits(host(g.img_off), t.img_off, "img_off")
+    assert_bits(host(g.poly_off), t.poly_off, "poly_off")
+    assert_bits(host(g.xy), t.xy, "xy")
+    assert_bits(host(g.label_id), t.label_id, "label_id")
+    want_pts, want_valid, _ = oracle_c.bbox_fold(t.poly_off, t.xy)
+    for mb, thr in ((2, 0.7), (2, 0.98)):
+        want_high, want_count = oracle_c.iou_filter(t.img_off, want_pts, want_valid, mb, thr)
+        out = ops.bbox_iou_fused(g.img_off, g.poly_off, g.xy, mb, thr)
+        assert_bits(host(out.pts), want_pts); assert_bits(host(out.high), want_high); assert_bits(host(out.count), want_count)
+        assert 0.02 < want_high.mean() < 0.5          # the generator's jittered copies do trigger the filter
+
+
+@pytest.mark.parametrize("lo,hi,n", [(0, 9, 3000), (30, 70, 600), (60, 130, 300), (200, 500, 60), (1000, 1100, 6)])
+def test_iou_box_tables(cuda_device, lo, hi, n):
+    d = cuda_device
+    img_off, pts, valid = tables.random_box_table(lo * 7 + n, n, lo, hi)
+    for mb, thr in ((2, 0.7), (2, 0.98), (5, 0.3)):
+        want_high, want_count = oracle_c.iou_filter(img_off, pts, valid, mb, thr)
+        high, count = ops.iou_filter(dev(img_off, d), dev(pts, d), dev(valid, d), mb, thr)
+        assert_bits(host(high), want_high, f"high {lo}-{hi} mb={mb} thr={thr}")
+        assert_bits(host(count), want_count, "count")
+    high, count = ops.iou_filter(dev(img_off, d), dev(pts, d), None, 2, 0.7)
+    want_high, want_count = oracle_c.iou_filter(img_off, pts, None, 2, 0.7)
+    assert_bits(host(high), want_high); assert_bits(host(count), want_count)
+
+
+def test_crowd_generator_and_worst_case(cuda_device):
+    d = cuda_device
+    io, pts = synth.make_crowd_boxes(3, 10, 40)
+    gio, gpts = synth_device.make_crowd(3, 10, 40, device=d)
+    assert_bits(host(gio), io); assert_bits(host(gpts), pts)
+    for thr in (0.7, 2.0):                      # thr 2.0: no pair can hit -> every pair is evaluated
+        want_high, want_count = oracle_c.iou_filter(io, pts, None, 2, thr)
+        high, count = ops.iou_filter(gio, gpts, None, 2, thr)
+        assert_bits(host(high), want_high); assert_bits(host(count), want_count)
+
+
+def test_near_threshold_pairs_take_exact_division(cuda_device):
+    """Pairs whose IoU sits within a few ulps of the threshold must agree with the oracle's division."""
+    d = cuda_device
+    rng = np.random.RandomState(11)
+    imgs = []
+    thr = 0.7
+    for _ in range(4000):
+        w = rng.uniform(1, 50); h = rng.uniform(1, 50)
+        # box B = same width, height scaled so that IoU = inter/union is ~thr
+        k = thr * (1 + rng.uniform(-3, 3) * 2.0 ** -52)
+        imgs.append([[(0.0, 0.0), (w, h)], [(0.0, 0.0), (w, h * k)]])
+    img_off, poly_off, xy = tables.csr_from_polygons(imgs)
+    pts, valid, _ = oracle_c.bbox_fold(poly_off, xy)
+    want_high, _ = oracle_c.iou_filter(img_off, pts, valid, 2, thr)
+    assert 0.2 < want_high.mean() < 0.8
+    high, _ = ops.iou_filter(dev(img_off, d), dev(pts, d), dev(valid, d), 2, thr)
+    assert_bits(host(high), want_high)
+
+
+# ---------------------------------------------------------------- K0 / K4 / K5
+def test_hash_strings(cuda_device):
+    d = cuda_device
+    strs = ["", "a", "ab", "abcdefg", "abcdefgh", "abcdefghi", "https://img.example.com/123.jpg", "行人/车.jpg" * 3]
+    strs += [synth.url_of(i) for i in range(0, 3000, 7)] + ["x" * k for k in range(1, 40)]
+    off, data = oracle_c.pack_strings(strs)
+    want = oracle_c.hash_strings_buf(off, data)
+    assert np.array_equal(want, oracle_np.hash_strings(strs))
+    got = ops.hash_strings(dev(off, d), dev(data, d))
+    assert_bits(host(got), want, "hash")
+
+
+@pytest.mark.parametrize("keep", ["first", "last", False])
+@pytest.mark.parametrize("n,groups,pnull", [(1, 1, 0.0), (5000, 700, 0.02), (200000, 150000, 0.001), (3000, 3000, 1.0)])
+def test_dedup(cuda_device, keep, n, groups, pnull):
+    d = cuda_device
+    rng = np.random.RandomState(n + groups)
+    pool = rng.randint(0, 2 ** 63, size=groups, dtype=np.int64).astype(np.uint64)
+    pool[0] = np.uint64(0xFFFFFFFFFFFFFFFF)             # the table's EMPTY sentinel as a real key
+    keys = pool[rng.randint(0, groups, size=n)]
+    null = (rng.rand(n) < pnull).astype(np.uint8)
+    want_keep, want_rep = oracle_c.dedup(keys, null, keep)
+    got_keep, got_rep = ops.dedup(dev(keys, d), dev(null, d), keep)
+    assert_bits(host(got_keep), want_keep, "keep"); assert_bits(host(got_rep), want_rep, "rep")
+    got_keep, got_rep = ops.dedup(dev(keys, d), None, keep)
+    want_keep, want_rep = oracle_c.dedup(keys, np.zeros(n, np.uint8), keep)
+    assert_bits(host(got_keep), want_keep); assert_bits(host(got_rep), want_rep)
+
+
+def test_dedup_with_row_ids(cuda_device):
+    d = cuda_device
+    rng = np.random.RandomState(4)
+    n = 50000
+    keys = rng.randint(0, 9000, size=n).astype(np.uint64)
+    ids = rng.permutation(n).astype(np.int64) * 3 + 11
+    keep, rep = ops.dedup(dev(keys, d), None, "first", row_id=dev(ids, d))
+    first = {}
+    for k, i in zip(keys, ids):
+        first[k] = min(first.get(k, 1 << 62), i)
+    want_rep = np.array([first[k] for k in keys], np.int64)
+    assert_bits(host(rep), want_rep); assert_bits(host(keep), (want_rep == ids).astype(np.uint8))
+
+
+@pytest.mark.parametrize("n,nr", [(4000, 0), (4000, 900), (100000, 60000)])
+def test_antijoin(cuda_device, n, nr):
+    d = cuda_device
+    rng = np.random.RandomState(n + nr)
+    mk = rng.randint(0, 120000, size=n).astype(np.uint64)
+    rk = rng.randint(0, 120000, size=nr).astype(np.uint64)
+    mn = (rng.rand(n) < 0.01).astype(np.uint8); rn = (rng.rand(nr) < 0.05).astype(np.uint8)
+    want_keep, want_rr = oracle_c.antijoin(mk, mn, rk, rn)
+    keep, rr = ops.antijoin(dev(mk, d), dev(mn, d), dev(rk, d), dev(rn, d))
+    assert_bits(host(keep), want_keep); assert_bits(host(rr), want_rr)
+
+
+def test_url_pipeline_device(cuda_device):
+    """Device-generated URL bytes -> hash -> dedup equals the oracle on the numpy twin's URLs."""
+    d = cuda_device
+    n = 30000
+    url_id, off, data = synth_device.make_urls(9, 0, n, d)
+    ids = synth.url_ids_of(9, np.arange(n))
+    assert_bits(host(url_id), ids)
+    strs = [synth.url_of(i) for i in ids]
+    woff, wdata = oracle_c.pack_strings(strs)
+    assert_bits(host(off), woff); assert_bits(host(data), wdata)
+    keys = ops.hash_strings(off, data)
+    want_keys = oracle_c.hash_strings_buf(woff, wdata)
+    assert_bits(host(keys), want_keys)
+    keep, rep = ops.dedup(keys, None, "first")
+    want_keep, want_rep = oracle_c.dedup(want_keys, np.zeros(n, np.uint8), "first")
+    assert_bits(host(keep), want_keep); assert_bits(host(rep), want_rep)
+    assert 0.03 < 1 - want_keep.mean() < 0.07
+    # reference set with 10 % overlap
+    rid, roff, rdata = synth_device.make_urls(9, 0, n // 2, d, n_main_for_ref=n)
+    assert_bits(host(rid), synth.ref_ids_of(9, np.arange(n // 2), n))
+    rkeys = ops.hash_strings(roff, rdata)
+    k2, rr = ops.antijoin(keys, None, rkeys, None)
+    wk2, wrr = oracle_c.antijoin(want_keys, np.zeros(n, np.uint8), host(rkeys), np.zeros(n // 2, np.uint8))
+    assert_bits(host(k2), wk2); assert_bits(host(rr), wrr)
+
+
+# ---------------------------------------------------------------- K3 / K6 / YOLO
+def test_label_lut(cuda_device):
+    d = cuda_device
+    t = synth.make_table(2, 0, 5000)
+    lab = t.label_id.copy()
+    lab[::97] = -1
+    nv = 100
+    rng = np.random.RandomState(0)
+    lut_new = rng.randint(0, nv, nv).astype(np.int32); lut_ntok = rng.randint(0, 4, nv).astype(np.int32)
+    lut_nrep = np.minimum(lut_ntok, rng.randint(0, 3, nv)).astype(np.int32)
+    want_new, want_rr, want_c = oracle_c.label_lut(t.img_off, lab, lut_new, lut_ntok, lut_nrep)
+    new, rr, cnt = ops.label_lut(dev(t.img_off, d), dev(lab, d), dev(lut_new, d), dev(lut_ntok, d), dev(lut_nrep, d))
+    assert_bits(host(new), want_new); assert_bits(host(rr), want_rr)
+    assert dict(zip(ops.COUNTER_NAMES, [int(x) for x in host(cnt)])) == want_c
+    w2, r2, c2 = oracle_np.label_lut(t.img_off[:200], lab[:t.img_off[199]], lut_new, lut_ntok, lut_nrep)
+    assert np.array_equal(w2, want_new[:t.img_off[199]])
+
+
+@pytest.mark.parametrize("n_img,n_cat", [(1, 1), (300, 4), (70000, 20), (5000, 256)])
+def test_split_expand_and_assign(cuda_device, n_img, n_cat):
+    d = cuda_device
+    t = synth.make_table(n_cat, 0, n_img)
+    lab = t.label_id.copy(); lab[::53] = -1
+    rng = np.random.RandomState(n_cat)
+    cat = rng.randint(-1, n_cat, synth.N_LABELS).astype(np.int32)
+    wi, wb, wc, woff = oracle_c.split_expand(t.img_off, lab, cat, n_cat)
+    ei, eb, ec, coff = ops.split_expand(dev(t.img_off, d), dev(lab, d), dev(cat, d), n_cat)
+    assert_bits(host(coff), woff); assert_bits(host(ei), wi); assert_bits(host(eb), wb); assert_bits(host(ec), wc)
+    if n_img <= 300:
+        ni, nb, nc, noff = oracle_np.split_expand(t.img_off, lab, cat, n_cat)
+        assert np.array_equal(ni, wi) and np.array_equal(nb, wb) and np.array_equal(noff, woff)
+    want_split, want_pos = oracle_np.split_assign(woff, 0.8, 0.1, 0.1, 42)
+    perm = np.concatenate([np.random.RandomState(42).permutation(int(woff[c + 1] - woff[c])) for c in range(n_cat)] + [np.zeros(0, np.int64)]).astype(np.int64)
+    sizes = np.diff(woff)
+    ntr = np.array([int(n * 0.8) for n in sizes], np.int64); nva = np.array([int(n * 0.1) for n in sizes], np.int64)
+    if len(perm):
+        split, pos = ops.split_assign(coff, dev(perm, d), dev(ntr, d), dev(nva, d))
+        assert_bits(host(split), want_split); assert_bits(host(pos), want_pos)
+
+
+def test_yolo_normalise(cuda_device):
+    d = cuda_device
+    img_off, poly_off, xy = tables.random_polygon_table(8, 300)
+    pts, valid, _ = oracle_c.bbox_fold(poly_off, xy)
+    n_img = len(img_off) - 1
+    wh = np.tile(np.array([1920.0, 1080.0]), n_img); wh[10] = 0.0
+    out, ok = ops.yolo_normalise(dev(img_off, d), dev(pts, d), dev(valid, d), dev(wh, d))
+    out, ok = host(out), host(ok)
+    for i in range(n_img):
+        for q in range(img_off[i], img_off[i + 1]):
+            w = oracle_np.yolo_norm(tuple(pts[4 * q:4 * q + 4]), wh[2 * i], wh[2 * i + 1]) if valid[q] and wh[2 * i] and wh[2 * i + 1] else None
+            assert bool(ok[q]) == (w is not None), (i, q)
+            if w is not None:
+                assert np.array(w).tobytes() == out[4 * q:4 * q + 4].tobytes()
+
+
+# ---------------------------------------------------------------- host-buffer entry points
+def test_host_entry_points(cuda_device):
+    t = synth.make_table(12, 0, 40000)
+    want_pts, want_valid, want_arg = oracle_c.bbox_fold(t.poly_off, t.xy)
+    want_high, want_count = oracle_c.iou_filter(t.img_off, want_pts, want_valid, 2, 0.7)
+    for chunk in (0, 1777, 100000):
+        out = ops.bbox_iou_host(t.img_off, t.poly_off, t.xy, 2, 0.7, want_pts=True, want_arg=True, chunk_images=chunk)
+        assert_bits(out["pts"], want_pts); assert_bits(out["valid"], want_valid); assert_bits(out["arg"], want_arg)
+        assert_bits(out["high"], want_high); assert_bits(out["count"], want_count)
+    strs = [synth.url_of(i) for i in synth.url_ids_of(12, np.arange(20000))]
+    off, data = oracle_c.pack_strings(strs)
+    null = np.zeros(len(strs), np.uint8); null[5] = null[77] = 1
+    keep, rep = ops.dedup_host(off, data, null, "first")
+    wk, wr = oracle_c.dedup(oracle_c.hash_strings_buf(off, data), null, "first")
+    assert_bits(keep, wk); assert_bits(rep, wr)
