@@ -11,8 +11,6 @@
 
 namespace dyd {
 
-constexpr int GROUP = 8;                 // lanes cooperating on one polygon
-constexpr int GROUPS_PER_WARP = 4;
 constexpr int WARP_BOX_CAP = 64;         // images with more objects go to the block-per-image kernel
 constexpr int PAIR_LUT_N = WARP_BOX_CAP * (WARP_BOX_CAP - 1) / 2;   // 2016
 constexpr int IDX_NONE = 0x7fffffff;
@@ -29,27 +27,28 @@ struct CornerIdx {
 };
 
 // ---------------------------------------------------------------------------------------
-// Fast path: V <= 32, values only.  Each lane holds vertices gl, gl+8, gl+16, gl+24 (one
-// coalesced 128-byte request per group and step).  CPython's fold equals
+// Fast path: V <= G*S, values only.  G lanes cooperate on one polygon; lane gl holds vertices
+// gl, gl+G, gl+2G, ... (S slots), so each step of a group is one contiguous 16*G-byte request.
+// CPython's fold equals
 //     first vertex is NaN ? that NaN : min over the non-NaN values,
 // so the lanes reduce with +-inf identities (a NaN never wins a strict comparison) and lane 0,
 // which owns vertex 0, applies the NaN rule.  Equal values have equal bits except +-0.0; when a
 // result is zero the group finds the FIRST zero in vertex order and takes its sign.
 // The result is valid in the group's lane 0.
 // ---------------------------------------------------------------------------------------
-template <typename LoadFn>
+template <int G, int S, typename LoadFn>
 __device__ __forceinline__ Corner group_bbox_fast(LoadFn load, int V, int gl, unsigned gmask) {
-    double2 v[4];
-    bool in[4];
+    double2 v[S];
+    bool in[S];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        int k = gl + GROUP * t;
+    for (int t = 0; t < S; ++t) {
+        int k = gl + G * t;
         in[t] = k < V;
         v[t] = in[t] ? load(k) : make_double2(0.0, 0.0);
     }
     Corner c{pos_inf(), pos_inf(), neg_inf(), neg_inf()};
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < S; ++t) {
         if (in[t]) {
             c.mnx = v[t].x < c.mnx ? v[t].x : c.mnx;
             c.mxx = v[t].x > c.mxx ? v[t].x : c.mxx;
@@ -58,7 +57,7 @@ __device__ __forceinline__ Corner group_bbox_fast(LoadFn load, int V, int gl, un
         }
     }
 #pragma unroll
-    for (int off = GROUP / 2; off >= 1; off >>= 1) {
+    for (int off = G / 2; off >= 1; off >>= 1) {
         double o;
         o = __shfl_xor_sync(gmask, c.mnx, off); c.mnx = o < c.mnx ? o : c.mnx;
         o = __shfl_xor_sync(gmask, c.mxx, off); c.mxx = o > c.mxx ? o : c.mxx;
@@ -71,13 +70,13 @@ __device__ __forceinline__ Corner group_bbox_fast(LoadFn load, int V, int gl, un
     if (__any_sync(gmask, zx | zy)) {
         int kx = IDX_NONE, ky = IDX_NONE;          // (vertex index << 1) | sign of this lane's first zero
 #pragma unroll
-        for (int t = 3; t >= 0; --t) {
-            int k = gl + GROUP * t;
+        for (int t = S - 1; t >= 0; --t) {
+            int k = gl + G * t;
             if (in[t] && v[t].x == 0.0) kx = (k << 1) | (is_neg_bits(v[t].x) ? 1 : 0);
             if (in[t] && v[t].y == 0.0) ky = (k << 1) | (is_neg_bits(v[t].y) ? 1 : 0);
         }
 #pragma unroll
-        for (int off = GROUP / 2; off >= 1; off >>= 1) {
+        for (int off = G / 2; off >= 1; off >>= 1) {
             kx = min(kx, __shfl_xor_sync(gmask, kx, off));
             ky = min(ky, __shfl_xor_sync(gmask, ky, off));
         }
@@ -96,7 +95,7 @@ __device__ __forceinline__ Corner group_bbox_fast(LoadFn load, int V, int gl, un
 
 // ---------------------------------------------------------------------------------------
 // General path: any V, tracks the vertex index of every extreme (needed for d_arg and for
-// V > 32).  (value, index) with "smaller index wins ties" is associative, so lanes fold their
+// V > G*S).  (value, index) with "smaller index wins ties" is associative, so lanes fold their
 // strided vertices and the group combines by butterfly; NaNs are skipped except at vertex 0.
 // Result valid in the group's lane 0.
 // ---------------------------------------------------------------------------------------
@@ -109,24 +108,24 @@ __device__ __forceinline__ void take_max(double& m, int& im, double o, int io) {
     m = t ? o : m; im = t ? io : im;
 }
 
-template <typename LoadFn>
+template <int G, int S, typename LoadFn>
 __device__ __forceinline__ Corner group_bbox_indexed(LoadFn load, int V, int gl, unsigned gmask, CornerIdx& ci) {
     Corner c{pos_inf(), pos_inf(), neg_inf(), neg_inf()};
     ci = CornerIdx{IDX_NONE, IDX_NONE, IDX_NONE, IDX_NONE};
     double2 v0 = make_double2(0.0, 0.0);
-    for (int k0 = 0; k0 < V; k0 += 4 * GROUP) {
-        double2 v[4];
-        bool in[4];
+    for (int k0 = 0; k0 < V; k0 += S * G) {
+        double2 v[S];
+        bool in[S];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            int k = k0 + gl + GROUP * t;
+        for (int t = 0; t < S; ++t) {
+            int k = k0 + gl + G * t;
             in[t] = k < V;
             v[t] = in[t] ? load(k) : make_double2(0.0, 0.0);
         }
         if (k0 == 0) v0 = v[0];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            int k = k0 + gl + GROUP * t;
+        for (int t = 0; t < S; ++t) {
+            int k = k0 + gl + G * t;
             if (in[t]) {
                 // first non-NaN value is taken unconditionally, later ones on strict comparison
                 if (v[t].x == v[t].x) {
@@ -141,7 +140,7 @@ __device__ __forceinline__ Corner group_bbox_indexed(LoadFn load, int V, int gl,
         }
     }
 #pragma unroll
-    for (int off = GROUP / 2; off >= 1; off >>= 1) {
+    for (int off = G / 2; off >= 1; off >>= 1) {
         double o; int io;
         o = __shfl_xor_sync(gmask, c.mnx, off); io = __shfl_xor_sync(gmask, ci.mnx, off); take_min(c.mnx, ci.mnx, o, io);
         o = __shfl_xor_sync(gmask, c.mxx, off); io = __shfl_xor_sync(gmask, ci.mxx, off); take_max(c.mxx, ci.mxx, o, io);
@@ -153,6 +152,13 @@ __device__ __forceinline__ Corner group_bbox_indexed(LoadFn load, int V, int gl,
         if (v0.y != v0.y) { c.mny = c.mxy = v0.y; ci.mny = ci.mxy = 0; }
     }
     return c;
+}
+
+// One group folds a polygon of V vertices read through `load(k)`; picks the path.
+template <int G, int S, bool ARG, typename LoadFn>
+__device__ __forceinline__ Corner group_bbox(LoadFn load, int V, int gl, unsigned gmask, CornerIdx& ci) {
+    if (ARG || V > G * S) return group_bbox_indexed<G, S>(load, V, gl, gmask, ci);
+    return group_bbox_fast<G, S>(load, V, gl, gmask);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -191,14 +197,25 @@ __device__ __forceinline__ bool iou_hits(const Box& a, const Box& b, double thr,
 }
 
 // Pair k -> (s, t), s < t, ordered by t then s: k = t(t-1)/2 + s.  Valid for an image with n
-// boxes iff t < n, i.e. k < n(n-1)/2; the table does not depend on n.
-__device__ __forceinline__ void fill_pair_lut(unsigned short* st, int tid, int nthreads) {
-    for (int k = tid; k < PAIR_LUT_N; k += nthreads) {
-        int t = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)k)) * 0.5f);
-        while (t * (t - 1) / 2 > k) --t;
-        while ((t + 1) * t / 2 <= k) ++t;
-        st[k] = (unsigned short)((t << 8) | (k - t * (t - 1) / 2));
-    }
+// boxes iff t < n, i.e. k < n(n-1)/2; the table does not depend on n.  Built at compile time,
+// lives in global memory (4 KB, L2 resident) and is copied to shared memory by each CTA.
+struct PairTable {
+    unsigned short st[PAIR_LUT_N + 8];     // (t << 8) | s ; padded to a multiple of 16 bytes
+};
+constexpr PairTable make_pair_table() {
+    PairTable t{};
+    int k = 0;
+    for (int tt = 1; tt < WARP_BOX_CAP; ++tt)
+        for (int s = 0; s < tt; ++s) t.st[k++] = (unsigned short)((tt << 8) | s);
+    return t;
+}
+__device__ const PairTable g_pair_table = make_pair_table();
+static_assert(sizeof(PairTable) % 16 == 0, "pair table must be copyable in 16-byte pieces");
+
+__device__ __forceinline__ void load_pair_lut(unsigned short* st, int tid, int nthreads) {
+    const uint4* src = reinterpret_cast<const uint4*>(g_pair_table.st);
+    uint4* dst = reinterpret_cast<uint4*>(st);
+    for (int k = tid; k < (int)(sizeof(PairTable) / 16); k += nthreads) dst[k] = __ldg(src + k);
 }
 
 // Warp-level any-pair test over n boxes stored as rows of 4 doubles in shared memory.

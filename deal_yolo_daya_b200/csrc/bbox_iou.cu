@@ -1,11 +1,16 @@
-// K1 (polygon -> corner points), K2 (box count + any-pair IoU) and the fused K1+K2 path.
+// K1 (polygon -> corner points), K2 (box count + any-pair IoU) and the direct-load fused path.
 //
-// Direct-load variant ("v1"): warps read the vertex stream with 128-bit non-allocating loads,
-// an 8-lane group per polygon, four polygons per warp step.  The fused kernel keeps each
-// image's boxes in shared memory for the pair test, so boxes are written to HBM once and
-// never re-read.  Images with more than WARP_BOX_CAP objects are appended to a worklist and
-// finished by a block-per-image kernel (shared-memory SoA tile, circular half-range pairing).
-#include "bbox_core.cuh"
+// Direct-load kernels: warps read the vertex stream with 128-bit non-allocating loads, a
+// G-lane group per polygon (32/G polygons per warp step).  The fused kernel keeps each image's
+// boxes in shared memory for the pair test, so boxes are written to HBM once and never
+// re-read.  Images with more than WARP_BOX_CAP objects go to a worklist and are finished by a
+// block-per-image kernel (shared-memory SoA tile, circular half-range pairing).
+// The TMA-staged, warp-specialised fused kernel lives in bbox_tma.cu; dyd_bbox_iou_fused
+// picks between the two (DYD_FUSED=direct|tma, default tma).
+#include <stdlib.h>
+#include <string.h>
+
+#include "kernels.cuh"
 
 namespace dyd {
 
@@ -13,49 +18,59 @@ constexpr int CTA_THREADS = 256;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
 constexpr int CROWD_SMEM_BOXES = 1024;
 
-struct CrowdList {
-    unsigned long long count;   // number of deferred images
-    unsigned long long pad;
-    // int32 image ids follow
-};
-__device__ __forceinline__ int* crowd_ids(void* ws) { return reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + sizeof(CrowdList)); }
-
 __device__ __forceinline__ void store_corner(double* pts, int64_t p, const Corner& c) {
     double2* o = reinterpret_cast<double2*>(pts + 4 * p);
     stg_stream_f64x2(o, make_double2(c.mnx, c.mny));
     stg_stream_f64x2(o + 1, make_double2(c.mxx, c.mxy));
 }
 
-// One group folds polygon [a, a+V) of the global vertex array.  Result in the group's lane 0.
-template <bool ARG>
+// One G-lane group folds polygon [a, a+V) of the global vertex array (32/G register slots per
+// lane).  Result in the group's lane 0.
+template <bool ARG, int G>
 __device__ __forceinline__ Corner fold_polygon(const double2* __restrict__ xy2, int64_t a, int V, int gl,
                                                unsigned gmask, CornerIdx& ci) {
     auto load = [&](int k) { return ldg_stream_f64x2(xy2 + a + k); };
-    if (ARG || V > 4 * GROUP) return group_bbox_indexed(load, V, gl, gmask, ci);
-    return group_bbox_fast(load, V, gl, gmask);
+    return group_bbox<G, 32 / G, ARG>(load, V, gl, gmask, ci);
 }
 
 // ------------------------------------------------------------------------------- K1
-template <bool ARG>
+template <bool ARG, int G>
 __global__ void __launch_bounds__(CTA_THREADS)
 bbox_kernel(const int64_t* __restrict__ poly_off, const double2* __restrict__ xy2, int64_t n_poly,
             double* __restrict__ pts, uint8_t* __restrict__ valid, int32_t* __restrict__ arg) {
-    const int lane = threadIdx.x & 31, gl = lane & (GROUP - 1), g = lane / GROUP;
-    const unsigned gmask = 0xffu << (g * GROUP);
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), g = lane / G;
+    const unsigned gmask = (G == 32 ? FULL : ((1u << G) - 1u) << (g * G));
     const int64_t warp = (blockIdx.x * (int64_t)CTA_THREADS + threadIdx.x) >> 5;
-    const int64_t p = warp * GROUPS_PER_WARP + g;
+    const int64_t p = warp * (32 / G) + g;
     if (p >= n_poly) return;                       // whole group leaves together
     const int64_t a = __ldg(poly_off + p), b = __ldg(poly_off + p + 1);
     const int64_t Vl = b - a;
     const int V = Vl > 0x7fffffff ? 0x7fffffff : (int)Vl;
     Corner c{0.0, 0.0, 0.0, 0.0};
     CornerIdx ci{-1, -1, -1, -1};
-    if (V > 0) c = fold_polygon<ARG>(xy2, a, V, gl, gmask, ci);
+    if (V > 0) c = fold_polygon<ARG, G>(xy2, a, V, gl, gmask, ci);
     if (gl == 0) {
         store_corner(pts, p, c);
         valid[p] = V > 0 ? 1 : 0;
         if (ARG) *reinterpret_cast<int4*>(arg + 4 * p) = make_int4(ci.mnx, ci.mny, ci.mxx, ci.mxy);
     }
+}
+
+// Number of boxes before the first null bbox among objects [q0, q0+n) (warp-cooperative).
+__device__ __forceinline__ int64_t valid_prefix(const uint8_t* __restrict__ valid, int64_t q0, int64_t n, int lane) {
+    if (valid == nullptr) return n;
+    for (int64_t base = 0; base < n; base += 32) {
+        const int64_t j = base + lane;
+        const bool bad = j < n && valid[q0 + j] == 0;
+        const unsigned m = __ballot_sync(FULL, bad);
+        if (m) return base + (__ffs(m) - 1);
+    }
+    return n;
+}
+
+__device__ __forceinline__ void defer_image(void* ws, int64_t img) {
+    unsigned long long slot = atomicAdd(&reinterpret_cast<CrowdList*>(ws)->count, 1ULL);
+    crowd_ids(ws)[slot] = (int)img;
 }
 
 // ------------------------------------------------------------------------------- K2 (warp per image)
@@ -64,165 +79,193 @@ iou_warp_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ 
                 int64_t n_img, int64_t min_boxes, double thr, uint8_t* __restrict__ high,
                 int32_t* __restrict__ count, void* ws) {
     __shared__ __align__(16) double sbox[CTA_WARPS][WARP_BOX_CAP * 4];
-    __shared__ unsigned short lut[PAIR_LUT_N];
-    fill_pair_lut(lut, threadIdx.x, CTA_THREADS);
+    __shared__ __align__(16) unsigned short lut[PAIR_LUT_N + 8];
+    load_pair_lut(lut, threadIdx.x, CTA_THREADS);
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t img = blockIdx.x * (int64_t)CTA_WARPS + w;
-    if (img >= n_img) return;
     const bool zero_hits = 0.0 >= thr;
-    const int64_t q0 = __ldg(img_off + img), q1 = __ldg(img_off + img + 1);
-    const int64_t n = q1 - q0;
-    // effective boxes = prefix before the first null bbox
-    int64_t n_eff = n;
-    if (valid != nullptr) {
-        for (int64_t base = 0; base < n; base += 32) {
-            int64_t j = base + lane;
-            bool bad = j < n && valid[q0 + j] == 0;
-            unsigned m = __ballot_sync(FULL, bad);
-            if (m) { n_eff = base + (__ffs(m) - 1); break; }
+    for (int64_t img = blockIdx.x * (int64_t)CTA_WARPS + w; img < n_img; img += (int64_t)gridDim.x * CTA_WARPS) {
+        const int64_t q0 = __ldg(img_off + img), q1 = __ldg(img_off + img + 1);
+        const int64_t n = q1 - q0;
+        if (n > WARP_BOX_CAP) {                      // crowded: the block kernel computes count and high
+            if (lane == 0) defer_image(ws, img);
+            continue;
         }
-    }
-    if (lane == 0) count[img] = (int32_t)(n_eff > 0x7fffffff ? 0x7fffffff : n_eff);
-    bool hit = false, deferred = false;
-    if (n_eff >= min_boxes && n_eff >= 2) {
-        if (n_eff <= WARP_BOX_CAP) {
+        const int n_eff = (int)valid_prefix(valid, q0, n, lane);
+        bool hit = false;
+        if (n_eff >= min_boxes && n_eff >= 2) {
             const double2* src = reinterpret_cast<const double2*>(pts + 4 * q0);
-            for (int j = lane; j < (int)n_eff; j += 32) {
+            __syncwarp();
+            for (int j = lane; j < n_eff; j += 32) {
                 double2 p1 = ldg_stream_f64x2(src + 2 * j), p2 = ldg_stream_f64x2(src + 2 * j + 1);
                 Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
                 double2* d = reinterpret_cast<double2*>(&sbox[w][4 * j]);
                 d[0] = make_double2(bx.x1, bx.y1); d[1] = make_double2(bx.x2, bx.y2);
             }
             __syncwarp();
-            hit = warp_any_pair(sbox[w], (int)n_eff, thr, zero_hits, lut, lane);
-        } else {
-            deferred = true;
-            if (lane == 0) {
-                unsigned long long slot = atomicAdd(&reinterpret_cast<CrowdList*>(ws)->count, 1ULL);
-                crowd_ids(ws)[slot] = (int)img;
-            }
+            hit = warp_any_pair(sbox[w], n_eff, thr, zero_hits, lut, lane);
         }
+        if (lane == 0) { count[img] = n_eff; high[img] = hit ? 1 : 0; }
     }
-    if (lane == 0 && !deferred) high[img] = hit ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------- K2 (block per crowded image)
+// Processes the worklist: computes the valid prefix, writes count and high.
 __global__ void __launch_bounds__(CTA_THREADS)
-iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const int32_t* __restrict__ count,
-                 double thr, uint8_t* __restrict__ high, void* ws) {
+iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
+                 int64_t min_boxes, double thr, uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
     __shared__ double sx1[CROWD_SMEM_BOXES], sy1[CROWD_SMEM_BOXES], sx2[CROWD_SMEM_BOXES], sy2[CROWD_SMEM_BOXES];
     __shared__ int found;
+    __shared__ long long first_bad;
     const unsigned long long n_list = reinterpret_cast<CrowdList*>(ws)->count;
     const int* ids = crowd_ids(ws);
     const bool zero_hits = 0.0 >= thr;
     for (unsigned long long e = blockIdx.x; e < n_list; e += gridDim.x) {
         const int64_t img = ids[e];
-        const int64_t q0 = img_off[img];
-        const int n = count[img];
+        const int64_t q0 = img_off[img], n_all = img_off[img + 1] - q0;
+        __syncthreads();                              // previous image fully consumed
+        if (threadIdx.x == 0) { found = 0; first_bad = n_all; }
+        __syncthreads();
+        if (valid != nullptr) {
+            long long mine = n_all;
+            for (int64_t j = threadIdx.x; j < n_all; j += CTA_THREADS)
+                if (valid[q0 + j] == 0) { mine = j; break; }
+            if (mine < n_all) atomicMin(&first_bad, mine);
+        }
+        __syncthreads();
+        const int64_t n64 = first_bad;
+        const int n = n64 > 0x7fffffff ? 0x7fffffff : (int)n64;
+        const bool want = n64 >= min_boxes && n >= 2;
         const double2* src = reinterpret_cast<const double2*>(pts + 4 * q0);
         const bool in_smem = n <= CROWD_SMEM_BOXES;
-        __syncthreads();                              // previous image fully consumed
-        if (threadIdx.x == 0) found = 0;
-        if (in_smem) {
+        if (want && in_smem) {
             for (int j = threadIdx.x; j < n; j += CTA_THREADS) {
-                double2 p1 = ldg_stream_f64x2(src + 2 * j), p2 = ldg_stream_f64x2(src + 2 * j + 1);
+                double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
                 Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
                 sx1[j] = bx.x1; sy1[j] = bx.y1; sx2[j] = bx.x2; sy2[j] = bx.y2;
             }
         }
         __syncthreads();
-        // circular half-range pairing: box s meets s+1 .. s+(n-1)/2 (mod n); for even n the
-        // antipodal pair is taken by the lower half only.  Covers every unordered pair once.
-        const int half = (n - 1) / 2;
-        const bool even = (n & 1) == 0;
-        for (int s = threadIdx.x; s < n; s += CTA_THREADS) {
-            Box a;
-            if (in_smem) a = Box{sx1[s], sy1[s], sx2[s], sy2[s]};
-            else { double2 p1 = ldg_f64x2(src + 2 * s), p2 = ldg_f64x2(src + 2 * s + 1); a = box_from_points(p1.x, p1.y, p2.x, p2.y); }
-            const int dmax = half + ((even && s < n / 2) ? 1 : 0);
-            bool mine = false;
-            for (int d = 1; d <= dmax && !mine; ++d) {
-                int t = s + d; if (t >= n) t -= n;
-                Box b;
-                if (in_smem) b = Box{sx1[t], sy1[t], sx2[t], sy2[t]};
-                else { double2 p1 = ldg_f64x2(src + 2 * t), p2 = ldg_f64x2(src + 2 * t + 1); b = box_from_points(p1.x, p1.y, p2.x, p2.y); }
-                mine = iou_hits(a, b, thr, zero_hits);
-                if ((d & 15) == 0 && *(volatile int*)&found) break;
+        if (want) {
+            // circular half-range pairing: box s meets s+1 .. s+(n-1)/2 (mod n); for even n the
+            // antipodal pair is taken by the lower half only.  Covers every unordered pair once.
+            const int half = (n - 1) / 2;
+            const bool even = (n & 1) == 0;
+            for (int s = threadIdx.x; s < n; s += CTA_THREADS) {
+                Box a;
+                if (in_smem) a = Box{sx1[s], sy1[s], sx2[s], sy2[s]};
+                else { double2 p1 = ldg_f64x2(src + 2 * s), p2 = ldg_f64x2(src + 2 * s + 1); a = box_from_points(p1.x, p1.y, p2.x, p2.y); }
+                const int dmax = half + ((even && s < n / 2) ? 1 : 0);
+                bool mine = false;
+                for (int d = 1; d <= dmax && !mine; ++d) {
+                    int t = s + d; if (t >= n) t -= n;
+                    Box b;
+                    if (in_smem) b = Box{sx1[t], sy1[t], sx2[t], sy2[t]};
+                    else { double2 p1 = ldg_f64x2(src + 2 * t), p2 = ldg_f64x2(src + 2 * t + 1); b = box_from_points(p1.x, p1.y, p2.x, p2.y); }
+                    mine = iou_hits(a, b, thr, zero_hits);
+                    if ((d & 15) == 0 && *(volatile int*)&found) break;
+                }
+                if (mine) found = 1;
+                if (*(volatile int*)&found) break;
             }
-            if (mine) found = 1;
-            if (*(volatile int*)&found) break;
         }
         __syncthreads();
-        if (threadIdx.x == 0) high[img] = found ? 1 : 0;
+        if (threadIdx.x == 0) { high[img] = found ? 1 : 0; count[img] = n; }
     }
 }
 
-// ------------------------------------------------------------------------------- fused K1 + K2
-template <bool ARG>
+// ------------------------------------------------------------------------------- fused K1 + K2 (direct loads)
+template <bool ARG, int G>
 __global__ void __launch_bounds__(CTA_THREADS)
 fused_warp_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off,
                   const double2* __restrict__ xy2, int64_t n_img, int64_t min_boxes, double thr,
                   double* __restrict__ pts, uint8_t* __restrict__ valid, int32_t* __restrict__ arg,
                   uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
     __shared__ __align__(16) double sbox[CTA_WARPS][WARP_BOX_CAP * 4];
-    __shared__ unsigned short lut[PAIR_LUT_N];
-    fill_pair_lut(lut, threadIdx.x, CTA_THREADS);
+    __shared__ __align__(16) unsigned short lut[PAIR_LUT_N + 8];
+    load_pair_lut(lut, threadIdx.x, CTA_THREADS);
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int gl = lane & (GROUP - 1), g = lane / GROUP;
-    const unsigned gmask = 0xffu << (g * GROUP);
-    const int64_t img = blockIdx.x * (int64_t)CTA_WARPS + w;
-    if (img >= n_img) return;
+    const int gl = lane & (G - 1), g = lane / G;
+    const unsigned gmask = (G == 32 ? FULL : ((1u << G) - 1u) << (g * G));
     const bool zero_hits = 0.0 >= thr;
-    const int64_t q0 = __ldg(img_off + img), q1 = __ldg(img_off + img + 1);
-    const int64_t n = q1 - q0;
-    int64_t n_eff = n;
-    for (int64_t base = 0; base < n; base += GROUPS_PER_WARP) {
-        const int64_t j = base + g;
-        const bool active = j < n;
-        int V = 1;
-        if (active) {
-            const int64_t p = q0 + j;
-            const int64_t a = __ldg(poly_off + p), b = __ldg(poly_off + p + 1);
-            const int64_t Vl = b - a;
-            V = Vl > 0x7fffffff ? 0x7fffffff : (int)Vl;
-            Corner c{0.0, 0.0, 0.0, 0.0};
-            CornerIdx ci{-1, -1, -1, -1};
-            if (V > 0) c = fold_polygon<ARG>(xy2, a, V, gl, gmask, ci);
-            if (gl == 0) {
-                store_corner(pts, p, c);
-                valid[p] = V > 0 ? 1 : 0;
-                if (ARG) *reinterpret_cast<int4*>(arg + 4 * p) = make_int4(ci.mnx, ci.mny, ci.mxx, ci.mxy);
-                if (j < WARP_BOX_CAP) {
-                    Box bx = box_from_points(c.mnx, c.mny, c.mxx, c.mxy);
-                    double2* d = reinterpret_cast<double2*>(&sbox[w][4 * j]);
-                    d[0] = make_double2(bx.x1, bx.y1); d[1] = make_double2(bx.x2, bx.y2);
+    for (int64_t img = blockIdx.x * (int64_t)CTA_WARPS + w; img < n_img; img += (int64_t)gridDim.x * CTA_WARPS) {
+        const int64_t q0 = __ldg(img_off + img), q1 = __ldg(img_off + img + 1);
+        const int64_t n = q1 - q0;
+        int64_t n_eff = n;
+        __syncwarp();
+        for (int64_t base = 0; base < n; base += 32 / G) {
+            const int64_t j = base + g;
+            const bool active = j < n;
+            int V = 1;
+            if (active) {
+                const int64_t p = q0 + j;
+                const int64_t a = __ldg(poly_off + p), b = __ldg(poly_off + p + 1);
+                const int64_t Vl = b - a;
+                V = Vl > 0x7fffffff ? 0x7fffffff : (int)Vl;
+                Corner c{0.0, 0.0, 0.0, 0.0};
+                CornerIdx ci{-1, -1, -1, -1};
+                if (V > 0) c = fold_polygon<ARG, G>(xy2, a, V, gl, gmask, ci);
+                if (gl == 0) {
+                    store_corner(pts, p, c);
+                    valid[p] = V > 0 ? 1 : 0;
+                    if (ARG) *reinterpret_cast<int4*>(arg + 4 * p) = make_int4(ci.mnx, ci.mny, ci.mxx, ci.mxy);
+                    if (j < WARP_BOX_CAP) {
+                        Box bx = box_from_points(c.mnx, c.mny, c.mxx, c.mxy);
+                        double2* d = reinterpret_cast<double2*>(&sbox[w][4 * j]);
+                        d[0] = make_double2(bx.x1, bx.y1); d[1] = make_double2(bx.x2, bx.y2);
+                    }
                 }
             }
+            const unsigned bad = __ballot_sync(FULL, active && gl == 0 && V <= 0);
+            if (bad && n_eff == n) n_eff = base + (__ffs(bad) - 1) / G;
         }
-        const unsigned bad = __ballot_sync(FULL, active && gl == 0 && V <= 0);
-        if (bad && n_eff == n) n_eff = base + (__ffs(bad) - 1) / GROUP;
-    }
-    __syncwarp();
-    if (lane == 0) count[img] = (int32_t)(n_eff > 0x7fffffff ? 0x7fffffff : n_eff);
-    bool hit = false, deferred = false;
-    if (n_eff >= min_boxes && n_eff >= 2) {
-        if (n_eff <= WARP_BOX_CAP) {
-            hit = warp_any_pair(sbox[w], (int)n_eff, thr, zero_hits, lut, lane);
-        } else {
-            deferred = true;
-            if (lane == 0) {
-                __threadfence();                       // boxes visible to the crowd kernel's loads
-                unsigned long long slot = atomicAdd(&reinterpret_cast<CrowdList*>(ws)->count, 1ULL);
-                crowd_ids(ws)[slot] = (int)img;
-            }
+        __syncwarp();
+        if (n > WARP_BOX_CAP) {                      // crowded: finished by the block kernel after this one
+            if (lane == 0) defer_image(ws, img);
+            continue;
         }
+        bool hit = false;
+        if (n_eff >= min_boxes && n_eff >= 2) hit = warp_any_pair(sbox[w], (int)n_eff, thr, zero_hits, lut, lane);
+        if (lane == 0) { count[img] = (int32_t)n_eff; high[img] = hit ? 1 : 0; }
     }
-    if (lane == 0 && !deferred) high[img] = hit ? 1 : 0;
 }
 
 static inline int crowd_grid() { return NUM_SMS * 4; }
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int launch_crowd(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid, int64_t min_boxes,
+                 double thr, uint8_t* d_high, int32_t* d_count, void* ws, cudaStream_t s) {
+    iou_crowd_kernel<<<crowd_grid(), CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, ws);
+    return launch_check("iou_crowd_kernel");
+}
+
+template <bool ARG>
+static int launch_bbox(int G, unsigned grid, cudaStream_t s, const int64_t* po, const double2* xy2, int64_t n,
+                       double* pts, uint8_t* valid, int32_t* arg) {
+    switch (G) {
+        case 2: bbox_kernel<ARG, 2><<<grid, CTA_THREADS, 0, s>>>(po, xy2, n, pts, valid, arg); break;
+        case 8: bbox_kernel<ARG, 8><<<grid, CTA_THREADS, 0, s>>>(po, xy2, n, pts, valid, arg); break;
+        default: bbox_kernel<ARG, 4><<<grid, CTA_THREADS, 0, s>>>(po, xy2, n, pts, valid, arg); break;
+    }
+    return launch_check("bbox_kernel");
+}
+
+template <bool ARG>
+static int launch_fused_direct(int G, unsigned grid, cudaStream_t s, const int64_t* io, const int64_t* po,
+                               const double2* xy2, int64_t n_img, int64_t mb, double thr, double* pts, uint8_t* valid,
+                               int32_t* arg, uint8_t* high, int32_t* count, void* ws) {
+    switch (G) {
+        case 2: fused_warp_kernel<ARG, 2><<<grid, CTA_THREADS, 0, s>>>(io, po, xy2, n_img, mb, thr, pts, valid, arg, high, count, ws); break;
+        case 8: fused_warp_kernel<ARG, 8><<<grid, CTA_THREADS, 0, s>>>(io, po, xy2, n_img, mb, thr, pts, valid, arg, high, count, ws); break;
+        default: fused_warp_kernel<ARG, 4><<<grid, CTA_THREADS, 0, s>>>(io, po, xy2, n_img, mb, thr, pts, valid, arg, high, count, ws); break;
+    }
+    return launch_check("fused_warp_kernel");
+}
 
 }  // namespace dyd
 
@@ -230,7 +273,7 @@ using namespace dyd;
 
 extern "C" size_t dyd_iou_workspace_bytes(int64_t n_img) {
     if (n_img < 0) n_img = 0;
-    return sizeof(CrowdList) + sizeof(int) * (size_t)n_img + 16;
+    return crowd_list_bytes(n_img) + tile_desc_bytes(n_img);
 }
 
 extern "C" int dyd_bbox_minmax(const int64_t* d_poly_off, const double* d_xy, int64_t n_poly,
@@ -240,13 +283,14 @@ extern "C" int dyd_bbox_minmax(const int64_t* d_poly_off, const double* d_xy, in
     DYD_REQUIRE(d_poly_off && d_pts && d_valid, DYD_E_ARG, "null pointer");
     DYD_REQUIRE(((uintptr_t)d_xy & 15) == 0 && ((uintptr_t)d_pts & 15) == 0 && ((uintptr_t)d_arg & 15) == 0,
                 DYD_E_ALIGN, "xy / pts / arg must be 16-byte aligned");
-    const int64_t warps = (n_poly + GROUPS_PER_WARP - 1) / GROUPS_PER_WARP;
+    const int G = env_int("DYD_GROUP", 4);
+    const int per_warp = 32 / (G == 2 || G == 8 ? G : 4);
+    const int64_t warps = (n_poly + per_warp - 1) / per_warp;
     const int64_t grid = (warps + CTA_WARPS - 1) / CTA_WARPS;
     DYD_REQUIRE(grid <= 0x7fffffff, DYD_E_ARG, "too many polygons for one launch");
     const double2* xy2 = reinterpret_cast<const double2*>(d_xy);
-    if (d_arg) bbox_kernel<true><<<(unsigned)grid, CTA_THREADS, 0, as_stream(stream)>>>(d_poly_off, xy2, n_poly, d_pts, d_valid, d_arg);
-    else bbox_kernel<false><<<(unsigned)grid, CTA_THREADS, 0, as_stream(stream)>>>(d_poly_off, xy2, n_poly, d_pts, d_valid, nullptr);
-    return launch_check("bbox_kernel");
+    if (d_arg) return launch_bbox<true>(G, (unsigned)grid, as_stream(stream), d_poly_off, xy2, n_poly, d_pts, d_valid, d_arg);
+    return launch_bbox<false>(G, (unsigned)grid, as_stream(stream), d_poly_off, xy2, n_poly, d_pts, d_valid, nullptr);
 }
 
 extern "C" int dyd_iou_filter(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid,
@@ -259,11 +303,11 @@ extern "C" int dyd_iou_filter(const int64_t* d_img_off, const double* d_pts, con
     DYD_REQUIRE(workspace_bytes >= dyd_iou_workspace_bytes(n_img), DYD_E_WORKSPACE, "workspace too small");
     cudaStream_t s = as_stream(stream);
     DYD_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(CrowdList), s));
-    const int64_t grid = (n_img + CTA_WARPS - 1) / CTA_WARPS;
-    iou_warp_kernel<<<(unsigned)grid, CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, n_img, min_boxes, thr, d_high, d_count, d_workspace);
+    const int64_t want = (n_img + CTA_WARPS - 1) / CTA_WARPS;
+    const unsigned grid = (unsigned)(want < NUM_SMS * 32 ? want : NUM_SMS * 32);
+    iou_warp_kernel<<<grid, CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, n_img, min_boxes, thr, d_high, d_count, d_workspace);
     if (int rc = launch_check("iou_warp_kernel")) return rc;
-    iou_crowd_kernel<<<crowd_grid(), CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_count, thr, d_high, d_workspace);
-    return launch_check("iou_crowd_kernel");
+    return launch_crowd(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, d_workspace, s);
 }
 
 extern "C" int dyd_bbox_iou_fused(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
@@ -278,11 +322,21 @@ extern "C" int dyd_bbox_iou_fused(const int64_t* d_img_off, const int64_t* d_pol
     DYD_REQUIRE(workspace_bytes >= dyd_iou_workspace_bytes(n_img), DYD_E_WORKSPACE, "workspace too small");
     cudaStream_t s = as_stream(stream);
     DYD_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(CrowdList), s));
-    const int64_t grid = (n_img + CTA_WARPS - 1) / CTA_WARPS;
-    const double2* xy2 = reinterpret_cast<const double2*>(d_xy);
-    if (d_arg) fused_warp_kernel<true><<<(unsigned)grid, CTA_THREADS, 0, s>>>(d_img_off, d_poly_off, xy2, n_img, min_boxes, thr, d_pts, d_valid, d_arg, d_high, d_count, d_workspace);
-    else fused_warp_kernel<false><<<(unsigned)grid, CTA_THREADS, 0, s>>>(d_img_off, d_poly_off, xy2, n_img, min_boxes, thr, d_pts, d_valid, nullptr, d_high, d_count, d_workspace);
-    if (int rc = launch_check("fused_warp_kernel")) return rc;
-    iou_crowd_kernel<<<crowd_grid(), CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_count, thr, d_high, d_workspace);
-    return launch_check("iou_crowd_kernel");
+    const char* variant = getenv("DYD_FUSED");
+    const bool direct = variant && strcmp(variant, "direct") == 0;
+    // the staged kernel bulk-copies offset slices: they must be 16-byte addressable
+    const bool tma_ok = ((uintptr_t)d_img_off & 15) == 0 && ((uintptr_t)d_poly_off & 15) == 0;
+    if (!direct && tma_ok) {
+        if (int rc = launch_fused_tma(d_img_off, d_poly_off, d_xy, n_img, n_poly, min_boxes, thr, d_pts, d_valid, d_arg,
+                                      d_high, d_count, d_workspace, s)) return rc;
+    } else {
+        const int G = env_int("DYD_GROUP", 4);
+        const int64_t want = (n_img + CTA_WARPS - 1) / CTA_WARPS;
+        const unsigned grid = (unsigned)(want < NUM_SMS * 32 ? want : NUM_SMS * 32);
+        const double2* xy2 = reinterpret_cast<const double2*>(d_xy);
+        int rc = d_arg ? launch_fused_direct<true>(G, grid, s, d_img_off, d_poly_off, xy2, n_img, min_boxes, thr, d_pts, d_valid, d_arg, d_high, d_count, d_workspace)
+                       : launch_fused_direct<false>(G, grid, s, d_img_off, d_poly_off, xy2, n_img, min_boxes, thr, d_pts, d_valid, nullptr, d_high, d_count, d_workspace);
+        if (rc) return rc;
+    }
+    return launch_crowd(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, d_workspace, s);
 }

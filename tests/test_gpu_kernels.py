@@ -6,6 +6,8 @@ the full-size properties live in test_gpu_scale.py.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -33,14 +35,30 @@ def assert_bits(a, b, what=""):
         raise AssertionError(f"{what}: {len(bad)} mismatches, first at {bad[:8]}: got {a[bad[:8]]} want {b[bad[:8]]}")
 
 
+VARIANTS = (("tma", "4"), ("direct", "4"), ("direct", "8"), ("direct", "2"))   # (DYD_FUSED, DYD_GROUP)
+
+
+def set_variant(fused, group):
+    os.environ["DYD_FUSED"] = fused
+    os.environ["DYD_GROUP"] = group
+
+
+@pytest.fixture(autouse=True)
+def _default_variant():
+    yield
+    os.environ.pop("DYD_FUSED", None); os.environ.pop("DYD_GROUP", None)
+
+
 def check_bbox(poly_off, xy, d):
     want_pts, want_valid, want_arg = oracle_c.bbox_fold(poly_off, xy)
-    for want_arg_flag in (False, True):
-        pts, valid, arg = ops.bbox_minmax(dev(poly_off, d), dev(xy, d), want_arg=want_arg_flag)
-        assert_bits(host(pts), want_pts, f"pts(arg={want_arg_flag})")
-        assert_bits(host(valid), want_valid, "valid")
-        if want_arg_flag:
-            assert_bits(host(arg), want_arg, "arg")
+    for group in ("4", "8", "2"):
+        set_variant("tma", group)
+        for want_arg_flag in (False, True):
+            pts, valid, arg = ops.bbox_minmax(dev(poly_off, d), dev(xy, d), want_arg=want_arg_flag)
+            assert_bits(host(pts), want_pts, f"pts(arg={want_arg_flag}, G={group})")
+            assert_bits(host(valid), want_valid, "valid")
+            if want_arg_flag:
+                assert_bits(host(arg), want_arg, "arg")
     return want_pts, want_valid
 
 
@@ -48,14 +66,17 @@ def check_fused(img_off, poly_off, xy, d, params=((2, 0.7), (2, 0.98), (1, 0.0),
     want_pts, want_valid, want_arg = oracle_c.bbox_fold(poly_off, xy)
     for mb, thr in params:
         want_high, want_count = oracle_c.iou_filter(img_off, want_pts, want_valid, mb, thr)
-        for flag in (False, True):
-            out = ops.bbox_iou_fused(dev(img_off, d), dev(poly_off, d), dev(xy, d), mb, thr, want_arg=flag)
-            assert_bits(host(out.pts), want_pts, "fused pts")
-            assert_bits(host(out.valid), want_valid, "fused valid")
-            assert_bits(host(out.high), want_high, f"fused high mb={mb} thr={thr}")
-            assert_bits(host(out.count), want_count, "fused count")
-            if flag:
-                assert_bits(host(out.arg), want_arg, "fused arg")
+        for fused, group in VARIANTS:
+            set_variant(fused, group)
+            for flag in (False, True):
+                tag = f"{fused}/G{group}/arg={flag} mb={mb} thr={thr}"
+                out = ops.bbox_iou_fused(dev(img_off, d), dev(poly_off, d), dev(xy, d), mb, thr, want_arg=flag)
+                assert_bits(host(out.pts), want_pts, "fused pts " + tag)
+                assert_bits(host(out.valid), want_valid, "fused valid " + tag)
+                assert_bits(host(out.high), want_high, "fused high " + tag)
+                assert_bits(host(out.count), want_count, "fused count " + tag)
+                if flag:
+                    assert_bits(host(out.arg), want_arg, "fused arg " + tag)
         high, count = ops.iou_filter(dev(img_off, d), dev(want_pts, d), dev(want_valid, d), mb, thr)
         assert_bits(host(high), want_high, f"k2 high mb={mb} thr={thr}")
         assert_bits(host(count), want_count, "k2 count")
@@ -76,6 +97,15 @@ def test_random_polygons_with_specials(cuda_device, seed):
     img_off, poly_off, xy = tables.random_polygon_table(seed, 400, max_polys=14, max_verts=70)
     check_bbox(poly_off, xy, cuda_device)
     check_fused(img_off, poly_off, xy, cuda_device)
+
+
+@pytest.mark.parametrize("n_img,max_polys,max_verts", [(997, 3, 9), (240, 80, 6), (61, 6, 900), (13, 300, 5), (1201, 10, 33)])
+def test_fused_tile_shapes(cuda_device, n_img, max_polys, max_verts):
+    """Tile geometry of the staged kernel: ragged tails, stages that overflow (vertex or object
+    capacity -> fallback lane), crowded images inside fast tiles."""
+    img_off, poly_off, xy = tables.random_polygon_table(n_img + max_polys, n_img, max_polys=max_polys,
+                                                        max_verts=max_verts, p_empty=0.02, p_special=0.01)
+    check_fused(img_off, poly_off, xy, cuda_device, params=((2, 0.7), (1, 0.0)))
 
 
 def test_empty_and_tiny(cuda_device):
@@ -101,8 +131,11 @@ def test_synth_table_device_equals_numpy_and_oracle(cuda_device, seed, n):
     want_pts, want_valid, _ = oracle_c.bbox_fold(t.poly_off, t.xy)
     for mb, thr in ((2, 0.7), (2, 0.98)):
         want_high, want_count = oracle_c.iou_filter(t.img_off, want_pts, want_valid, mb, thr)
-        out = ops.bbox_iou_fused(g.img_off, g.poly_off, g.xy, mb, thr)
-        assert_bits(host(out.pts), want_pts); assert_bits(host(out.high), want_high); assert_bits(host(out.count), want_count)
+        for fused, group in VARIANTS[:2]:
+            set_variant(fused, group)
+            out = ops.bbox_iou_fused(g.img_off, g.poly_off, g.xy, mb, thr)
+            assert_bits(host(out.pts), want_pts, fused); assert_bits(host(out.valid), want_valid, fused)
+            assert_bits(host(out.high), want_high, fused); assert_bits(host(out.count), want_count, fused)
         assert 0.02 < want_high.mean() < 0.5          # the generator's jittered copies do trigger the filter
 
 

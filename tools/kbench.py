@@ -65,20 +65,27 @@ def main():
         print(f"{name:28s} median {ms:8.3f} ms  best {best:8.3f} ms  {gbs:8.1f} GB/s  {100 * gbs / peak:5.1f}% of {kind} peak  "
               f"{units / (ms * 1e-3) / 1e6:10.1f} M {unit_name}/s", flush=True)
 
+    import os
     if "fused" in which:
         buf = ops.FusedBuffers(n_img, n_poly, dev)
         by = 16 * n_vert + 8 * (n_poly + 1) + 32 * n_poly + n_poly + 8 * (n_img + 1) + 5 * n_img
-        for thr in (0.7, 0.98):
-            ms, best = time_ms(lambda: ops.bbox_iou_fused(t.img_off, t.poly_off, t.xy, 2, thr, out=buf), args.reps)
-            report(f"fused K1+K2 thr={thr}", ms, best, by, n_img, "images")
+        for fused, group in (("tma", "4"), ("direct", "4"), ("direct", "8")):
+            os.environ["DYD_FUSED"] = fused; os.environ["DYD_GROUP"] = group
+            for thr in (0.7, 0.98):
+                ms, best = time_ms(lambda: ops.bbox_iou_fused(t.img_off, t.poly_off, t.xy, 2, thr, out=buf), args.reps)
+                report(f"fused {fused}/G{group} thr={thr}", ms, best, by, n_img, "images")
+        os.environ["DYD_FUSED"] = "tma"; os.environ["DYD_GROUP"] = "4"
         bufa = ops.FusedBuffers(n_img, n_poly, dev, want_arg=True)
         ms, best = time_ms(lambda: ops.bbox_iou_fused(t.img_off, t.poly_off, t.xy, 2, 0.7, want_arg=True, out=bufa), args.reps)
-        report("fused K1+K2 +arg", ms, best, by + 16 * n_poly, n_img, "images")
+        report("fused tma +arg", ms, best, by + 16 * n_poly, n_img, "images")
         del bufa
     if "k1" in which:
         by = 16 * n_vert + 8 * (n_poly + 1) + 33 * n_poly
-        ms, best = time_ms(lambda: ops.bbox_minmax(t.poly_off, t.xy), args.reps)
-        report("K1 bbox (allocs incl.)", ms, best, by, n_poly, "polygons")
+        for group in ("4", "8", "2"):
+            os.environ["DYD_GROUP"] = group
+            ms, best = time_ms(lambda: ops.bbox_minmax(t.poly_off, t.xy), args.reps)
+            report(f"K1 bbox G{group} (allocs incl.)", ms, best, by, n_poly, "polygons")
+        os.environ["DYD_GROUP"] = "4"
     if "k2" in which:
         pts, valid, _ = ops.bbox_minmax(t.poly_off, t.xy)
         by = 33 * n_poly + 8 * (n_img + 1) + 5 * n_img
