@@ -18,7 +18,7 @@ inline size_t crowd_list_bytes(int64_t n_img) {
     return (sizeof(CrowdList) + sizeof(int) * (size_t)n_img + 15) & ~(size_t)15;
 }
 
-constexpr int TILE_IMAGES = 12;              // images per staged tile
+constexpr int TILE_IMAGES = 3;               // images per staged tile (~24 objects: one lane each)
 struct TileDesc {                            // 32 bytes, written by the descriptor pre-pass
     long long q0, q1;                        // object range  [img_off[i0], img_off[i1])
     long long v0, v1;                        // vertex range  [poly_off[q0], poly_off[q1])
