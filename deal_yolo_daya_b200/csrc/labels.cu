@@ -59,6 +59,26 @@ label_lut_kernel(const int64_t* __restrict__ img_off, const int32_t* __restrict_
     }
 }
 
+// per-vocabulary occurrence counts (the unmatched-label table of processor.py:591-593 is derived
+// from them on the host); shared-memory privatised for vocabularies that fit, global atomics otherwise
+constexpr int HIST_SMEM = 4096;
+__global__ void __launch_bounds__(LB_THREADS)
+label_hist_kernel(const int32_t* __restrict__ label_id, int64_t n_box, int32_t n_vocab, unsigned long long* hist) {
+    __shared__ unsigned sh[HIST_SMEM];
+    const bool priv = n_vocab <= HIST_SMEM;
+    if (priv) for (int v = threadIdx.x; v < n_vocab; v += LB_THREADS) sh[v] = 0;
+    __syncthreads();
+    const int64_t per = (n_box + gridDim.x - 1) / gridDim.x;
+    const int64_t a = blockIdx.x * per, b = min(a + per, n_box);
+    for (int64_t q = a + threadIdx.x; q < b; q += LB_THREADS) {
+        const int32_t v = label_id[q];
+        if (v < 0 || v >= n_vocab) continue;
+        if (priv) atomicAdd(&sh[v], 1u); else atomicAdd(&hist[v], 1ULL);
+    }
+    __syncthreads();
+    if (priv) for (int v = threadIdx.x; v < n_vocab; v += LB_THREADS) if (sh[v]) atomicAdd(&hist[v], (unsigned long long)sh[v]);
+}
+
 // ------------------------------------------------------------------------------- K6
 __device__ __forceinline__ int category_of(const int32_t* __restrict__ label_id, const int32_t* __restrict__ cat_of_label,
                                            int32_t n_vocab, int64_t q) {
@@ -221,6 +241,20 @@ extern "C" int dyd_label_lut(const int64_t* d_img_off, const int32_t* d_label_id
                                                            n_vocab, d_new_id, d_row_replaced,
                                                            reinterpret_cast<unsigned long long*>(d_counters));
     return launch_check("label_lut_kernel");
+}
+
+extern "C" int dyd_label_hist(const int32_t* d_label_id, int64_t n_box, int32_t n_vocab, uint64_t* d_hist, void* stream) {
+    DYD_REQUIRE(n_box >= 0 && n_vocab >= 0, DYD_E_ARG, "negative count");
+    if (n_vocab == 0) return 0;
+    DYD_REQUIRE(d_hist && (n_box == 0 || d_label_id), DYD_E_ARG, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    DYD_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * n_vocab, s));
+    if (n_box == 0) return 0;
+    // each block covers at most ~1M objects so the 32-bit private counters cannot overflow
+    int64_t grid = (n_box + (1 << 20) - 1) >> 20;
+    if (grid < NUM_SMS * 2) grid = NUM_SMS * 2;
+    label_hist_kernel<<<(unsigned)grid, LB_THREADS, 0, s>>>(d_label_id, n_box, n_vocab, reinterpret_cast<unsigned long long*>(d_hist));
+    return launch_check("label_hist_kernel");
 }
 
 extern "C" size_t dyd_split_workspace_bytes(int64_t n_img, int32_t n_cat) {

@@ -25,6 +25,8 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from . import _hostlane
+
 _EXACT = 2 ** 53
 
 
@@ -43,8 +45,8 @@ class PolygonBatch:
     n_rows: int
     docs: list                      # parsed document per row, None where the cell is not decodable JSON
     objs: list                      # per row: list of the dict objects (reference order)
-    points: list                    # per object: list of its valid point dicts
-    hostlane: np.ndarray            # uint8 per object: 1 = evaluate on the host lane
+    points: list                    # per object: its valid point dicts (host-lane objects: their two corner points)
+    hostlane: np.ndarray            # uint8 per object: 1 = evaluated on the host lane
     img_off: np.ndarray             # int64[n_rows+1]
     poly_off: np.ndarray            # int64[n_obj+1]
     xy: np.ndarray                  # float64[2*n_vert]
@@ -82,9 +84,11 @@ def parse_polygons(cells) -> PolygonBatch:
                 for p in good:
                     xy.append(p["x"]); xy.append(p["y"])
                 poly_cnt.append(len(good)); lane.append(0)
+                points.append(good)
             else:
+                # host exception lane, evaluated here so that a raising polygon raises in row order
                 poly_cnt.append(0); lane.append(1)
-            points.append(good)
+                points.append(_hostlane.corner_points(good))
             row_objs.append(obj)
         docs.append(doc); objs_per_row.append(row_objs); img_cnt.append(len(row_objs))
     n_rows = len(docs)

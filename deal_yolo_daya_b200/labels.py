@@ -1,0 +1,397 @@
+"""Label remap (step 5.5) and rule-based split (step 6): DataFrame cores.
+
+Strings stay on the host: names are dictionary-encoded in the reference's traversal order
+(row, JSON column, object), the per-vocabulary tables are built with the reference's string
+rules (utils.py:635-679) and every per-object / per-row decision -- which name is rewritten,
+all counters, the per-label histogram, the category grouping and the split ids -- is taken by
+the K3 / K6 kernels on the encoded ids.  The host then re-serialises the documents exactly as
+the reference does (``json.dumps(..., ensure_ascii=False)`` of the mutated parsed document).
+
+reference: processor.py:516-652 (remap), :654-831 (split); utils.py:635-679 (string rules).
+"""
+from __future__ import annotations
+
+import copy
+import json
+import re
+
+import numpy as np
+import pandas as pd
+
+COL_ANN = "结果字段-目标检测标签配置"
+COL_NEW = "新_结果字段-目标检测标签配置"
+_SEP = re.compile(r"[,，;；|]")
+
+
+def _kernels():
+    from . import processor
+    return processor.KERNELS
+
+
+def split_labels(raw):
+    """_split_object_labels (utils.py:659-662)."""
+    if not raw:
+        return []
+    return [t.strip() for t in _SEP.split(str(raw)) if t.strip()]
+
+
+def split_label_cell(cell):
+    """_split_label_cell (utils.py:635-643)."""
+    if pd.isna(cell):
+        return []
+    text = str(cell).strip()
+    if not text:
+        return []
+    return [t.strip() for t in _SEP.split(text) if t.strip()]
+
+
+def default_json_columns(df):
+    return [c for c in (COL_NEW, COL_ANN) if c in df.columns]
+
+
+def mapping_from_frame(mapping_df: pd.DataFrame, old_col=None, new_col=None) -> dict:
+    """Label map of processor.py:533-545."""
+    if not old_col or not new_col:
+        cols = list(mapping_df.columns)
+        if len(cols) < 2:
+            raise ValueError("标签对照表至少需要两列")
+        old_col = old_col or cols[0]
+        new_col = new_col or cols[1]
+    out = {}
+    for _, r in mapping_df.iterrows():
+        a = str(r.get(old_col, "")).strip()
+        b = str(r.get(new_col, "")).strip()
+        if a and a.lower() != "nan" and b and b.lower() != "nan":
+            out[a] = b
+    return out
+
+
+def rules_from_frame(rules_df: pd.DataFrame, rule_mode="wide", label_col=None, category_col=None) -> dict:
+    """label -> category of processor.py:690-703."""
+    l2c = {}
+    if rule_mode == "wide":
+        for col in rules_df.columns:
+            cat = str(col).strip()
+            if not cat:
+                continue
+            for cell in rules_df[col].dropna():
+                for lab in split_label_cell(cell):
+                    l2c[lab] = cat
+    elif rule_mode == "two_column":
+        for _, r in rules_df.iterrows():
+            lab = str(r.get(label_col, "")).strip()
+            cat = str(r.get(category_col, "")).strip()
+            if lab and cat and lab.lower() != "nan" and cat.lower() != "nan":
+                l2c[lab] = cat
+    return l2c
+
+
+# =============================================================================================
+# remap
+# =============================================================================================
+class _Vocab:
+    def __init__(self):
+        self.ids, self.names = {}, []
+
+    def get(self, name: str) -> int:
+        i = self.ids.get(name)
+        if i is None:
+            i = len(self.names)
+            self.ids[name] = i
+            self.names.append(name)
+        return i
+
+
+def remap_df(df: pd.DataFrame, label_map: dict, json_columns=None):
+    """DataFrame core of replace_labels_by_mapping -> (frame, summary, diff_rows, unmatched counter)."""
+    df = df.copy()
+    if json_columns is None:
+        json_columns = default_json_columns(df)
+    cols = [c for c in json_columns if c in df.columns]
+    n_rows = len(df)
+    invalid_json_rows = 0
+    # ---- ingest: decode cells, dictionary-encode names in reference traversal order ----
+    cells = []          # (row position, column, doc, objects) for every re-serialised cell
+    cell_cnt, label_ids = [], []
+    exotic = []         # (cell index, object index) whose name is neither str nor None
+    vocab = _Vocab()
+    col_values = {c: df[c].tolist() for c in cols}
+    for r in range(n_rows):
+        for c in cols:
+            text = col_values[c][r]
+            if not isinstance(text, str) or not text:
+                continue
+            try:
+                doc = json.loads(text)
+            except json.JSONDecodeError:
+                invalid_json_rows += 1
+                continue
+            objs = doc.get("objects")
+            if not isinstance(objs, list):
+                continue
+            n = 0
+            for k, obj in enumerate(objs):
+                if not isinstance(obj, dict):
+                    continue
+                name = obj.get("name")
+                if name is None:
+                    label_ids.append(-1)
+                elif isinstance(name, str):
+                    label_ids.append(vocab.get(name))
+                else:
+                    label_ids.append(-2); exotic.append((len(cells), k))
+                n += 1
+            cells.append((r, c, doc, objs)); cell_cnt.append(n)
+    # ---- per-vocabulary tables (string rules of utils.py:659-679) ----
+    n_raw = len(vocab.names)
+    toks_of, norm_of = [], []
+    for v in range(n_raw):
+        raw = vocab.names[v]
+        toks = split_labels(raw)
+        toks_of.append(toks)
+        norm_of.append(raw if not raw else ",".join(sorted(set(label_map.get(t, t) for t in toks))))
+    lut_ntok = np.array([0 if not vocab.names[v] else len(toks_of[v]) for v in range(n_raw)], np.int32)
+    lut_nrep = np.array([0 if not vocab.names[v] else sum(1 for t in toks_of[v] if t in label_map) for v in range(n_raw)], np.int32)
+    lut_new = np.array([vocab.get(norm_of[v]) for v in range(n_raw)], np.int32)       # may append new names
+    n_vocab = len(vocab.names)
+    pad = n_vocab - n_raw
+    lut_new = np.concatenate([lut_new, np.arange(n_raw, n_vocab, dtype=np.int32)])
+    lut_ntok = np.concatenate([lut_ntok, np.zeros(pad, np.int32)])
+    lut_nrep = np.concatenate([lut_nrep, np.zeros(pad, np.int32)])
+    # ---- device: rewrite decisions, counters, histogram ----
+    cell_off = np.zeros(len(cells) + 1, np.int64)
+    np.cumsum(np.array(cell_cnt, np.int64), out=cell_off[1:])
+    ids = np.array(label_ids, np.int32) if label_ids else np.zeros(0, np.int32)
+    dev_ids = np.where(ids == -2, -1, ids).astype(np.int32)       # exotic names are settled on the host lane below
+    if len(cells):
+        new_id, cell_rep, cnt, hist = _kernels().label_lut(cell_off, dev_ids, lut_new, lut_ntok, lut_nrep)
+    else:
+        new_id = np.zeros(0, np.int32); cell_rep = np.zeros(0, np.uint8); hist = np.zeros(n_vocab, np.uint64)
+        cnt = dict(total_objects=0, missing_name_objects=0, total_labels=0, replaced_labels=0, replaced_objects=0, replaced_rows=0)
+    cnt["missing_name_objects"] -= len(exotic)                    # they were sent as "no name"; corrected here
+    # ---- unmatched labels in first-encounter order (processor.py:591-593) ----
+    unmatched = {}
+    for v in range(n_raw):
+        h = int(hist[v]) if v < len(hist) else 0
+        if h == 0 or not vocab.names[v]:
+            continue
+        for t in toks_of[v]:
+            if t not in label_map:
+                unmatched[t] = unmatched.get(t, 0) + h
+    # ---- host lane: names that are not strings (numbers, lists ...) follow CPython semantics ----
+    row_touched = np.zeros(n_rows, bool)
+    exotic_set = {}
+    for ci, k in exotic:
+        exotic_set.setdefault(ci, set()).add(k)
+    # ---- egress: rewrite names, re-serialise, collect diff rows ----
+    diff_rows = []
+    sources = df["source"].tolist() if "source" in df.columns else [None] * n_rows
+    for ci, (r, c, doc, objs) in enumerate(cells):
+        q = int(cell_off[ci])
+        pairs = []
+        for k, obj in enumerate(objs):
+            if not isinstance(obj, dict):
+                continue
+            v = int(ids[q])
+            if v >= 0:
+                if lut_nrep[v] > 0:
+                    obj["name"] = vocab.names[int(new_id[q])]
+                if vocab.names[v] != norm_of[v]:
+                    pairs.append((vocab.names[v], norm_of[v]))
+            elif v == -2:
+                raw = obj.get("name")
+                for t in split_labels(raw):
+                    if t not in label_map:
+                        unmatched[t] = unmatched.get(t, 0) + 1
+                if raw:
+                    toks = split_labels(raw)
+                    new = ",".join(sorted(set(label_map.get(t, t) for t in toks)))
+                    nrep = sum(1 for t in toks if t in label_map)
+                    cnt["total_labels"] += len(toks)
+                else:
+                    new, nrep = raw, 0
+                if nrep > 0:
+                    obj["name"] = new
+                    cnt["replaced_labels"] += nrep; cnt["replaced_objects"] += 1
+                    row_touched[r] = True
+                if raw != new:
+                    pairs.append((raw, new))
+            q += 1
+        if cell_rep[ci]:
+            row_touched[r] = True
+        doc["objects"] = objs
+        df.iat[r, df.columns.get_loc(c)] = json.dumps(doc, ensure_ascii=False)
+        if pairs:
+            diff_rows.append({"source": sources[r], "column": c,
+                              "before": "；".join(p[0] for p in pairs), "after": "；".join(p[1] for p in pairs)})
+    summary = {
+        "total_rows": n_rows, "replaced_rows": int(row_touched.sum()), "total_objects": cnt["total_objects"],
+        "replaced_objects": cnt["replaced_objects"], "total_labels": cnt["total_labels"],
+        "replaced_labels": cnt["replaced_labels"], "invalid_json_rows": invalid_json_rows,
+        "missing_name_objects": cnt["missing_name_objects"], "mapping_size": len(label_map),
+        "unmatched_labels": len(unmatched),
+    }
+    return df, summary, diff_rows, unmatched
+
+
+# =============================================================================================
+# split
+# =============================================================================================
+def _parse_objects(text):
+    """_parse_data_objects (utils.py:645-657)."""
+    if not isinstance(text, str) or not text:
+        return None, [], "空数据"
+    try:
+        doc = json.loads(text)
+        objs = doc.get("objects", [])
+        if not isinstance(objs, list):
+            return doc, [], "objects不是列表"
+        return doc, objs, None
+    except json.JSONDecodeError:
+        return None, [], "JSON解析失败"
+    except Exception as e:  # noqa: BLE001 - the reference reports str(e)
+        return None, [], str(e)
+
+
+def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
+             train_ratio=0.8, val_ratio=0.1, test_ratio=0.1, random_seed=42):
+    """DataFrame core of split_dataset_by_rules -> dict(categories={cat: {train,val,test}}, unclassified,
+    split_counts, summary).  Category grouping (K6) and the split ids come from the device; the
+    permutation is numpy's legacy MT19937 shuffle, which is what DataFrame.sample applies."""
+    tot = train_ratio + val_ratio + test_ratio
+    train_ratio /= tot; val_ratio /= tot; test_ratio /= tot
+    if json_columns is None:
+        json_columns = default_json_columns(df)
+    jcols_present = [c for c in json_columns if c in df.columns]
+    n_rows = len(df)
+    col_values = {c: df[c].tolist() for c in jcols_present}
+    sources = df["source"].tolist() if "source" in df.columns else [None] * n_rows
+    # ---- ingest: (object, label) entries per row, labels dictionary-encoded ----
+    vocab = _Vocab()
+    cat_ids, cat_names = {}, []
+    entry_cnt = np.zeros(n_rows, np.int64)
+    entry_label, entry_obj = [], []          # per entry: label id / (row, object) payload
+    row_info = [None] * n_rows               # (doc, combo) for classifiable rows
+    events = []                              # unclassified rows & split_counts rows in reference order
+    for r in range(n_rows):
+        text = None
+        for c in json_columns:
+            if c in col_values and isinstance(col_values[c][r], str) and col_values[c][r]:
+                text = col_values[c][r]
+                break
+        doc, objs, err = _parse_objects(text)
+        if err or not objs:
+            events.append(("bad_row", r, err or "标注字段objects为空"))
+            continue
+        labset = set()
+        for obj in objs:
+            if isinstance(obj, dict) and obj.get("name"):
+                labset.update(split_labels(obj.get("name")))
+        combo = "，".join(sorted(labset)) if labset else ""
+        row_info[r] = (doc, combo)
+        n = 0
+        per_obj = []
+        for obj in objs:
+            if not isinstance(obj, dict):
+                continue
+            labs = split_labels(obj.get("name"))
+            per_obj.append((obj, labs))
+            for lab in labs:
+                v = vocab.get(lab)
+                entry_label.append(v); entry_obj.append(obj); n += 1
+                cat = l2c.get(lab)
+                if cat is not None and cat not in cat_ids:
+                    cat_ids[cat] = len(cat_names); cat_names.append(cat)
+        entry_cnt[r] = n
+        events.append(("row", r, per_obj))
+    n_cat = len(cat_names)
+    cat_of_label = np.array([cat_ids[l2c[name]] if name in l2c else -1 for name in vocab.names], np.int32) \
+        if vocab.names else np.zeros(0, np.int32)
+    row_off = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(entry_cnt, out=row_off[1:])
+    labels = np.array(entry_label, np.int32) if entry_label else np.zeros(0, np.int32)
+    # ---- device: stable grouping by category, then split ids from the host permutation ----
+    if n_cat and len(labels):
+        exp_row, exp_entry, exp_cat, cat_off = _kernels().split_expand(row_off, labels, cat_of_label, n_cat)
+    else:
+        exp_row = np.zeros(0, np.int64); exp_entry = np.zeros(0, np.int64); cat_off = np.zeros(n_cat + 1, np.int64)
+    sizes = np.diff(cat_off)
+    n_train = np.array([int(n * train_ratio) for n in sizes], np.int64)
+    n_val = np.array([int(n * val_ratio) for n in sizes], np.int64)
+    perms = [np.random.RandomState(random_seed).permutation(int(n)) for n in sizes]
+    perm = np.concatenate(perms).astype(np.int64) if perms else np.zeros(0, np.int64)
+    if len(perm):
+        split_id, pos = _kernels().split_assign(cat_off, perm, n_train, n_val)
+    else:
+        split_id = np.zeros(0, np.uint8); pos = np.zeros(0, np.int64)
+    # ---- egress: per-category frames ----
+    categories, cat_counts = {}, {}
+    for ci, cat in enumerate(cat_names):
+        a, b = int(cat_off[ci]), int(cat_off[ci + 1])
+        if b == a:
+            continue
+        cat_counts[cat] = b - a
+        order = np.empty(b - a, np.int64)
+        order[pos[a:b]] = np.arange(b - a)             # shuffled position -> original expanded row
+        rows_idx = exp_row[a:b][order]
+        frame = df.iloc[rows_idx].reset_index(drop=True)
+        cells, labs, combos = [], [], []
+        for e, r in zip(exp_entry[a:b][order], rows_idx):
+            doc, combo = row_info[int(r)]
+            lab = vocab.names[int(labels[e])]
+            one = copy.deepcopy(entry_obj[int(e)]); one["name"] = lab
+            nd = {k: v for k, v in doc.items() if k != "objects"}
+            nd["objects"] = [one]
+            cells.append(json.dumps(nd, ensure_ascii=False)); labs.append(lab); combos.append(combo)
+        for c in json_columns:
+            if c in df.columns:
+                frame[c] = cells
+        frame["分类标签"] = labs
+        frame["分类类别"] = cat
+        frame["原始标签组合"] = combos
+        sp = split_id[a:b][order]
+        categories[cat] = {"train": frame[sp == 0], "val": frame[sp == 1], "test": frame[sp == 2]}
+    # ---- egress: unclassified rows and split_counts in reference order ----
+    unc_rows, unc_reason, unc_label = [], [], []
+    counts = []
+    has_label_col = False
+    for ev in events:
+        if ev[0] == "bad_row":
+            _, r, why = ev
+            unc_rows.append(r); unc_reason.append(why); unc_label.append(None)
+            counts.append({"source": sources[r], "原始标签组合": "", "拆分条数": 0, "是否可分类": "否", "无法分类原因": why})
+            continue
+        _, r, per_obj = ev
+        combo = row_info[r][1]
+        n_exp, reasons, any_ok = 0, set(), False
+        for obj, labs in per_obj:
+            if not labs:
+                unc_rows.append(r); unc_reason.append("标注框缺少name字段"); unc_label.append(None)
+                continue
+            for lab in labs:
+                if lab not in l2c:
+                    why = f"标签{lab}未在规则中定义"
+                    unc_rows.append(r); unc_reason.append(why); unc_label.append(lab); has_label_col = True
+                    reasons.add(why)
+                else:
+                    any_ok = True; n_exp += 1
+        if not any_ok:
+            unc_rows.append(r); unc_label.append(None)
+            unc_reason.append("；".join(sorted(reasons)) if reasons else "标签无法匹配规则")
+        status = "否" if not any_ok else ("部分可分类" if reasons else "是")
+        counts.append({"source": sources[r], "原始标签组合": combo, "拆分条数": n_exp, "是否可分类": status,
+                       "无法分类原因": "；".join(sorted(reasons))})
+    if unc_rows:
+        unc = df.iloc[unc_rows].reset_index(drop=True)
+        unc["无法分类原因"] = unc_reason
+        if has_label_col:
+            unc["无法分类标签"] = pd.Series(unc_label, dtype=object).where(pd.Series([x is not None for x in unc_label]), np.nan)
+    else:
+        unc = pd.DataFrame()
+    return {
+        "categories": categories,
+        "unclassified": unc,
+        "split_counts": pd.DataFrame(counts),
+        "summary": {"categories": n_cat, "classified": int(sum(cat_counts.values())), "unclassified": len(unc_rows),
+                    "category_counts": cat_counts},
+    }

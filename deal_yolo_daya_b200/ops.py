@@ -193,6 +193,18 @@ def label_lut(img_off, label_id, lut_new, lut_ntok, lut_nrep):
     return new_id, row_rep, counters
 
 
+def label_hist(label_id, n_vocab):
+    """Occurrences of each vocabulary id (uint64[n_vocab])."""
+    _need_cuda(label_id)
+    lib = _lib.load()
+    dev = label_id.device
+    hist = torch.empty(max(n_vocab, 1), dtype=torch.uint64, device=dev)[:n_vocab]
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_label_hist(_ptr(_chk(label_id, torch.int32, "label_id")), label_id.numel(), n_vocab,
+                                      _ptr(hist), _stream(dev)), "dyd_label_hist")
+    return hist
+
+
 def split_expand(img_off, label_id, cat_of_label, n_cat):
     """Category expansion (processor.py:751-775).  Returns (exp_img, exp_box, exp_cat, cat_off)."""
     _need_cuda(img_off, label_id, cat_of_label)

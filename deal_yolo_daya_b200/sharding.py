@@ -1,0 +1,164 @@
+"""Multi-GPU form of the hot path: one process per GPU over torch.distributed.
+
+Rows are partitioned across ranks by image (contiguous global ranges).  K1 / K2 / K3 are
+independent per image and need no communication.  Dedup (K4) and the
+anti-join (K5) have one real exchange step each: every rank buckets its (hash64, global row
+id) records by owner rank = mix(hash) mod P, the buckets travel with one variable-size
+all-to-all (NCCL over NVLink on GPUs, gloo in the CPU tests), the owner runs the local hash
+table kernel -- global row ids make ``atomicMin`` pick the global first occurrence -- and the
+keep bit + representative row travel back with the reverse all-to-all.
+
+torch is plumbing here: the bucket permutation (a stable sort of owner ids), the collectives
+and buffer ownership.  The table work itself is the CUDA kernels behind ``ops.dedup`` /
+``ops.antijoin``; the ``local_*`` parameters exist so that the CPU (gloo) tests can exercise
+this exchange logic with a stand-in defined under tests/.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+_GOLD = -7046029254386353131        # 0x9E3779B97F4A7C15 as int64
+
+
+def owner_of(keys_i64: torch.Tensor, world: int) -> torch.Tensor:
+    """Owner rank of each key (keys viewed as int64; wrap-around multiply, top bits)."""
+    mixed = keys_i64 * _GOLD
+    top = (mixed >> 33) & 0x7FFFFFFF
+    return (top % world).to(torch.int64)
+
+
+def _exchange(send: torch.Tensor, send_counts: torch.Tensor, group=None):
+    """Variable-size all-to-all of rows of `send` (already ordered by destination rank)."""
+    world = dist.get_world_size(group)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc = send_counts.tolist(); rc = recv_counts.tolist()
+    recv = torch.empty((sum(rc),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    assert len(sc) == world
+    return recv, sc, rc
+
+
+def _bucket(keys_i64, world):
+    owner = owner_of(keys_i64, world)
+    order = torch.sort(owner, stable=True).indices
+    counts = torch.bincount(owner, minlength=world).to(torch.int64)
+    return order, counts
+
+
+def dedup_global(keys: torch.Tensor, null: torch.Tensor | None, row_base: int, keep="first",
+                 group=None, local_dedup=None):
+    """Global drop_duplicates keep-mask for this rank's rows (processor.py:140-144).
+
+    keys uint64[n] (this rank's rows, global row id = row_base + local index), null uint8[n].
+    Returns (keep uint8[n], rep int64[n]) exactly as the single-GPU ``ops.dedup`` would on the
+    concatenated table.
+    """
+    if local_dedup is None:
+        from . import ops
+        local_dedup = lambda k, ids, mode: ops.dedup(k, None, mode, row_id=ids)  # noqa: E731
+    world = dist.get_world_size(group)
+    dev = keys.device
+    n = keys.numel()
+    ids = torch.arange(row_base, row_base + n, dtype=torch.int64, device=dev)
+    k64 = keys.view(torch.int64)
+    live = torch.ones(n, dtype=torch.bool, device=dev) if null is None else (null == 0)
+    live_idx = torch.nonzero(live).squeeze(1)
+    order, counts = _bucket(k64[live_idx], world)
+    sel = live_idx[order]
+    send = torch.stack([k64[sel], ids[sel]], dim=1).contiguous()
+    recv, sc, rc = _exchange(send, counts.to(dev), group)
+    if recv.shape[0]:
+        rkeep, rrep = local_dedup(recv[:, 0].contiguous().view(torch.uint64), recv[:, 1].contiguous(), keep)
+    else:
+        rkeep = torch.empty(0, dtype=torch.uint8, device=dev); rrep = torch.empty(0, dtype=torch.int64, device=dev)
+    back = torch.stack([rkeep.to(torch.int64), rrep], dim=1).contiguous()
+    ans = torch.empty((send.shape[0], 2), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(ans, back, output_split_sizes=sc, input_split_sizes=rc, group=group)
+    keep_out = torch.zeros(n, dtype=torch.uint8, device=dev)
+    rep_out = torch.zeros(n, dtype=torch.int64, device=dev)
+    keep_out[sel] = ans[:, 0].to(torch.uint8)
+    rep_out[sel] = ans[:, 1]
+    # null cells are one global group: first / last / count across ranks
+    if null is not None:
+        nidx = torch.nonzero(~live).squeeze(1)
+        big = torch.iinfo(torch.int64).max
+        stats = torch.tensor([ids[nidx].min().item() if nidx.numel() else big,
+                              -(ids[nidx].max().item()) if nidx.numel() else big,
+                              ], dtype=torch.int64, device=dev)
+        dist.all_reduce(stats, op=dist.ReduceOp.MIN, group=group)
+        cnt = torch.tensor([nidx.numel()], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+        first, last, total = int(stats[0]), -int(stats[1]), int(cnt[0])
+        if nidx.numel():
+            if keep == "first":
+                rep_out[nidx] = first; keep_out[nidx] = (ids[nidx] == first).to(torch.uint8)
+            elif keep == "last":
+                rep_out[nidx] = last; keep_out[nidx] = (ids[nidx] == last).to(torch.uint8)
+            else:
+                rep_out[nidx] = first; keep_out[nidx] = 1 if total == 1 else 0
+    return keep_out, rep_out
+
+
+def antijoin_global(main_keys, main_null, ref_keys, ref_null, ref_row_base: int, group=None, local_antijoin=None):
+    """Global anti-join for this rank's main rows against the union of all ranks' reference rows.
+
+    Both tables are hash-partitioned to owners (one all-to-all each), probed locally, and the
+    keep bit + first matching global reference row travel back (reverse all-to-all).
+    """
+    if local_antijoin is None:
+        from . import ops
+        local_antijoin = lambda mk, rk: ops.antijoin(mk, None, rk, None)  # noqa: E731
+    world = dist.get_world_size(group)
+    dev = main_keys.device
+    n = main_keys.numel()
+    m64 = main_keys.view(torch.int64); r64 = ref_keys.view(torch.int64)
+    # reference side: ref.dropna()
+    rlive = torch.nonzero(ref_null == 0).squeeze(1) if ref_null is not None else torch.arange(r64.numel(), device=dev)
+    rorder, rcounts = _bucket(r64[rlive], world)
+    rsel = rlive[rorder]
+    rsend = torch.stack([r64[rsel], rsel + ref_row_base], dim=1).contiguous()
+    rrecv, _, _ = _exchange(rsend, rcounts.to(dev), group)
+    # main side: null cells never match
+    mlive = torch.nonzero(main_null == 0).squeeze(1) if main_null is not None else torch.arange(n, device=dev)
+    morder, mcounts = _bucket(m64[mlive], world)
+    msel = mlive[morder]
+    msend = m64[msel].contiguous().unsqueeze(1)
+    mrecv, sc, rc = _exchange(msend, mcounts.to(dev), group)
+    # owner-local probe; reference rows keep their arrival order, so map the local hit index back
+    # to the smallest global reference row holding that key
+    rk = rrecv[:, 0].contiguous(); rid = rrecv[:, 1].contiguous()
+    if rk.numel():
+        order = torch.sort(rid, stable=True).indices          # ascending global row -> first row wins ties
+        rk = rk[order].contiguous(); rid = rid[order].contiguous()
+    keep_l, hit_l = local_antijoin(mrecv[:, 0].contiguous().view(torch.uint64), rk.view(torch.uint64))
+    grow = torch.where(hit_l >= 0, rid[hit_l.clamp(min=0)] if rid.numel() else hit_l, hit_l)
+    back = torch.stack([keep_l.to(torch.int64), grow], dim=1).contiguous()
+    ans = torch.empty((msend.shape[0], 2), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(ans, back, output_split_sizes=sc, input_split_sizes=rc, group=group)
+    keep_out = torch.ones(n, dtype=torch.uint8, device=dev)
+    ref_out = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    keep_out[msel] = ans[:, 0].to(torch.uint8)
+    ref_out[msel] = ans[:, 1]
+    return keep_out, ref_out
+
+
+def image_ranges(vertex_prefix, world: int):
+    """Contiguous image ranges balanced by vertex count (bytes, not image counts, balance).
+
+    vertex_prefix int64[n_img+1] = poly_off[img_off[i]] (host numpy or CPU tensor).
+    Returns a list of (i0, i1) per rank.
+    """
+    import numpy as np
+    vp = np.asarray(vertex_prefix, dtype=np.int64)
+    n = len(vp) - 1
+    total = int(vp[-1] - vp[0])
+    cuts = [0]
+    for r in range(1, world):
+        target = vp[0] + (total * r) // world
+        cuts.append(int(np.searchsorted(vp, target, side="left")))
+    cuts.append(n)
+    for r in range(1, len(cuts)):
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]

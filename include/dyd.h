@@ -127,6 +127,10 @@ int dyd_label_lut(const int64_t* d_img_off, const int32_t* d_label_id, int64_t n
                   int32_t n_vocab, int32_t* d_new_id, uint8_t* d_row_replaced,
                   uint64_t* d_counters, void* stream);
 
+/* Occurrences of every vocabulary id among the objects (uint64[n_vocab], zeroed by the call);
+ * with the host's token tables this gives the unmatched-label counts of processor.py:591-593. */
+int dyd_label_hist(const int32_t* d_label_id, int64_t n_box, int32_t n_vocab, uint64_t* d_hist, void* stream);
+
 /* ---------------------------------------------------------------- K6 ------
  * label -> category expansion of processor.py:751-775: one expanded row per
  * object whose label has a category, stably grouped by category (encounter

@@ -389,3 +389,26 @@ def run_hot_path(df: pd.DataFrame, ref: pd.DataFrame | None, min_boxes=2, thr=0.
     r, _ = replace_ptlist_df(d)
     _, other = iou_split_df(r, min_boxes, thr)
     return other
+
+
+def run_hot_path_files(workdir, merged_csv, ref_csv=None, min_boxes=2, thr=0.7):
+    """The same chain through CSV files, the way the reference's step functions hand data to each
+    other (read_csv -> step -> to_csv, utf-8-sig, index=False; processor.py:125/158, 181/213,
+    235/309, 379/404-407).  Returns the number of rows the pipeline continues with."""
+    from pathlib import Path
+    w = Path(workdir)
+    enc = "utf-8-sig"
+    d = dedup_df(pd.read_csv(merged_csv, encoding=enc, parse_dates=False))
+    d.to_csv(w / "deduplicate_result.csv", index=False, encoding=enc)
+    cur = w / "deduplicate_result.csv"
+    if ref_csv is not None:
+        f = ref_filter_df(pd.read_csv(cur, encoding=enc, parse_dates=False), pd.read_csv(ref_csv, encoding=enc, parse_dates=False))
+        f.to_csv(w / "filtered_main.csv", index=False, encoding=enc)
+        cur = w / "filtered_main.csv"
+    r, exc = replace_ptlist_df(pd.read_csv(cur, encoding=enc))
+    r.to_csv(w / "processed_replaced_ptlist.csv", index=False, encoding=enc)
+    exc.to_csv(w / "processed_excluded.csv", index=False, encoding=enc)
+    hi, ot = iou_split_df(pd.read_csv(w / "processed_replaced_ptlist.csv", encoding=enc), min_boxes, thr)
+    hi.to_csv(w / f"high_iou_{thr:.2f}.csv", index=False, encoding=enc)
+    ot.to_csv(w / "other_data.csv", index=False, encoding=enc)
+    return len(ot)
