@@ -29,20 +29,28 @@ constexpr int NW = 16;                         // warps per CTA (1 CTA per SM)
 constexpr int CAP_V = 640;                     // vertices per stage (10 KB)
 constexpr int CAP_P = 48;                      // objects per stage
 constexpr int TMA_THREADS = 32 * NW;
-enum { MODE_FAST = 0, MODE_FALLBACK = 1 };
+constexpr int IMG_SLOTS = (T + 3) & ~1;        // img_off slice: T+1 entries + alignment shift, even count
+constexpr int QCAP = 64;                       // survivor queue entries per warp (power of two)
+enum { MODE_FAST = 0, MODE_DIRECT = 1, MODE_DEFER = 2 };
+static_assert(CAP_P <= 64 && T <= 8, "queue entries pack (object, object, image) into 16 bits; validity masks are 64-bit");
 
+struct __align__(16) TileInfo {                // double-buffered: tile k+1 is described while K2 still works on tile k
+    long long img[IMG_SLOTS];                  // img_off slice starting at image (i0 & ~1)
+    long long q0, v0;
+    int ni, np, pshift, ishift, mode, pad[3];
+};
 struct __align__(16) Stage {
     double2 vert[CAP_V];
     double box[CAP_P * 4];                     // (x1, y1, x2, y2) after extract_boxes' min/max
     long long poly[CAP_P + 2];                 // poly_off slice starting at object (q0 & ~1)
-    long long img[(T + 3) & ~1];               // img_off slice starting at image (i0 & ~1), even entry count
+    TileInfo info[2];
     unsigned char bvalid[CAP_P];
+    unsigned short queue[QCAP];
     unsigned long long bar;
-    long long q0, v0;
-    int ni, np, pshift, ishift, mode, pad[3];
+    unsigned long long pad;
 };
 static_assert(sizeof(double2) * CAP_V % 16 == 0 && sizeof(double) * CAP_P * 4 % 16 == 0 &&
-                  sizeof(long long) * (CAP_P + 2) % 16 == 0 && sizeof(long long) * ((T + 3) & ~1) % 16 == 0 && CAP_P % 16 == 0,
+                  sizeof(long long) * (CAP_P + 2) % 16 == 0 && sizeof(TileInfo) % 16 == 0 && CAP_P % 16 == 0,
               "bulk-copy destinations must stay 16-byte aligned");
 
 struct Smem {
@@ -126,6 +134,19 @@ __device__ __forceinline__ Corner fold_sequential(LoadFn load, int V, CornerIdx&
     return c;
 }
 
+// Exact overlap pre-test of calculate_iou (processor.py:329-335): the pair can only reach the
+// threshold if both max(0, .) terms are positive.  Same selects and subtractions as iou_hits.
+__device__ __forceinline__ bool boxes_overlap(const Box& a, const Box& b) {
+    const double xi1 = pymax(a.x1, b.x1), yi1 = pymax(a.y1, b.y1);
+    const double xi2 = pymin(a.x2, b.x2), yi2 = pymin(a.y2, b.y2);
+    return __dsub_rn(xi2, xi1) > 0.0 && __dsub_rn(yi2, yi1) > 0.0;
+}
+__device__ __forceinline__ Box load_box(const double* sb, int q) {
+    const double2* p = reinterpret_cast<const double2*>(sb + 4 * q);
+    const double2 lo = p[0], hi = p[1];
+    return Box{lo.x, lo.y, hi.x, hi.y};
+}
+
 template <bool ARG>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off,
@@ -145,40 +166,47 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
 
     const bool zero_hits = 0.0 >= thr;
     const int64_t stride = (int64_t)gridDim.x * NW;
-    int64_t k = (int64_t)blockIdx.x * NW + warp;
+    const int64_t k0 = (int64_t)blockIdx.x * NW + warp;
     uint32_t phase = 0;
     TileDesc nxt{0, 0, 0, 0};
-    if (lane == 0 && k < n_tiles) nxt = desc[k];
+    if (lane == 0 && k0 < n_tiles) nxt = desc[k0];
 
-    for (; k < n_tiles; k += stride) {
+    // Stage fill, executed by lane 0 only: describe tile k in `ti` and start its copies.
+    auto fill = [&](TileInfo& ti, int64_t k) {
         const int64_t i0 = k * T;
         const int ni = (int)min((int64_t)T, n_img - i0);
-        // ---------------- stage fill (lane 0) ----------------
-        if (lane == 0) {
-            const TileDesc d = nxt;
-            if (k + stride < n_tiles) nxt = desc[k + stride];                // in flight while this tile is processed
-            const int64_t nv = d.v1 - d.v0, np = d.q1 - d.q0;
-            const int pshift = (int)(d.q0 & 1);
-            const int64_t ne = (pshift + np + 2) & ~1LL;                     // poly_off entries copied (even count)
-            const int ishift = (int)(i0 & 1);
-            const int64_t nie = (ishift + ni + 2) & ~1;                      // img_off entries copied (even count)
-            const bool fits = nv <= CAP_V && pshift + np + 1 <= CAP_P;
-            const bool tail_ok = (d.q0 - pshift) + ne <= n_poly + 1 && (i0 - ishift) + nie <= n_img + 1;
-            st.q0 = d.q0; st.v0 = d.v0; st.ni = ni; st.pshift = pshift; st.ishift = ishift;
-            if (fits && tail_ok) {
-                st.np = (int)np; st.mode = MODE_FAST;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the stage vs. async writes
-                mbar_arrive_expect_tx(&st.bar, (uint32_t)(16 * nv + 8 * ne + 8 * nie));
-                if (nv > 0) bulk_g2s(st.vert, xy2 + d.v0, (uint32_t)(16 * nv), &st.bar);
-                bulk_g2s(st.poly, poly_off + (d.q0 - pshift), (uint32_t)(8 * ne), &st.bar);
-                bulk_g2s(st.img, img_off + (i0 - ishift), (uint32_t)(8 * nie), &st.bar);
-            } else {
-                st.np = (int)min(np, (int64_t)0x7fffffff); st.mode = MODE_FALLBACK;
-            }
+        const TileDesc d = nxt;
+        if (k + stride < n_tiles) nxt = desc[k + stride];                    // in flight while tile k is processed
+        const int64_t nv = d.v1 - d.v0, np = d.q1 - d.q0;
+        const int pshift = (int)(d.q0 & 1), ishift = (int)(i0 & 1);
+        const int64_t ne = (pshift + np + 2) & ~1LL;                         // poly_off entries copied (even count)
+        const int64_t nie = (ishift + ni + 2) & ~1;                          // img_off entries copied (even count)
+        const bool objs_fit = pshift + np + 1 <= CAP_P;
+        const bool tail_ok = (d.q0 - pshift) + ne <= n_poly + 1 && (i0 - ishift) + nie <= n_img + 1;
+        ti.q0 = d.q0; ti.v0 = d.v0; ti.ni = ni; ti.pshift = pshift; ti.ishift = ishift;
+        ti.np = (int)min(np, (int64_t)0x7fffffff);
+        if (objs_fit && nv <= CAP_V && tail_ok) {
+            ti.mode = MODE_FAST;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of the stage vs. async writes
+            mbar_arrive_expect_tx(&st.bar, (uint32_t)(16 * nv + 8 * ne + 8 * nie));
+            if (nv > 0) bulk_g2s(st.vert, xy2 + d.v0, (uint32_t)(16 * nv), &st.bar);
+            bulk_g2s(st.poly, poly_off + (d.q0 - pshift), (uint32_t)(8 * ne), &st.bar);
+            bulk_g2s(ti.img, img_off + (i0 - ishift), (uint32_t)(8 * nie), &st.bar);
+        } else if (objs_fit) {
+            ti.mode = MODE_DIRECT;                                            // vertices do not fit: K1 reads HBM directly
+            for (int j = 0; j <= ni; ++j) ti.img[ishift + j] = __ldg(img_off + i0 + j);
+        } else {
+            ti.mode = MODE_DEFER;                                             // too many objects: block-per-image kernel
         }
+    };
+
+    if (lane == 0 && k0 < n_tiles) fill(st.info[0], k0);
+    unsigned it = 0;
+    for (int64_t k = k0; k < n_tiles; k += stride, ++it) {
+        TileInfo& ti = st.info[it & 1];
         __syncwarp();
-        const int mode = st.mode, np = st.np, pshift = st.pshift, ishift = st.ishift;
-        const int64_t q0 = st.q0, v0 = st.v0;
+        const int mode = ti.mode, np = ti.np, pshift = ti.pshift, ishift = ti.ishift, ni = ti.ni;
+        const int64_t q0 = ti.q0, v0 = ti.v0, i0 = k * T;
         if (mode == MODE_FAST) {
             mbar_wait(&st.bar, phase);
             phase ^= 1;
@@ -206,7 +234,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             stg_stream_f64x2(o + 1, make_double2(c.mxx, c.mxy));
             valid[p] = V > 0 ? 1 : 0;
             if (ARG) *reinterpret_cast<int4*>(arg + 4 * p) = make_int4(ci.mnx, ci.mny, ci.mxx, ci.mxy);
-            if (mode == MODE_FAST) {
+            if (mode != MODE_DEFER) {
                 const Box bx = box_from_points(c.mnx, c.mny, c.mxx, c.mxy);
                 double2* sb = reinterpret_cast<double2*>(st.box + 4 * pl);
                 sb[0] = make_double2(bx.x1, bx.y1); sb[1] = make_double2(bx.x2, bx.y2);
@@ -214,29 +242,78 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             }
         }
         __syncwarp();
-        // ---------------- K2: box count + any-pair IoU per image ----------------
-        for (int j = 0; j < ni; ++j) {
-            const int64_t img = i0 + j;
-            int n = WARP_BOX_CAP + 1, lq = 0;
-            if (mode == MODE_FAST) { lq = (int)(st.img[ishift + j] - q0); n = (int)(st.img[ishift + j + 1] - st.img[ishift + j]); }
-            if (n > WARP_BOX_CAP) {                           // crowded image or fallback tile -> block kernel
-                if (lane == 0) {
-                    unsigned long long slot = atomicAdd(&reinterpret_cast<CrowdList*>(ws)->count, 1ULL);
-                    crowd_ids(ws)[slot] = (int)img;
-                }
-                continue;
+        // The vertex / offset buffers are free again: start the next tile's copies now so that they
+        // land while K2 works on this tile's boxes.
+        if (lane == 0 && k + stride < n_tiles) fill(st.info[(it + 1) & 1], k + stride);
+
+        // ---------------- K2: box counts + any-pair IoU, flattened over the tile's images ----------------
+        if (mode == MODE_DEFER) {
+            if (lane < ni) {
+                unsigned long long slot = atomicAdd(&reinterpret_cast<CrowdList*>(ws)->count, 1ULL);
+                crowd_ids(ws)[slot] = (int)(i0 + lane);
             }
-            int n_eff = n;
-            for (int base = 0; base < n; base += 32) {
-                const int jj = base + lane;
-                const unsigned m = __ballot_sync(FULL, jj < n && st.bvalid[lq + jj] == 0);
-                if (m) { n_eff = base + (__ffs(m) - 1); break; }
-            }
-            bool hit = false;
-            if (n_eff >= min_boxes && n_eff >= 2) hit = warp_any_pair(st.box + 4 * lq, n_eff, thr, zero_hits, sm.lut, lane);
-            if (lane == 0) { count[img] = n_eff; high[img] = hit ? 1 : 0; }
+            continue;
         }
-        __syncwarp();                                         // stage fully consumed before lane 0 refills it
+        // bit p of `inv` = object p of the tile is a null bbox
+        const unsigned inv_lo = __ballot_sync(FULL, lane < np && st.bvalid[lane] == 0);
+        const unsigned inv_hi = __ballot_sync(FULL, lane + 32 < np && st.bvalid[(lane + 32) % CAP_P] == 0);
+        const unsigned long long inv = ((unsigned long long)inv_hi << 32) | inv_lo;
+        int lq[T], neff[T], cum[T];
+        int total = 0;
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            lq[j] = 0; neff[j] = 0;
+            if (j < ni) {
+                const int a = (int)(ti.img[ishift + j] - q0), n = (int)(ti.img[ishift + j + 1] - ti.img[ishift + j]);
+                const unsigned long long m = (inv >> a) & (n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL));
+                const int ne = m ? __ffsll((long long)m) - 1 : n;           // boxes before the first null bbox
+                lq[j] = a; neff[j] = ne;
+                if (ne >= min_boxes && ne >= 2) total += ne * (ne - 1) / 2;
+            }
+            cum[j] = total;
+        }
+        unsigned hits = 0;
+        int qhead = 0, qtail = 0;
+        auto exact_pass = [&](int cnt) {           // dense evaluation of queued pairs with the full IoU arithmetic
+            bool hit = false; int j = 0;
+            if (lane < cnt) {
+                const unsigned e = st.queue[(qhead + lane) & (QCAP - 1)];
+                j = e >> 12;
+                hit = iou_hits(load_box(st.box, e & 63), load_box(st.box, (e >> 6) & 63), thr, zero_hits);
+            }
+            hits |= __reduce_or_sync(FULL, hit ? (1u << j) : 0u);
+            qhead += cnt;
+            __syncwarp();                          // queue slots read above may be overwritten by the next append
+        };
+        for (int base = 0; base < total; base += 32) {
+            const int kq = base + lane;
+            bool surv = false; unsigned entry = 0;
+            if (kq < total) {
+                int j = 0, first = 0, off = 0;
+#pragma unroll
+                for (int jj = 0; jj < T - 1; ++jj) if (kq >= cum[jj]) { j = jj + 1; first = cum[jj]; }
+#pragma unroll
+                for (int jj = 0; jj < T; ++jj) if (j == jj) off = lq[jj];
+                const unsigned stp = sm.lut[kq - first];
+                const int ia = off + (stp & 0xff), ib = off + (stp >> 8);
+                surv = zero_hits || boxes_overlap(load_box(st.box, ia), load_box(st.box, ib));
+                entry = (unsigned)ia | ((unsigned)ib << 6) | ((unsigned)j << 12);
+            }
+            const unsigned m = __ballot_sync(FULL, surv);
+            if (m) {
+                if (surv) st.queue[(qtail + __popc(m & ((1u << lane) - 1u))) & (QCAP - 1)] = (unsigned short)entry;
+                qtail += __popc(m);
+                __syncwarp();
+                if (qtail - qhead >= 32) exact_pass(32);
+            }
+        }
+        if (qtail > qhead) exact_pass(qtail - qhead);
+        if (lane < ni) {
+            int ne = 0; bool h = false;
+#pragma unroll
+            for (int j = 0; j < T; ++j) if (lane == j) { ne = neff[j]; h = (hits >> j) & 1u; }
+            count[i0 + lane] = ne; high[i0 + lane] = h ? 1 : 0;
+        }
     }
 }
 
