@@ -43,6 +43,7 @@ PROTOTYPES = {
     "dyd_yolo_normalise": (_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
     "dyd_bbox_iou_host": (_int, [_p, _p, _p, _i64, _i64, _f64, _p, _p, _p, _p, _p, _i64]),
     "dyd_dedup_host": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
+    "dyd_host_release": (_int, []),
     "dyd_synth_counts": (_int, [_u64, _i64, _i64, _p, _i32, _p, _p]),
     "dyd_synth_nvert": (_int, [_u64, _i64, _i64, _p, _p, _p]),
     "dyd_synth_fill": (_int, [_u64, _i64, _i64, _p, _p, _p, _p, _p]),

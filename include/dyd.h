@@ -175,6 +175,10 @@ int dyd_bbox_iou_host(const int64_t* h_img_off, const int64_t* h_poly_off, const
                       double* h_pts, uint8_t* h_valid, int32_t* h_arg,
                       uint8_t* h_high, int32_t* h_count, int64_t chunk_images);
 
+/* The two host entry points cache their transient device buffers in a library-owned CUDA memory
+ * pool (per device); this returns the cached blocks of the current device to the driver. */
+int dyd_host_release(void);
+
 /* Same idea for the URL column: hash + dedup (+ anti-join when n_ref > 0) from host
  * Arrow buffers to host masks.  h_ref_* may be NULL when n_ref == 0.              */
 int dyd_dedup_host(const int64_t* h_off, const uint8_t* h_bytes, const uint8_t* h_null, int64_t n,
