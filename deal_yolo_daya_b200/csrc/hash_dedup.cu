@@ -71,13 +71,16 @@ hash_strings_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------- K4
-template <bool IDS>
+// KIND 0: rows are 0..n-1 (null flags honoured); 1: explicit global row ids in a separate array;
+// 2: interleaved (key, id) records as they arrive from the exchange (keys = records, row_id unused)
+template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
 dedup_insert_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
                     const int64_t* __restrict__ row_id, int64_t n, int keep_mode,
                     TableHeader* hdr, Slot* tab, unsigned* cnt, int shift, uint64_t mask) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     const bool live = r < n;
+    constexpr bool IDS = KIND != 0;
     const bool isnull = live && !IDS && null != nullptr && null[r] != 0;
     const unsigned nm = __ballot_sync(FULL, isnull);
     if (nm) {                                          // rows ascend with the lane: aggregate per warp
@@ -86,8 +89,10 @@ dedup_insert_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
         if (lane == 31 - __clz(nm)) atomicMax(&hdr->null_last, (long long)r);
     }
     if (!live || isnull) return;
-    const unsigned long long key = norm_key(keys[r]);
-    const unsigned long long rid = IDS ? (unsigned long long)row_id[r] : (unsigned long long)r;
+    const long long id = KIND == 2 ? (long long)keys[2 * r + 1] : (KIND == 1 ? row_id[r] : r);
+    if (IDS && id < 0) return;                          // padding of a fixed-capacity exchange bucket
+    const unsigned long long key = norm_key(KIND == 2 ? keys[2 * r] : keys[r]);
+    const unsigned long long rid = (unsigned long long)id;
     uint64_t s = home_slot(key, shift);
     for (;;) {
         unsigned long long prev = atomicCAS(&tab[s].key, EMPTY, key);
@@ -101,7 +106,7 @@ dedup_insert_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
     }
 }
 
-template <bool IDS>
+template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
 dedup_lookup_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
                     const int64_t* __restrict__ row_id, int64_t n, int keep_mode,
@@ -110,14 +115,16 @@ dedup_lookup_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
                     uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= n) return;
-    const long long rid = IDS ? row_id[r] : r;
+    constexpr bool IDS = KIND != 0;
+    const long long rid = KIND == 2 ? (long long)keys[2 * r + 1] : (KIND == 1 ? row_id[r] : r);
+    if (IDS && rid < 0) { rep[r] = -1; keep[r] = 0; return; }
     if (!IDS && null != nullptr && null[r] != 0) {
         const long long rp = keep_mode == 1 ? hdr->null_last : (long long)hdr->null_first;
         rep[r] = rp;
         keep[r] = keep_mode == 2 ? (hdr->null_count == 1) : (rp == rid);
         return;
     }
-    const unsigned long long key = norm_key(keys[r]);
+    const unsigned long long key = norm_key(KIND == 2 ? keys[2 * r] : keys[r]);
     uint64_t s = home_slot(key, shift);
     while (tab[s].key != key) s = (s + 1) & mask;      // the key was inserted by the previous kernel
     const long long rp = (long long)tab[s].row;
@@ -160,15 +167,71 @@ antijoin_probe_kernel(const unsigned long long* __restrict__ keys, const uint8_t
     keep[r] = k; ref_row[r] = rr;
 }
 
+// ------------------------------------------------------------------------------- multi-GPU exchange helpers
+// Owner rank of a key; must match sharding.owner_of() on the Python side.
+__device__ __forceinline__ int owner_of(unsigned long long key, int world) {
+    const unsigned long long mixed = key * 0x9E3779B97F4A7C15ULL;
+    return (int)(((mixed >> 33) & 0x7FFFFFFFULL) % (unsigned)world);
+}
+
+// (key, global row id) records scattered into `world` fixed-capacity buckets (pre-filled with padding
+// by a 0xFF memset: key = EMPTY, id = -1).  Order inside a bucket is arbitrary: the ids carry it.
+__global__ void __launch_bounds__(HT_THREADS)
+shard_bucket_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t row_base,
+                    int64_t n, int world, int64_t cap, long long* __restrict__ records,
+                    unsigned long long* cursors, int* overflow) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    const bool live = r < n && (null == nullptr || null[r] == 0);
+    const unsigned long long key = live ? keys[r] : 0ULL;
+    const int own = live ? owner_of(key, world) : -1;
+    const unsigned peers = __match_any_sync(FULL, own);          // one atomic per (warp, owner)
+    if (!live) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&cursors[own], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const unsigned long long slot = base + __popc(peers & ((1u << lane) - 1u));
+    if (slot >= (unsigned long long)cap) { *overflow = 1; return; }
+    long long* rec = records + 2 * ((int64_t)own * cap + (int64_t)slot);
+    rec[0] = (long long)key; rec[1] = row_base + r;
+}
+
+// owner side: (id, rep | keep << 62) per received record
+__global__ void __launch_bounds__(HT_THREADS)
+shard_pack_reply_kernel(const long long* __restrict__ records, const uint8_t* __restrict__ keep,
+                        const int64_t* __restrict__ rep, int64_t m, long long* __restrict__ reply) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= m) return;
+    const long long id = records[2 * r + 1];
+    reply[2 * r] = id;
+    reply[2 * r + 1] = id < 0 ? -1 : (rep[r] | ((long long)(keep[r] ? 1 : 0) << 62));
+}
+
+// origin side: place the answers at the rows they belong to
+__global__ void __launch_bounds__(HT_THREADS)
+shard_unpack_kernel(const long long* __restrict__ reply, int64_t m, int64_t row_base, int64_t n,
+                    uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= m) return;
+    const long long id = reply[2 * r];
+    if (id < 0) return;
+    const long long local = id - row_base;
+    if (local < 0 || local >= n) return;
+    const long long v = reply[2 * r + 1];
+    keep[local] = (uint8_t)((v >> 62) & 1);
+    rep[local] = v & ((1LL << 62) - 1);
+}
+
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + HT_THREADS - 1) / HT_THREADS); }
 
-template <bool IDS>
+template <int KIND>
 static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64_t* d_row_id, int64_t n, int keep_mode,
                       uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
     DYD_REQUIRE(n >= 0 && n < (1LL << 40), DYD_E_ARG, "bad row count");
     DYD_REQUIRE(keep_mode >= 0 && keep_mode <= 2, DYD_E_ARG, "keep_mode must be 0 (first), 1 (last) or 2 (False)");
     if (n == 0) return 0;
-    DYD_REQUIRE(d_keys && d_keep && d_rep && ws && (!IDS || d_row_id), DYD_E_ARG, "null pointer");
+    DYD_REQUIRE(d_keys && d_keep && d_rep && ws && (KIND != 1 || d_row_id), DYD_E_ARG, "null pointer");
     DYD_REQUIRE(((uintptr_t)ws & 15) == 0, DYD_E_ALIGN, "workspace must be 16-byte aligned");
     DYD_REQUIRE(ws_bytes >= dyd_dedup_workspace_bytes(n), DYD_E_WORKSPACE, "workspace too small");
     const uint64_t cap = table_capacity(n);
@@ -180,10 +243,10 @@ static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64
     DYD_CUDA(cudaMemsetAsync(ws, 0xFF, sizeof(TableHeader) + cap * sizeof(Slot), s));
     DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
     if (keep_mode == 2) DYD_CUDA(cudaMemsetAsync(cnt, 0, cap * sizeof(unsigned), s));
-    dedup_insert_kernel<IDS><<<grid_for(n), HT_THREADS, 0, s>>>(
+    dedup_insert_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(
         reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1);
     if (int rc = launch_check("dedup_insert_kernel")) return rc;
-    dedup_lookup_kernel<IDS><<<grid_for(n), HT_THREADS, 0, s>>>(
+    dedup_lookup_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(
         reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1, d_keep, d_rep);
     return launch_check("dedup_lookup_kernel");
 }
@@ -207,12 +270,51 @@ extern "C" size_t dyd_dedup_workspace_bytes(int64_t n) {
 
 extern "C" int dyd_dedup(const uint64_t* d_keys, const uint8_t* d_null, int64_t n, int keep_mode,
                          uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
-    return dedup_impl<false>(d_keys, d_null, nullptr, n, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
+    return dedup_impl<0>(d_keys, d_null, nullptr, n, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
 }
 
 extern "C" int dyd_dedup_ids(const uint64_t* d_keys, const int64_t* d_row_id, int64_t n, int keep_mode,
                              uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
-    return dedup_impl<true>(d_keys, nullptr, d_row_id, n, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
+    return dedup_impl<1>(d_keys, nullptr, d_row_id, n, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
+}
+
+extern "C" int dyd_dedup_records(const int64_t* d_records, int64_t m, int keep_mode,
+                                 uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
+    return dedup_impl<2>(reinterpret_cast<const uint64_t*>(d_records), nullptr, nullptr, m, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
+}
+
+extern "C" int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
+                                int64_t cap, int64_t* d_records, uint64_t* d_cursors, int32_t* d_overflow, void* stream) {
+    DYD_REQUIRE(n >= 0 && world >= 1 && cap >= 0, DYD_E_ARG, "bad arguments");
+    DYD_REQUIRE(d_records && d_cursors && d_overflow && (n == 0 || d_keys), DYD_E_ARG, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    DYD_CUDA(cudaMemsetAsync(d_records, 0xFF, sizeof(int64_t) * 2 * (size_t)world * (size_t)cap, s));
+    DYD_CUDA(cudaMemsetAsync(d_cursors, 0, sizeof(uint64_t) * world, s));
+    DYD_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
+    if (n == 0) return 0;
+    shard_bucket_kernel<<<grid_for(n), HT_THREADS, 0, s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
+                                                          world, cap, reinterpret_cast<long long*>(d_records),
+                                                          reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
+    return launch_check("shard_bucket_kernel");
+}
+
+extern "C" int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,
+                                    int64_t* d_reply, void* stream) {
+    DYD_REQUIRE(m >= 0, DYD_E_ARG, "negative count");
+    if (m == 0) return 0;
+    DYD_REQUIRE(d_records && d_keep && d_rep && d_reply, DYD_E_ARG, "null pointer");
+    shard_pack_reply_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_records), d_keep, d_rep, m,
+                                                                                reinterpret_cast<long long*>(d_reply));
+    return launch_check("shard_pack_reply_kernel");
+}
+
+extern "C" int dyd_shard_unpack(const int64_t* d_reply, int64_t m, int64_t row_base, int64_t n,
+                                uint8_t* d_keep, int64_t* d_rep, void* stream) {
+    DYD_REQUIRE(m >= 0 && n >= 0, DYD_E_ARG, "negative count");
+    if (m == 0) return 0;
+    DYD_REQUIRE(d_reply && d_keep && d_rep, DYD_E_ARG, "null pointer");
+    shard_unpack_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_reply), m, row_base, n, d_keep, d_rep);
+    return launch_check("shard_unpack_kernel");
 }
 
 extern "C" size_t dyd_antijoin_workspace_bytes(int64_t n_ref) {

@@ -101,6 +101,59 @@ def dedup_global(keys: torch.Tensor, null: torch.Tensor | None, row_base: int, k
     return keep_out, rep_out
 
 
+class DedupExchange:
+    """Sync-free sharded dedup (the production multi-GPU form of K4).
+
+    Fixed-capacity buckets make every all-to-all equal-sized, so nothing has to come back to the host
+    between kernels: bucket kernel -> NCCL all-to-all -> dedup on the received records -> reply
+    pack -> reverse all-to-all -> unpack.  The one host read is the overflow flag at the end; if a
+    bucket overflowed (heavily skewed keys) the exact-size path `dedup_global` redoes the step.
+    Buffers are allocated once and reused across calls.
+    """
+
+    def __init__(self, n_local: int, world: int, device, slack: float = 1.10):
+        from . import _lib
+        self.lib = _lib.load()
+        self.n, self.world, self.dev = n_local, world, device
+        self.cap = int(n_local / world * slack) + 4096
+        m = world * self.cap
+        self.send = torch.empty(2 * m, dtype=torch.int64, device=device)
+        self.recv = torch.empty(2 * m, dtype=torch.int64, device=device)
+        self.reply = torch.empty(2 * m, dtype=torch.int64, device=device)
+        self.back = torch.empty(2 * m, dtype=torch.int64, device=device)
+        self.cursors = torch.empty(world, dtype=torch.uint64, device=device)
+        self.overflow = torch.empty(1, dtype=torch.int32, device=device)
+        self.keep_r = torch.empty(m, dtype=torch.uint8, device=device)
+        self.rep_r = torch.empty(m, dtype=torch.int64, device=device)
+        self.ws = torch.empty(self.lib.dyd_dedup_workspace_bytes(m), dtype=torch.uint8, device=device)
+        self.keep = torch.empty(n_local, dtype=torch.uint8, device=device)
+        self.rep = torch.empty(n_local, dtype=torch.int64, device=device)
+
+    def run(self, keys: torch.Tensor, row_base: int, keep="first", group=None, check_overflow=True):
+        from . import _lib
+        from .ops import KEEP_MODES, _ptr, _stream
+        lib, dev, m = self.lib, self.dev, self.world * self.cap
+        assert keys.numel() == self.n and keys.dtype == torch.uint64
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            _lib.check(lib.dyd_shard_bucket(_ptr(keys), None, row_base, self.n, self.world, self.cap, _ptr(self.send),
+                                            _ptr(self.cursors), _ptr(self.overflow), s), "dyd_shard_bucket")
+            dist.all_to_all_single(self.recv, self.send, group=group)
+            _lib.check(lib.dyd_dedup_records(_ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_r), _ptr(self.rep_r),
+                                             _ptr(self.ws), self.ws.numel(), s), "dyd_dedup_records")
+            _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, _ptr(self.reply), s),
+                       "dyd_shard_pack_reply")
+            dist.all_to_all_single(self.back, self.reply, group=group)
+            _lib.check(lib.dyd_shard_unpack(_ptr(self.back), m, row_base, self.n, _ptr(self.keep), _ptr(self.rep), s),
+                       "dyd_shard_unpack")
+        if check_overflow:
+            flag = self.overflow.clone()
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.item()):
+                return dedup_global(keys, None, row_base, keep, group)
+        return self.keep, self.rep
+
+
 def antijoin_global(main_keys, main_null, ref_keys, ref_null, ref_row_base: int, group=None, local_antijoin=None):
     """Global anti-join for this rank's main rows against the union of all ranks' reference rows.
 

@@ -105,6 +105,21 @@ int dyd_dedup_ids(const uint64_t* d_keys, const int64_t* d_row_id, int64_t n, in
                   uint8_t* d_keep, int64_t* d_rep,
                   void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-GPU exchange helpers for K4 (one process per GPU; the all-to-all itself is NCCL).
+ * _bucket: scatters (key, row_base + row) records into `world` buckets of `cap` records each
+ *          (int64[world*cap*2], padding = id -1), owner = mix(key) mod world; *d_overflow = 1 if a
+ *          bucket was too small (the caller then uses exact-size splits).  Null rows are skipped.
+ * dyd_dedup_ids ignores padded records.  _pack_reply builds (id, rep | keep << 62) answers on the
+ * owner; _unpack places them at rows id - row_base on the origin.                              */
+int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
+                     int64_t cap, int64_t* d_records, uint64_t* d_cursors, int32_t* d_overflow, void* stream);
+int dyd_dedup_records(const int64_t* d_records, int64_t m, int keep_mode, uint8_t* d_keep, int64_t* d_rep,
+                      void* d_workspace, size_t workspace_bytes, void* stream);   /* K4 on received (key, id) records */
+int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,
+                         int64_t* d_reply, void* stream);
+int dyd_shard_unpack(const int64_t* d_reply, int64_t m, int64_t row_base, int64_t n,
+                     uint8_t* d_keep, int64_t* d_rep, void* stream);
+
 /* ---------------------------------------------------------------- K5 ------
  * Anti-join of processor.py:194-199: keep[r] = main value not in
  * set(ref.dropna()); null main rows are always kept.  d_ref_row[r] = first

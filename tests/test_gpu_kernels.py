@@ -335,3 +335,36 @@ def test_host_entry_points(cuda_device):
     keep, rep = ops.dedup_host(off, data, null, "first")
     wk, wr = oracle_c.dedup(oracle_c.hash_strings_buf(off, data), null, "first")
     assert_bits(keep, wk); assert_bits(rep, wr)
+
+
+def test_exchange_kernels_single_rank_roundtrip(cuda_device):
+    """bucket -> (identity exchange) -> dedup on records -> reply -> unpack equals plain dedup;
+    world=4 bucket layout is exercised by treating the 4 buckets as arriving from 4 ranks."""
+    import ctypes as C
+    from deal_yolo_daya_b200 import _lib
+    from deal_yolo_daya_b200.ops import _ptr, _stream
+    lib = _lib.load(); d = cuda_device
+    rng = np.random.RandomState(5)
+    n, world = 60000, 4
+    keys = (rng.randint(0, 20000, size=n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+    for keep in ("first", "last", False):
+        want_keep, want_rep = oracle_c.dedup(keys, np.zeros(n, np.uint8), keep)
+        want_rep = want_rep + 1000                               # global ids = row_base + row
+        cap = n // world + 2000
+        m = world * cap
+        t = lambda *shape, dt=torch.int64: torch.empty(*shape, dtype=dt, device=d)   # noqa: E731
+        send, reply = t(2 * m), t(2 * m)
+        cursors, overflow = t(world, dt=torch.uint64), t(1, dt=torch.int32)
+        keep_r, rep_r = t(m, dt=torch.uint8), t(m)
+        ws = t(lib.dyd_dedup_workspace_bytes(m), dt=torch.uint8)
+        out_keep, out_rep = t(n, dt=torch.uint8), t(n)
+        k = dev(keys, d); s = _stream(d)
+        _lib.check(lib.dyd_shard_bucket(_ptr(k), None, 1000, n, world, cap, _ptr(send), _ptr(cursors), _ptr(overflow), s), "bucket")
+        assert int(overflow.item()) == 0 and int(cursors.cpu().numpy().astype(np.int64).sum()) == n
+        _lib.check(lib.dyd_dedup_records(_ptr(send), m, ops.KEEP_MODES[keep], _ptr(keep_r), _ptr(rep_r), _ptr(ws), ws.numel(), s), "records")
+        _lib.check(lib.dyd_shard_pack_reply(_ptr(send), _ptr(keep_r), _ptr(rep_r), m, _ptr(reply), s), "pack")
+        _lib.check(lib.dyd_shard_unpack(_ptr(reply), m, 1000, n, _ptr(out_keep), _ptr(out_rep), s), "unpack")
+        assert_bits(host(out_keep), want_keep, f"keep {keep}"); assert_bits(host(out_rep), want_rep, f"rep {keep}")
+    # overflow is reported, never silent
+    _lib.check(lib.dyd_shard_bucket(_ptr(k), None, 0, n, world, 100, _ptr(send), _ptr(cursors), _ptr(overflow), s), "bucket")
+    assert int(overflow.item()) == 1
