@@ -35,6 +35,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+emit = None
 
 METRIC = "images/sec, ptList->bbox+IoU filter+dedup"
 UNIT = "images/s"
@@ -175,7 +176,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -192,6 +193,14 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    # only the JSON line may reach stdout: library banners (e.g. "NCCL version ...") are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
@@ -242,13 +251,13 @@ def main():
 
     for _ in range(max(args.warmup, 1)):
         step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start(); time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()                      # every rank enters the timed region together
     torch.cuda.synchronize()
     e0.record()
     for i in range(args.steps):
@@ -371,7 +380,7 @@ def main():
                                                   "no JSON/CSV work, the kernel-for-kernel comparison"}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline_csr"] = {"error": str(e)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

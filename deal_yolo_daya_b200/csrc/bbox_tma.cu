@@ -96,16 +96,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- descriptor pre-pass: resolves the img_off -> poly_off chain once per tile -------------------
+// ---- descriptor pre-pass: resolves the img_off -> poly_off chain and picks the tile's lane ----------
 __global__ void __launch_bounds__(256)
 tile_desc_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off, int64_t n_img,
-                 int64_t n_tiles, TileDesc* __restrict__ desc) {
+                 int64_t n_poly, int64_t n_tiles, TileDesc* __restrict__ desc) {
     const int64_t k = blockIdx.x * 256LL + threadIdx.x;
     if (k >= n_tiles) return;
     const int64_t i0 = k * T, i1 = min(i0 + T, n_img);
+    const int ni = (int)(i1 - i0);
+    const int64_t q0 = img_off[i0], q1 = img_off[i1];
+    const int64_t v0 = poly_off[q0], v1 = poly_off[q1];
+    const int64_t np = q1 - q0, nv = v1 - v0;
+    const int pshift = (int)(q0 & 1), ishift = (int)(i0 & 1);
+    const int64_t ne = (pshift + np + 2) & ~1LL;                             // poly_off entries a bulk copy would read
+    const int64_t nie = (ishift + ni + 2) & ~1;                              // img_off entries a bulk copy would read
+    const bool objs_fit = pshift + np + 1 <= CAP_P;
+    const bool tail_ok = (q0 - pshift) + ne <= n_poly + 1 && (i0 - ishift) + nie <= n_img + 1;
     TileDesc d;
-    d.q0 = img_off[i0]; d.q1 = img_off[i1];
-    d.v0 = poly_off[d.q0]; d.v1 = poly_off[d.q1];
+    d.q0 = q0; d.v0 = v0;
+    d.np = (int)min(np, (int64_t)0x7fffffff); d.nv = (int)min(nv, (int64_t)0x7fffffff);
+    d.mode = !objs_fit ? MODE_DEFER : ((nv <= CAP_V && tail_ok) ? MODE_FAST : MODE_DIRECT);
+    d.pad = 0;
     desc[k] = d;
 }
 
@@ -168,7 +179,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
     const int64_t stride = (int64_t)gridDim.x * NW;
     const int64_t k0 = (int64_t)blockIdx.x * NW + warp;
     uint32_t phase = 0;
-    TileDesc nxt{0, 0, 0, 0};
+    TileDesc nxt{0, 0, 0, 0, MODE_DEFER, 0};
     if (lane == 0 && k0 < n_tiles) nxt = desc[k0];
 
     // Stage fill, executed by lane 0 only: describe tile k in `ti` and start its copies.
@@ -177,26 +188,17 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
         const int ni = (int)min((int64_t)T, n_img - i0);
         const TileDesc d = nxt;
         if (k + stride < n_tiles) nxt = desc[k + stride];                    // in flight while tile k is processed
-        const int64_t nv = d.v1 - d.v0, np = d.q1 - d.q0;
         const int pshift = (int)(d.q0 & 1), ishift = (int)(i0 & 1);
-        const int64_t ne = (pshift + np + 2) & ~1LL;                         // poly_off entries copied (even count)
-        const int64_t nie = (ishift + ni + 2) & ~1;                          // img_off entries copied (even count)
-        const bool objs_fit = pshift + np + 1 <= CAP_P;
-        const bool tail_ok = (d.q0 - pshift) + ne <= n_poly + 1 && (i0 - ishift) + nie <= n_img + 1;
-        ti.q0 = d.q0; ti.v0 = d.v0; ti.ni = ni; ti.pshift = pshift; ti.ishift = ishift;
-        ti.np = (int)min(np, (int64_t)0x7fffffff);
-        if (objs_fit && nv <= CAP_V && tail_ok) {
-            ti.mode = MODE_FAST;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of the stage vs. async writes
-            mbar_arrive_expect_tx(&st.bar, (uint32_t)(16 * nv + 8 * ne + 8 * nie));
-            if (nv > 0) bulk_g2s(st.vert, xy2 + d.v0, (uint32_t)(16 * nv), &st.bar);
-            bulk_g2s(st.poly, poly_off + (d.q0 - pshift), (uint32_t)(8 * ne), &st.bar);
-            bulk_g2s(ti.img, img_off + (i0 - ishift), (uint32_t)(8 * nie), &st.bar);
-        } else if (objs_fit) {
-            ti.mode = MODE_DIRECT;                                            // vertices do not fit: K1 reads HBM directly
+        ti.q0 = d.q0; ti.v0 = d.v0; ti.ni = ni; ti.pshift = pshift; ti.ishift = ishift; ti.np = d.np; ti.mode = d.mode;
+        if (d.mode == MODE_FAST) {
+            const uint32_t ne = (uint32_t)(pshift + d.np + 2) & ~1u;         // poly_off entries copied (even count)
+            const uint32_t nie = (uint32_t)(ishift + ni + 2) & ~1u;          // img_off entries copied (even count)
+            mbar_arrive_expect_tx(&st.bar, 16u * (uint32_t)d.nv + 8u * ne + 8u * nie);
+            if (d.nv > 0) bulk_g2s(st.vert, xy2 + d.v0, 16u * (uint32_t)d.nv, &st.bar);
+            bulk_g2s(st.poly, poly_off + (d.q0 - pshift), 8u * ne, &st.bar);
+            bulk_g2s(ti.img, img_off + (i0 - ishift), 8u * nie, &st.bar);
+        } else if (d.mode == MODE_DIRECT) {                                   // vertices do not fit: K1 reads HBM directly
             for (int j = 0; j <= ni; ++j) ti.img[ishift + j] = __ldg(img_off + i0 + j);
-        } else {
-            ti.mode = MODE_DEFER;                                             // too many objects: block-per-image kernel
         }
     };
 
@@ -212,6 +214,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             phase ^= 1;
         }
         // ---------------- K1: one lane per polygon ----------------
+        bool nan_box = false;
         for (int pl = lane; pl < np; pl += 32) {
             const int64_t p = q0 + pl;
             Corner c{0.0, 0.0, 0.0, 0.0};
@@ -235,6 +238,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             valid[p] = V > 0 ? 1 : 0;
             if (ARG) *reinterpret_cast<int4*>(arg + 4 * p) = make_int4(ci.mnx, ci.mny, ci.mxx, ci.mxy);
             if (mode != MODE_DEFER) {
+                nan_box |= (c.mnx != c.mnx) | (c.mny != c.mny) | (c.mxx != c.mxx) | (c.mxy != c.mxy);
                 const Box bx = box_from_points(c.mnx, c.mny, c.mxx, c.mxy);
                 double2* sb = reinterpret_cast<double2*>(st.box + 4 * pl);
                 sb[0] = make_double2(bx.x1, bx.y1); sb[1] = make_double2(bx.x2, bx.y2);
@@ -254,10 +258,12 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             }
             continue;
         }
+        // Without NaN coordinates the two cross comparisons per axis are a superset of the exact
+        // overlap test, which the survivors get anyway; a tile holding a NaN box uses the exact selects.
+        const bool exact_pre = __any_sync(FULL, nan_box);
         // bit p of `inv` = object p of the tile is a null bbox
         const unsigned inv_lo = __ballot_sync(FULL, lane < np && st.bvalid[lane] == 0);
-        const unsigned inv_hi = __ballot_sync(FULL, lane + 32 < np && st.bvalid[(lane + 32) % CAP_P] == 0);
-        const unsigned long long inv = ((unsigned long long)inv_hi << 32) | inv_lo;
+        const unsigned inv_hi = np > 32 ? __ballot_sync(FULL, lane + 32 < np && st.bvalid[(lane + 32) % CAP_P] == 0) : 0u;
         int lq[T], neff[T], cum[T];
         int total = 0;
 #pragma unroll
@@ -265,8 +271,12 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             lq[j] = 0; neff[j] = 0;
             if (j < ni) {
                 const int a = (int)(ti.img[ishift + j] - q0), n = (int)(ti.img[ishift + j + 1] - ti.img[ishift + j]);
-                const unsigned long long m = (inv >> a) & (n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL));
-                const int ne = m ? __ffsll((long long)m) - 1 : n;           // boxes before the first null bbox
+                int ne = n;                                                  // boxes before the first null bbox
+                if (inv_lo | inv_hi) {
+                    const unsigned long long inv = ((unsigned long long)inv_hi << 32) | inv_lo;
+                    const unsigned long long m = (inv >> a) & (n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL));
+                    if (m) ne = __ffsll((long long)m) - 1;
+                }
                 lq[j] = a; neff[j] = ne;
                 if (ne >= min_boxes && ne >= 2) total += ne * (ne - 1) / 2;
             }
@@ -296,7 +306,9 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
                 for (int jj = 0; jj < T; ++jj) if (j == jj) off = lq[jj];
                 const unsigned stp = sm.lut[kq - first];
                 const int ia = off + (stp & 0xff), ib = off + (stp >> 8);
-                surv = zero_hits || boxes_overlap(load_box(st.box, ia), load_box(st.box, ib));
+                const Box ba = load_box(st.box, ia), bb = load_box(st.box, ib);
+                surv = zero_hits || (exact_pre ? boxes_overlap(ba, bb)
+                                               : (ba.x2 > bb.x1 && bb.x2 > ba.x1 && ba.y2 > bb.y1 && bb.y2 > ba.y1));
                 entry = (unsigned)ia | ((unsigned)ib << 6) | ((unsigned)j << 12);
             }
             const unsigned m = __ballot_sync(FULL, surv);
@@ -323,7 +335,7 @@ int launch_fused_tma(const int64_t* d_img_off, const int64_t* d_poly_off, const 
                      void* ws, cudaStream_t s) {
     const int64_t n_tiles = n_tiles_of(n_img);
     TileDesc* desc = tile_descs(ws, n_img);
-    tile_desc_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(d_img_off, d_poly_off, n_img, n_tiles, desc);
+    tile_desc_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(d_img_off, d_poly_off, n_img, n_poly, n_tiles, desc);
     if (int rc = launch_check("tile_desc_kernel")) return rc;
     const size_t smem = sizeof(Smem);
     const int64_t want = (n_tiles + NW - 1) / NW;

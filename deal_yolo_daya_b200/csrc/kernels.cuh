@@ -20,8 +20,12 @@ inline size_t crowd_list_bytes(int64_t n_img) {
 
 constexpr int TILE_IMAGES = 3;               // images per staged tile (~24 objects: one lane each)
 struct TileDesc {                            // 32 bytes, written by the descriptor pre-pass
-    long long q0, q1;                        // object range  [img_off[i0], img_off[i1])
-    long long v0, v1;                        // vertex range  [poly_off[q0], poly_off[q1])
+    long long q0;                            // first object  img_off[i0]
+    long long v0;                            // first vertex  poly_off[q0]
+    int np;                                  // objects of the tile (clamped to INT_MAX)
+    int nv;                                  // vertices of the tile (clamped to INT_MAX)
+    int mode;                                // how the fused kernel handles the tile (MODE_*)
+    int pad;
 };
 inline int64_t n_tiles_of(int64_t n_img) { return (n_img + TILE_IMAGES - 1) / TILE_IMAGES; }
 inline size_t tile_desc_bytes(int64_t n_img) { return sizeof(TileDesc) * (size_t)n_tiles_of(n_img) + 16; }
