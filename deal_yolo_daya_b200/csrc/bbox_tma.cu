@@ -26,7 +26,7 @@ namespace dyd {
 
 constexpr int T = TILE_IMAGES;
 constexpr int NW = 16;                         // warps per CTA (1 CTA per SM)
-constexpr int CAP_V = 640;                     // vertices per stage (10 KB)
+constexpr int CAP_V = 704;                     // vertices per stage (11 KB)
 constexpr int CAP_P = 48;                      // objects per stage
 constexpr int TMA_THREADS = 32 * NW;
 constexpr int IMG_SLOTS = (T + 3) & ~1;        // img_off slice: T+1 entries + alignment shift, even count
@@ -179,15 +179,19 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
     const int64_t stride = (int64_t)gridDim.x * NW;
     const int64_t k0 = (int64_t)blockIdx.x * NW + warp;
     uint32_t phase = 0;
-    TileDesc nxt{0, 0, 0, 0, MODE_DEFER, 0};
+    // lane 0 keeps the descriptors of its next two tiles in registers, so the load issued during one
+    // tile is consumed a full tile later and never stalls the fill
+    TileDesc nxt{0, 0, 0, 0, MODE_DEFER, 0}, far{0, 0, 0, 0, MODE_DEFER, 0};
     if (lane == 0 && k0 < n_tiles) nxt = desc[k0];
+    if (lane == 0 && k0 + stride < n_tiles) far = desc[k0 + stride];
 
     // Stage fill, executed by lane 0 only: describe tile k in `ti` and start its copies.
     auto fill = [&](TileInfo& ti, int64_t k) {
         const int64_t i0 = k * T;
         const int ni = (int)min((int64_t)T, n_img - i0);
         const TileDesc d = nxt;
-        if (k + stride < n_tiles) nxt = desc[k + stride];                    // in flight while tile k is processed
+        nxt = far;
+        if (k + 2 * stride < n_tiles) far = desc[k + 2 * stride];            // consumed two tiles from now
         const int pshift = (int)(d.q0 & 1), ishift = (int)(i0 & 1);
         ti.q0 = d.q0; ti.v0 = d.v0; ti.ni = ni; ti.pshift = pshift; ti.ishift = ishift; ti.np = d.np; ti.mode = d.mode;
         if (d.mode == MODE_FAST) {
