@@ -152,6 +152,35 @@ def csr_port_throughput(n_img: int):
     return n_img / best, oracle_c.num_threads()
 
 
+def dropin_files_throughput(n_rows: int, device: int):
+    """images/s of the drop-in's own step functions on CSV files (dedup -> ptList->bbox -> IoU filter),
+    the same chain and file contract the reference arm runs; CSV I/O is pandas in both."""
+    import contextlib
+    import io
+    import pandas as pd
+    from deal_yolo_daya_b200 import processor as P, synth
+    os.environ["DYD_DEVICE"] = str(device)
+    t = synth.make_table(SEED, 0, n_rows)
+    rows = synth.table_to_rows(t)
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        merged = td / "merged.csv"
+        pd.DataFrame(rows, columns=[P.COL_SRC, P.COL_ANN]).to_csv(merged, index=False, encoding="utf-8-sig")
+        best, steps = float("inf"), None
+        for _ in range(2):
+            with contextlib.redirect_stdout(io.StringIO()):
+                t0 = time.perf_counter()
+                P.deduplicate_csv_by_source(str(merged), str(td / "dedup.csv"))
+                t1 = time.perf_counter()
+                P.process_csv_replace_ptlist(str(td / "dedup.csv"), str(td / "rep.csv"), str(td / "exc.csv"))
+                t2 = time.perf_counter()
+                P.filter_by_box_count_and_iou(str(td / "rep.csv"), str(td / "hi.csv"), str(td / "other.csv"), MIN_BOXES, THR)
+                t3 = time.perf_counter()
+            if t3 - t0 < best:
+                best, steps = t3 - t0, {"dedup_s": t1 - t0, "replace_ptlist_s": t2 - t1, "iou_filter_s": t3 - t2}
+    return n_rows / best, steps
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -373,6 +402,13 @@ def main():
                                 "sample": f"{rows} synthetic C2 rows per process as reference-format CSV, {cores} processes "
                                           f"(oracle/pipeline_port.run_hot_path_files: dedup -> ptList->bbox -> IoU filter through CSV files)",
                                 "one_core_value": v1}
+        try:
+            vd, dsteps = dropin_files_throughput(20_000, local)
+            line["dropin_files"] = {"value": vd, "unit": UNIT, "rows": 20_000, "seconds": dsteps,
+                                    "note": "this repo's processor.py step functions on CSV files (native JSON ingest/egress + CUDA kernels; "
+                                            "pandas read_csv/to_csv as in the reference); compare with cpu_baseline.one_core_value"}
+        except Exception as e:  # noqa: BLE001
+            line["dropin_files"] = {"error": str(e)[:200]}
         try:
             vc, thr_c = csr_port_throughput(400_000)
             line["cpu_baseline_csr"] = {"value": vc, "unit": UNIT, "cores": thr_c, "kind": "port",

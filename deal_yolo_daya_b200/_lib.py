@@ -48,6 +48,13 @@ PROTOTYPES = {
     "dyd_bbox_iou_host": (_int, [_p, _p, _p, _i64, _i64, _f64, _p, _p, _p, _p, _p, _i64]),
     "dyd_dedup_host": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
     "dyd_host_release": (_int, []),
+    "dyd_ingest_cells": (_int, [_p, _p, _p, _i64, _int, _int, _p]),
+    "dyd_ingest_free": (None, [_p]),
+    "dyd_ingest_sizes": (_int, [_p, _p, _p, _p]),
+    "dyd_ingest_export_polygons": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _int]),
+    "dyd_ingest_export_boxes": (_int, [_p, _p, _p, _p, _p, _int]),
+    "dyd_egress_ptlist": (_int, [_p, _p, _p, _p, _p, _p, _p, _int]),
+    "dyd_py_float_repr": (_int, [_f64, C.c_char_p]),
     "dyd_synth_counts": (_int, [_u64, _i64, _i64, _p, _i32, _p, _p]),
     "dyd_synth_nvert": (_int, [_u64, _i64, _i64, _p, _p, _p]),
     "dyd_synth_fill": (_int, [_u64, _i64, _i64, _p, _p, _p, _p, _p]),

@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libdyd.so"
-SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "synth.cu", "host_pipeline.cu"]
+SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "synth.cu", "host_pipeline.cu", "ingest.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -35,7 +35,7 @@ def needs_build() -> bool:
     if not OUT.exists():
         return True
     t = OUT.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dyd.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) + [PKG.parent / "include" / "dyd.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

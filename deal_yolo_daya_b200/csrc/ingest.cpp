@@ -1,0 +1,641 @@
+// Native columnar ingest / egress of the annotation JSON cells, host C++.
+//
+// ingest  : UTF-8 cell texts -> ragged CSR (img_off, poly_off, xy) for step 4 (polygons) or
+//           (img_off, pts, valid) for step 5 (two-point boxes), multi-threaded, one pass per row.
+// egress  : step 4's output cell = the reference's json.dumps(ensure_ascii=False) of the parsed
+//           document with every ptList replaced by two corner points (processor.py:262-279).  When the
+//           input text is already in json.dumps' canonical form (which it is whenever a json.dumps-
+//           based tool wrote it) that output equals the input text with each ptList value spliced
+//           out for `[{"x": X1, "y": Y1}, {"x": X2, "y": Y2}]`, X/Y being the ORIGINAL number literals
+//           of the vertices K1 selected -- no float formatting, no Python objects.
+//
+// Anything this file is not certain about is NOT guessed: the row is flagged SLOW and the Python
+// layer (ingest.py) handles it with CPython's own json module.  SLOW covers: text that is not
+// canonical (strict mode), non-dict documents / elements, duplicate keys, values an fp64 array
+// cannot carry (null / strings / ints beyond 2^53 as coordinates), malformed JSON.
+// Canonical form is verified, not assumed: separators, string escapes, and every number literal
+// must equal CPython's repr of its parsed value (shortest round-trip digits, repr's fixed/exponent
+// switch at 1e16 / 1e-4, ".0" suffix), computed here with std::to_chars / std::from_chars.
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <vector>
+
+#include "../../include/dyd.h"
+
+namespace {
+
+enum RowStatus : uint8_t { ROW_OK = 0, ROW_SLOW = 1, ROW_NOT_TEXT = 2 };
+enum Kind : uint8_t { K_OBJ, K_ARR, K_STR, K_INT, K_FLT, K_TRUE, K_FALSE, K_NULL };
+
+struct Span { uint32_t off, len; };
+
+struct Vertex { double x, y; Span sx, sy; };
+
+struct Poly {
+    uint32_t splice_off, splice_len;     // bytes of the row text replaced by the new ptList value
+    uint8_t splice_kind;                 // 0: replace ptList value; 1: append `"ptList": V` into polygon dict;
+                                         // 2: append `"polygon": {"ptList": V}` into the object
+    uint8_t container_empty;             // for kinds 1/2: the dict being appended to is `{}`
+    uint32_t v_begin, v_count;           // vertices (row-local index into RowOut::verts)
+};
+
+struct RowOut {
+    uint8_t status = ROW_SLOW;
+    std::vector<Poly> polys;
+    std::vector<Vertex> verts;
+    Span width{0, 0}, height{0, 0};      // literal spans of top-level width / height (len 0 = absent)
+    uint8_t width_kind = K_NULL, height_kind = K_NULL;
+    // step 5
+    std::vector<double> boxes;           // 4 per box
+    std::vector<uint8_t> bvalid;
+};
+
+struct Fail {};
+
+// keys of one JSON object (raw spans), inline storage: no heap traffic per dict
+struct KeySet {
+    static constexpr int CAP = 32;
+    Span k[CAP];
+    int n = 0;
+};
+
+// ---------------------------------------------------------------- CPython float repr
+// repr(float) from the shortest round-trip digits (float_repr_style "short", format code 'r').
+static int py_float_repr(double v, char* out) {
+    if (std::isnan(v)) { memcpy(out, "NaN", 3); return 3; }
+    if (std::isinf(v)) { if (v > 0) { memcpy(out, "Infinity", 8); return 8; } memcpy(out, "-Infinity", 9); return 9; }
+    char* p = out;
+    if (std::signbit(v)) { *p++ = '-'; v = -v; }
+    if (v == 0.0) { memcpy(p, "0.0", 3); return (int)(p - out) + 3; }
+    char sci[40];
+    auto r = std::to_chars(sci, sci + sizeof(sci), v, std::chars_format::scientific);   // shortest round-trip
+    // sci = d[.ddd]e[+-]XX
+    char digits[24]; int nd = 0;
+    const char* q = sci;
+    for (; q < r.ptr && *q != 'e'; ++q) if (*q != '.') digits[nd++] = *q;
+    int e10 = 0; { ++q; bool neg = *q == '-'; ++q; for (; q < r.ptr; ++q) e10 = e10 * 10 + (*q - '0'); if (neg) e10 = -e10; }
+    const int decpt = e10 + 1;
+    if (decpt <= -4 || decpt > 16) {
+        *p++ = digits[0];
+        if (nd > 1) { *p++ = '.'; memcpy(p, digits + 1, nd - 1); p += nd - 1; }
+        *p++ = 'e';
+        int ex = decpt - 1;
+        *p++ = ex < 0 ? '-' : '+';
+        if (ex < 0) ex = -ex;
+        char eb[8]; int ne = 0;
+        do { eb[ne++] = (char)('0' + ex % 10); ex /= 10; } while (ex);
+        if (ne < 2) eb[ne++] = '0';
+        while (ne) *p++ = eb[--ne];
+    } else if (decpt <= 0) {
+        *p++ = '0'; *p++ = '.';
+        for (int i = 0; i < -decpt; ++i) *p++ = '0';
+        memcpy(p, digits, nd); p += nd;
+    } else if (decpt >= nd) {
+        memcpy(p, digits, nd); p += nd;
+        for (int i = 0; i < decpt - nd; ++i) *p++ = '0';
+        *p++ = '.'; *p++ = '0';
+    } else {
+        memcpy(p, digits, decpt); p += decpt;
+        *p++ = '.';
+        memcpy(p, digits + decpt, nd - decpt); p += nd - decpt;
+    }
+    return (int)(p - out);
+}
+
+// ---------------------------------------------------------------- tokenizer
+struct Parser {
+    const char* base;       // row text
+    const char* p;
+    const char* end;
+    bool strict;            // canonical json.dumps(ensure_ascii=False) formatting required
+
+    [[noreturn]] static void fail() { throw Fail{}; }
+    void need(bool c) const { if (!c) fail(); }
+    uint32_t at() const { return (uint32_t)(p - base); }
+
+    void ws() { if (!strict) while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) ++p; }
+    void lit(const char* s, size_t n) { need((size_t)(end - p) >= n && memcmp(p, s, n) == 0); p += n; }
+    // after an item inside a container: returns true if another item follows
+    bool more(char close) {
+        ws();
+        need(p < end);
+        if (*p == close) { ++p; return false; }
+        need(*p == ','); ++p;
+        if (strict) { need(p < end && *p == ' '); ++p; } else ws();
+        return true;
+    }
+    void colon() {
+        ws();
+        need(p < end && *p == ':'); ++p;
+        if (strict) { need(p < end && *p == ' '); ++p; } else ws();
+    }
+    // string: returns the span of the raw contents (between the quotes); `plain` = no escapes inside
+    Span str(bool* plain = nullptr) {
+        need(p < end && *p == '"'); ++p;
+        const char* s = p;
+        bool pl = true;
+        for (;;) {
+            need(p < end);
+            unsigned char c = (unsigned char)*p;
+            if (c == '"') break;
+            if (c == '\\') {
+                pl = false;
+                need(p + 1 < end);
+                char e = p[1];
+                if (e == 'u') {
+                    need(p + 5 < end);
+                    unsigned cp = 0;
+                    for (int i = 2; i < 6; ++i) {
+                        char h = p[i]; unsigned d;
+                        if (h >= '0' && h <= '9') d = h - '0';
+                        else if (h >= 'a' && h <= 'f') d = h - 'a' + 10;
+                        else if (h >= 'A' && h <= 'F') { d = h - 'A' + 10; if (strict) fail(); }
+                        else fail();
+                        cp = cp * 16 + d;
+                    }
+                    // json.dumps(ensure_ascii=False) writes \u only for control characters without a short escape
+                    if (strict) need(cp < 0x20 && cp != '\n' && cp != '\r' && cp != '\t' && cp != '\b' && cp != '\f');
+                    p += 6;
+                } else {
+                    bool ok = e == '"' || e == '\\' || e == 'n' || e == 'r' || e == 't' || e == 'b' || e == 'f';
+                    if (!strict) ok = ok || e == '/';
+                    need(ok);
+                    p += 2;
+                }
+                continue;
+            }
+            need(c >= 0x20);                // raw control characters are not valid JSON (json.loads strict=True)
+            ++p;
+        }
+        Span sp{(uint32_t)(s - base), (uint32_t)(p - s)};
+        ++p;
+        if (plain) *plain = pl;
+        return sp;
+    }
+    // number / literal scalar: returns kind, literal span, value (for numbers and bools)
+    Kind scalar(Span* sp, double* val, bool* exact = nullptr) {
+        need(p < end);
+        if (exact) *exact = true;
+        const char* s = p;
+        char c = *p;
+        if (c == 't') { lit("true", 4); *sp = {(uint32_t)(s - base), 4}; *val = 1.0; return K_TRUE; }
+        if (c == 'f') { lit("false", 5); *sp = {(uint32_t)(s - base), 5}; *val = 0.0; return K_FALSE; }
+        if (c == 'n') { lit("null", 4); *sp = {(uint32_t)(s - base), 4}; *val = 0.0; return K_NULL; }
+        if (c == 'N') { lit("NaN", 3); *sp = {(uint32_t)(s - base), 3}; *val = std::nan(""); return K_FLT; }
+        if (c == 'I') { lit("Infinity", 8); *sp = {(uint32_t)(s - base), 8}; *val = INFINITY; return K_FLT; }
+        if (c == '-' && p + 1 < end && p[1] == 'I') { lit("-Infinity", 9); *sp = {(uint32_t)(s - base), 9}; *val = -INFINITY; return K_FLT; }
+        // JSON number grammar: -?(0|[1-9]\d*)(\.\d+)?([eE][+-]?\d+)?
+        if (*p == '-') ++p;
+        need(p < end && *p >= '0' && *p <= '9');
+        if (*p == '0') ++p; else while (p < end && *p >= '0' && *p <= '9') ++p;
+        bool is_float = false;
+        if (p < end && *p == '.') { is_float = true; ++p; need(p < end && *p >= '0' && *p <= '9'); while (p < end && *p >= '0' && *p <= '9') ++p; }
+        if (p < end && (*p == 'e' || *p == 'E')) {
+            is_float = true; ++p;
+            if (p < end && (*p == '+' || *p == '-')) ++p;
+            need(p < end && *p >= '0' && *p <= '9');
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+        }
+        *sp = {(uint32_t)(s - base), (uint32_t)(p - s)};
+        if (is_float) {
+            double v = 0.0;
+            auto r = std::from_chars(s, p, v);            // correctly rounded, like float()
+            if (r.ec == std::errc::result_out_of_range) {
+                // float("1e999") is inf, float("1e-999") is 0.0: redo with strtod semantics
+                std::string tmp(s, p); v = strtod(tmp.c_str(), nullptr);
+            } else need(r.ec == std::errc() && r.ptr == p);
+            *val = v;
+            if (strict) {                                   // literal must be repr(v)
+                char buf[40]; int n = py_float_repr(v, buf);
+                need((size_t)n == (size_t)(p - s) && memcmp(buf, s, n) == 0);
+            }
+            return K_FLT;
+        }
+        // integer: exact in fp64 up to 2^53 (larger ones may be carried along, not used as coordinates);
+        // "-0" is not what json.dumps writes for an int
+        const char* d = s; bool neg = false;
+        if (*d == '-') { neg = true; ++d; }
+        uint64_t u = 0; bool ok = (size_t)(p - d) <= 16;
+        if (ok) { for (const char* t = d; t < p; ++t) u = u * 10 + (uint64_t)(*t - '0'); ok = u <= (1ULL << 53); }
+        if (strict && neg) need(!(ok && u == 0));
+        if (exact) *exact = ok;
+        *val = ok ? (neg ? -(double)u : (double)u) : 0.0;
+        return K_INT;
+    }
+    // skip any value (validating it); returns its kind
+    Kind skip() {
+        need(p < end);
+        if (*p == '{') {
+            ++p; ws();
+            if (p < end && *p == '}') { ++p; return K_OBJ; }
+            KeySet keys;
+            do { Span k = str(); check_dup(keys, k); colon(); skip(); } while (more('}'));
+            return K_OBJ;
+        }
+        if (*p == '[') {
+            ++p; ws();
+            if (p < end && *p == ']') { ++p; return K_ARR; }
+            do { skip(); } while (more(']'));
+            return K_ARR;
+        }
+        if (*p == '"') { str(); return K_STR; }
+        Span sp; double v;
+        Kind k = scalar(&sp, &v);
+        // a huge integer literal is fine when it is only carried along, scalar() already bounded it;
+        return k;
+    }
+    // json.loads keeps the last of duplicate keys, json.dumps then writes one: a splice would differ
+    void check_dup(KeySet& keys, Span k) {
+        for (int i = 0; i < keys.n; ++i) if (keys.k[i].len == k.len && memcmp(base + keys.k[i].off, base + k.off, k.len) == 0) fail();
+        need(keys.n < KeySet::CAP);          // very wide dicts go to the slow lane
+        keys.k[keys.n++] = k;
+    }
+    bool key_is(Span k, const char* s) const { size_t n = strlen(s); return k.len == n && memcmp(base + k.off, s, n) == 0; }
+};
+
+// ---------------------------------------------------------------- step 4: polygons
+static void parse_point(Parser& ps, RowOut& out, bool& valid_point) {
+    // one element of a ptList; a valid point is a dict with both "x" and "y" (processor.py:253)
+    valid_point = false;
+    ps.need(ps.p < ps.end);
+    if (*ps.p != '{') { ps.skip(); return; }
+    ++ps.p; ps.ws();
+    if (ps.p < ps.end && *ps.p == '}') { ++ps.p; return; }
+    KeySet keys;
+    bool hx = false, hy = false, num_ok = true;
+    Vertex v{};
+    do {
+        bool plain; Span k = ps.str(&plain); ps.check_dup(keys, k); ps.colon();
+        bool isx = plain && ps.key_is(k, "x"), isy = plain && ps.key_is(k, "y");
+        if (isx || isy) {
+            ps.need(ps.p < ps.end);
+            if (*ps.p == '{' || *ps.p == '[' || *ps.p == '"') { ps.skip(); num_ok = false; }
+            else {
+                Span sp; double val; bool exact; Kind kd = ps.scalar(&sp, &val, &exact);
+                if (kd == K_NULL || !exact) num_ok = false;
+                if (isx) { hx = true; v.x = val; v.sx = sp; } else { hy = true; v.y = val; v.sy = sp; }
+            }
+        } else ps.skip();
+    } while (ps.more('}'));
+    if (hx && hy) {
+        if (!num_ok) Parser::fail();          // None / string / container coordinate: CPython semantics -> slow lane
+        valid_point = true;
+        out.verts.push_back(v);
+    }
+}
+
+static void parse_polygon_row(const char* text, size_t len, bool strict, RowOut& out) {
+    Parser ps{text, text, text + len, strict};
+    ps.ws();
+    ps.need(ps.p < ps.end && *ps.p == '{');
+    ++ps.p; ps.ws();
+    bool have_objects = false;
+    KeySet top_keys;
+    if (ps.p < ps.end && *ps.p == '}') { ++ps.p; }
+    else do {
+        bool plain; Span k = ps.str(&plain); ps.check_dup(top_keys, k); ps.colon();
+        if (plain && ps.key_is(k, "objects")) {
+            have_objects = true;
+            ps.need(ps.p < ps.end && *ps.p == '[');          // a non-list "objects" is iterated differently by the reference
+            ++ps.p; ps.ws();
+            if (ps.p < ps.end && *ps.p == ']') { ++ps.p; continue; }
+            do {
+                ps.need(ps.p < ps.end && *ps.p == '{');      // non-dict objects are dropped by the reference: no splice
+                const uint32_t obj_open = ps.at();
+                ++ps.p; ps.ws();
+                Poly poly{}; poly.v_begin = (uint32_t)out.verts.size();
+                bool have_polygon = false;
+                bool obj_empty = false;
+                KeySet okeys;
+                if (ps.p < ps.end && *ps.p == '}') { obj_empty = true; }
+                else do {
+                    bool pl2; Span ok = ps.str(&pl2); ps.check_dup(okeys, ok); ps.colon();
+                    if (pl2 && ps.key_is(ok, "polygon")) {
+                        have_polygon = true;
+                        ps.need(ps.p < ps.end && *ps.p == '{');          // .get on a non-dict raises in the reference
+                        ++ps.p; ps.ws();
+                        bool have_pt = false, pg_empty = false;
+                        KeySet pkeys;
+                        if (ps.p < ps.end && *ps.p == '}') { pg_empty = true; }
+                        else do {
+                            bool pl3; Span pk = ps.str(&pl3); ps.check_dup(pkeys, pk); ps.colon();
+                            if (pl3 && ps.key_is(pk, "ptList")) {
+                                have_pt = true;
+                                ps.need(ps.p < ps.end && *ps.p == '[');  // iterating a non-list ptList: slow lane
+                                const uint32_t s = ps.at();
+                                ++ps.p; ps.ws();
+                                if (ps.p < ps.end && *ps.p == ']') { ++ps.p; }
+                                else do { bool vp; parse_point(ps, out, vp); } while (ps.more(']'));
+                                poly.splice_off = s; poly.splice_len = ps.at() - s; poly.splice_kind = 0;
+                            } else ps.skip();
+                        } while (ps.more('}'));
+                        if (pg_empty) ++ps.p;
+                        if (!have_pt) {                                  // "ptList" appended to the polygon dict
+                            poly.splice_off = ps.at() - 1; poly.splice_len = 0; poly.splice_kind = 1; poly.container_empty = pg_empty;
+                        }
+                    } else ps.skip();
+                } while (ps.more('}'));
+                if (obj_empty) ++ps.p;
+                if (!have_polygon) {                                     // "polygon" appended to the object
+                    poly.splice_off = ps.at() - 1; poly.splice_len = 0; poly.splice_kind = 2; poly.container_empty = obj_empty;
+                }
+                (void)obj_open;
+                poly.v_count = (uint32_t)out.verts.size() - poly.v_begin;
+                out.polys.push_back(poly);
+            } while (ps.more(']'));
+        } else if (plain && (ps.key_is(k, "width") || ps.key_is(k, "height"))) {
+            ps.need(ps.p < ps.end);
+            const bool w = ps.key_is(k, "width");
+            if (*ps.p == '{' || *ps.p == '[' || *ps.p == '"') Parser::fail();   // Python object needed: slow lane
+            Span sp; double val; Kind kd = ps.scalar(&sp, &val);
+            if (w) { out.width = sp; out.width_kind = kd; } else { out.height = sp; out.height_kind = kd; }
+        } else ps.skip();
+    } while (ps.more('}'));
+    ps.ws();
+    ps.need(ps.p == ps.end);
+    if (!have_objects) Parser::fail();        // the reference appends "objects": [] -- left to the slow lane
+    out.status = ROW_OK;
+}
+
+// ---------------------------------------------------------------- step 5: two-point boxes (lenient)
+static void parse_box_row(const char* text, size_t len, RowOut& out) {
+    Parser ps{text, text, text + len, false};
+    ps.ws();
+    ps.need(ps.p < ps.end && *ps.p == '{');
+    ++ps.p; ps.ws();
+    KeySet top_keys;
+    bool stop = false;                       // an object raised in the reference: later objects are not looked at
+    if (ps.p < ps.end && *ps.p == '}') { ++ps.p; }
+    else do {
+        bool plain; Span k = ps.str(&plain); ps.check_dup(top_keys, k); ps.colon();
+        if (plain && ps.key_is(k, "objects")) {
+            ps.need(ps.p < ps.end && *ps.p == '[');
+            ++ps.p; ps.ws();
+            if (ps.p < ps.end && *ps.p == ']') { ++ps.p; continue; }
+            do {
+                ps.need(ps.p < ps.end);
+                if (*ps.p != '{') { ps.skip(); continue; }               // non-dict object: skipped
+                ++ps.p; ps.ws();
+                KeySet okeys;
+                int npts = -1;                                           // -1: no ptList seen (treated as [])
+                double c[4] = {0, 0, 0, 0}; bool has[4] = {false, false, false, false}, isnull[4] = {false, false, false, false};
+                bool pts_are_dicts = true;
+                if (ps.p < ps.end && *ps.p == '}') { ++ps.p; continue; }
+                do {
+                    bool pl2; Span ok = ps.str(&pl2); ps.check_dup(okeys, ok); ps.colon();
+                    if (pl2 && ps.key_is(ok, "polygon")) {
+                        ps.need(ps.p < ps.end);
+                        if (*ps.p != '{') Parser::fail();                // AttributeError in the reference: truncation -- slow lane decides
+                        ++ps.p; ps.ws();
+                        KeySet pkeys;
+                        if (ps.p < ps.end && *ps.p == '}') { ++ps.p; continue; }
+                        do {
+                            bool pl3; Span pk = ps.str(&pl3); ps.check_dup(pkeys, pk); ps.colon();
+                            if (pl3 && ps.key_is(pk, "ptList")) {
+                                ps.need(ps.p < ps.end && *ps.p == '[');  // len() of other types: slow lane
+                                ++ps.p; ps.ws();
+                                npts = 0;
+                                if (ps.p < ps.end && *ps.p == ']') { ++ps.p; continue; }
+                                do {
+                                    const int slot = npts++;
+                                    ps.need(ps.p < ps.end);
+                                    if (*ps.p != '{') { ps.skip(); pts_are_dicts = false; continue; }
+                                    ++ps.p; ps.ws();
+                                    KeySet qkeys;
+                                    if (ps.p < ps.end && *ps.p == '}') { ++ps.p; continue; }
+                                    do {
+                                        bool pl4; Span qk = ps.str(&pl4); ps.check_dup(qkeys, qk); ps.colon();
+                                        const bool isx = pl4 && ps.key_is(qk, "x"), isy = pl4 && ps.key_is(qk, "y");
+                                        if ((isx || isy) && slot < 2) {
+                                            ps.need(ps.p < ps.end);
+                                            if (*ps.p == '{' || *ps.p == '[' || *ps.p == '"') Parser::fail();   // non-numeric coordinate: slow lane
+                                            Span sp; double val; bool exact; Kind kd = ps.scalar(&sp, &val, &exact);
+                                            if (!exact) Parser::fail();                     // int beyond 2^53: CPython big-int arithmetic
+                                            const int idx = slot * 2 + (isy ? 1 : 0);
+                                            has[idx] = true; c[idx] = val; isnull[idx] = kd == K_NULL;
+                                        } else ps.skip();
+                                    } while (ps.more('}'));
+                                } while (ps.more(']'));
+                            } else ps.skip();
+                        } while (ps.more('}'));
+                    } else ps.skip();
+                } while (ps.more('}'));
+                if (stop || npts != 2 || !pts_are_dicts || !(has[0] && has[1] && has[2] && has[3])) continue;
+                if (isnull[0] || isnull[1] || isnull[2] || isnull[3]) {
+                    // min(None, .) raises TypeError inside extract_boxes: the scan ends, the prefix is kept
+                    out.boxes.insert(out.boxes.end(), {0.0, 0.0, 0.0, 0.0}); out.bvalid.push_back(0);
+                    stop = true;
+                    continue;
+                }
+                out.boxes.insert(out.boxes.end(), {c[0], c[1], c[2], c[3]}); out.bvalid.push_back(1);
+            } while (ps.more(']'));
+        } else ps.skip();
+    } while (ps.more('}'));
+    ps.ws();
+    ps.need(ps.p == ps.end);
+    out.status = ROW_OK;
+}
+
+}  // namespace
+
+struct dyd_ingest {
+    int mode = 0;                            // 0 polygons (step 4), 1 boxes (step 5)
+    int64_t n_rows = 0;
+    std::vector<RowOut> rows;
+    std::vector<int64_t> obj_base, vert_base;    // exclusive prefix over rows
+    int64_t n_obj = 0, n_vert = 0, n_slow = 0;
+};
+
+namespace {
+
+template <typename F>
+void parallel_rows(int64_t n, int n_threads, F f) {
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n / 256));
+    if (n_threads <= 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        const int64_t a = t * per, b = std::min(n, a + per);
+        if (a < b) th.emplace_back([=] { f(a, b); });
+    }
+    for (auto& t : th) t.join();
+}
+
+const char kNullPt[] = "[{\"x\": null, \"y\": null}, {\"x\": null, \"y\": null}]";
+
+// bytes of the replacement ptList value for one polygon
+inline size_t ptlist_value_len(const RowOut& r, const Poly& p, const int32_t* arg, const uint8_t* valid, int64_t q) {
+    if (!valid[q] || p.v_count == 0) return sizeof(kNullPt) - 1;
+    const Vertex* v = r.verts.data() + p.v_begin;
+    return 32 + v[arg[4 * q]].sx.len + v[arg[4 * q + 1]].sy.len + v[arg[4 * q + 2]].sx.len + v[arg[4 * q + 3]].sy.len;
+}
+inline char* put(char* o, const char* s, size_t n) { memcpy(o, s, n); return o + n; }
+inline char* ptlist_value_write(char* o, const char* text, const RowOut& r, const Poly& p, const int32_t* arg,
+                                const uint8_t* valid, int64_t q) {
+    if (!valid[q] || p.v_count == 0) return put(o, kNullPt, sizeof(kNullPt) - 1);
+    const Vertex* v = r.verts.data() + p.v_begin;
+    const Span a = v[arg[4 * q]].sx, b = v[arg[4 * q + 1]].sy, c = v[arg[4 * q + 2]].sx, d = v[arg[4 * q + 3]].sy;
+    o = put(o, "[{\"x\": ", 7); o = put(o, text + a.off, a.len);
+    o = put(o, ", \"y\": ", 7); o = put(o, text + b.off, b.len);
+    o = put(o, "}, {\"x\": ", 9); o = put(o, text + c.off, c.len);
+    o = put(o, ", \"y\": ", 7); o = put(o, text + d.off, d.len);
+    return put(o, "}]", 2);
+}
+inline size_t wrap_len(const Poly& p) {      // extra bytes around the value for appended keys
+    if (p.splice_kind == 0) return 0;
+    const size_t lead = p.container_empty ? 0 : 2;                       // ", "
+    return lead + (p.splice_kind == 1 ? 10 : 23);                        // "ptList":_  |  "polygon": {"ptList":_ ... }
+}
+
+}  // namespace
+
+extern "C" int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const uint8_t* is_text, int64_t n_rows,
+                                int mode, int n_threads, dyd_ingest** out) {
+    if (!out || n_rows < 0 || (n_rows > 0 && (!text || !off)) || (mode != 0 && mode != 1)) return DYD_E_ARG;
+    dyd_ingest* h = new dyd_ingest();
+    h->mode = mode; h->n_rows = n_rows;
+    h->rows.resize((size_t)n_rows);
+    parallel_rows(n_rows, n_threads, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            RowOut& ro = h->rows[(size_t)r];
+            if (is_text && !is_text[r]) { ro.status = ROW_NOT_TEXT; continue; }
+            const char* s = reinterpret_cast<const char*>(text) + off[r];
+            const size_t len = (size_t)(off[r + 1] - off[r]);
+            try {
+                if (len >= (1ull << 31)) throw Fail{};
+                if (mode == 0) parse_polygon_row(s, len, true, ro); else parse_box_row(s, len, ro);
+            } catch (const Fail&) {
+                ro = RowOut(); ro.status = ROW_SLOW;
+            } catch (const std::bad_alloc&) {
+                ro = RowOut(); ro.status = ROW_SLOW;
+            }
+        }
+    });
+    h->obj_base.resize((size_t)n_rows + 1); h->vert_base.resize((size_t)n_rows + 1);
+    int64_t no = 0, nv = 0, ns = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const RowOut& ro = h->rows[(size_t)r];
+        h->obj_base[(size_t)r] = no; h->vert_base[(size_t)r] = nv;
+        if (ro.status == ROW_SLOW) ++ns;
+        no += mode == 0 ? (int64_t)ro.polys.size() : (int64_t)ro.bvalid.size();
+        nv += (int64_t)ro.verts.size();
+    }
+    h->obj_base[(size_t)n_rows] = no; h->vert_base[(size_t)n_rows] = nv;
+    h->n_obj = no; h->n_vert = nv; h->n_slow = ns;
+    *out = h;
+    return 0;
+}
+
+extern "C" void dyd_ingest_free(dyd_ingest* h) { delete h; }
+
+extern "C" int dyd_ingest_sizes(const dyd_ingest* h, int64_t* n_obj, int64_t* n_vert, int64_t* n_slow) {
+    if (!h) return DYD_E_ARG;
+    if (n_obj) *n_obj = h->n_obj;
+    if (n_vert) *n_vert = h->n_vert;
+    if (n_slow) *n_slow = h->n_slow;
+    return 0;
+}
+
+// mode 0: status[n], img_off[n+1], poly_off[n_obj+1], xy[2*n_vert], wh_off[2n] (-1 absent) / wh_len[2n] / wh_kind[2n]
+extern "C" int dyd_ingest_export_polygons(const dyd_ingest* h, uint8_t* status, int64_t* img_off, int64_t* poly_off, double* xy,
+                                          int64_t* wh_off, int32_t* wh_len, uint8_t* wh_kind, int n_threads) {
+    if (!h || h->mode != 0 || !status || !img_off || !poly_off) return DYD_E_ARG;
+    const int64_t n = h->n_rows;
+    img_off[n] = h->n_obj; poly_off[h->n_obj] = h->n_vert;
+    parallel_rows(n, n_threads, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            const RowOut& ro = h->rows[(size_t)r];
+            status[r] = ro.status;
+            img_off[r] = h->obj_base[(size_t)r];
+            int64_t q = h->obj_base[(size_t)r]; const int64_t vb = h->vert_base[(size_t)r];
+            for (const Poly& p : ro.polys) poly_off[q++] = vb + p.v_begin;
+            if (xy) { double* o = xy + 2 * vb; for (const Vertex& v : ro.verts) { *o++ = v.x; *o++ = v.y; } }
+            if (wh_off) {
+                wh_off[2 * r] = ro.width.len ? (int64_t)ro.width.off : -1; wh_len[2 * r] = (int32_t)ro.width.len; wh_kind[2 * r] = ro.width_kind;
+                wh_off[2 * r + 1] = ro.height.len ? (int64_t)ro.height.off : -1; wh_len[2 * r + 1] = (int32_t)ro.height.len; wh_kind[2 * r + 1] = ro.height_kind;
+            }
+        }
+    });
+    return 0;
+}
+
+// mode 1: status[n], img_off[n+1], pts[4*n_obj], valid[n_obj]
+extern "C" int dyd_ingest_export_boxes(const dyd_ingest* h, uint8_t* status, int64_t* img_off, double* pts, uint8_t* valid, int n_threads) {
+    if (!h || h->mode != 1 || !status || !img_off) return DYD_E_ARG;
+    const int64_t n = h->n_rows;
+    img_off[n] = h->n_obj;
+    parallel_rows(n, n_threads, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            const RowOut& ro = h->rows[(size_t)r];
+            status[r] = ro.status;
+            const int64_t q = h->obj_base[(size_t)r];
+            img_off[r] = q;
+            if (!ro.bvalid.empty()) {
+                memcpy(pts + 4 * q, ro.boxes.data(), sizeof(double) * ro.boxes.size());
+                memcpy(valid + q, ro.bvalid.data(), ro.bvalid.size());
+            }
+        }
+    });
+    return 0;
+}
+
+// Output cell texts of step 4 for the ROW_OK rows (other rows get length 0).  Two calls: with out == NULL the
+// per-row lengths are written to out_off[1..n] as an inclusive prefix (out_off[0] = 0); then with out != NULL.
+extern "C" int dyd_egress_ptlist(const dyd_ingest* h, const uint8_t* text, const int64_t* off, const int32_t* arg,
+                                 const uint8_t* valid, int64_t* out_off, uint8_t* out, int n_threads) {
+    if (!h || h->mode != 0 || !text || !off || !out_off || (h->n_obj > 0 && (!arg || !valid))) return DYD_E_ARG;
+    const int64_t n = h->n_rows;
+    if (!out) {
+        parallel_rows(n, n_threads, [&](int64_t a, int64_t b) {
+            for (int64_t r = a; r < b; ++r) {
+                const RowOut& ro = h->rows[(size_t)r];
+                int64_t len = 0;
+                if (ro.status == ROW_OK) {
+                    len = off[r + 1] - off[r];
+                    int64_t q = h->obj_base[(size_t)r];
+                    for (const Poly& p : ro.polys) { len += (int64_t)ptlist_value_len(ro, p, arg, valid, q) + (int64_t)wrap_len(p) - (int64_t)p.splice_len; ++q; }
+                }
+                out_off[r + 1] = len;
+            }
+        });
+        out_off[0] = 0;
+        for (int64_t r = 0; r < n; ++r) out_off[r + 1] += out_off[r];
+        return 0;
+    }
+    parallel_rows(n, n_threads, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            const RowOut& ro = h->rows[(size_t)r];
+            if (ro.status != ROW_OK) continue;
+            const char* src = reinterpret_cast<const char*>(text) + off[r];
+            const uint32_t len = (uint32_t)(off[r + 1] - off[r]);
+            char* o = reinterpret_cast<char*>(out) + out_off[r];
+            uint32_t cur = 0;
+            int64_t q = h->obj_base[(size_t)r];
+            for (const Poly& p : ro.polys) {
+                o = put(o, src + cur, p.splice_off - cur);
+                if (p.splice_kind == 0) {
+                    o = ptlist_value_write(o, src, ro, p, arg, valid, q);
+                } else {
+                    if (!p.container_empty) o = put(o, ", ", 2);
+                    if (p.splice_kind == 2) o = put(o, "\"polygon\": {", 12);
+                    o = put(o, "\"ptList\": ", 10);
+                    o = ptlist_value_write(o, src, ro, p, arg, valid, q);
+                    if (p.splice_kind == 2) o = put(o, "}", 1);
+                }
+                cur = p.splice_off + p.splice_len;
+                ++q;
+            }
+            o = put(o, src + cur, len - cur);
+        }
+    });
+    return 0;
+}
+
+extern "C" int dyd_py_float_repr(double v, char* out40) { return py_float_repr(v, out40); }

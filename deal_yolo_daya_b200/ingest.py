@@ -163,6 +163,20 @@ def pack_strings(values):
     ``astype(str)`` (processor.py:194-198).
     """
     n = len(values)
+    try:                                            # Arrow fast path: all cells are str or missing
+        import pyarrow as pa
+        arr = pa.array(values, type=pa.large_string(), from_pandas=True)
+        if arr.offset != 0:
+            arr = pa.concat_arrays([arr])
+        bufs = arr.buffers()
+        off = np.frombuffer(bufs[1], dtype=np.int64, count=n + 1).copy()
+        data = np.frombuffer(bufs[2], dtype=np.uint8).copy() if bufs[2] is not None else np.zeros(0, np.uint8)
+        null = np.zeros(n, np.uint8) if arr.null_count == 0 else (~np.asarray(arr.is_valid())).astype(np.uint8)
+        if arr.null_count:                          # Arrow leaves the offsets of null slots untouched (zero length)
+            pass
+        return off, data, null
+    except Exception:  # noqa: BLE001 - mixed-type column: CPython loop below
+        pass
     null = np.zeros(n, np.uint8)
     chunks = []
     off = np.zeros(n + 1, np.int64)

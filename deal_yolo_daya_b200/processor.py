@@ -108,7 +108,7 @@ class CudaKernels:
 
 
 KERNELS = CudaKernels()
-STATS = {"hostlane_objects": 0, "hostlane_rows": 0, "hash_collisions": 0}    # observability, last call
+STATS = {"hostlane_objects": 0, "hostlane_rows": 0, "hash_collisions": 0, "native_rows": 0, "slow_rows": 0}    # observability, last call
 
 
 # =============================================================================================
@@ -266,7 +266,46 @@ def replace_ptlist_cells(cells):
     K1 finds, per polygon, which vertex supplies min_x / min_y / max_x / max_y; the output cell is
     the reference's ``json.dumps`` of the document with every dict object's ptList replaced by the
     two corner points built from the ORIGINAL JSON numbers at those indices (int stays int).
+
+    Fast lane: the native parser (csrc/ingest.cpp) builds the CSR buffers and splices the output
+    text for every row whose text is in json.dumps form; rows it flags go through the CPython lane
+    below (json.loads / json.dumps), which is also the whole path when DYD_NATIVE_INGEST=0.
     """
+    from . import native
+    cells = list(cells)
+    if not native.enabled() or not cells:
+        return _replace_ptlist_cells_python(cells)
+    ing = native.Ingest(cells, 0).polygons()
+    try:
+        STATS["native_rows"] = int((ing.status == native.ROW_OK).sum())
+        if ing.n_obj:
+            _, valid, arg = KERNELS.bbox(ing.poly_off, ing.xy)
+        else:
+            valid = np.zeros(0, np.uint8); arg = np.zeros(0, np.int32)
+        out_bytes, out_off = ing.egress_ptlist(arg, valid)
+        blob = out_bytes.tobytes()
+        out, widths, heights = [None] * ing.n, [None] * ing.n, [None] * ing.n
+        slow = []
+        for r in range(ing.n):
+            st = ing.status[r]
+            if st == native.ROW_OK:
+                out[r] = blob[out_off[r]:out_off[r + 1]].decode("utf-8", "surrogatepass")
+                widths[r] = ing.scalar(r, 0); heights[r] = ing.scalar(r, 1)
+            elif st == native.ROW_SLOW:
+                slow.append(r)
+    finally:
+        ing.close()
+    STATS["hostlane_objects"] = 0
+    if slow:                                   # CPython lane for the rows the native parser declined
+        o2, w2, h2 = _replace_ptlist_cells_python([cells[r] for r in slow])
+        for i, r in enumerate(slow):
+            out[r], widths[r], heights[r] = o2[i], w2[i], h2[i]
+    STATS["slow_rows"] = len(slow)
+    return out, widths, heights
+
+
+def _replace_ptlist_cells_python(cells):
+    """CPython lane of step 4: json.loads per cell, K1 on the packed vertices, json.dumps per cell."""
     batch = ingest.parse_polygons(cells)
     STATS["hostlane_objects"] = int(batch.hostlane.sum())
     if batch.n_obj:
@@ -344,15 +383,39 @@ def process_csv_replace_ptlist(
 # step 5: box-count + IoU quality filter                             reference: processor.py:321-407
 # =============================================================================================
 def high_iou_mask(cells, min_boxes: int = 2, iou_threshold: float = 0.98) -> np.ndarray:
-    """bool per row: len(boxes) >= min_boxes and some pair has IoU >= threshold (K2)."""
-    batch = ingest.parse_boxes(cells)
-    STATS["hostlane_rows"] = len(batch.host_rows)
-    if batch.n_rows == 0:
+    """bool per row: len(boxes) >= min_boxes and some pair has IoU >= threshold (K2).
+
+    Fast lane: native parse of the two-point boxes (csrc/ingest.cpp, mode 1); rows it declines are
+    parsed by the CPython lane; rows holding values fp64 cannot carry are evaluated by _hostlane.
+    """
+    from . import native
+    cells = list(cells)
+    n = len(cells)
+    if n == 0:
         return np.zeros(0, bool)
-    high, _ = KERNELS.iou(batch.img_off, batch.pts, batch.valid, min_boxes, iou_threshold)
-    mask = high.astype(bool)
-    for r in batch.host_rows:                       # rows holding values fp64 cannot carry
-        mask[r] = _hostlane.row_is_high_iou(cells[r], min_boxes, iou_threshold)
+    mask = np.zeros(n, bool)
+    slow = list(range(n))
+    if native.enabled():
+        ing = native.Ingest(cells, 1).boxes()
+        try:
+            if ing.n > 0:
+                high, _ = KERNELS.iou(ing.img_off, ing.pts, ing.valid, min_boxes, iou_threshold)
+                ok = ing.status != native.ROW_SLOW          # non-text cells have no boxes: not high
+                mask[ok] = high.astype(bool)[ok]
+            slow = [int(r) for r in np.nonzero(ing.status == native.ROW_SLOW)[0]]
+        finally:
+            ing.close()
+    STATS["slow_rows"] = len(slow)
+    STATS["hostlane_rows"] = 0
+    if slow:
+        sub = [cells[r] for r in slow]
+        batch = ingest.parse_boxes(sub)
+        STATS["hostlane_rows"] = len(batch.host_rows)
+        high, _ = KERNELS.iou(batch.img_off, batch.pts, batch.valid, min_boxes, iou_threshold)
+        m2 = high.astype(bool)
+        for i in batch.host_rows:                   # rows holding values fp64 cannot carry
+            m2[i] = _hostlane.row_is_high_iou(sub[i], min_boxes, iou_threshold)
+        mask[np.array(slow)] = m2
     return mask
 
 

@@ -199,6 +199,29 @@ int dyd_host_release(void);
 int dyd_dedup_host(const int64_t* h_off, const uint8_t* h_bytes, const uint8_t* h_null, int64_t n,
                    int keep_mode, uint8_t* h_keep, int64_t* h_rep);
 
+/* ------------------------------------------------ native ingest / egress (host) ---
+ * Multi-threaded C++ replacement of the per-row json.loads / Python loops of processor.py:262-296
+ * (step 4) and :341-366 (step 5).  `text`/`off` = the cells as one UTF-8 buffer with int64 offsets,
+ * `is_text[r] == 0` marks non-string cells (NaN).  mode 0: polygons of every dict object (strict:
+ * the text must be in json.dumps(ensure_ascii=False) form so that the output cell can be spliced);
+ * mode 1: two-point boxes with the prefix-truncation rule.  Rows the parser is not certain about get
+ * status 1 (SLOW) and contribute no objects: the caller handles them with CPython's json module.
+ * The handle owns the parse results until dyd_ingest_free.                                        */
+typedef struct dyd_ingest dyd_ingest;
+int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const uint8_t* is_text, int64_t n_rows,
+                     int mode, int n_threads, dyd_ingest** out);
+void dyd_ingest_free(dyd_ingest* h);
+int dyd_ingest_sizes(const dyd_ingest* h, int64_t* n_obj, int64_t* n_vert, int64_t* n_slow);
+int dyd_ingest_export_polygons(const dyd_ingest* h, uint8_t* status, int64_t* img_off, int64_t* poly_off, double* xy,
+                               int64_t* wh_off, int32_t* wh_len, uint8_t* wh_kind, int n_threads);
+int dyd_ingest_export_boxes(const dyd_ingest* h, uint8_t* status, int64_t* img_off, double* pts, uint8_t* valid, int n_threads);
+/* Output cells of step 4: input text with every ptList value replaced by the two corner points built
+ * from the original number literals selected by K1's arg indices.  Call with out == NULL to get the
+ * offsets (out_off int64[n_rows+1]), then again with the buffer.                                  */
+int dyd_egress_ptlist(const dyd_ingest* h, const uint8_t* text, const int64_t* off, const int32_t* arg,
+                      const uint8_t* valid, int64_t* out_off, uint8_t* out, int n_threads);
+int dyd_py_float_repr(double v, char* out40);     /* CPython repr(float); used by the canonical-form check */
+
 /* ------------------------------------------------ synthetic tables (§8d) ---
  * Device-side twin of deal_yolo_daya_b200/synth.py (bit-identical output).       */
 int dyd_synth_counts(uint64_t seed, int64_t first_img, int64_t n_img, const uint64_t* d_pois_thr,

@@ -1,0 +1,229 @@
+"""Native (C++) ingest / egress against the CPython lane and the reference's golden outputs.
+
+Runs on CPU: the kernels are replaced by the oracle stand-in, the subject under test is host code
+(csrc/ingest.cpp through deal_yolo_daya_b200/native.py).  Every case is checked both ways: the
+native lane must give byte-identical results to the CPython lane, and for the cases meant to be
+canonical it must actually have taken them (otherwise the comparison would be vacuous).
+"""
+from __future__ import annotations
+
+import gzip
+import io
+import json
+import random
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from deal_yolo_daya_b200 import ingest, native, processor as P, synth
+from tests.oracle_kernels import OracleKernels
+
+G = Path(__file__).resolve().parent / "golden"
+ANN, NEW = P.COL_ANN, P.COL_NEW
+
+
+@pytest.fixture(autouse=True)
+def _oracle_facade(monkeypatch):
+    monkeypatch.setattr(P, "KERNELS", OracleKernels())
+
+
+def both_lanes_replace(cells, monkeypatch):
+    monkeypatch.setenv("DYD_NATIVE_INGEST", "1")
+    a = P.replace_ptlist_cells(cells)
+    stats = dict(P.STATS)
+    monkeypatch.setenv("DYD_NATIVE_INGEST", "0")
+    b = P.replace_ptlist_cells(cells)
+    return a, b, stats
+
+
+def same_scalars(x, y):
+    return len(x) == len(y) and all(type(p) is type(q) and (p == q or (p != p and q != q)) for p, q in zip(x, y))
+
+
+def test_float_repr_is_cpython_repr():
+    import ctypes as C
+    from deal_yolo_daya_b200 import _lib
+    lib = _lib.load(); buf = C.create_string_buffer(40)
+    rng = random.Random(3)
+    vals = [0.0, -0.0, 1e15, 1e16, 9999999999999998.0, 1e-4, 9.999e-5, 1e-5, 5e-324, 1.7976931348623157e308, 0.1, 1 / 3, 1920.0, 123.456]
+    vals += [rng.uniform(-3000, 3000) for _ in range(20000)] + [round(rng.uniform(0, 2000), rng.randint(0, 8)) for _ in range(20000)]
+    vals += [np.frombuffer(rng.getrandbits(64).to_bytes(8, "little"), np.float64)[0].item() for _ in range(20000)]
+    for v in vals:
+        n = lib.dyd_py_float_repr(C.c_double(v), buf)
+        want = "NaN" if v != v else json.dumps(v)
+        assert buf.raw[:n].decode() == want, v
+
+
+def test_golden_rows_take_the_native_lane_and_match(monkeypatch):
+    df = pd.read_csv(io.StringIO(gzip.open(G / "expected" / "filtered_main.csv.gz", "rt", encoding="utf-8").read()))
+    cells = df[ANN].tolist()
+    a, b, stats = both_lanes_replace(cells, monkeypatch)
+    assert a[0] == b[0] and same_scalars(a[1], b[1]) and same_scalars(a[2], b[2])
+    want = pd.read_csv(io.StringIO(gzip.open(G / "expected" / "processed_replaced_ptlist.csv.gz", "rt", encoding="utf-8").read()))
+    kept = [c for c, src in zip(a[0], cells) if isinstance(src, str)]
+    assert [c if c is not None else None for c in kept] == [c if isinstance(c, str) else None for c in want[NEW].tolist()]
+    # the synthetic rows and most hand-written rows are canonical: the native lane must have taken them
+    assert stats["native_rows"] >= 55 and stats["slow_rows"] <= 12
+
+
+def test_synthetic_table_full_precision(monkeypatch):
+    t = synth.make_table(11, 500, 300)
+    cells = [r[1] for r in synth.table_to_rows(t)]             # 17-digit doubles: repr round trip
+    a, b, stats = both_lanes_replace(cells, monkeypatch)
+    assert a == b and stats["native_rows"] == 300 and stats["slow_rows"] == 0
+
+
+CANON = lambda d: json.dumps(d, ensure_ascii=False)  # noqa: E731
+
+
+def edge_docs():
+    pt = lambda x, y: {"x": x, "y": y}  # noqa: E731
+    docs = [
+        {"objects": []},
+        {"width": 5, "height": 6.5, "objects": [{}]},
+        {"objects": [{"name": "a"}]},                                         # polygon appended to the object
+        {"objects": [{"polygon": {}}]},                                       # ptList appended to an empty polygon
+        {"objects": [{"polygon": {"k": 1}}]},                                 # ptList appended after other keys
+        {"objects": [{"polygon": {"ptList": []}}]},
+        {"objects": [{"polygon": {"ptList": [pt(1, 2)]}, "z": [1, {"q": None}]}]},
+        {"objects": [{"polygon": {"ptList": [pt(True, False), pt(2, 3)]}}]},  # bools are ints for min/max
+        {"objects": [{"polygon": {"ptList": [pt(1e22, -1e-7), pt(1.5e300, 5e-324), pt(-0.0, 0.0)]}}]},
+        {"objects": [{"polygon": {"ptList": [pt(float("nan"), 1.0), pt(float("inf"), float("-inf"))]}}]},
+        {"objects": [{"polygon": {"ptList": [pt(10.0, 5), pt(10, 5.0), pt(10, 7)]}}]},
+        {"objects": [{"polygon": {"ptList": [{"x": 1}, 5, "s", None, [1], pt(3, 4)]}}]},
+        {"objects": [{"name": "含\"引号\n换行\t制表\x01控制", "polygon": {"ptList": [pt(1, 1)]}}], "路径": "C:\\x"},
+        {"width": None, "height": True, "objects": [{"polygon": {"ptList": [pt(9007199254740992, 1)]}}]},
+        {"id": 123456789012345678901234567890, "objects": [{"polygon": {"ptList": [pt(1, 2), pt(3, 4)]}}]},
+    ]
+    return docs
+
+
+SLOW_TEXTS = [
+    '{"objects":[{"polygon":{"ptList":[{"x":1,"y":2}]}}]}',                  # compact separators
+    '{"objects": [{"polygon": {"ptList": [{"x": 1.50, "y": 2}]}}]}',         # 1.50 is not repr(1.5)
+    '{"objects": [{"polygon": {"ptList": [{"x": 1e3, "y": 2}]}}]}',          # 1e3 -> 1000.0
+    '{"objects": [{"polygon": {"ptList": [{"x": -0, "y": 2}]}}]}',           # -0 -> 0
+    '{"objects": [{"polygon": {"ptList": [{"x": 1, "y": 2}]}}], "a": "\\u4e2d"}',   # escaped non-ASCII
+    '{"objects": [{"polygon": {"ptList": [{"x": 1, "y": 2}]}}], "a": "\\/"}',
+    ' {"objects": []}',                                                       # leading whitespace
+    '{"objects": [1, {"polygon": {"ptList": [{"x": 1, "y": 2}]}}]}',          # non-dict object is dropped
+    '{"objects": [{"polygon": {"ptList": [{"x": 1, "y": 2}]}, "polygon": {}}]}',    # duplicate key
+    '{"objects": [{"polygon": {"ptList": [{"x": 1, "x": 3, "y": 2}]}}]}',
+    '{"a": 1}',                                                               # no objects key
+    '{"objects": [{"polygon": {"ptList": [{"x": 9007199254740993, "y": 2}]}}]}',    # int beyond 2^53 as coordinate
+    '{"objects": [{"polygon": {"ptList": [{"x": 1, "y": 2}]}}], "width": "w"}',
+    '{"objects": [oops',
+    '[1, 2]',
+    '{"objects": [{"polygon": {"ptList": [{"x": 01, "y": 2}]}}]}',
+]
+
+
+def test_edge_documents_both_lanes_agree(monkeypatch):
+    cells = [CANON(d) for d in edge_docs()]
+    a, b, stats = both_lanes_replace(cells, monkeypatch)
+    assert a[0] == b[0] and same_scalars(a[1], b[1]) and same_scalars(a[2], b[2])
+    assert stats["native_rows"] >= len(cells) - 1                              # only the 2^53+ row may go slow
+    from oracle import pipeline_port as port                                   # and they equal the reference's algorithm
+    assert a[0] == [port.replace_cell(c) for c in cells]
+
+
+def test_non_canonical_rows_fall_to_the_cpython_lane(monkeypatch):
+    from oracle import pipeline_port as port
+    ok = [t for t in SLOW_TEXTS if t not in ('[1, 2]',)]                       # a list document crashes the reference
+    a, b, stats = both_lanes_replace(ok, monkeypatch)
+    assert stats["native_rows"] == 0 and stats["slow_rows"] == len(ok)
+    assert a[0] == b[0] == [port.replace_cell(c) for c in ok]
+    with pytest.raises(AttributeError):
+        monkeypatch.setenv("DYD_NATIVE_INGEST", "1")
+        P.replace_ptlist_cells(['[1, 2]'])
+    with pytest.raises(TypeError):
+        P.replace_ptlist_cells([CANON({"objects": [{"polygon": {"ptList": [{"x": None, "y": 1}, {"x": 2, "y": 3}]}}]})])
+
+
+def rand_doc(rng):
+    def num():
+        k = rng.random()
+        if k < 0.3:
+            return rng.randint(-50, 4000)
+        if k < 0.9:
+            return round(rng.uniform(-10, 2000), rng.randint(0, 12))
+        return rng.choice([0.0, -0.0, 1e-7, 123456789.0, 1e16, float("inf"), float("nan"), True])
+    objs = []
+    for _ in range(rng.randint(0, 6)):
+        o = {}
+        if rng.random() < 0.8:
+            o["name"] = rng.choice(["cls01", "行人", "a,b；c", "", 'q"uote', "tab\t"])
+        if rng.random() < 0.9:
+            pg = {}
+            if rng.random() < 0.2:
+                pg["kind"] = "poly"
+            if rng.random() < 0.9:
+                pg["ptList"] = [({"x": num(), "y": num()} if rng.random() < 0.93 else rng.choice([{"x": 1}, {}, 7, "p", None]))
+                                for _ in range(rng.randint(0, 9))]
+            o["polygon"] = pg
+        if rng.random() < 0.3:
+            o["extra"] = {"k": [1, 2.5, None, {"z": "w"}], "e": {}}
+        objs.append(o)
+    d = {}
+    if rng.random() < 0.8:
+        d["width"] = rng.choice([1920, 1080.0, None, 0])
+    d["objects"] = objs
+    if rng.random() < 0.8:
+        d["height"] = rng.choice([1080, 720.5, True])
+    return d
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_documents(monkeypatch, seed):
+    from oracle import pipeline_port as port
+    rng = random.Random(seed)
+    cells = []
+    for _ in range(400):
+        d = rand_doc(rng)
+        t = CANON(d)
+        if rng.random() < 0.15:                                # a non-canonical rendering of the same document
+            t = json.dumps(d, ensure_ascii=rng.random() < 0.5, separators=rng.choice([(",", ":"), (", ", ": "), (" , ", " : ")]),
+                           indent=rng.choice([None, 1]))
+        cells.append(t)
+    cells += [float("nan"), None]
+    a, b, stats = both_lanes_replace(cells, monkeypatch)
+    assert a[0] == b[0] and same_scalars(a[1], b[1]) and same_scalars(a[2], b[2])
+    assert a[0][:-2] == [port.replace_cell(c) for c in cells[:-2]] and a[0][-2:] == [None, None]
+    assert stats["native_rows"] > 250
+
+
+def test_boxes_mode_matches_cpython_lane(monkeypatch):
+    rng = random.Random(5)
+    rows = []
+    for _ in range(600):
+        objs = []
+        for _ in range(rng.randint(0, 7)):
+            k = rng.random()
+            if k < 0.7:
+                pl = [{"x": rng.uniform(0, 50), "y": rng.randint(0, 50)}, {"x": rng.uniform(0, 60), "y": rng.uniform(0, 60)}]
+            elif k < 0.78:
+                pl = [{"x": None, "y": None}, {"x": None, "y": None}]
+            elif k < 0.84:
+                pl = [{"x": 1, "y": 2}]
+            elif k < 0.9:
+                pl = [{"x": 1, "y": 2}, 5]
+            elif k < 0.95:
+                pl = [{"x": None, "y": 3}, {"x": 2, "y": 3}]
+            else:
+                pl = [{"x": "a", "y": 3}, {"x": 2, "y": 3}]
+            o = {"name": "n", "polygon": {"ptList": pl}} if rng.random() < 0.95 else rng.choice([7, {"name": "x"}, {"polygon": None}])
+            objs.append(o)
+        text = json.dumps({"objects": objs}, separators=rng.choice([(",", ":"), (", ", ": ")]), indent=rng.choice([None, None, 2]))
+        rows.append(text)
+    rows += ["{bad", float("nan"), '{"objects": 5}', '{"a": 1}', "[]"]
+    from oracle import pipeline_port as port
+    want = np.array([port.is_high_iou(port.boxes_of_cell(t), 2, 0.02) for t in rows])
+    monkeypatch.setenv("DYD_NATIVE_INGEST", "1")
+    got = P.high_iou_mask(rows, 2, 0.02)
+    native_slow = P.STATS["slow_rows"]
+    monkeypatch.setenv("DYD_NATIVE_INGEST", "0")
+    got2 = P.high_iou_mask(rows, 2, 0.02)
+    assert np.array_equal(got, want) and np.array_equal(got2, want)
+    assert native_slow < 0.2 * len(rows) and want.sum() > 20
