@@ -45,7 +45,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=4_000_000)
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--which", default="fused,k1,k2,hash,dedup,antijoin,crowd")
+    ap.add_argument("--which", default="fused,k1,k2,hash,dedup,antijoin,crowd,labels")
     args = ap.parse_args()
     which = set(args.which.split(","))
     _lib.load()
@@ -115,6 +115,25 @@ def main():
             report(f"K2 crowd {tag}", ms, best, 32 * nb + 13 * nc, nc, "images")
             if thr == 2.0:
                 print(f"    {pairs / (ms * 1e-3) / 1e9:.1f} G pairs/s over {nc} images, {nb} boxes", flush=True)
+    if "labels" in which:
+        import numpy as np
+        nv, ncat = 100, 20
+        rng = np.random.RandomState(0)
+        lut_new = torch.from_numpy(rng.randint(0, nv, nv).astype(np.int32)).to(dev)
+        lut_ntok = torch.from_numpy(np.ones(nv, np.int32)).to(dev)
+        lut_nrep = torch.from_numpy((rng.rand(nv) < 0.8).astype(np.int32)).to(dev)
+        cat = torch.from_numpy(rng.randint(-1, ncat, nv).astype(np.int32)).to(dev)
+        ms, best = time_ms(lambda: ops.label_lut(t.img_off, t.label_id, lut_new, lut_ntok, lut_nrep), args.reps)
+        report("K3 label LUT", ms, best, 8 * n_poly + 9 * n_img, n_poly, "objects")
+        ms, best = time_ms(lambda: ops.label_hist(t.label_id, nv), args.reps)
+        report("K3 label histogram", ms, best, 4 * n_poly, n_poly, "objects")
+        ei, eb, ec, co = ops.split_expand(t.img_off, t.label_id, cat, ncat)
+        ms, best = time_ms(lambda: ops.split_expand(t.img_off, t.label_id, cat, ncat), max(3, args.reps // 2))
+        report("K6 split expand (2 passes)", ms, best, 8 * n_poly + 8 * n_img + 20 * ei.numel(), n_poly, "objects")
+        pts, valid, _ = ops.bbox_minmax(t.poly_off, t.xy)
+        wh = torch.tensor([1920.0, 1080.0], dtype=torch.float64, device=dev).repeat(n_img)
+        ms, best = time_ms(lambda: ops.yolo_normalise(t.img_off, pts, valid, wh), args.reps)
+        report("YOLO normalise", ms, best, 66 * n_poly + 24 * n_img, n_poly, "objects")
     print(json.dumps([{"name": r[0], "ms": r[1], "best_ms": r[2], "gbs": r[3], "frac": r[4]} for r in rows]))
 
 
