@@ -54,6 +54,7 @@ PROTOTYPES = {
     "dyd_ingest_export_polygons": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _int]),
     "dyd_ingest_export_boxes": (_int, [_p, _p, _p, _p, _p, _int]),
     "dyd_egress_ptlist": (_int, [_p, _p, _p, _p, _p, _p, _p, _int]),
+    "dyd_csv_write": (_int, [_p, _p, _p, _p, _i32, _i64, _p, _p, _int]),
     "dyd_py_float_repr": (_int, [_f64, C.c_char_p]),
     "dyd_synth_counts": (_int, [_u64, _i64, _i64, _p, _i32, _p, _p]),
     "dyd_synth_nvert": (_int, [_u64, _i64, _i64, _p, _p, _p]),

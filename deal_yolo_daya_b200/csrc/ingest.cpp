@@ -639,3 +639,91 @@ extern "C" int dyd_egress_ptlist(const dyd_ingest* h, const uint8_t* text, const
 }
 
 extern "C" int dyd_py_float_repr(double v, char* out40) { return py_float_repr(v, out40); }
+
+// ---------------------------------------------------------------- CSV egress
+// Body of DataFrame.to_csv(index=False) for frames made of string / float64 / int64 / bool columns,
+// byte-identical to pandas (which drives CPython's csv.writer with QUOTE_MINIMAL): a field is quoted
+// iff it contains ',', '"', '\n' or '\r' (quotes doubled); missing values are empty; floats are
+// repr(float); rows end with '\n'.  The header line (and BOM) is written by the caller.
+// Column kinds: 0 string (Arrow large_string + validity bytes), 1 float64, 2 int64, 3 bool (uint8).
+namespace {
+
+struct CsvCol { int kind; const int64_t* off; const uint8_t* data; const uint8_t* valid; };
+
+inline size_t csv_field_len(const CsvCol& c, int64_t r) {
+    switch (c.kind) {
+        case 0: {
+            if (c.valid && !c.valid[r]) return 0;
+            const uint8_t* s = c.data + c.off[r]; const int64_t n = c.off[r + 1] - c.off[r];
+            size_t q = 0; bool need = false;
+            for (int64_t i = 0; i < n; ++i) { const uint8_t ch = s[i]; if (ch == '"') { ++q; need = true; } else if (ch == ',' || ch == '\n' || ch == '\r') need = true; }
+            return (size_t)n + (need ? q + 2 : 0);
+        }
+        case 1: {
+            const double v = reinterpret_cast<const double*>(c.data)[r];
+            if (v != v) return 0;
+            if (std::isinf(v)) return v > 0 ? 3 : 4;                 // str(float): "inf" / "-inf" (JSON spells it Infinity)
+            char b[40]; return (size_t)py_float_repr(v, b);
+        }
+        case 2: { char b[24]; auto e = std::to_chars(b, b + 24, reinterpret_cast<const int64_t*>(c.data)[r]); return (size_t)(e.ptr - b); }
+        default: return c.data[r] ? 4 : 5;
+    }
+}
+inline char* csv_field_write(char* o, const CsvCol& c, int64_t r) {
+    switch (c.kind) {
+        case 0: {
+            if (c.valid && !c.valid[r]) return o;
+            const uint8_t* s = c.data + c.off[r]; const int64_t n = c.off[r + 1] - c.off[r];
+            bool need = false;
+            for (int64_t i = 0; i < n && !need; ++i) { const uint8_t ch = s[i]; need = ch == '"' || ch == ',' || ch == '\n' || ch == '\r'; }
+            if (!need) { memcpy(o, s, (size_t)n); return o + n; }
+            *o++ = '"';
+            for (int64_t i = 0; i < n; ++i) { if (s[i] == '"') *o++ = '"'; *o++ = (char)s[i]; }
+            *o++ = '"';
+            return o;
+        }
+        case 1: {
+            const double v = reinterpret_cast<const double*>(c.data)[r];
+            if (v != v) return o;
+            if (std::isinf(v)) { if (v > 0) { memcpy(o, "inf", 3); return o + 3; } memcpy(o, "-inf", 4); return o + 4; }
+            return o + py_float_repr(v, o);
+        }
+        case 2: { auto e = std::to_chars(o, o + 24, reinterpret_cast<const int64_t*>(c.data)[r]); return e.ptr; }
+        default: if (c.data[r]) { memcpy(o, "True", 4); return o + 4; } memcpy(o, "False", 5); return o + 5;
+    }
+}
+
+}  // namespace
+
+// kinds[c], offs[c] (string columns), datas[c], valids[c] (may be NULL).  With out == NULL fills row_off
+// (int64[n_rows+1], exclusive prefix of row byte lengths); with out != NULL writes the rows.
+extern "C" int dyd_csv_write(const int32_t* kinds, const int64_t* const* offs, const uint8_t* const* datas,
+                             const uint8_t* const* valids, int32_t n_cols, int64_t n_rows, int64_t* row_off,
+                             uint8_t* out, int n_threads) {
+    if (!kinds || !datas || !row_off || n_cols < 2 || n_rows < 0) return DYD_E_ARG;     // single-column frames quote empty fields
+    std::vector<CsvCol> cols((size_t)n_cols);
+    for (int c = 0; c < n_cols; ++c) {
+        cols[(size_t)c] = CsvCol{kinds[c], offs ? offs[c] : nullptr, datas[c], valids ? valids[c] : nullptr};
+        if (kinds[c] < 0 || kinds[c] > 3 || !datas[c] || (kinds[c] == 0 && !cols[(size_t)c].off)) return DYD_E_ARG;
+    }
+    if (!out) {
+        parallel_rows(n_rows, n_threads, [&](int64_t a, int64_t b) {
+            for (int64_t r = a; r < b; ++r) {
+                size_t len = (size_t)n_cols;                      // commas + newline
+                for (const CsvCol& c : cols) len += csv_field_len(c, r);
+                row_off[r + 1] = (int64_t)len;
+            }
+        });
+        row_off[0] = 0;
+        for (int64_t r = 0; r < n_rows; ++r) row_off[r + 1] += row_off[r];
+        return 0;
+    }
+    parallel_rows(n_rows, n_threads, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            char* o = reinterpret_cast<char*>(out) + row_off[r];
+            for (int c = 0; c < n_cols; ++c) { if (c) *o++ = ','; o = csv_field_write(o, cols[(size_t)c], r); }
+            *o++ = '\n';
+        }
+    });
+    return 0;
+}

@@ -132,3 +132,70 @@ class Ingest:
         _lib.check(self.lib.dyd_ingest_export_boxes(self.h, _p(self.status), _p(self.img_off), _p(self.pts), _p(self.valid), _threads()),
                    "dyd_ingest_export_boxes")
         return self
+
+
+# ------------------------------------------------------------------------------------------------
+# CSV egress: DataFrame.to_csv(path, index=False, encoding=...) with the body written natively
+# ------------------------------------------------------------------------------------------------
+def _csv_column(col):
+    """-> (kind, off, data, valid, keepalive) or None when the column needs pandas' own formatting."""
+    import pandas as pd
+    import pyarrow as pa
+    dt = col.dtype
+    if dt == np.float64:
+        a = np.ascontiguousarray(col.to_numpy())
+        return 1, None, a.view(np.uint8), None, a
+    if dt == np.int64:
+        a = np.ascontiguousarray(col.to_numpy())
+        return 2, None, a.view(np.uint8), None, a
+    if dt == np.bool_:
+        a = np.ascontiguousarray(col.to_numpy()).astype(np.uint8)
+        return 3, None, a, None, a
+    if isinstance(dt, pd.StringDtype) or dt == object:
+        try:
+            arr = pa.array(col, type=pa.large_string(), from_pandas=True)      # raises on non-str objects
+        except Exception:  # noqa: BLE001
+            return None
+        if arr.offset != 0:
+            arr = pa.concat_arrays([arr])
+        bufs = arr.buffers()
+        n = len(arr)
+        off = np.frombuffer(bufs[1], dtype=np.int64, count=n + 1)
+        data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None and bufs[2].size else np.zeros(1, np.uint8)
+        valid = None if arr.null_count == 0 else np.asarray(arr.is_valid()).astype(np.uint8)
+        return 0, off, data, valid, arr
+    return None
+
+
+def to_csv(df, path, encoding="utf-8-sig") -> None:
+    """``df.to_csv(path, index=False, encoding=encoding)``, byte-identical, body rows written by
+    csrc/ingest.cpp (multi-threaded).  Falls back to pandas for frames it does not cover."""
+    import csv
+    import io
+    enc = (encoding or "utf-8").lower().replace("_", "-")
+    cols = None
+    if enabled() and df.shape[1] >= 2 and enc in ("utf-8", "utf-8-sig", "utf8") and df.columns.is_unique:
+        cols = [_csv_column(df[c]) for c in df.columns]
+        if any(c is None for c in cols):
+            cols = None
+    if cols is None:
+        df.to_csv(path, index=False, encoding=encoding)
+        return
+    lib = _lib.load()
+    n, nc = len(df), len(cols)
+    kinds = (C.c_int32 * nc)(*[c[0] for c in cols])
+    offs = (C.c_void_p * nc)(*[c[1].ctypes.data if c[1] is not None else None for c in cols])
+    datas = (C.c_void_p * nc)(*[c[2].ctypes.data for c in cols])
+    valids = (C.c_void_p * nc)(*[c[3].ctypes.data if c[3] is not None else None for c in cols])
+    row_off = np.empty(n + 1, np.int64)
+    a = (kinds, offs, datas, valids, nc, n, _p(row_off))
+    _lib.check(lib.dyd_csv_write(*a, None, _threads()), "dyd_csv_write(size)")
+    body = np.empty(int(row_off[-1]), np.uint8)
+    _lib.check(lib.dyd_csv_write(*a, _p(body), _threads()), "dyd_csv_write(write)")
+    head = io.StringIO()
+    csv.writer(head, lineterminator="\n", quoting=csv.QUOTE_MINIMAL).writerow([str(c) for c in df.columns])
+    with open(path, "wb") as f:
+        if enc == "utf-8-sig":
+            f.write(b"\xef\xbb\xbf")
+        f.write(head.getvalue().encode("utf-8"))
+        f.write(body.tobytes() if body.size < (1 << 20) else memoryview(body))

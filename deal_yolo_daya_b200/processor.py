@@ -108,6 +108,13 @@ class CudaKernels:
 
 
 KERNELS = CudaKernels()
+
+
+def _to_csv(df: pd.DataFrame, path, encoding) -> None:
+    """df.to_csv(path, index=False, encoding=encoding) through the native body writer (byte-identical;
+    pandas writes the frames the native writer does not cover)."""
+    from . import native
+    native.to_csv(df, path, encoding)
 STATS = {"hostlane_objects": 0, "hostlane_rows": 0, "hash_collisions": 0, "native_rows": 0, "slow_rows": 0}    # observability, last call
 
 
@@ -184,7 +191,7 @@ def deduplicate_csv_by_source(
             d = os.path.dirname(output_file)
             if d and not os.path.exists(d):
                 os.makedirs(d, exist_ok=True)
-            out.to_csv(output_file, index=False, encoding=encoding)
+            _to_csv(out, output_file, encoding)
             if verbose:
                 print(f"去重后的文件已保存至：{os.path.abspath(output_file)}")
         except Exception as e:
@@ -249,7 +256,7 @@ def remove_duplicates_between_csv(
         d = os.path.dirname(output_csv)
         if d and not os.path.exists(d):
             os.makedirs(d, exist_ok=True)
-        out.to_csv(output_csv, index=False, encoding=encoding)
+        _to_csv(out, output_csv, encoding)
         if verbose:
             print(f"结果已保存至：{os.path.abspath(output_csv)}")
     except Exception as e:
@@ -372,10 +379,10 @@ def process_csv_replace_ptlist(
         return None
     res, excluded = replace_ptlist_df(df)
     Path(output_csv_path).parent.mkdir(parents=True, exist_ok=True)
-    res.to_csv(output_csv_path, index=False, encoding="utf-8-sig")
+    _to_csv(res, output_csv_path, "utf-8-sig")
     if excluded_output_file is not None:
         Path(excluded_output_file).parent.mkdir(parents=True, exist_ok=True)
-        excluded.to_csv(excluded_output_file, index=False, encoding="utf-8-sig")
+        _to_csv(excluded, excluded_output_file, "utf-8-sig")
     return {"filtered_rows": len(res), "excluded_rows": len(excluded), "excluded_output": excluded_output_file}
 
 
@@ -443,8 +450,8 @@ def filter_by_box_count_and_iou(
     hi, ot = filter_by_box_count_and_iou_df(df, min_boxes, iou_threshold)
     Path(high_iou_csv).parent.mkdir(parents=True, exist_ok=True)
     Path(other_csv).parent.mkdir(parents=True, exist_ok=True)
-    hi.to_csv(high_iou_csv, index=False, encoding="utf-8-sig")
-    ot.to_csv(other_csv, index=False, encoding="utf-8-sig")
+    _to_csv(hi, high_iou_csv, "utf-8-sig")
+    _to_csv(ot, other_csv, "utf-8-sig")
 
 
 # =============================================================================================
@@ -471,7 +478,7 @@ def replace_labels_by_mapping(
     out, summary, diff_rows, unmatched = remap_df(df, label_map, json_columns)
     output_csv_path = Path(output_csv_path)
     output_csv_path.parent.mkdir(parents=True, exist_ok=True)
-    out.to_csv(output_csv_path, index=False, encoding="utf-8-sig")
+    _to_csv(out, output_csv_path, "utf-8-sig")
     diff_path = None
     if diff_excel_path:
         diff_path = Path(diff_excel_path)

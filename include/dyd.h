@@ -220,6 +220,11 @@ int dyd_ingest_export_boxes(const dyd_ingest* h, uint8_t* status, int64_t* img_o
  * offsets (out_off int64[n_rows+1]), then again with the buffer.                                  */
 int dyd_egress_ptlist(const dyd_ingest* h, const uint8_t* text, const int64_t* off, const int32_t* arg,
                       const uint8_t* valid, int64_t* out_off, uint8_t* out, int n_threads);
+/* Body rows of DataFrame.to_csv(index=False) for string / float64 / int64 / bool columns (kinds 0-3),
+ * byte-identical to pandas + csv.QUOTE_MINIMAL.  out == NULL: fill row_off[n_rows+1]; else write. */
+int dyd_csv_write(const int32_t* kinds, const int64_t* const* offs, const uint8_t* const* datas,
+                  const uint8_t* const* valids, int32_t n_cols, int64_t n_rows, int64_t* row_off,
+                  uint8_t* out, int n_threads);
 int dyd_py_float_repr(double v, char* out40);     /* CPython repr(float); used by the canonical-form check */
 
 /* ------------------------------------------------ synthetic tables (§8d) ---

@@ -1,0 +1,58 @@
+"""Native CSV writer == pandas.DataFrame.to_csv(index=False), byte for byte."""
+from __future__ import annotations
+
+import gzip
+import io
+import random
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from deal_yolo_daya_b200 import native
+
+G = Path(__file__).resolve().parent / "golden"
+
+
+def both(df, tmp_path, enc="utf-8-sig"):
+    a, b = tmp_path / "a.csv", tmp_path / "b.csv"
+    native.to_csv(df, a, enc)
+    df.to_csv(b, index=False, encoding=enc)
+    return a.read_bytes(), b.read_bytes()
+
+
+@pytest.mark.parametrize("name", ["processed_replaced_ptlist", "other_0.70_2", "dedup_first", "high_iou_0.70_2", "other_data_label_replaced"])
+def test_golden_frames(tmp_path, name):
+    df = pd.read_csv(io.StringIO(gzip.open(G / "expected" / f"{name}.csv.gz", "rt", encoding="utf-8").read()))
+    x, y = both(df, tmp_path)
+    assert x == y
+    assert x.decode("utf-8-sig") == gzip.open(G / "expected" / f"{name}.csv.gz", "rt", encoding="utf-8").read()
+
+
+def test_adversarial_strings_and_numbers(tmp_path):
+    rng = random.Random(1)
+    alphabet = ['a', 'b', ',', '"', '\n', '\r', ' ', '\t', "'", '中', '😀', ';', '\\', '\x00', '\x0b', '""', ',"']
+    strs = ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, 12))) for _ in range(3000)]
+    strs[5] = None; strs[6] = ""; strs[7] = "nan"; strs[8] = '"'; strs[9] = ","
+    f = np.array([rng.choice([0.0, -0.0, 1920.0, 0.1, 1e-5, 1e16, 1e22, 5e-324, 1.7976931348623157e308, float("nan"), float("inf"), -float("inf"),
+                              rng.uniform(-1e6, 1e6), round(rng.uniform(0, 2000), 3)]) for _ in range(3000)])
+    i = np.array([rng.choice([0, -1, 1, 2 ** 63 - 1, -2 ** 63, rng.randint(-10 ** 12, 10 ** 12)]) for _ in range(3000)], dtype=np.int64)
+    b = np.array([rng.random() < 0.5 for _ in range(3000)])
+    df = pd.DataFrame({"s": strs, "f": f, "i": i, "b": b, "o": pd.Series(strs[::-1], dtype=object), "weird,name": strs, 'q"': f})
+    for enc in ("utf-8-sig", "utf-8"):
+        x, y = both(df, tmp_path, enc)
+        assert x == y
+    # empty frame, frame with no rows kept
+    x, y = both(df.iloc[0:0], tmp_path)
+    assert x == y
+
+
+def test_falls_back_to_pandas_for_uncovered_frames(tmp_path):
+    one = pd.DataFrame({"a": ["", None, "x"]})                               # single column: csv quotes lone empty fields
+    mixed = pd.DataFrame({"a": [1, "x", 2.5], "b": [1, 2, 3]})               # object column with non-str values
+    dt = pd.DataFrame({"a": pd.to_datetime(["2024-01-01", "2024-01-02"]), "b": [1, 2]})
+    i32 = pd.DataFrame({"a": np.array([1, 2], np.int32), "b": ["x", "y"]})
+    for df in (one, mixed, dt, i32):
+        x, y = both(df, tmp_path)
+        assert x == y
