@@ -1,56 +1,59 @@
 // Fused K1+K2, TMA-staged (the sm_100a production path).
 //
-// One persistent CTA per SM, NW independent warps per CTA.  The image range is cut into tiles of
-// TILE_IMAGES images; a tile's vertices are one contiguous byte range of `xy`.  Each warp owns a
-// private shared-memory stage and its own mbarrier and loops over its tiles:
+// One persistent CTA per SM, NW independent warps per CTA.  A pre-pass kernel packs consecutive
+// images greedily into tiles of at most 32 objects / 6 images / TILE_CAP_V vertices (so every object
+// of a tile gets its own K1 lane and every tile fits a stage) and resolves the dependent
+// img_off -> poly_off -> xy address chain into 32-byte descriptors.  A tile's vertices are one
+// contiguous byte range of `xy`.  Each warp owns a private shared-memory stage and an mbarrier and
+// walks the tiles of its segments:
 //
-//   1. lane 0 reads the tile descriptor (resolved by a pre-pass kernel, so the dependent
-//      img_off -> poly_off -> xy address chain never stalls a compute warp) and issues
-//      cp.async.bulk (TMA, SASS UBLKCP) copies of the tile's vertex range, poly_off slice and
-//      img_off slice into the warp's stage; completion is counted in bytes on the mbarrier;
+//   1. lane 0 issues cp.async.bulk (TMA, SASS UBLKCP) copies of the tile's vertex range, poly_off
+//      slice and img_off slice into the stage; completion is counted in bytes on the mbarrier;
 //   2. K1: one lane per polygon folds its vertices straight out of shared memory with the
 //      reference's own left fold (strict comparisons from the first vertex on), which is
 //      CPython's min()/max() bit for bit -- ties, signed zeros and NaN order need no special
 //      cases -- and writes the two corner points to HBM once and the normalised box to the stage;
-//   3. K2: the warp runs the any-pair IoU test per image from the stage's boxes and writes
-//      count / high.
+//   3. the next tile's copies are issued (the vertex buffer is free again), so they land during
+//   4. K2: per-image box counts in parallel lanes, then all pairs of all images of the tile
+//      flattened over the lanes: exact overlap pre-test, survivors compacted into a small ring and
+//      evaluated densely with the full IoU arithmetic.
 //
-// Warps never synchronise with each other; while one warp waits for its copy the other warps of
-// the SM compute, so the copy engine keeps ~60 KB per SM in flight without any register cost.
-// Tiles that do not fit a stage (huge polygons, crowded tiles) or whose offset slices would make
-// a bulk copy run past the end of an array take the fallback lane: direct loads for K1 and the
-// block-per-image kernel for K2.
+// Warps never synchronise with each other; while one waits for its copy the others compute, so the
+// copy engine keeps tens of KB per SM in flight without any register cost.  A single image that
+// exceeds the stage is folded with direct loads (vertices) or handed to the block-per-image kernel
+// (more than 32 objects); tiles whose offset slices would make a bulk copy run past the end of an
+// array read them with plain loads.
 #include "kernels.cuh"
 
 namespace dyd {
 
-constexpr int T = TILE_IMAGES;
-constexpr int NW = 16;                         // warps per CTA (1 CTA per SM)
-constexpr int CAP_V = 704;                     // vertices per stage (11 KB)
-constexpr int CAP_P = 48;                      // objects per stage
+constexpr int NW = 18;                         // warps per CTA (1 CTA per SM)
+constexpr int CAP_V = TILE_CAP_V;
+constexpr int CAP_P = TILE_LANES;              // objects per tile = K1 lanes
+constexpr int TM = TILE_MAX_IMAGES;
 constexpr int TMA_THREADS = 32 * NW;
-constexpr int IMG_SLOTS = (T + 3) & ~1;        // img_off slice: T+1 entries + alignment shift, even count
+constexpr int IMG_SLOTS = 8;                   // img_off slice: <= TM+1 entries + alignment shift, even count
 constexpr int QCAP = 64;                       // survivor queue entries per warp (power of two)
-enum { MODE_FAST = 0, MODE_DIRECT = 1, MODE_DEFER = 2 };
-static_assert(CAP_P <= 64 && T <= 8, "queue entries pack (object, object, image) into 16 bits; validity masks are 64-bit");
+enum { MODE_FAST = 0, MODE_DIRECT = 1, MODE_DEFER = 2, MODE_END = 3 };
+static_assert(TM + 2 <= IMG_SLOTS && CAP_P == 32, "slice sizes");
 
-struct __align__(16) TileInfo {                // double-buffered: tile k+1 is described while K2 still works on tile k
+struct __align__(16) TileInfo {                // double-buffered: the next tile is described while K2 still works
     long long img[IMG_SLOTS];                  // img_off slice starting at image (i0 & ~1)
-    long long q0, v0;
-    int ni, np, pshift, ishift, mode, pad[3];
+    long long q0, v0, i0;
+    int ni, np, pshift, ishift, mode, pad;
 };
 struct __align__(16) Stage {
     double2 vert[CAP_V];
     double box[CAP_P * 4];                     // (x1, y1, x2, y2) after extract_boxes' min/max
-    long long poly[CAP_P + 2];                 // poly_off slice starting at object (q0 & ~1)
+    long long poly[CAP_P + 4];                 // poly_off slice starting at object (q0 & ~1)
     TileInfo info[2];
+    int cum[8], lq[8];                         // per image: inclusive pair count, first object
     unsigned char bvalid[CAP_P];
     unsigned short queue[QCAP];
     unsigned long long bar;
     unsigned long long pad;
 };
-static_assert(sizeof(double2) * CAP_V % 16 == 0 && sizeof(double) * CAP_P * 4 % 16 == 0 &&
-                  sizeof(long long) * (CAP_P + 2) % 16 == 0 && sizeof(TileInfo) % 16 == 0 && CAP_P % 16 == 0,
+static_assert(sizeof(double2) * CAP_V % 16 == 0 && sizeof(long long) * (CAP_P + 4) % 16 == 0 && sizeof(TileInfo) % 16 == 0,
               "bulk-copy destinations must stay 16-byte aligned");
 
 struct Smem {
@@ -96,28 +99,48 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- descriptor pre-pass: resolves the img_off -> poly_off chain and picks the tile's lane ----------
-__global__ void __launch_bounds__(256)
+// ---- descriptor pre-pass: one thread per segment packs its images greedily into tiles ----------------
+__global__ void __launch_bounds__(128)
 tile_desc_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off, int64_t n_img,
-                 int64_t n_poly, int64_t n_tiles, TileDesc* __restrict__ desc) {
-    const int64_t k = blockIdx.x * 256LL + threadIdx.x;
-    if (k >= n_tiles) return;
-    const int64_t i0 = k * T, i1 = min(i0 + T, n_img);
-    const int ni = (int)(i1 - i0);
-    const int64_t q0 = img_off[i0], q1 = img_off[i1];
-    const int64_t v0 = poly_off[q0], v1 = poly_off[q1];
-    const int64_t np = q1 - q0, nv = v1 - v0;
-    const int pshift = (int)(q0 & 1), ishift = (int)(i0 & 1);
-    const int64_t ne = (pshift + np + 2) & ~1LL;                             // poly_off entries a bulk copy would read
-    const int64_t nie = (ishift + ni + 2) & ~1;                              // img_off entries a bulk copy would read
-    const bool objs_fit = pshift + np + 1 <= CAP_P;
-    const bool tail_ok = (q0 - pshift) + ne <= n_poly + 1 && (i0 - ishift) + nie <= n_img + 1;
-    TileDesc d;
-    d.q0 = q0; d.v0 = v0;
-    d.np = (int)min(np, (int64_t)0x7fffffff); d.nv = (int)min(nv, (int64_t)0x7fffffff);
-    d.mode = !objs_fit ? MODE_DEFER : ((nv <= CAP_V && tail_ok) ? MODE_FAST : MODE_DIRECT);
-    d.pad = 0;
-    desc[k] = d;
+                 int64_t n_poly, int64_t n_seg, TileDesc* __restrict__ desc) {
+    const int64_t s = blockIdx.x * 128LL + threadIdx.x;
+    if (s >= n_seg) return;
+    const int64_t i_begin = s * SEG_IMAGES, i_end = min(i_begin + SEG_IMAGES, n_img);
+    TileDesc* out = desc + s * SEG_IMAGES;
+    int cnt = 0;
+    int64_t qa = img_off[i_begin], va = poly_off[qa];
+    // current tile
+    int64_t t_i0 = i_begin, t_q0 = qa, t_v0 = va; int t_ni = 0; int64_t t_np = 0, t_nv = 0;
+    auto flush = [&](int forced_mode) {
+        TileDesc d;
+        d.q0 = t_q0; d.v0 = t_v0; d.i0 = (int)t_i0;
+        d.nv = (int)min(t_nv, (int64_t)0x7fffffff); d.np = (short)min(t_np, (int64_t)32767); d.ni = (unsigned char)t_ni;
+        int mode = forced_mode;
+        if (mode == MODE_FAST) {                               // bulk copies read whole 16-byte units: stay inside the arrays
+            const int pshift = (int)(t_q0 & 1), ishift = (int)(t_i0 & 1);
+            const int64_t ne = (pshift + t_np + 2) & ~1LL, nie = (ishift + t_ni + 2) & ~1LL;
+            if ((t_q0 - pshift) + ne > n_poly + 1 || (t_i0 - ishift) + nie > n_img + 1) mode = MODE_DIRECT;
+        }
+        d.mode = (unsigned char)mode; d.cnt = 0; d.pad[0] = d.pad[1] = d.pad[2] = 0;
+        out[cnt++] = d;
+    };
+    for (int64_t i = i_begin; i < i_end; ++i) {
+        const int64_t qb = img_off[i + 1], vb = poly_off[qb];
+        const int64_t n_i = qb - qa, v_i = vb - va;
+        const bool lanes_ok = n_i <= TILE_LANES, verts_ok = v_i <= TILE_CAP_V;
+        if (t_ni > 0 && (t_ni == TILE_MAX_IMAGES || t_np + n_i > TILE_LANES || t_nv + v_i > TILE_CAP_V || !lanes_ok || !verts_ok)) {
+            flush(MODE_FAST);
+            t_i0 = i; t_q0 = qa; t_v0 = va; t_ni = 0; t_np = 0; t_nv = 0;
+        }
+        t_ni += 1; t_np += n_i; t_nv += v_i;
+        if (!lanes_ok || !verts_ok) {                          // an image that exceeds a stage is a tile of its own
+            flush(lanes_ok ? MODE_DIRECT : MODE_DEFER);
+            t_i0 = i + 1; t_q0 = qb; t_v0 = vb; t_ni = 0; t_np = 0; t_nv = 0;
+        }
+        qa = qb; va = vb;
+    }
+    if (t_ni > 0) flush(MODE_FAST);
+    out[0].cnt = (unsigned char)cnt;
 }
 
 // The reference's fold for one polygon (processor.py:256-259): running values start at vertex 0 and
@@ -162,7 +185,7 @@ template <bool ARG>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off,
                  const double2* __restrict__ xy2, const TileDesc* __restrict__ desc,
-                 int64_t n_img, int64_t n_poly, int64_t n_tiles, int64_t min_boxes, double thr,
+                 int64_t n_img, int64_t n_poly, int64_t n_seg, int64_t min_boxes, double thr,
                  double* __restrict__ pts, uint8_t* __restrict__ valid, int32_t* __restrict__ arg,
                  uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -177,23 +200,41 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
 
     const bool zero_hits = 0.0 >= thr;
     const int64_t stride = (int64_t)gridDim.x * NW;
-    const int64_t k0 = (int64_t)blockIdx.x * NW + warp;
     uint32_t phase = 0;
-    // lane 0 keeps the descriptors of its next two tiles in registers, so the load issued during one
-    // tile is consumed a full tile later and never stalls the fill
-    TileDesc nxt{0, 0, 0, 0, MODE_DEFER, 0}, far{0, 0, 0, 0, MODE_DEFER, 0};
-    if (lane == 0 && k0 < n_tiles) nxt = desc[k0];
-    if (lane == 0 && k0 + stride < n_tiles) far = desc[k0 + stride];
 
-    // Stage fill, executed by lane 0 only: describe tile k in `ti` and start its copies.
-    auto fill = [&](TileInfo& ti, int64_t k) {
-        const int64_t i0 = k * T;
-        const int ni = (int)min((int64_t)T, n_img - i0);
+    // Lane 0 walks the descriptors of this warp's segments two tiles ahead of the tile being
+    // processed: the load issued while one tile is filled is consumed a full tile later.
+    struct Cursor { int64_t seg; int j, cnt; };
+    Cursor c_nxt{(int64_t)blockIdx.x * NW + warp, 0, 0}, c_far{0, 0, 0};
+    TileDesc nxt{}, far{};
+    bool has_nxt = false, has_far = false;
+    auto advance = [&](const Cursor& c) { return c.j + 1 < c.cnt ? Cursor{c.seg, c.j + 1, c.cnt} : Cursor{c.seg + stride, 0, 0}; };
+    if (lane == 0) {
+        has_nxt = c_nxt.seg < n_seg;
+        if (has_nxt) {
+            nxt = desc[c_nxt.seg * SEG_IMAGES];
+            c_nxt.cnt = nxt.cnt;
+            c_far = advance(c_nxt);
+            has_far = c_far.seg < n_seg;
+            if (has_far) far = desc[c_far.seg * SEG_IMAGES + c_far.j];
+        }
+    }
+
+    // Stage fill, executed by lane 0 only: describe the next tile in `ti` and start its copies.
+    auto fill = [&](TileInfo& ti) {
+        if (!has_nxt) { ti.mode = MODE_END; return; }
         const TileDesc d = nxt;
-        nxt = far;
-        if (k + 2 * stride < n_tiles) far = desc[k + 2 * stride];            // consumed two tiles from now
+        nxt = far; c_nxt = c_far; has_nxt = has_far;
+        if (has_nxt) {
+            if (c_nxt.j == 0) c_nxt.cnt = nxt.cnt;
+            c_far = advance(c_nxt);
+            has_far = c_far.seg < n_seg;
+            if (has_far) far = desc[c_far.seg * SEG_IMAGES + c_far.j];
+        }
+        const int64_t i0 = d.i0;
+        const int ni = d.ni;
         const int pshift = (int)(d.q0 & 1), ishift = (int)(i0 & 1);
-        ti.q0 = d.q0; ti.v0 = d.v0; ti.ni = ni; ti.pshift = pshift; ti.ishift = ishift; ti.np = d.np; ti.mode = d.mode;
+        ti.q0 = d.q0; ti.v0 = d.v0; ti.i0 = i0; ti.ni = ni; ti.pshift = pshift; ti.ishift = ishift; ti.np = d.np; ti.mode = d.mode;
         if (d.mode == MODE_FAST) {
             const uint32_t ne = (uint32_t)(pshift + d.np + 2) & ~1u;         // poly_off entries copied (even count)
             const uint32_t nie = (uint32_t)(ishift + ni + 2) & ~1u;          // img_off entries copied (even count)
@@ -201,18 +242,21 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             if (d.nv > 0) bulk_g2s(st.vert, xy2 + d.v0, 16u * (uint32_t)d.nv, &st.bar);
             bulk_g2s(st.poly, poly_off + (d.q0 - pshift), 8u * ne, &st.bar);
             bulk_g2s(ti.img, img_off + (i0 - ishift), 8u * nie, &st.bar);
-        } else if (d.mode == MODE_DIRECT) {                                   // vertices do not fit: K1 reads HBM directly
+        } else {                                                              // offsets by plain loads
             for (int j = 0; j <= ni; ++j) ti.img[ishift + j] = __ldg(img_off + i0 + j);
+            const long long np = ti.img[ishift + ni] - d.q0;
+            ti.np = (int)min(np, (long long)0x7fffffff);
         }
     };
 
-    if (lane == 0 && k0 < n_tiles) fill(st.info[0], k0);
-    unsigned it = 0;
-    for (int64_t k = k0; k < n_tiles; k += stride, ++it) {
+    if (lane == 0) fill(st.info[0]);
+    for (unsigned it = 0;; ++it) {
         TileInfo& ti = st.info[it & 1];
         __syncwarp();
-        const int mode = ti.mode, np = ti.np, pshift = ti.pshift, ishift = ti.ishift, ni = ti.ni;
-        const int64_t q0 = ti.q0, v0 = ti.v0, i0 = k * T;
+        const int mode = ti.mode;
+        if (mode == MODE_END) break;
+        const int np = ti.np, pshift = ti.pshift, ishift = ti.ishift, ni = ti.ni;
+        const int64_t q0 = ti.q0, v0 = ti.v0, i0 = ti.i0;
         if (mode == MODE_FAST) {
             mbar_wait(&st.bar, phase);
             phase ^= 1;
@@ -252,7 +296,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
         __syncwarp();
         // The vertex / offset buffers are free again: start the next tile's copies now so that they
         // land while K2 works on this tile's boxes.
-        if (lane == 0 && k + stride < n_tiles) fill(st.info[(it + 1) & 1], k + stride);
+        if (lane == 0) fill(st.info[(it + 1) & 1]);
 
         // ---------------- K2: box counts + any-pair IoU, flattened over the tile's images ----------------
         if (mode == MODE_DEFER) {
@@ -265,27 +309,22 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
         // Without NaN coordinates the two cross comparisons per axis are a superset of the exact
         // overlap test, which the survivors get anyway; a tile holding a NaN box uses the exact selects.
         const bool exact_pre = __any_sync(FULL, nan_box);
-        // bit p of `inv` = object p of the tile is a null bbox
-        const unsigned inv_lo = __ballot_sync(FULL, lane < np && st.bvalid[lane] == 0);
-        const unsigned inv_hi = np > 32 ? __ballot_sync(FULL, lane + 32 < np && st.bvalid[(lane + 32) % CAP_P] == 0) : 0u;
-        int lq[T], neff[T], cum[T];
-        int total = 0;
-#pragma unroll
-        for (int j = 0; j < T; ++j) {
-            lq[j] = 0; neff[j] = 0;
-            if (j < ni) {
-                const int a = (int)(ti.img[ishift + j] - q0), n = (int)(ti.img[ishift + j + 1] - ti.img[ishift + j]);
-                int ne = n;                                                  // boxes before the first null bbox
-                if (inv_lo | inv_hi) {
-                    const unsigned long long inv = ((unsigned long long)inv_hi << 32) | inv_lo;
-                    const unsigned long long m = (inv >> a) & (n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL));
-                    if (m) ne = __ffsll((long long)m) - 1;
-                }
-                lq[j] = a; neff[j] = ne;
-                if (ne >= min_boxes && ne >= 2) total += ne * (ne - 1) / 2;
-            }
-            cum[j] = total;
+        const unsigned inv = __ballot_sync(FULL, lane < np && st.bvalid[lane] == 0);   // bit p: object p is a null bbox
+        // lane j < ni owns image j: its first object, its box count (prefix before the first null bbox), its pairs
+        int my_a = 0, my_ne = 0, my_pairs = 0;
+        if (lane < ni) {
+            my_a = (int)(ti.img[ishift + lane] - q0);
+            const int n = (int)(ti.img[ishift + lane + 1] - ti.img[ishift + lane]);
+            const unsigned m = n >= 32 ? (inv >> my_a) : ((inv >> my_a) & ((1u << n) - 1u));
+            my_ne = m ? __ffs(m) - 1 : n;
+            if (my_ne >= min_boxes && my_ne >= 2) my_pairs = my_ne * (my_ne - 1) / 2;
         }
+        int cum = my_pairs;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) { const int y = __shfl_up_sync(FULL, cum, off); if (lane >= off) cum += y; }
+        const int total = __shfl_sync(FULL, cum, 7);
+        if (lane < 8) { st.cum[lane] = cum; st.lq[lane] = my_a; }
+        __syncwarp();
         unsigned hits = 0;
         int qhead = 0, qtail = 0;
         auto exact_pass = [&](int cnt) {           // dense evaluation of queued pairs with the full IoU arithmetic
@@ -303,11 +342,10 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             const int kq = base + lane;
             bool surv = false; unsigned entry = 0;
             if (kq < total) {
-                int j = 0, first = 0, off = 0;
+                int j = 0;
 #pragma unroll
-                for (int jj = 0; jj < T - 1; ++jj) if (kq >= cum[jj]) { j = jj + 1; first = cum[jj]; }
-#pragma unroll
-                for (int jj = 0; jj < T; ++jj) if (j == jj) off = lq[jj];
+                for (int jj = 0; jj < TM - 1; ++jj) j += kq >= st.cum[jj] ? 1 : 0;
+                const int first = j ? st.cum[j - 1] : 0, off = st.lq[j];
                 const unsigned stp = sm.lut[kq - first];
                 const int ia = off + (stp & 0xff), ib = off + (stp >> 8);
                 const Box ba = load_box(st.box, ia), bb = load_box(st.box, ib);
@@ -324,12 +362,8 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             }
         }
         if (qtail > qhead) exact_pass(qtail - qhead);
-        if (lane < ni) {
-            int ne = 0; bool h = false;
-#pragma unroll
-            for (int j = 0; j < T; ++j) if (lane == j) { ne = neff[j]; h = (hits >> j) & 1u; }
-            count[i0 + lane] = ne; high[i0 + lane] = h ? 1 : 0;
-        }
+        if (lane < ni) { count[i0 + lane] = my_ne; high[i0 + lane] = (hits >> lane) & 1u; }
+        __syncwarp();                              // st.cum / st.lq / queue are rewritten by the next tile
     }
 }
 
@@ -337,21 +371,21 @@ int launch_fused_tma(const int64_t* d_img_off, const int64_t* d_poly_off, const 
                      int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
                      double* d_pts, uint8_t* d_valid, int32_t* d_arg, uint8_t* d_high, int32_t* d_count,
                      void* ws, cudaStream_t s) {
-    const int64_t n_tiles = n_tiles_of(n_img);
+    const int64_t n_seg = n_segments_of(n_img);
     TileDesc* desc = tile_descs(ws, n_img);
-    tile_desc_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(d_img_off, d_poly_off, n_img, n_poly, n_tiles, desc);
+    tile_desc_kernel<<<(unsigned)((n_seg + 127) / 128), 128, 0, s>>>(d_img_off, d_poly_off, n_img, n_poly, n_seg, desc);
     if (int rc = launch_check("tile_desc_kernel")) return rc;
     const size_t smem = sizeof(Smem);
-    const int64_t want = (n_tiles + NW - 1) / NW;
+    const int64_t want = (n_seg + NW - 1) / NW;
     const unsigned grid = (unsigned)(want < NUM_SMS ? want : NUM_SMS);
     const double2* xy2 = reinterpret_cast<const double2*>(d_xy);
     if (d_arg) {
         DYD_CUDA(cudaFuncSetAttribute(fused_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused_tma_kernel<true><<<grid, TMA_THREADS, smem, s>>>(d_img_off, d_poly_off, xy2, desc, n_img, n_poly, n_tiles, min_boxes, thr,
+        fused_tma_kernel<true><<<grid, TMA_THREADS, smem, s>>>(d_img_off, d_poly_off, xy2, desc, n_img, n_poly, n_seg, min_boxes, thr,
                                                                d_pts, d_valid, d_arg, d_high, d_count, ws);
     } else {
         DYD_CUDA(cudaFuncSetAttribute(fused_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused_tma_kernel<false><<<grid, TMA_THREADS, smem, s>>>(d_img_off, d_poly_off, xy2, desc, n_img, n_poly, n_tiles, min_boxes, thr,
+        fused_tma_kernel<false><<<grid, TMA_THREADS, smem, s>>>(d_img_off, d_poly_off, xy2, desc, n_img, n_poly, n_seg, min_boxes, thr,
                                                                 d_pts, d_valid, nullptr, d_high, d_count, ws);
     }
     return launch_check("fused_tma_kernel");

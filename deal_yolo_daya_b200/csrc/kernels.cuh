@@ -18,17 +18,28 @@ inline size_t crowd_list_bytes(int64_t n_img) {
     return (sizeof(CrowdList) + sizeof(int) * (size_t)n_img + 15) & ~(size_t)15;
 }
 
-constexpr int TILE_IMAGES = 3;               // images per staged tile (~24 objects: one lane each)
-struct TileDesc {                            // 32 bytes, written by the descriptor pre-pass
+// Tiles of the fused kernel: a pre-pass packs consecutive images greedily into tiles of at most
+// TILE_LANES objects (one K1 lane each), TILE_MAX_IMAGES images and TILE_CAP_V vertices.  Packing
+// restarts every SEG_IMAGES images so that segments are independent (one pre-pass thread each, one
+// warp of the main kernel each); a segment's descriptors live at desc[seg * SEG_IMAGES ...].
+constexpr int SEG_IMAGES = 32;
+constexpr int TILE_LANES = 32;
+constexpr int TILE_MAX_IMAGES = 6;
+constexpr int TILE_CAP_V = 672;              // vertices staged per tile (10.5 KB)
+struct TileDesc {                            // 32 bytes
     long long q0;                            // first object  img_off[i0]
     long long v0;                            // first vertex  poly_off[q0]
-    int np;                                  // objects of the tile (clamped to INT_MAX)
-    int nv;                                  // vertices of the tile (clamped to INT_MAX)
-    int mode;                                // how the fused kernel handles the tile (MODE_*)
-    int pad;
+    int i0;                                  // first image
+    int nv;                                  // vertices (clamped to INT_MAX)
+    short np;                                // objects (clamped; exact for fast / direct tiles)
+    unsigned char ni;                        // images
+    unsigned char mode;                      // MODE_*
+    unsigned char cnt;                       // tiles of the segment (valid in the segment's first descriptor)
+    unsigned char pad[3];
 };
-inline int64_t n_tiles_of(int64_t n_img) { return (n_img + TILE_IMAGES - 1) / TILE_IMAGES; }
-inline size_t tile_desc_bytes(int64_t n_img) { return sizeof(TileDesc) * (size_t)n_tiles_of(n_img) + 16; }
+static_assert(sizeof(TileDesc) == 32, "descriptor layout");
+inline int64_t n_segments_of(int64_t n_img) { return (n_img + SEG_IMAGES - 1) / SEG_IMAGES; }
+inline size_t tile_desc_bytes(int64_t n_img) { return sizeof(TileDesc) * (size_t)n_segments_of(n_img) * SEG_IMAGES + 16; }
 inline TileDesc* tile_descs(void* ws, int64_t n_img) {
     return reinterpret_cast<TileDesc*>(reinterpret_cast<char*>(ws) + crowd_list_bytes(n_img));
 }
