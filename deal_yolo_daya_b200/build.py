@@ -46,6 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
            "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("DYD_NVCC_FLAGS", "").split()          # tuning experiments: -DDYD_NW=.. -DDYD_TILE_CAP_V=..
     cmd += ["-o", str(OUT)] + [str(s) for s in sources()]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:

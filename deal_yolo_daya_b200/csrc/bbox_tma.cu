@@ -27,15 +27,18 @@
 
 namespace dyd {
 
-constexpr int NW = 18;                         // warps per CTA (1 CTA per SM)
+#ifndef DYD_NW
+#define DYD_NW 20
+#endif
+constexpr int NW = DYD_NW;                     // warps per CTA (1 CTA per SM)
 constexpr int CAP_V = TILE_CAP_V;
 constexpr int CAP_P = TILE_LANES;              // objects per tile = K1 lanes
 constexpr int TM = TILE_MAX_IMAGES;
 constexpr int TMA_THREADS = 32 * NW;
-constexpr int IMG_SLOTS = 8;                   // img_off slice: <= TM+1 entries + alignment shift, even count
+constexpr int IMG_SLOTS = (TM + 3) & ~1;        // img_off slice: <= TM+1 entries + alignment shift, even count
 constexpr int QCAP = 64;                       // survivor queue entries per warp (power of two)
 enum { MODE_FAST = 0, MODE_DIRECT = 1, MODE_DEFER = 2, MODE_END = 3 };
-static_assert(TM + 2 <= IMG_SLOTS && CAP_P == 32, "slice sizes");
+static_assert(TM + 2 <= IMG_SLOTS && TM <= 8 && CAP_P == 32 && SEG_IMAGES <= 255, "slice sizes");
 
 struct __align__(16) TileInfo {                // double-buffered: the next tile is described while K2 still works
     long long img[IMG_SLOTS];                  // img_off slice starting at image (i0 & ~1)

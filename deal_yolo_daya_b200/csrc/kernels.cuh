@@ -22,10 +22,19 @@ inline size_t crowd_list_bytes(int64_t n_img) {
 // TILE_LANES objects (one K1 lane each), TILE_MAX_IMAGES images and TILE_CAP_V vertices.  Packing
 // restarts every SEG_IMAGES images so that segments are independent (one pre-pass thread each, one
 // warp of the main kernel each); a segment's descriptors live at desc[seg * SEG_IMAGES ...].
-constexpr int SEG_IMAGES = 32;
+#ifndef DYD_SEG_IMAGES
+#define DYD_SEG_IMAGES 32
+#endif
+#ifndef DYD_TILE_MAX_IMAGES
+#define DYD_TILE_MAX_IMAGES 6
+#endif
+#ifndef DYD_TILE_CAP_V
+#define DYD_TILE_CAP_V 600
+#endif
+constexpr int SEG_IMAGES = DYD_SEG_IMAGES;
 constexpr int TILE_LANES = 32;
-constexpr int TILE_MAX_IMAGES = 6;
-constexpr int TILE_CAP_V = 672;              // vertices staged per tile (10.5 KB)
+constexpr int TILE_MAX_IMAGES = DYD_TILE_MAX_IMAGES;
+constexpr int TILE_CAP_V = DYD_TILE_CAP_V;   // vertices staged per tile (9.4 KB)
 struct TileDesc {                            // 32 bytes
     long long q0;                            // first object  img_off[i0]
     long long v0;                            // first vertex  poly_off[q0]
