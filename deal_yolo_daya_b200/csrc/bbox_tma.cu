@@ -102,48 +102,65 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- descriptor pre-pass: one thread per segment packs its images greedily into tiles ----------------
-__global__ void __launch_bounds__(128)
+// ---- descriptor pre-pass: one warp per segment packs its images greedily into tiles ------------------
+// Lane l fetches img_off[i_begin + l] and the poly_off entry it points to (two independent load levels
+// instead of a 32-step pointer chase).  Every lane then finds, from the two prefix arrays, where the
+// maximal tile starting at ITS image would end; lane 0 follows those jump pointers from image 0 (a
+// handful of shared-memory reads) and lane t writes the descriptor of tile t.
+static_assert(SEG_IMAGES == 32, "one lane per image of a segment");
+constexpr int DESC_WARPS = 8;
+__global__ void __launch_bounds__(32 * DESC_WARPS)
 tile_desc_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off, int64_t n_img,
                  int64_t n_poly, int64_t n_seg, TileDesc* __restrict__ desc) {
-    const int64_t s = blockIdx.x * 128LL + threadIdx.x;
+    __shared__ long long sq[DESC_WARPS][SEG_IMAGES + 1], sv[DESC_WARPS][SEG_IMAGES + 1];
+    __shared__ unsigned char snext[DESC_WARPS][SEG_IMAGES], sstart[DESC_WARPS][SEG_IMAGES + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t s = blockIdx.x * (int64_t)DESC_WARPS + w;
     if (s >= n_seg) return;
-    const int64_t i_begin = s * SEG_IMAGES, i_end = min(i_begin + SEG_IMAGES, n_img);
-    TileDesc* out = desc + s * SEG_IMAGES;
+    const int64_t i_begin = s * SEG_IMAGES;
+    const int n_here = (int)min((int64_t)SEG_IMAGES, n_img - i_begin);
+    {
+        const int e = min(lane, n_here);
+        const long long q = img_off[i_begin + e];
+        sq[w][e] = q; sv[w][e] = poly_off[q];
+        if (lane == 0 && n_here == SEG_IMAGES) {
+            const long long qe = img_off[i_begin + SEG_IMAGES];
+            sq[w][SEG_IMAGES] = qe; sv[w][SEG_IMAGES] = poly_off[qe];
+        }
+    }
+    __syncwarp();
+    if (lane < n_here) {                                       // end of the maximal tile that starts at image `lane`
+        const long long q0 = sq[w][lane], v0 = sv[w][lane];
+        int k = 1;
+        if (sq[w][lane + 1] - q0 <= TILE_LANES && sv[w][lane + 1] - v0 <= TILE_CAP_V)
+            while (k < TILE_MAX_IMAGES && lane + k < n_here && sq[w][lane + k + 1] - q0 <= TILE_LANES && sv[w][lane + k + 1] - v0 <= TILE_CAP_V) ++k;
+        snext[w][lane] = (unsigned char)(lane + k);
+    }
+    __syncwarp();
     int cnt = 0;
-    int64_t qa = img_off[i_begin], va = poly_off[qa];
-    // current tile
-    int64_t t_i0 = i_begin, t_q0 = qa, t_v0 = va; int t_ni = 0; int64_t t_np = 0, t_nv = 0;
-    auto flush = [&](int forced_mode) {
+    if (lane == 0) {
+        for (int pos = 0; pos < n_here; pos = snext[w][pos]) sstart[w][cnt++] = (unsigned char)pos;
+        sstart[w][cnt] = (unsigned char)n_here;
+    }
+    cnt = __shfl_sync(FULL, cnt, 0);
+    __syncwarp();
+    if (lane < cnt) {
+        const int a = sstart[w][lane], b = sstart[w][lane + 1];
+        const int64_t t_i0 = i_begin + a;
+        const long long t_q0 = sq[w][a], t_v0 = sv[w][a], t_np = sq[w][b] - t_q0, t_nv = sv[w][b] - t_v0;
+        const int t_ni = b - a;
         TileDesc d;
         d.q0 = t_q0; d.v0 = t_v0; d.i0 = (int)t_i0;
-        d.nv = (int)min(t_nv, (int64_t)0x7fffffff); d.np = (short)min(t_np, (int64_t)32767); d.ni = (unsigned char)t_ni;
-        int mode = forced_mode;
+        d.nv = (int)min(t_nv, (long long)0x7fffffff); d.np = (short)min(t_np, (long long)32767); d.ni = (unsigned char)t_ni;
+        int mode = t_np > TILE_LANES ? MODE_DEFER : (t_nv > TILE_CAP_V ? MODE_DIRECT : MODE_FAST);   // oversize = single image
         if (mode == MODE_FAST) {                               // bulk copies read whole 16-byte units: stay inside the arrays
             const int pshift = (int)(t_q0 & 1), ishift = (int)(t_i0 & 1);
             const int64_t ne = (pshift + t_np + 2) & ~1LL, nie = (ishift + t_ni + 2) & ~1LL;
             if ((t_q0 - pshift) + ne > n_poly + 1 || (t_i0 - ishift) + nie > n_img + 1) mode = MODE_DIRECT;
         }
-        d.mode = (unsigned char)mode; d.cnt = 0; d.pad[0] = d.pad[1] = d.pad[2] = 0;
-        out[cnt++] = d;
-    };
-    for (int64_t i = i_begin; i < i_end; ++i) {
-        const int64_t qb = img_off[i + 1], vb = poly_off[qb];
-        const int64_t n_i = qb - qa, v_i = vb - va;
-        const bool lanes_ok = n_i <= TILE_LANES, verts_ok = v_i <= TILE_CAP_V;
-        if (t_ni > 0 && (t_ni == TILE_MAX_IMAGES || t_np + n_i > TILE_LANES || t_nv + v_i > TILE_CAP_V || !lanes_ok || !verts_ok)) {
-            flush(MODE_FAST);
-            t_i0 = i; t_q0 = qa; t_v0 = va; t_ni = 0; t_np = 0; t_nv = 0;
-        }
-        t_ni += 1; t_np += n_i; t_nv += v_i;
-        if (!lanes_ok || !verts_ok) {                          // an image that exceeds a stage is a tile of its own
-            flush(lanes_ok ? MODE_DIRECT : MODE_DEFER);
-            t_i0 = i + 1; t_q0 = qb; t_v0 = vb; t_ni = 0; t_np = 0; t_nv = 0;
-        }
-        qa = qb; va = vb;
+        d.mode = (unsigned char)mode; d.cnt = lane == 0 ? (unsigned char)cnt : 0; d.pad[0] = d.pad[1] = d.pad[2] = 0;
+        desc[s * SEG_IMAGES + lane] = d;
     }
-    if (t_ni > 0) flush(MODE_FAST);
-    out[0].cnt = (unsigned char)cnt;
 }
 
 // The reference's fold for one polygon (processor.py:256-259): running values start at vertex 0 and
@@ -376,7 +393,7 @@ int launch_fused_tma(const int64_t* d_img_off, const int64_t* d_poly_off, const 
                      void* ws, cudaStream_t s) {
     const int64_t n_seg = n_segments_of(n_img);
     TileDesc* desc = tile_descs(ws, n_img);
-    tile_desc_kernel<<<(unsigned)((n_seg + 127) / 128), 128, 0, s>>>(d_img_off, d_poly_off, n_img, n_poly, n_seg, desc);
+    tile_desc_kernel<<<(unsigned)((n_seg + DESC_WARPS - 1) / DESC_WARPS), 32 * DESC_WARPS, 0, s>>>(d_img_off, d_poly_off, n_img, n_poly, n_seg, desc);
     if (int rc = launch_check("tile_desc_kernel")) return rc;
     const size_t smem = sizeof(Smem);
     const int64_t want = (n_seg + NW - 1) / NW;
