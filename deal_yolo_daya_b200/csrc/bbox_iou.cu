@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
 iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
                  int64_t min_boxes, double thr, uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
     __shared__ double sx1[CROWD_SMEM_BOXES], sy1[CROWD_SMEM_BOXES], sx2[CROWD_SMEM_BOXES], sy2[CROWD_SMEM_BOXES];
-    __shared__ int found;
+    __shared__ int found, has_nan;
     __shared__ long long first_bad;
     const unsigned long long n_list = reinterpret_cast<CrowdList*>(ws)->count;
     const int* ids = crowd_ids(ws);
@@ -124,7 +124,7 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
         const int64_t img = ids[e];
         const int64_t q0 = img_off[img], n_all = img_off[img + 1] - q0;
         __syncthreads();                              // previous image fully consumed
-        if (threadIdx.x == 0) { found = 0; first_bad = n_all; }
+        if (threadIdx.x == 0) { found = 0; has_nan = 0; first_bad = n_all; }
         __syncthreads();
         if (valid != nullptr) {
             long long mine = n_all;
@@ -143,27 +143,37 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
                 double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
                 Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
                 sx1[j] = bx.x1; sy1[j] = bx.y1; sx2[j] = bx.x2; sy2[j] = bx.y2;
+                if (bx.x1 != bx.x1 || bx.y1 != bx.y1 || bx.x2 != bx.x2 || bx.y2 != bx.y2) has_nan = 1;
             }
         }
         __syncthreads();
         if (want) {
             // circular half-range pairing: box s meets s+1 .. s+(n-1)/2 (mod n); for even n the
             // antipodal pair is taken by the lower half only.  Covers every unordered pair once.
+            // Without NaN coordinates four cross comparisons are a superset of the exact overlap test
+            // (processor.py:329-333); only surviving pairs pay for the full IoU arithmetic.
             const int half = (n - 1) / 2;
             const bool even = (n & 1) == 0;
+            const bool cheap = in_smem && !has_nan && !zero_hits;
             for (int s = threadIdx.x; s < n; s += CTA_THREADS) {
                 Box a;
                 if (in_smem) a = Box{sx1[s], sy1[s], sx2[s], sy2[s]};
                 else { double2 p1 = ldg_f64x2(src + 2 * s), p2 = ldg_f64x2(src + 2 * s + 1); a = box_from_points(p1.x, p1.y, p2.x, p2.y); }
                 const int dmax = half + ((even && s < n / 2) ? 1 : 0);
                 bool mine = false;
+                int t = s;
                 for (int d = 1; d <= dmax && !mine; ++d) {
-                    int t = s + d; if (t >= n) t -= n;
-                    Box b;
-                    if (in_smem) b = Box{sx1[t], sy1[t], sx2[t], sy2[t]};
-                    else { double2 p1 = ldg_f64x2(src + 2 * t), p2 = ldg_f64x2(src + 2 * t + 1); b = box_from_points(p1.x, p1.y, p2.x, p2.y); }
-                    mine = iou_hits(a, b, thr, zero_hits);
-                    if ((d & 15) == 0 && *(volatile int*)&found) break;
+                    ++t; if (t >= n) t -= n;
+                    if (cheap) {
+                        if (a.x2 > sx1[t] && sx2[t] > a.x1 && a.y2 > sy1[t] && sy2[t] > a.y1)
+                            mine = iou_hits(a, Box{sx1[t], sy1[t], sx2[t], sy2[t]}, thr, zero_hits);
+                    } else {
+                        Box b;
+                        if (in_smem) b = Box{sx1[t], sy1[t], sx2[t], sy2[t]};
+                        else { double2 p1 = ldg_f64x2(src + 2 * t), p2 = ldg_f64x2(src + 2 * t + 1); b = box_from_points(p1.x, p1.y, p2.x, p2.y); }
+                        mine = iou_hits(a, b, thr, zero_hits);
+                    }
+                    if ((d & 31) == 0 && *(volatile int*)&found) break;
                 }
                 if (mine) found = 1;
                 if (*(volatile int*)&found) break;

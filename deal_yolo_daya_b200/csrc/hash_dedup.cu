@@ -5,6 +5,8 @@
 // (UINT64_MAX under atomicMin, -1 under signed atomicMax).  A key equal to the EMPTY sentinel
 // is folded onto EMPTY-1; like any 64-bit collision it is caught by the host's string check of
 // dropped rows (d_rep / d_ref_row exist for that).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dyd {
@@ -77,12 +79,12 @@ template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
 dedup_insert_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
                     const int64_t* __restrict__ row_id, int64_t n, int keep_mode,
-                    TableHeader* hdr, Slot* tab, unsigned* cnt, int shift, uint64_t mask) {
+                    TableHeader* hdr, Slot* tab, unsigned* cnt, int shift, uint64_t mask, int pass_shift, unsigned pass) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     const bool live = r < n;
     constexpr bool IDS = KIND != 0;
     const bool isnull = live && !IDS && null != nullptr && null[r] != 0;
-    const unsigned nm = __ballot_sync(FULL, isnull);
+    const unsigned nm = pass == 0 ? __ballot_sync(FULL, isnull) : 0u;
     if (nm) {                                          // rows ascend with the lane: aggregate per warp
         const int lane = threadIdx.x & 31;
         if (lane == __ffs(nm) - 1) { atomicMin(&hdr->null_first, (unsigned long long)r); atomicAdd(&hdr->null_count, (unsigned long long)__popc(nm)); }
@@ -94,6 +96,7 @@ dedup_insert_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
     const unsigned long long key = norm_key(KIND == 2 ? keys[2 * r] : keys[r]);
     const unsigned long long rid = (unsigned long long)id;
     uint64_t s = home_slot(key, shift);
+    if ((unsigned)(s >> pass_shift) != pass) return;   // this pass works on another region of the table
     for (;;) {
         unsigned long long prev = atomicCAS(&tab[s].key, EMPTY, key);
         if (prev == EMPTY || prev == key) {
@@ -111,14 +114,15 @@ __global__ void __launch_bounds__(HT_THREADS)
 dedup_lookup_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
                     const int64_t* __restrict__ row_id, int64_t n, int keep_mode,
                     const TableHeader* __restrict__ hdr, const Slot* __restrict__ tab,
-                    const unsigned* __restrict__ cnt, int shift, uint64_t mask,
+                    const unsigned* __restrict__ cnt, int shift, uint64_t mask, int pass_shift, unsigned pass,
                     uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= n) return;
     constexpr bool IDS = KIND != 0;
     const long long rid = KIND == 2 ? (long long)keys[2 * r + 1] : (KIND == 1 ? row_id[r] : r);
-    if (IDS && rid < 0) { rep[r] = -1; keep[r] = 0; return; }
+    if (IDS && rid < 0) { if (pass == 0) { rep[r] = -1; keep[r] = 0; } return; }
     if (!IDS && null != nullptr && null[r] != 0) {
+        if (pass != 0) return;
         const long long rp = keep_mode == 1 ? hdr->null_last : (long long)hdr->null_first;
         rep[r] = rp;
         keep[r] = keep_mode == 2 ? (hdr->null_count == 1) : (rp == rid);
@@ -126,6 +130,7 @@ dedup_lookup_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
     }
     const unsigned long long key = norm_key(KIND == 2 ? keys[2 * r] : keys[r]);
     uint64_t s = home_slot(key, shift);
+    if ((unsigned)(s >> pass_shift) != pass) return;
     while (tab[s].key != key) s = (s + 1) & mask;      // the key was inserted by the previous kernel
     const long long rp = (long long)tab[s].row;
     rep[r] = rp;
@@ -243,12 +248,24 @@ static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64
     DYD_CUDA(cudaMemsetAsync(ws, 0xFF, sizeof(TableHeader) + cap * sizeof(Slot), s));
     DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
     if (keep_mode == 2) DYD_CUDA(cudaMemsetAsync(cnt, 0, cap * sizeof(unsigned), s));
-    dedup_insert_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(
-        reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1);
-    if (int rc = launch_check("dedup_insert_kernel")) return rc;
-    dedup_lookup_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(
-        reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1, d_keep, d_rep);
-    return launch_check("dedup_lookup_kernel");
+    // Large tables are worked region by region: each pass touches 1/2^k of the table (a slice that
+    // stays L2-resident) and skips the keys that hash elsewhere; the key array itself streams.
+    // (measured on B200, 10 M keys / 537 MB table: 1 pass 0.94 ms, 2 passes 0.79 ms, 4 passes 0.93 ms -- every
+    // pass re-reads the key array, so two halves is the sweet spot)
+    int log2_passes = cap * sizeof(Slot) > (256ull << 20) ? 1 : 0;
+    if (const char* e = getenv("DYD_DEDUP_PASSES_LOG2")) log2_passes = atoi(e);
+    const int pass_shift = log2u(cap) - log2_passes;
+    for (unsigned pass = 0; pass < (1u << log2_passes); ++pass) {
+        dedup_insert_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(
+            reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1, pass_shift, pass);
+        if (int rc = launch_check("dedup_insert_kernel")) return rc;
+    }
+    for (unsigned pass = 0; pass < (1u << log2_passes); ++pass) {
+        dedup_lookup_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(
+            reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1, pass_shift, pass, d_keep, d_rep);
+        if (int rc = launch_check("dedup_lookup_kernel")) return rc;
+    }
+    return 0;
 }
 
 }  // namespace dyd

@@ -1,5 +1,5 @@
 // Declarations shared by bbox_iou.cu (direct-load kernels, entry points) and bbox_tma.cu
-// (TMA-staged warp-specialised fused kernel).
+// (TMA-staged fused kernel with warp-private stages).
 #pragma once
 #include "bbox_core.cuh"
 
@@ -20,7 +20,7 @@ inline size_t crowd_list_bytes(int64_t n_img) {
 
 // Tiles of the fused kernel: a pre-pass packs consecutive images greedily into tiles of at most
 // TILE_LANES objects (one K1 lane each), TILE_MAX_IMAGES images and TILE_CAP_V vertices.  Packing
-// restarts every SEG_IMAGES images so that segments are independent (one pre-pass thread each, one
+// restarts every SEG_IMAGES images so that segments are independent (one pre-pass warp each, one
 // warp of the main kernel each); a segment's descriptors live at desc[seg * SEG_IMAGES ...].
 #ifndef DYD_SEG_IMAGES
 #define DYD_SEG_IMAGES 32
