@@ -3,14 +3,17 @@
 // Direct-load kernels: warps read the vertex stream with 128-bit non-allocating loads, a
 // G-lane group per polygon (32/G polygons per warp step).  The fused kernel keeps each image's
 // boxes in shared memory for the pair test, so boxes are written to HBM once and never
-// re-read.  Images with more than WARP_BOX_CAP objects go to a worklist and are finished by a
-// block-per-image kernel (shared-memory SoA tile, circular half-range pairing).
-// The TMA-staged, warp-specialised fused kernel lives in bbox_tma.cu; dyd_bbox_iou_fused
+// re-read.  The stand-alone K2 kernel packs consecutive images into 32-box tiles (one lane per
+// box, k2_tile.cuh).  Crowded images (more than 32 objects for K2, more than WARP_BOX_CAP for the
+// direct fused kernel) go to a worklist and are finished by a block-per-image kernel
+// (shared-memory SoA tile, circular half-range pairing).
+// The TMA-staged fused kernel lives in bbox_tma.cu; dyd_bbox_iou_fused
 // picks between the two (DYD_FUSED=direct|tma, default tma).
 #include <stdlib.h>
 #include <string.h>
 
 #include "kernels.cuh"
+#include "k2_tile.cuh"
 
 namespace dyd {
 
@@ -73,39 +76,77 @@ __device__ __forceinline__ void defer_image(void* ws, int64_t img) {
     crowd_ids(ws)[slot] = (int)img;
 }
 
-// ------------------------------------------------------------------------------- K2 (warp per image)
+// ------------------------------------------------------------------------------- K2 (warp per tile of images)
+// A warp takes 32 consecutive images, packs them greedily into tiles of at most 32 boxes and
+// K2_TM images (jump pointers, as in the fused kernel's pre-pass) and decides each tile with
+// k2_tile_any: one lane per box, so small images do not leave most of the warp idle.  An image
+// with more than 32 boxes goes to the block-per-image kernel.
+constexpr int K2_TM = 8;
+struct K2Warp {
+    K2Tile t;
+    long long off[33];                             // img_off slice of the warp's 32 images
+    unsigned char nxt[32], start[33];
+};
 __global__ void __launch_bounds__(CTA_THREADS)
-iou_warp_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
+iou_tile_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
                 int64_t n_img, int64_t min_boxes, double thr, uint8_t* __restrict__ high,
                 int32_t* __restrict__ count, void* ws) {
-    __shared__ __align__(16) double sbox[CTA_WARPS][WARP_BOX_CAP * 4];
-    __shared__ __align__(16) unsigned short lut[PAIR_LUT_N + 8];
-    load_pair_lut(lut, threadIdx.x, CTA_THREADS);
-    __syncthreads();
+    __shared__ __align__(16) K2Warp sw[CTA_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    K2Warp& s = sw[w];
     const bool zero_hits = 0.0 >= thr;
-    for (int64_t img = blockIdx.x * (int64_t)CTA_WARPS + w; img < n_img; img += (int64_t)gridDim.x * CTA_WARPS) {
-        const int64_t q0 = __ldg(img_off + img), q1 = __ldg(img_off + img + 1);
-        const int64_t n = q1 - q0;
-        if (n > WARP_BOX_CAP) {                      // crowded: the block kernel computes count and high
-            if (lane == 0) defer_image(ws, img);
-            continue;
+    const double2* pts2 = reinterpret_cast<const double2*>(pts);
+    const int64_t n_seg = (n_img + 31) / 32;
+    for (int64_t seg = blockIdx.x * (int64_t)CTA_WARPS + w; seg < n_seg; seg += (int64_t)gridDim.x * CTA_WARPS) {
+        const int64_t i_begin = seg * 32;
+        const int n_here = (int)min((int64_t)32, n_img - i_begin);
+        {
+            const int e = min(lane, n_here);
+            s.off[e] = __ldg(img_off + i_begin + e);
+            if (lane == 0) s.off[n_here] = __ldg(img_off + i_begin + n_here);
         }
-        const int n_eff = (int)valid_prefix(valid, q0, n, lane);
-        bool hit = false;
-        if (n_eff >= min_boxes && n_eff >= 2) {
-            const double2* src = reinterpret_cast<const double2*>(pts + 4 * q0);
-            __syncwarp();
-            for (int j = lane; j < n_eff; j += 32) {
-                double2 p1 = ldg_stream_f64x2(src + 2 * j), p2 = ldg_stream_f64x2(src + 2 * j + 1);
-                Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
-                double2* d = reinterpret_cast<double2*>(&sbox[w][4 * j]);
-                d[0] = make_double2(bx.x1, bx.y1); d[1] = make_double2(bx.x2, bx.y2);
+        __syncwarp();
+        if (lane < n_here) {                           // end of the maximal tile that starts at image `lane`
+            const long long q0 = s.off[lane];
+            int k = 1;
+            while (k < K2_TM && lane + k < n_here && s.off[lane + k + 1] - q0 <= 32) ++k;
+            s.nxt[lane] = (unsigned char)(lane + k);
+        }
+        __syncwarp();
+        int cnt = 0;
+        if (lane == 0) {
+            for (int pos = 0; pos < n_here; pos = s.nxt[pos]) s.start[cnt++] = (unsigned char)pos;
+            s.start[cnt] = (unsigned char)n_here;
+        }
+        cnt = __shfl_sync(FULL, cnt, 0);
+        __syncwarp();
+        for (int t = 0; t < cnt; ++t) {
+            const int a = s.start[t], b = s.start[t + 1], ni = b - a;
+            const int64_t q0 = s.off[a], np64 = s.off[b] - q0;
+            if (np64 > 32) {                           // a single crowded image
+                if (lane == 0) defer_image(ws, i_begin + a);
+                continue;
             }
-            __syncwarp();
-            hit = warp_any_pair(sbox[w], n_eff, thr, zero_hits, lut, lane);
+            const int np = (int)np64;
+            bool nan_box = false, bad = false;
+            if (lane < np) {
+                const double2 p1 = ldg_stream_f64x2(pts2 + 2 * (q0 + lane)), p2 = ldg_stream_f64x2(pts2 + 2 * (q0 + lane) + 1);
+                const Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
+                s.t.box_lo[lane] = make_double2(bx.x1, bx.y1); s.t.box_hi[lane] = make_double2(bx.x2, bx.y2);
+                nan_box = (bx.x1 != bx.x1) | (bx.y1 != bx.y1) | (bx.x2 != bx.x2) | (bx.y2 != bx.y2);
+                bad = valid != nullptr && valid[q0 + lane] == 0;
+            }
+            const unsigned inv = __ballot_sync(FULL, bad);
+            const bool exact_pre = __any_sync(FULL, nan_box);
+            int my_a = 0, my_n = 0, my_ne;
+            if (lane < ni) {
+                my_a = (int)(s.off[a + lane] - q0);
+                my_n = (int)(s.off[a + lane + 1] - s.off[a + lane]);
+            }
+            const unsigned hits = k2_tile_any<K2_TM>(s.t, inv, exact_pre, my_a, my_n, ni, np, min_boxes, thr, zero_hits, lane, my_ne);
+            if (lane < ni) { count[i_begin + a + lane] = my_ne; high[i_begin + a + lane] = (hits >> lane) & 1u; }
+            __syncwarp();                              // tile scratch is rewritten by the next tile
         }
-        if (lane == 0) { count[img] = n_eff; high[img] = hit ? 1 : 0; }
     }
 }
 
@@ -313,10 +354,10 @@ extern "C" int dyd_iou_filter(const int64_t* d_img_off, const double* d_pts, con
     DYD_REQUIRE(workspace_bytes >= dyd_iou_workspace_bytes(n_img), DYD_E_WORKSPACE, "workspace too small");
     cudaStream_t s = as_stream(stream);
     DYD_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(CrowdList), s));
-    const int64_t want = (n_img + CTA_WARPS - 1) / CTA_WARPS;
-    const unsigned grid = (unsigned)(want < NUM_SMS * 32 ? want : NUM_SMS * 32);
-    iou_warp_kernel<<<grid, CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, n_img, min_boxes, thr, d_high, d_count, d_workspace);
-    if (int rc = launch_check("iou_warp_kernel")) return rc;
+    const int64_t want = ((n_img + 31) / 32 + CTA_WARPS - 1) / CTA_WARPS;
+    const unsigned grid = (unsigned)(want < NUM_SMS * 16 ? want : NUM_SMS * 16);
+    iou_tile_kernel<<<grid, CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, n_img, min_boxes, thr, d_high, d_count, d_workspace);
+    if (int rc = launch_check("iou_tile_kernel")) return rc;
     return launch_crowd(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, d_workspace, s);
 }
 

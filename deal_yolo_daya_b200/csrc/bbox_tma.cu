@@ -24,6 +24,7 @@
 // (more than 32 objects); tiles whose offset slices would make a bulk copy run past the end of an
 // array read them with plain loads.
 #include "kernels.cuh"
+#include "k2_tile.cuh"
 
 namespace dyd {
 
@@ -36,7 +37,6 @@ constexpr int CAP_P = TILE_LANES;              // objects per tile = K1 lanes
 constexpr int TM = TILE_MAX_IMAGES;
 constexpr int TMA_THREADS = 32 * NW;
 constexpr int IMG_SLOTS = (TM + 3) & ~1;        // img_off slice: <= TM+1 entries + alignment shift, even count
-constexpr int QCAP = 64;                       // survivor queue entries per warp
 enum { MODE_FAST = 0, MODE_DIRECT = 1, MODE_DEFER = 2, MODE_END = 3 };
 static_assert(TM + 2 <= IMG_SLOTS && TM <= 8 && CAP_P == 32 && SEG_IMAGES <= 255, "slice sizes");
 
@@ -47,13 +47,10 @@ struct __align__(16) TileInfo {                // double-buffered: the next tile
 };
 struct __align__(16) Stage {
     double2 vert[CAP_V];
-    double2 box_lo[CAP_P], box_hi[CAP_P];      // (x1, y1) / (x2, y2) after extract_boxes' min/max; two arrays so
-                                               // that consecutive boxes are consecutive 16-byte bank groups
+    K2Tile k2;                                 // boxes of the tile + K2 scratch
     long long poly[CAP_P + 4];                 // poly_off slice starting at object (q0 & ~1)
     TileInfo info[2];
-    int lq[8];                                 // per image: first object (64 past the last image)
     unsigned char bvalid[CAP_P];
-    unsigned short queue[QCAP];                // pairs that passed the overlap pre-test: a | b << 6 | image << 12
     unsigned long long bar;
     unsigned long long pad;
 };
@@ -188,22 +185,6 @@ __device__ __forceinline__ Corner fold_sequential(LoadFn load, int V, CornerIdx&
     return c;
 }
 
-// Exact overlap pre-test of calculate_iou (processor.py:329-335): the pair can only reach the
-// threshold if both max(0, .) terms are positive.  Same selects and subtractions as iou_hits.
-__device__ __forceinline__ bool boxes_overlap(const Box& a, const Box& b) {
-    const double xi1 = pymax(a.x1, b.x1), yi1 = pymax(a.y1, b.y1);
-    const double xi2 = pymin(a.x2, b.x2), yi2 = pymin(a.y2, b.y2);
-    return __dsub_rn(xi2, xi1) > 0.0 && __dsub_rn(yi2, yi1) > 0.0;
-}
-__device__ __noinline__ bool iou_hits_cold(const Box& a, const Box& b, double thr, bool zero_hits) {
-    return iou_hits(a, b, thr, zero_hits);
-}
-template <typename StageT>
-__device__ __forceinline__ Box load_box(const StageT& st, int q) {
-    const double2 lo = st.box_lo[q], hi = st.box_hi[q];
-    return Box{lo.x, lo.y, hi.x, hi.y};
-}
-
 template <bool ARG>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off,
@@ -312,7 +293,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             if (mode != MODE_DEFER) {
                 nan_box |= (c.mnx != c.mnx) | (c.mny != c.mny) | (c.mxx != c.mxx) | (c.mxy != c.mxy);
                 const Box bx = box_from_points(c.mnx, c.mny, c.mxx, c.mxy);
-                st.box_lo[pl] = make_double2(bx.x1, bx.y1); st.box_hi[pl] = make_double2(bx.x2, bx.y2);
+                st.k2.box_lo[pl] = make_double2(bx.x1, bx.y1); st.k2.box_hi[pl] = make_double2(bx.x2, bx.y2);
                 st.bvalid[pl] = V > 0 ? 1 : 0;
             }
         }
@@ -329,92 +310,16 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
             }
             continue;
         }
-        // Lane b owns box b of the tile and meets the boxes of its own image at circular distance
-        // d = 1 .. n/2 (every unordered pair exactly once).  Pass 1 is an overlap pre-test: without NaN
-        // coordinates the two cross comparisons per axis are a superset of the exact test, which the
-        // survivors get anyway; a tile holding a NaN box uses the reference's selects in the reference's
-        // argument order (lower index first).  Pass 2 runs the full arithmetic on the survivors (~5 %).
         const bool exact_pre = __any_sync(FULL, nan_box);
         const unsigned inv = __ballot_sync(FULL, lane < np && st.bvalid[lane] == 0);   // bit p: object p is a null bbox
-        // lane j < ni also owns image j: its first object and its box count (prefix before the first null bbox)
-        int my_a = 64, my_ne = 0, my_act = 0;
+        int my_a = 0, my_n = 0, my_ne;
         if (lane < ni) {
             my_a = (int)(ti.img[ishift + lane] - q0);
-            const int n = (int)(ti.img[ishift + lane + 1] - ti.img[ishift + lane]);
-            const unsigned m = n >= 32 ? (inv >> my_a) : ((inv >> my_a) & ((1u << n) - 1u));
-            my_ne = m ? __ffs(m) - 1 : n;
-            if (my_ne >= min_boxes && my_ne >= 2) my_act = my_ne;
+            my_n = (int)(ti.img[ishift + lane + 1] - ti.img[ishift + lane]);
         }
-        if (lane < 8) st.lq[lane] = my_a;
-        __syncwarp();
-        int j = 0;                                 // image of box `lane`: the last one starting at or before it
-#pragma unroll
-        for (int t = 1; t < TM; ++t) j += lane >= st.lq[t] ? 1 : 0;
-        const int first = __shfl_sync(FULL, my_a, j), ne = __shfl_sync(FULL, my_act, j);
-        const int a = lane - first;
-        const int half = (lane < np && a < ne) ? ne >> 1 : 0;
-        const int maxhalf = __reduce_max_sync(FULL, half);
-        const Box mine = load_box(st, lane);       // lanes that own no box read stale data and never use it
-        unsigned sv = 0;                           // bit d: the pair at distance d passed the pre-test
-        for (int d = 1; d <= maxhalf; ++d) {
-            const bool on = d <= half && (2 * d != ne || a < d);      // even n: distance n/2 pairs appear twice
-            int pb = a + d;
-            pb = pb >= ne ? pb - ne : pb;
-            const int ib = on ? first + pb : lane;
-            const Box o = load_box(st, ib);
-            bool ov;
-            if (exact_pre) ov = ib > lane ? boxes_overlap(mine, o) : boxes_overlap(o, mine);
-            else ov = mine.x2 > o.x1 && o.x2 > mine.x1 && mine.y2 > o.y1 && o.y2 > mine.y1;
-            if (on && (zero_hits || ov)) sv |= 1u << d;
-        }
-        unsigned hits = 0;
-        if (__any_sync(FULL, sv != 0)) {
-            // Survivors sit unevenly in the lanes: spread them over a small queue so that the full
-            // arithmetic runs on dense warps.
-            const int cnt = __popc(sv);
-            int incl = cnt;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += y; }
-            const int total = __shfl_sync(FULL, incl, 31);
-            if (total <= QCAP) {
-                int pos = incl - cnt;
-                for (unsigned m = sv; m; m &= m - 1) {
-                    const int d = __ffs(m) - 1;
-                    int pb = a + d;
-                    pb = pb >= ne ? pb - ne : pb;
-                    const int ib = first + pb;
-                    st.queue[pos++] = (unsigned short)(min(lane, ib) | (max(lane, ib) << 6) | (j << 12));
-                }
-                __syncwarp();
-                for (int base = 0; base < total; base += 32) {
-                    bool hit = false; int jj = 0;
-                    if (base + lane < total) {
-                        const unsigned e = st.queue[base + lane];
-                        jj = e >> 12;
-                        hit = iou_hits(load_box(st, e & 63), load_box(st, (e >> 6) & 63), thr, zero_hits);
-                    }
-                    hits |= __reduce_or_sync(FULL, hit ? (1u << jj) : 0u);
-                }
-            } else {                               // crowded tile: every lane works through its own pairs
-                while (__any_sync(FULL, sv != 0)) {
-                    bool hit = false;
-                    if (sv) {
-                        const int d = __ffs(sv) - 1;
-                        sv &= sv - 1;
-                        int pb = a + d;
-                        pb = pb >= ne ? pb - ne : pb;
-                        const int ib = first + pb;
-                        const Box o = load_box(st, ib);
-                        // without NaN the arithmetic is symmetric in its arguments bit for bit
-                        hit = (exact_pre && ib < lane) ? iou_hits_cold(o, mine, thr, zero_hits) : iou_hits(mine, o, thr, zero_hits);
-                    }
-                    hits |= __reduce_or_sync(FULL, hit ? (1u << j) : 0u);
-                    if ((hits >> j) & 1u) sv = 0;  // any() is settled for this image
-                }
-            }
-        }
+        const unsigned hits = k2_tile_any<TM>(st.k2, inv, exact_pre, my_a, my_n, ni, np, min_boxes, thr, zero_hits, lane, my_ne);
         if (lane < ni) { count[i0 + lane] = my_ne; high[i0 + lane] = (hits >> lane) & 1u; }
-        __syncwarp();                              // st.lq / queue are rewritten by the next tile
+        __syncwarp();                              // st.k2 scratch is rewritten by the next tile
     }
 }
 
