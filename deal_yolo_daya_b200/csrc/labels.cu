@@ -19,19 +19,27 @@ label_lut_kernel(const int64_t* __restrict__ img_off, const int32_t* __restrict_
     const int64_t i1 = min(i0 + IMG_PER_CTA, n_img);
     const int64_t q0 = img_off[i0], q1 = img_off[i1];
     unsigned long long c_obj = 0, c_miss = 0, c_lab = 0, c_rlab = 0, c_robj = 0, c_rrow = 0;
-    // phase 1: coalesced sweep over the block's objects
-    for (int64_t q = q0 + threadIdx.x; q < q1; q += LB_THREADS) {
-        int32_t v = label_id[q];
+    auto remap = [&](int32_t v) {
         int32_t out = v;
         ++c_obj;
         if (v < 0 || v >= n_vocab) { ++c_miss; }
         else {
             c_lab += (unsigned)__ldg(lut_ntok + v);
-            int32_t nr = __ldg(lut_nrep + v);
+            const int32_t nr = __ldg(lut_nrep + v);
             if (nr > 0) { out = __ldg(lut_new + v); c_rlab += (unsigned)nr; ++c_robj; }
         }
-        new_id[q] = out;
+        return out;
+    };
+    // phase 1: coalesced sweep over the block's objects, four labels per thread and access where
+    // the arrays allow 128-bit accesses (the ragged ends of the block's range go one by one)
+    const bool vec = ((reinterpret_cast<uintptr_t>(label_id) | reinterpret_cast<uintptr_t>(new_id)) & 15) == 0;
+    const int64_t qa = vec ? min(q1, (q0 + 3) & ~(int64_t)3) : q1, qb = vec ? qa + ((q1 - qa) & ~(int64_t)3) : q1;
+    for (int64_t q = q0 + threadIdx.x; q < qa; q += LB_THREADS) new_id[q] = remap(label_id[q]);
+    for (int64_t q = qa + 4 * (int64_t)threadIdx.x; q < qb; q += 4 * LB_THREADS) {
+        const int4 v = *reinterpret_cast<const int4*>(label_id + q);
+        *reinterpret_cast<int4*>(new_id + q) = make_int4(remap(v.x), remap(v.y), remap(v.z), remap(v.w));
     }
+    for (int64_t q = qb + threadIdx.x; q < q1; q += LB_THREADS) new_id[q] = remap(label_id[q]);
     // phase 2: one thread per image decides row_replaced (labels are L1/L2 hot from phase 1)
     const int64_t i = i0 + threadIdx.x;
     if (i < i1) {
@@ -68,13 +76,19 @@ label_hist_kernel(const int32_t* __restrict__ label_id, int64_t n_box, int32_t n
     const bool priv = n_vocab <= HIST_SMEM;
     if (priv) for (int v = threadIdx.x; v < n_vocab; v += LB_THREADS) sh[v] = 0;
     __syncthreads();
-    const int64_t per = (n_box + gridDim.x - 1) / gridDim.x;
-    const int64_t a = blockIdx.x * per, b = min(a + per, n_box);
-    for (int64_t q = a + threadIdx.x; q < b; q += LB_THREADS) {
-        const int32_t v = label_id[q];
-        if (v < 0 || v >= n_vocab) continue;
+    auto add = [&](int32_t v) {
+        if (v < 0 || v >= n_vocab) return;
         if (priv) atomicAdd(&sh[v], 1u); else atomicAdd(&hist[v], 1ULL);
+    };
+    const int64_t per = (((n_box + gridDim.x - 1) / gridDim.x) + 3) & ~(int64_t)3;     // multiple of 4: slices stay aligned
+    const int64_t a = min(blockIdx.x * per, n_box), b = min(a + per, n_box);
+    const bool vec = (reinterpret_cast<uintptr_t>(label_id) & 15) == 0;
+    const int64_t bv = vec ? a + ((b - a) & ~(int64_t)3) : a;
+    for (int64_t q = a + 4 * (int64_t)threadIdx.x; q < bv; q += 4 * LB_THREADS) {
+        const int4 v = *reinterpret_cast<const int4*>(label_id + q);
+        add(v.x); add(v.y); add(v.z); add(v.w);
     }
+    for (int64_t q = bv + threadIdx.x; q < b; q += LB_THREADS) add(label_id[q]);
     __syncthreads();
     if (priv) for (int v = threadIdx.x; v < n_vocab; v += LB_THREADS) if (sh[v]) atomicAdd(&hist[v], (unsigned long long)sh[v]);
 }
@@ -201,22 +215,34 @@ split_assign_kernel(const int64_t* __restrict__ cat_off, int32_t n_cat, const in
 }
 
 // ------------------------------------------------------------------------------- YOLO normalisation
+// processor.py:1045-1052.  A block owns IMG_PER_CTA consecutive images = one contiguous object range:
+// the image offsets and sizes go to shared memory, then one thread per object streams its corner
+// points in and its (cx, cy, w, h) out with 128-bit accesses and finds its image by bisection.
 __global__ void __launch_bounds__(LB_THREADS)
 yolo_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
             const double* __restrict__ img_wh, int64_t n_img, double* __restrict__ out, uint8_t* __restrict__ ok) {
-    const int64_t i = blockIdx.x * (int64_t)LB_THREADS + threadIdx.x;
-    if (i >= n_img) return;
-    const double W = img_wh[2 * i], H = img_wh[2 * i + 1];
-    for (int64_t q = img_off[i]; q < img_off[i + 1]; ++q) {
-        const double p1x = pts[4 * q], p1y = pts[4 * q + 1], p2x = pts[4 * q + 2], p2y = pts[4 * q + 3];
-        const double x1 = pymin(p1x, p2x), x2 = pymax(p1x, p2x), y1 = pymin(p1y, p2y), y2 = pymax(p1y, p2y);
+    __shared__ long long soff[IMG_PER_CTA + 1];
+    __shared__ double2 swh[IMG_PER_CTA];
+    const int64_t i0 = blockIdx.x * (int64_t)IMG_PER_CTA;
+    const int n_here = (int)min((int64_t)IMG_PER_CTA, n_img - i0);
+    for (int k = threadIdx.x; k <= n_here; k += LB_THREADS) soff[k] = img_off[i0 + k];
+    for (int k = threadIdx.x; k < n_here; k += LB_THREADS) swh[k] = reinterpret_cast<const double2*>(img_wh)[i0 + k];
+    __syncthreads();
+    const int64_t q0 = soff[0], q1 = soff[n_here];
+    const double2* pts2 = reinterpret_cast<const double2*>(pts);
+    double2* out2 = reinterpret_cast<double2*>(out);
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += LB_THREADS) {
+        int lo = 0, hi = n_here;                   // last image whose first object is <= q (skips empty images)
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= q) lo = mid; else hi = mid; }
+        const double W = swh[lo].x, H = swh[lo].y;
+        const double2 p1 = ldg_stream_f64x2(pts2 + 2 * q), p2 = ldg_stream_f64x2(pts2 + 2 * q + 1);
+        const double x1 = pymin(p1.x, p2.x), x2 = pymax(p1.x, p2.x), y1 = pymin(p1.y, p2.y), y2 = pymax(p1.y, p2.y);
         const double bw = pymax(__dsub_rn(x2, x1), 0.0), bh = pymax(__dsub_rn(y2, y1), 0.0);
         const bool good = (valid == nullptr || valid[q]) && !(bw <= 0.0) && !(bh <= 0.0) && W != 0.0 && H != 0.0;
         ok[q] = good ? 1 : 0;
-        out[4 * q] = __ddiv_rn(__ddiv_rn(__dadd_rn(x1, x2), 2.0), W);
-        out[4 * q + 1] = __ddiv_rn(__ddiv_rn(__dadd_rn(y1, y2), 2.0), H);
-        out[4 * q + 2] = __ddiv_rn(bw, W);
-        out[4 * q + 3] = __ddiv_rn(bh, H);
+        stg_stream_f64x2(out2 + 2 * q, make_double2(__ddiv_rn(__ddiv_rn(__dadd_rn(x1, x2), 2.0), W),
+                                                    __ddiv_rn(__ddiv_rn(__dadd_rn(y1, y2), 2.0), H)));
+        stg_stream_f64x2(out2 + 2 * q + 1, make_double2(__ddiv_rn(bw, W), __ddiv_rn(bh, H)));
     }
 }
 
@@ -316,7 +342,9 @@ extern "C" int dyd_yolo_normalise(const int64_t* d_img_off, const double* d_pts,
     DYD_REQUIRE(n_img >= 0 && n_box >= 0, DYD_E_ARG, "negative count");
     if (n_img == 0 || n_box == 0) return 0;
     DYD_REQUIRE(d_img_off && d_pts && d_img_wh && d_cxcywh && d_ok, DYD_E_ARG, "null pointer");
-    const int64_t grid = (n_img + LB_THREADS - 1) / LB_THREADS;
+    DYD_REQUIRE(((uintptr_t)d_pts & 15) == 0 && ((uintptr_t)d_cxcywh & 15) == 0 && ((uintptr_t)d_img_wh & 15) == 0, DYD_E_ALIGN,
+                "pts / img_wh / cxcywh must be 16-byte aligned");
+    const int64_t grid = (n_img + IMG_PER_CTA - 1) / IMG_PER_CTA;
     yolo_kernel<<<(unsigned)grid, LB_THREADS, 0, as_stream(stream)>>>(d_img_off, d_pts, d_valid, d_img_wh, n_img, d_cxcywh, d_ok);
     return launch_check("yolo_kernel");
 }
