@@ -56,6 +56,11 @@ PROTOTYPES = {
     "dyd_egress_ptlist": (_int, [_p, _p, _p, _p, _p, _p, _p, _int]),
     "dyd_csv_write": (_int, [_p, _p, _p, _p, _i32, _i64, _p, _p, _int]),
     "dyd_py_float_repr": (_int, [_f64, C.c_char_p]),
+    "dyd_csv_open": (_int, [_p, _i64, _p, _p, _i32, _i32, _p]),
+    "dyd_csv_info": (_int, [_p, _p, _p, _p, _p, _p]),
+    "dyd_csv_measure": (_int, [_p, _i64, _p, _p, _p, _p, _i32]),
+    "dyd_csv_fill": (_int, [_p, _i32, _p, _p, _p, _p, _i32]),
+    "dyd_csv_close": (None, [_p]),
     "dyd_synth_counts": (_int, [_u64, _i64, _i64, _p, _i32, _p, _p]),
     "dyd_synth_nvert": (_int, [_u64, _i64, _i64, _p, _p, _p]),
     "dyd_synth_fill": (_int, [_u64, _i64, _i64, _p, _p, _p, _p, _p]),

@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libdyd.so"
-SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "synth.cu", "host_pipeline.cu", "ingest.cpp"]
+SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "synth.cu", "host_pipeline.cu", "ingest.cpp", "csv_read.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

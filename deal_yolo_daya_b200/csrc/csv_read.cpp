@@ -1,0 +1,388 @@
+// Native CSV ingest: the tokenizer behind `pd.read_csv(path, encoding="utf-8[-sig]")`
+// (processor.py:124-128, 181-182, 235, 379) for the text columns of the pipeline, multi-threaded.
+//
+// It restates the state machine of pandas' C tokenizer (pandas/_libs/src/parser/tokenizer.c,
+// tokenize_bytes) for the options the reference uses -- delimiter ',', quotechar '"', doublequote,
+// no escapechar / comment, skip_blank_lines, \n and \r\n terminators:
+//   * a quote opens a quoted field only as the first byte of a field; inside an unquoted field it is
+//     an ordinary byte; after the closing quote of a quoted field further bytes are appended ("ab"c -> abc)
+//   * "" inside a quoted field is one quote; terminators inside a quoted field are data
+//   * empty and whitespace-only (space / tab) lines are skipped; a UTF-8 BOM at offset 0 is skipped
+//   * cells equal to one of pandas' NA strings (passed in by the caller) are missing values
+// What it does NOT decide is handed back to pandas: header names (the caller parses the header record
+// with pandas), dtype inference of columns that are not certainly text (the caller re-parses those
+// columns with pandas from the cell texts this file extracts), and every input with a feature
+// outside the list above (bare \r terminators, NUL bytes, ragged rows, EOF inside a quoted field,
+// invalid UTF-8): those set FLAG_UNSUPPORTED and the caller runs pd.read_csv on the whole file.
+//
+// Parallel tokenisation: the input is cut at line feeds into one chunk per thread; a chunk is
+// scanned under both hypotheses for its first byte (outside / inside a quoted field) and the chunks
+// are stitched left to right, which fixes the true hypothesis of each.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/dyd.h"
+
+namespace {
+
+enum : int32_t { FLAG_UNSUPPORTED = 1, FLAG_EMPTY = 2 };
+
+template <typename F>
+void parallel_ranges(int64_t n, int n_threads, int64_t grain, F f) {
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n / grain));
+    if (n_threads <= 1) { f(0, n, 0); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        const int64_t a = t * per, b = std::min(n, a + per);
+        if (a < b) th.emplace_back([=] { f(a, b, t); });
+    }
+    for (auto& t : th) t.join();
+}
+
+// ---- phase A: line feeds that terminate a record -------------------------------------------------
+enum QState : uint8_t { FIELD_START, IN_FIELD, IN_QUOTED, QUOTE_IN_QUOTED };
+
+struct ChunkScan {
+    std::vector<int64_t> lf;     // positions of record-terminating '\n' inside the chunk
+    bool ends_in_quote = false;  // state after the chunk's last byte is inside a quoted field
+    bool bad = false;            // bare '\r' outside quotes or NUL byte
+};
+
+void scan_chunk(const uint8_t* d, int64_t begin, int64_t end, int64_t n, bool start_in_quote, ChunkScan& out) {
+    QState st = start_in_quote ? IN_QUOTED : FIELD_START;
+    int64_t i = begin;
+    while (i < end) {
+        if (st == IN_QUOTED) {
+            const void* q = memchr(d + i, '"', (size_t)(end - i));
+            if (memchr(d + i, 0, (size_t)((q ? (const uint8_t*)q : d + end) - (d + i)))) out.bad = true;
+            if (!q) { i = end; break; }
+            i = (const uint8_t*)q - d + 1;
+            st = QUOTE_IN_QUOTED;
+            continue;
+        }
+        const uint8_t c = d[i];
+        if (st == QUOTE_IN_QUOTED && c == '"') { st = IN_QUOTED; ++i; continue; }
+        switch (c) {
+            case ',': st = FIELD_START; break;
+            case '\n': out.lf.push_back(i); st = FIELD_START; break;
+            case '\r':
+                if (i + 1 >= n || d[i + 1] != '\n') out.bad = true;       // bare CR terminator: not restated here
+                st = IN_FIELD;                                              // the following '\n' ends the record
+                break;
+            case '"': st = (st == FIELD_START) ? IN_QUOTED : IN_FIELD; break;
+            case 0: out.bad = true; st = IN_FIELD; break;
+            default: st = IN_FIELD; break;
+        }
+        ++i;
+    }
+    out.ends_in_quote = (st == IN_QUOTED);
+}
+
+// ---- one record ---------------------------------------------------------------------------------
+// Walks the record that starts at `p` (state START_FIELD) and ends at `e` (exclusive: the position of
+// its terminating '\n', or the end of the data).  A '\r' directly before `e` belongs to the terminator.
+// F(field_index, ptr, len) receives raw pieces of a field; a field may arrive in several pieces
+// (around "" and around the closing quote).  G(field_index) closes a field.  Returns the field count,
+// or -1 when the data ends inside a quoted field.
+template <typename Piece, typename Close>
+inline int walk_record(const uint8_t* p, const uint8_t* e, Piece piece, Close close) {
+    if (e > p && e[-1] == '\r') --e;
+    int f = 0;
+    for (;;) {
+        // START_FIELD
+        if (p < e && *p == '"') {
+            ++p;
+            for (;;) {                                   // IN_QUOTED_FIELD
+                const uint8_t* q = (const uint8_t*)memchr(p, '"', (size_t)(e - p));
+                if (!q) return -1;
+                if (q > p) piece(f, p, (int64_t)(q - p));
+                p = q + 1;
+                if (p < e && *p == '"') { piece(f, p, 1); ++p; continue; }      // "" -> one quote
+                break;
+            }
+            // QUOTE_IN_QUOTED_FIELD followed by anything but a delimiter: the rest is an unquoted tail
+        }
+        const uint8_t* q = (const uint8_t*)memchr(p, ',', (size_t)(e - p));
+        const uint8_t* stop = q ? q : e;
+        if (stop > p) piece(f, p, (int64_t)(stop - p));
+        close(f);
+        ++f;
+        if (!q) return f;
+        p = q + 1;
+    }
+}
+
+inline bool is_blank(const uint8_t* p, const uint8_t* e) {
+    if (e > p && e[-1] == '\r') --e;
+    for (; p < e; ++p) if (*p != ' ' && *p != '\t') return false;
+    return true;
+}
+
+// strict UTF-8 (what CPython's decoder and Arrow accept): no overlongs, no surrogates, <= U+10FFFF
+inline bool utf8_ok(const uint8_t* s, int64_t n) {
+    int64_t i = 0;
+    while (i < n) {
+        if (i + 8 <= n) {                                 // ASCII fast path
+            uint64_t w;
+            memcpy(&w, s + i, 8);
+            if (!(w & 0x8080808080808080ULL)) { i += 8; continue; }
+        }
+        const uint8_t c = s[i];
+        if (c < 0x80) { ++i; continue; }
+        int len;
+        uint32_t cp;
+        if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; }
+        else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; }
+        else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; }
+        else return false;
+        if (i + len > n) return false;
+        for (int k = 1; k < len; ++k) {
+            if ((s[i + k] & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (s[i + k] & 0x3F);
+        }
+        if ((len == 2 && cp < 0x80) || (len == 3 && cp < 0x800) || (len == 4 && cp < 0x10000)) return false;
+        if (cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+        i += len;
+    }
+    return true;
+}
+
+// A cell pandas cannot turn into a number, a boolean or a missing value: its first byte cannot start
+// any of those literals.  (Conservative: anything else is "uncertain" and goes back to pandas.)
+inline bool certainly_text(const uint8_t* s, int64_t n) {
+    if (n == 0) return false;
+    const uint8_t c = s[0];
+    if (c >= 0x80 || c == '{' || c == '[') return true;
+    if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z')) {
+        switch (c | 0x20) { case 'i': case 'n': case 't': case 'f': case 'e': case 'j': return false; default: return true; }
+    }
+    return false;
+}
+
+struct Csv {
+    const uint8_t* d = nullptr;
+    int64_t n = 0;
+    std::vector<std::string> na;                 // pandas' NA strings
+    int64_t header_begin = 0, header_end = 0;    // header record, terminator excluded
+    std::vector<int64_t> row_begin, row_end;     // data records (non-blank lines after the header)
+    int32_t n_cols = 0, flags = 0;
+    // measure()
+    std::vector<std::vector<int64_t>> off;       // per column: n_rows + 1 offsets of the unescaped cell text
+    std::vector<std::vector<uint8_t>> isna;      // per column: 1 = missing
+
+    bool is_na(const uint8_t* s, int64_t len) const {
+        if (len == 0) return true;
+        if (len > 9) return false;
+        for (const auto& v : na) if ((int64_t)v.size() == len && memcmp(v.data(), s, (size_t)len) == 0) return true;
+        return false;
+    }
+};
+
+}  // namespace
+
+extern "C" int dyd_csv_open(const uint8_t* data, int64_t n, const uint8_t* na_bytes, const int64_t* na_off, int32_t n_na,
+                            int32_t threads, void** handle) {
+    if (!handle || n < 0 || (n > 0 && !data) || n_na < 0 || (n_na > 0 && (!na_bytes || !na_off))) return DYD_E_ARG;
+    Csv* c = new Csv();
+    c->d = data; c->n = n;
+    for (int32_t k = 0; k < n_na; ++k) c->na.emplace_back((const char*)na_bytes + na_off[k], (size_t)(na_off[k + 1] - na_off[k]));
+    *handle = c;
+    const uint8_t* d = data;
+    int64_t start = (n >= 3 && d[0] == 0xEF && d[1] == 0xBB && d[2] == 0xBF) ? 3 : 0;
+
+    // ---- phase A: chunk boundaries right after a '\n', two hypotheses per chunk, stitch
+    int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::min<int64_t>(T, std::max<int64_t>(1, (n - start) / (1 << 20)));
+    std::vector<int64_t> cut(T + 1, n);
+    cut[0] = start;
+    for (int t = 1; t < T; ++t) {
+        int64_t pos = start + (n - start) / T * t;
+        pos = std::max(pos, cut[t - 1]);
+        const void* q = pos < n ? memchr(d + pos, '\n', (size_t)(n - pos)) : nullptr;
+        cut[t] = q ? (const uint8_t*)q - d + 1 : n;
+    }
+    std::vector<ChunkScan> out_u(T), out_q(T);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                if (cut[t] >= cut[t + 1]) return;
+                scan_chunk(d, cut[t], cut[t + 1], n, false, out_u[t]);
+                if (t > 0) scan_chunk(d, cut[t], cut[t + 1], n, true, out_q[t]);
+            });
+        for (auto& t : th) t.join();
+    }
+    std::vector<int64_t> lf;
+    bool in_quote = false, bad = false;
+    for (int t = 0; t < T; ++t) {
+        if (cut[t] >= cut[t + 1]) continue;
+        const ChunkScan& s = in_quote ? out_q[t] : out_u[t];
+        lf.insert(lf.end(), s.lf.begin(), s.lf.end());
+        bad |= s.bad;
+        in_quote = s.ends_in_quote;
+    }
+    if (in_quote) bad = true;                                     // EOF inside a quoted field: pandas raises
+    if (bad) { c->flags |= FLAG_UNSUPPORTED; return 0; }
+
+    // ---- lines -> records: drop blank lines, first record is the header, count fields
+    const int64_t n_lines = (int64_t)lf.size() + ((lf.empty() ? start : lf.back() + 1) < n ? 1 : 0);
+    auto line_begin = [&](int64_t k) { return k == 0 ? start : lf[k - 1] + 1; };
+    auto line_end = [&](int64_t k) { return k < (int64_t)lf.size() ? lf[k] : n; };
+    std::vector<uint8_t> keep((size_t)n_lines);
+    std::vector<int32_t> nf((size_t)n_lines);
+    parallel_ranges(n_lines, threads, 4096, [&](int64_t a, int64_t b, int) {
+        for (int64_t k = a; k < b; ++k) {
+            const uint8_t *p = d + line_begin(k), *e = d + line_end(k);
+            keep[k] = !is_blank(p, e);
+            nf[k] = keep[k] ? walk_record(p, e, [](int, const uint8_t*, int64_t) {}, [](int) {}) : 0;
+        }
+    });
+    int64_t hdr = -1;
+    for (int64_t k = 0; k < n_lines; ++k) if (keep[k]) { hdr = k; break; }
+    if (hdr < 0) { c->flags |= FLAG_EMPTY | FLAG_UNSUPPORTED; return 0; }
+    c->header_begin = line_begin(hdr);
+    c->header_end = line_end(hdr);
+    if (c->header_end > c->header_begin && d[c->header_end - 1] == '\r') --c->header_end;
+    c->n_cols = nf[hdr];
+    c->row_begin.reserve((size_t)(n_lines - hdr));
+    c->row_end.reserve((size_t)(n_lines - hdr));
+    for (int64_t k = hdr + 1; k < n_lines; ++k) {
+        if (!keep[k]) continue;
+        if (nf[k] != c->n_cols) { c->flags |= FLAG_UNSUPPORTED; return 0; }     // ragged (or EOF in quotes): pandas decides
+        c->row_begin.push_back(line_begin(k));
+        c->row_end.push_back(line_end(k));
+    }
+    if (c->n_cols <= 0) c->flags |= FLAG_UNSUPPORTED;
+    return 0;
+}
+
+extern "C" int dyd_csv_info(void* handle, int64_t* n_rows, int32_t* n_cols, int64_t* header_begin, int64_t* header_end,
+                            int32_t* flags) {
+    if (!handle) return DYD_E_ARG;
+    const Csv* c = (const Csv*)handle;
+    if (n_rows) *n_rows = (int64_t)c->row_begin.size();
+    if (n_cols) *n_cols = c->n_cols;
+    if (header_begin) *header_begin = c->header_begin;
+    if (header_end) *header_end = c->header_end;
+    if (flags) *flags = c->flags;
+    return 0;
+}
+
+// Sizes every cell.  col_bytes[j] = unescaped bytes of column j, col_nulls[j] = missing cells,
+// col_text[j] = 1 iff every window of `window` consecutive rows holds a cell that is certainly text
+// (pandas infers dtypes per chunk of that many rows), col_utf8[j] = 1 iff all cells are valid UTF-8.
+extern "C" int dyd_csv_measure(void* handle, int64_t window, int64_t* col_bytes, int64_t* col_nulls, uint8_t* col_text,
+                               uint8_t* col_utf8, int32_t threads) {
+    if (!handle || window <= 0 || !col_bytes || !col_nulls || !col_text || !col_utf8) return DYD_E_ARG;
+    Csv* c = (Csv*)handle;
+    if (c->flags & FLAG_UNSUPPORTED) return DYD_E_ARG;
+    const int64_t nr = (int64_t)c->row_begin.size();
+    const int nc = c->n_cols;
+    c->off.assign(nc, std::vector<int64_t>((size_t)nr + 1, 0));
+    c->isna.assign(nc, std::vector<uint8_t>((size_t)nr, 0));
+    const int64_t n_win = std::max<int64_t>((nr + window - 1) / window, 1);
+    int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    // per thread: one flag per (column, window) and per column, merged after the join
+    std::vector<std::vector<uint8_t>> t_text((size_t)T), t_bad((size_t)T);
+    const uint8_t* d = c->d;
+    parallel_ranges(nr, T, 2048, [&](int64_t ra, int64_t rb, int t) {
+        auto& text = t_text[t];
+        auto& bad = t_bad[t];
+        text.assign((size_t)(nc * n_win), 0);
+        bad.assign((size_t)nc, 0);
+        std::string scratch;
+        for (int64_t r = ra; r < rb; ++r) {
+            const int64_t w = r / window;
+            int pieces = 0;
+            int64_t len = 0;
+            const uint8_t* first = nullptr;
+            walk_record(d + c->row_begin[r], d + c->row_end[r],
+                [&](int, const uint8_t* p, int64_t l) {
+                    if (pieces == 0) first = p;
+                    else { if (pieces == 1) scratch.assign((const char*)first, (size_t)len); scratch.append((const char*)p, (size_t)l); }
+                    ++pieces; len += l;
+                },
+                [&](int f) {
+                    const uint8_t* s = pieces <= 1 ? first : (const uint8_t*)scratch.data();
+                    c->off[f][r + 1] = len;
+                    if (c->is_na(s, len)) c->isna[f][r] = 1;
+                    else if (certainly_text(s, len)) text[(size_t)(f * n_win + w)] = 1;
+                    if (len && !utf8_ok(s, len)) bad[f] = 1;
+                    pieces = 0; len = 0; first = nullptr;
+                });
+        }
+    });
+    std::vector<std::vector<uint8_t>> win_text(nc, std::vector<uint8_t>((size_t)n_win, 0));
+    std::vector<uint8_t> bad_utf8((size_t)nc, 0);
+    for (int t = 0; t < T; ++t) {
+        if (t_text[t].empty()) continue;
+        for (int j = 0; j < nc; ++j) {
+            bad_utf8[j] |= t_bad[t][j];
+            for (int64_t w = 0; w < n_win; ++w) win_text[j][w] |= t_text[t][(size_t)(j * n_win + w)];
+        }
+    }
+    for (int j = 0; j < nc; ++j) {
+        int64_t acc = 0, nulls = 0;
+        auto& o = c->off[j];
+        for (int64_t r = 0; r < nr; ++r) { const int64_t l = o[r + 1]; o[r] = acc; acc += c->isna[j][r] ? 0 : l; nulls += c->isna[j][r]; }
+        o[nr] = acc;
+        col_bytes[j] = acc; col_nulls[j] = nulls;
+        uint8_t all = nr > 0;
+        for (int64_t w = 0; w < (nr + window - 1) / window; ++w) all &= win_text[j][w];
+        col_text[j] = all; col_utf8[j] = !bad_utf8[j];
+    }
+    return 0;
+}
+
+// Writes the selected columns: Arrow large_string buffers (offsets int64[n_rows+1], data, validity
+// bitmap (n_rows+7)/8 bytes, LSB first; may be NULL when the column has no missing cell).
+extern "C" int dyd_csv_fill(void* handle, int32_t n_sel, const int32_t* cols, int64_t* const* off_out, uint8_t* const* data_out,
+                            uint8_t* const* bitmap_out, int32_t threads) {
+    if (!handle || n_sel < 0 || (n_sel > 0 && (!cols || !off_out || !data_out || !bitmap_out))) return DYD_E_ARG;
+    Csv* c = (Csv*)handle;
+    if (c->off.empty() && c->n_cols > 0) return DYD_E_ARG;
+    const int64_t nr = (int64_t)c->row_begin.size();
+    std::vector<int> slot((size_t)c->n_cols, -1);
+    for (int k = 0; k < n_sel; ++k) {
+        if (cols[k] < 0 || cols[k] >= c->n_cols || !off_out[k] || !data_out[k]) return DYD_E_ARG;
+        slot[cols[k]] = k;
+        memcpy(off_out[k], c->off[cols[k]].data(), sizeof(int64_t) * (size_t)(nr + 1));
+    }
+    const uint8_t* d = c->d;
+    parallel_ranges(nr, threads, 2048, [&](int64_t a, int64_t b, int) {
+        for (int64_t r = a; r < b; ++r) {
+            int64_t pos = 0;
+            int cur = -1;
+            walk_record(d + c->row_begin[r], d + c->row_end[r],
+                [&](int f, const uint8_t* p, int64_t l) {
+                    const int k = slot[f];
+                    if (k < 0 || c->isna[f][r]) return;
+                    if (cur != f) { cur = f; pos = c->off[f][r]; }
+                    memcpy(data_out[k] + pos, p, (size_t)l);
+                    pos += l;
+                },
+                [](int) {});
+        }
+    });
+    for (int k = 0; k < n_sel; ++k) {
+        if (!bitmap_out[k]) continue;
+        const auto& na = c->isna[cols[k]];
+        uint8_t* bm = bitmap_out[k];
+        parallel_ranges((nr + 7) / 8, threads, 1 << 16, [&](int64_t a, int64_t b, int) {
+            for (int64_t i = a; i < b; ++i) {
+                uint8_t v = 0;
+                for (int bit = 0; bit < 8 && i * 8 + bit < nr; ++bit) v |= (uint8_t)((na[i * 8 + bit] ? 0 : 1) << bit);
+                bm[i] = v;
+            }
+        });
+    }
+    return 0;
+}
+
+extern "C" void dyd_csv_close(void* handle) { delete (Csv*)handle; }

@@ -199,3 +199,133 @@ def to_csv(df, path, encoding="utf-8-sig") -> None:
             f.write(b"\xef\xbb\xbf")
         f.write(head.getvalue().encode("utf-8"))
         f.write(body.tobytes() if body.size < (1 << 20) else memoryview(body))
+
+
+# ------------------------------------------------------------------------------------------------
+# CSV ingest: pd.read_csv(path, encoding="utf-8[-sig]") with the text columns tokenised natively
+# ------------------------------------------------------------------------------------------------
+_READ_STATS = {"native": 0, "pandas": 0, "delegated_columns": 0}
+_STR_PROBE = None
+
+
+def _pandas_infers_arrow_str() -> bool:
+    """True when this pandas gives text columns the pyarrow-backed ``str`` dtype (pandas >= 3): only
+    then can Arrow buffers become the column without creating one Python object per cell."""
+    global _STR_PROBE
+    if _STR_PROBE is None:
+        import io
+        import pandas as pd
+        try:
+            a = pd.read_csv(io.StringIO("a\nx\n"))["a"].array
+            _STR_PROBE = type(a).__name__ == "ArrowStringArray" and str(a.dtype) == "str" and \
+                str(a._pa_array.type) == "large_string"
+        except Exception:  # noqa: BLE001
+            _STR_PROBE = False
+    return _STR_PROBE
+
+
+def _buffer_lines(n_cols: int) -> int:
+    """Rows per dtype-inference chunk of pandas' low-memory C reader (parsers.pyx, TextReader.__cinit__)."""
+    heuristic = 2 ** 20 // max(n_cols, 1)
+    b = 1
+    while b * 2 < heuristic:
+        b *= 2
+    return b
+
+
+def _na_table():
+    from pandas._libs.parsers import STR_NA_VALUES
+    vals = sorted(v.encode("utf-8") for v in STR_NA_VALUES)
+    off = np.zeros(len(vals) + 1, np.int64)
+    off[1:] = np.cumsum([len(v) for v in vals])
+    return np.frombuffer(b"".join(vals) or b"\0", dtype=np.uint8), off, len(vals)
+
+
+def read_csv(path, encoding="utf-8", **kwargs):
+    """``pd.read_csv(path, encoding=encoding, **kwargs)`` -- same frame, text columns tokenised by
+    csrc/csv_read.cpp.  Anything the native reader does not cover (other encodings or keyword
+    arguments, an unusual dialect, ragged rows, pandas without the Arrow ``str`` dtype, small files)
+    is read by pandas itself."""
+    import io
+    import pandas as pd
+    enc = (encoding or "utf-8").lower().replace("_", "-")
+    extra = {k: v for k, v in kwargs.items() if not (k == "parse_dates" and v is False)}
+
+    def fallback():
+        _READ_STATS["pandas"] += 1
+        return pd.read_csv(path, encoding=encoding, **kwargs)
+
+    if not enabled() or extra or enc not in ("utf-8", "utf8", "utf-8-sig") or not isinstance(path, (str, os.PathLike)):
+        return fallback()
+    try:
+        size = os.path.getsize(path)
+    except OSError:
+        return fallback()
+    if size < int(os.environ.get("DYD_CSV_NATIVE_MIN_BYTES", str(1 << 20))) or not _pandas_infers_arrow_str():
+        return fallback()
+    import pyarrow as pa
+    lib = _lib.load()
+    data = np.fromfile(path, dtype=np.uint8)
+    na_bytes, na_off, n_na = _na_table()
+    h = C.c_void_p()
+    _lib.check(lib.dyd_csv_open(_p(data), data.size, _p(na_bytes), _p(na_off), n_na, _threads(), C.byref(h)), "dyd_csv_open")
+    try:
+        nr, nc, hb, he, fl = C.c_int64(), C.c_int32(), C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(lib.dyd_csv_info(h, C.byref(nr), C.byref(nc), C.byref(hb), C.byref(he), C.byref(fl)), "dyd_csv_info")
+        n_rows, n_cols = nr.value, nc.value
+        if fl.value & 1 or n_rows == 0:
+            return fallback()
+        try:                                   # header names: pandas' own rules (duplicates, unnamed, quoting)
+            names = list(pd.read_csv(io.BytesIO(data[hb.value:he.value].tobytes() + b"\n"), nrows=0, encoding="utf-8").columns)
+        except Exception:  # noqa: BLE001
+            return fallback()
+        if len(names) != n_cols:
+            return fallback()
+        window = _buffer_lines(n_cols)
+        col_bytes = np.zeros(n_cols, np.int64); col_nulls = np.zeros(n_cols, np.int64)
+        col_text = np.zeros(n_cols, np.uint8); col_utf8 = np.zeros(n_cols, np.uint8)
+        _lib.check(lib.dyd_csv_measure(h, window, _p(col_bytes), _p(col_nulls), _p(col_text), _p(col_utf8), _threads()),
+                   "dyd_csv_measure")
+        if not col_utf8.all():
+            return fallback()                  # pandas raises UnicodeDecodeError
+        uncertain = [j for j in range(n_cols) if not col_text[j]]
+        if uncertain and n_rows > window:
+            return fallback()                  # per-chunk inference of mixed columns: pandas' own business
+        sel = list(range(n_cols))              # every column's cell texts, one parallel pass
+        offs = [np.empty(n_rows + 1, np.int64) for _ in sel]
+        datas = [np.empty(max(int(col_bytes[j]), 1), np.uint8) for j in sel]
+        maps = [np.empty((n_rows + 7) // 8, np.uint8) if col_nulls[j] else None for j in sel]
+        cols = (C.c_int32 * len(sel))(*sel)
+        a_off = (C.c_void_p * len(sel))(*[o.ctypes.data for o in offs])
+        a_dat = (C.c_void_p * len(sel))(*[d.ctypes.data for d in datas])
+        a_map = (C.c_void_p * len(sel))(*[m.ctypes.data if m is not None else None for m in maps])
+        _lib.check(lib.dyd_csv_fill(h, len(sel), cols, a_off, a_dat, a_map, _threads()), "dyd_csv_fill")
+        columns = {}
+        str_dtype = pd.StringDtype(storage="pyarrow", na_value=np.nan)
+        from pandas.arrays import ArrowStringArray
+        import pyarrow.compute as pc
+        for j in sel:
+            bufs = [pa.py_buffer(maps[j]) if maps[j] is not None else None, pa.py_buffer(offs[j]), pa.py_buffer(datas[j])]
+            arr = pa.Array.from_buffers(pa.large_string(), n_rows, bufs, null_count=int(col_nulls[j]))
+            if col_text[j]:
+                columns[j] = ArrowStringArray(pa.chunked_array([arr]), dtype=str_dtype)
+                continue
+            # numbers, booleans, empty columns ...: pandas infers the dtype from the same tokens, handed over
+            # as a header-less one-column CSV with every cell quoted (a missing cell is an empty one)
+            ls = pa.large_string()
+            lines = pc.binary_join_element_wise(pa.scalar('"', ls), pc.replace_substring(pc.fill_null(arr, pa.scalar("", ls)), '"', '""'),
+                                                pa.scalar('"\n', ls), pa.scalar("", ls))
+            lo, hi = lines.offset, lines.offset + len(lines)
+            o = np.frombuffer(lines.buffers()[1], dtype=np.int64)
+            text = lines.buffers()[2].slice(int(o[lo]), int(o[hi] - o[lo])).to_pybytes()      # the cells' lines, back to back
+            one = pd.read_csv(io.BytesIO(text), header=None, encoding="utf-8", skip_blank_lines=False)
+            if one.shape != (n_rows, 1):
+                return fallback()
+            columns[j] = one.iloc[:, 0].array
+            _READ_STATS["delegated_columns"] += 1
+    finally:
+        lib.dyd_csv_close(h)
+    df = pd.DataFrame({i: columns[i] for i in range(n_cols)}, copy=False)
+    df.columns = names
+    _READ_STATS["native"] += 1
+    return df

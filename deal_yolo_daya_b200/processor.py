@@ -115,6 +115,15 @@ def _to_csv(df: pd.DataFrame, path, encoding) -> None:
     pandas writes the frames the native writer does not cover)."""
     from . import native
     native.to_csv(df, path, encoding)
+
+
+def _read_csv(path, **kwargs):
+    """pd.read_csv(path, **kwargs) with the text columns tokenised natively (csrc/csv_read.cpp); the
+    same frame, dtype for dtype (tests/test_native_csv_read.py)."""
+    from . import native
+    return native.read_csv(path, **kwargs)
+
+
 STATS = {"hostlane_objects": 0, "hostlane_rows": 0, "hash_collisions": 0, "native_rows": 0, "slow_rows": 0}    # observability, last call
 
 
@@ -173,7 +182,7 @@ def deduplicate_csv_by_source(
     if not csv_path.endswith(".csv"):
         raise ValueError(f"文件不是CSV格式：{csv_path}（请传入.csv后缀的文件）")
     try:
-        df = pd.read_csv(csv_path, encoding=encoding, parse_dates=False)
+        df = _read_csv(csv_path, encoding=encoding, parse_dates=False)
         if verbose:
             print(f"成功读取CSV文件：{os.path.basename(csv_path)}")
             print(f"读取后原始数据行数：{len(df)}")
@@ -235,8 +244,8 @@ def remove_duplicates_between_csv(
         if not p.endswith(".csv"):
             raise ValueError(f"文件不是CSV格式：{p}（请传入.csv后缀文件）")
     try:
-        df_main = pd.read_csv(main_csv, encoding=encoding, parse_dates=False)
-        df_ref = pd.read_csv(ref_csv, encoding=encoding, parse_dates=False)
+        df_main = _read_csv(main_csv, encoding=encoding, parse_dates=False)
+        df_ref = _read_csv(ref_csv, encoding=encoding, parse_dates=False)
         if verbose:
             print(f"读取主文件：{len(df_main)}行")
             print(f"读取参考文件：{len(df_ref)}行")
@@ -366,7 +375,7 @@ def process_csv_replace_ptlist(
         excluded_output_file: Optional[str] = "processed_excluded.csv"
 ):
     try:
-        df = pd.read_csv(input_csv_path, encoding="utf-8-sig")
+        df = _read_csv(input_csv_path, encoding="utf-8-sig")
         print(f"成功读取CSV，共 {len(df)} 行数据")
     except FileNotFoundError:
         print(f"错误：未找到文件 {input_csv_path}")
@@ -440,7 +449,7 @@ def filter_by_box_count_and_iou(
         iou_threshold: float = 0.98
 ):
     try:
-        df = pd.read_csv(input_csv_path, encoding="utf-8-sig")
+        df = _read_csv(input_csv_path, encoding="utf-8-sig")
     except Exception as e:
         print(f"读取失败：{e}")
         return
@@ -472,7 +481,7 @@ def replace_labels_by_mapping(
         unmatched_excel_path: Optional[str] = None,
         sample_size: int = 30,
 ):
-    df = pd.read_csv(input_csv_path, encoding="utf-8-sig")
+    df = _read_csv(input_csv_path, encoding="utf-8-sig")
     mapping_df = pd.read_excel(mapping_excel_path, sheet_name=sheet_name) if sheet_name else pd.read_excel(mapping_excel_path)
     label_map = mapping_from_frame(mapping_df, old_col, new_col)
     out, summary, diff_rows, unmatched = remap_df(df, label_map, json_columns)
@@ -527,7 +536,7 @@ def split_dataset_by_rules(
         raise FileNotFoundError(f"输入CSV不存在：{input_csv_path}")
     if not os.path.exists(rules_excel_path):
         raise FileNotFoundError(f"规则Excel不存在：{rules_excel_path}")
-    df = pd.read_csv(input_csv_path, encoding="utf-8-sig")
+    df = _read_csv(input_csv_path, encoding="utf-8-sig")
     rules_df = pd.read_excel(rules_excel_path, sheet_name=sheet_name) if sheet_name else pd.read_excel(rules_excel_path)
     l2c = rules_from_frame(rules_df, rule_mode, label_col, category_col)
     res = split_df(df, l2c, json_columns, train_ratio, val_ratio, test_ratio, random_seed)

@@ -227,6 +227,25 @@ int dyd_csv_write(const int32_t* kinds, const int64_t* const* offs, const uint8_
                   uint8_t* out, int n_threads);
 int dyd_py_float_repr(double v, char* out40);     /* CPython repr(float); used by the canonical-form check */
 
+/* ------------------------------------------------------- CSV ingest (§8f-2) ---
+ * The tokenizer behind pd.read_csv(path, encoding="utf-8[-sig]") (processor.py:124-128, 181-182, 235,
+ * 379, 424, 530, 678) for the text columns of the pipeline: pandas' C tokenizer state machine for the
+ * default dialect, multi-threaded, producing Arrow large_string buffers.  Header names, dtype inference
+ * of columns that are not certainly text, and every input outside the restated dialect (flags bit 0)
+ * stay with pandas (deal_yolo_daya_b200/native.py:read_csv).
+ * na_bytes/na_off: pandas' NA strings (pandas._libs.parsers.STR_NA_VALUES), packed.              */
+int dyd_csv_open(const uint8_t* data, int64_t n, const uint8_t* na_bytes, const int64_t* na_off, int32_t n_na,
+                 int32_t threads, void** handle);
+int dyd_csv_info(void* handle, int64_t* n_rows, int32_t* n_cols, int64_t* header_begin, int64_t* header_end, int32_t* flags);
+/* window = rows per dtype-inference chunk of pandas' low-memory reader.  Per column: unescaped bytes,
+ * missing cells, 1 iff every window holds a cell that is certainly text, 1 iff valid UTF-8.         */
+int dyd_csv_measure(void* handle, int64_t window, int64_t* col_bytes, int64_t* col_nulls, uint8_t* col_text,
+                    uint8_t* col_utf8, int32_t threads);
+/* Arrow buffers of the selected columns: offsets int64[n_rows+1], data, validity bitmap (may be NULL). */
+int dyd_csv_fill(void* handle, int32_t n_sel, const int32_t* cols, int64_t* const* off_out, uint8_t* const* data_out,
+                 uint8_t* const* bitmap_out, int32_t threads);
+void dyd_csv_close(void* handle);
+
 /* ------------------------------------------------ synthetic tables (§8d) ---
  * Device-side twin of deal_yolo_daya_b200/synth.py (bit-identical output).       */
 int dyd_synth_counts(uint64_t seed, int64_t first_img, int64_t n_img, const uint64_t* d_pois_thr,
