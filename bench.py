@@ -154,7 +154,7 @@ def csr_port_throughput(n_img: int):
 
 def dropin_files_throughput(n_rows: int, device: int):
     """images/s of the drop-in's own step functions on CSV files (dedup -> ptList->bbox -> IoU filter),
-    the same chain and file contract the reference arm runs; CSV I/O is pandas in both."""
+    the same chain and file contract the reference arm runs."""
     import contextlib
     import io
     import pandas as pd
