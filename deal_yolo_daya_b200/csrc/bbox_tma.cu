@@ -23,6 +23,8 @@
 // exceeds the stage is folded with direct loads (vertices) or handed to the block-per-image kernel
 // (more than 32 objects); tiles whose offset slices would make a bulk copy run past the end of an
 // array read them with plain loads.
+#include <cstddef>
+
 #include "kernels.cuh"
 #include "k2_tile.cuh"
 
@@ -207,47 +209,59 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
 
     // Lane 0 walks the descriptors of this warp's segments two tiles ahead of the tile being
     // processed: the load issued while one tile is filled is consumed a full tile later.
+    // The descriptors stay in registers as the two raw 16-byte words they were loaded as and are taken
+    // apart only when consumed: unpacking at load time would make the warp wait for the load it just issued.
     struct Cursor { int64_t seg; int j, cnt; };
+    struct Raw { ulonglong2 a, b; };               // a = (q0, v0), b = (i0 | nv << 32, np | ni << 16 | mode << 24 | cnt << 32)
+    static_assert(sizeof(TileDesc) == 32 && offsetof(TileDesc, i0) == 16 && offsetof(TileDesc, nv) == 20 && offsetof(TileDesc, np) == 24 &&
+                  offsetof(TileDesc, ni) == 26 && offsetof(TileDesc, mode) == 27 && offsetof(TileDesc, cnt) == 28, "TileDesc layout");
+    auto load_raw = [&](int64_t idx) {
+        const ulonglong2* q = reinterpret_cast<const ulonglong2*>(desc + idx);
+        return Raw{__ldg(q), __ldg(q + 1)};
+    };
+    auto cnt_of = [](const Raw& r) { return (int)((r.b.y >> 32) & 0xff); };
     Cursor c_nxt{(int64_t)blockIdx.x * NW + warp, 0, 0}, c_far{0, 0, 0};
-    TileDesc nxt{}, far{};
+    Raw nxt{}, far{};
     bool has_nxt = false, has_far = false;
     auto advance = [&](const Cursor& c) { return c.j + 1 < c.cnt ? Cursor{c.seg, c.j + 1, c.cnt} : Cursor{c.seg + stride, 0, 0}; };
     if (lane == 0) {
         has_nxt = c_nxt.seg < n_seg;
         if (has_nxt) {
-            nxt = desc[c_nxt.seg * SEG_IMAGES];
-            c_nxt.cnt = nxt.cnt;
+            nxt = load_raw(c_nxt.seg * SEG_IMAGES);
+            c_nxt.cnt = cnt_of(nxt);
             c_far = advance(c_nxt);
             has_far = c_far.seg < n_seg;
-            if (has_far) far = desc[c_far.seg * SEG_IMAGES + c_far.j];
+            if (has_far) far = load_raw(c_far.seg * SEG_IMAGES + c_far.j);
         }
     }
 
     // Stage fill, executed by lane 0 only: describe the next tile in `ti` and start its copies.
     auto fill = [&](TileInfo& ti) {
         if (!has_nxt) { ti.mode = MODE_END; return; }
-        const TileDesc d = nxt;
+        const Raw r = nxt;
         nxt = far; c_nxt = c_far; has_nxt = has_far;
         if (has_nxt) {
-            if (c_nxt.j == 0) c_nxt.cnt = nxt.cnt;
+            if (c_nxt.j == 0) c_nxt.cnt = cnt_of(nxt);
             c_far = advance(c_nxt);
             has_far = c_far.seg < n_seg;
-            if (has_far) far = desc[c_far.seg * SEG_IMAGES + c_far.j];
+            if (has_far) far = load_raw(c_far.seg * SEG_IMAGES + c_far.j);
         }
-        const int64_t i0 = d.i0;
-        const int ni = d.ni;
-        const int pshift = (int)(d.q0 & 1), ishift = (int)(i0 & 1);
-        ti.q0 = d.q0; ti.v0 = d.v0; ti.i0 = i0; ti.ni = ni; ti.pshift = pshift; ti.ishift = ishift; ti.np = d.np; ti.mode = d.mode;
-        if (d.mode == MODE_FAST) {
-            const uint32_t ne = (uint32_t)(pshift + d.np + 2) & ~1u;         // poly_off entries copied (even count)
+        const int64_t d_q0 = (int64_t)r.a.x, d_v0 = (int64_t)r.a.y;
+        const int64_t i0 = (int64_t)(int)(r.b.x & 0xffffffffu);
+        const int d_nv = (int)(r.b.x >> 32), d_np = (int)(short)(r.b.y & 0xffff);
+        const int ni = (int)((r.b.y >> 16) & 0xff), d_mode = (int)((r.b.y >> 24) & 0xff);
+        const int pshift = (int)(d_q0 & 1), ishift = (int)(i0 & 1);
+        ti.q0 = d_q0; ti.v0 = d_v0; ti.i0 = i0; ti.ni = ni; ti.pshift = pshift; ti.ishift = ishift; ti.np = d_np; ti.mode = d_mode;
+        if (d_mode == MODE_FAST) {
+            const uint32_t ne = (uint32_t)(pshift + d_np + 2) & ~1u;         // poly_off entries copied (even count)
             const uint32_t nie = (uint32_t)(ishift + ni + 2) & ~1u;          // img_off entries copied (even count)
-            mbar_arrive_expect_tx(&st.bar, 16u * (uint32_t)d.nv + 8u * ne + 8u * nie);
-            if (d.nv > 0) bulk_g2s(st.vert, xy2 + d.v0, 16u * (uint32_t)d.nv, &st.bar);
-            bulk_g2s(st.poly, poly_off + (d.q0 - pshift), 8u * ne, &st.bar);
+            mbar_arrive_expect_tx(&st.bar, 16u * (uint32_t)d_nv + 8u * ne + 8u * nie);
+            if (d_nv > 0) bulk_g2s(st.vert, xy2 + d_v0, 16u * (uint32_t)d_nv, &st.bar);
+            bulk_g2s(st.poly, poly_off + (d_q0 - pshift), 8u * ne, &st.bar);
             bulk_g2s(ti.img, img_off + (i0 - ishift), 8u * nie, &st.bar);
         } else {                                                              // offsets by plain loads
             for (int j = 0; j <= ni; ++j) ti.img[ishift + j] = __ldg(img_off + i0 + j);
-            const long long np = ti.img[ishift + ni] - d.q0;
+            const long long np = ti.img[ishift + ni] - d_q0;
             ti.np = (int)min(np, (long long)0x7fffffff);
         }
     };
