@@ -187,6 +187,59 @@ __device__ __forceinline__ Corner fold_sequential(LoadFn load, int V, CornerIdx&
     return c;
 }
 
+// The same fold over a polygon staged in shared memory, software-pipelined: the loads of the next
+// DYD_K1_PIPE vertices are in flight while the current ones are compared (a shared-memory round trip is
+// ~30 cycles, one group of compares ~50).  `base` may be read up to 3 * DYD_K1_PIPE entries past the
+// polygon's end: that is still inside the stage (the caller guarantees it) and the values are not used.
+#ifndef DYD_K1_PIPE
+#define DYD_K1_PIPE 4
+#endif
+template <bool ARG>
+__device__ __forceinline__ void fold_step(Corner& c, CornerIdx& ci, const double2 v, int k) {
+    if (ARG) {
+        if (v.x < c.mnx) { c.mnx = v.x; ci.mnx = k; }
+        if (v.x > c.mxx) { c.mxx = v.x; ci.mxx = k; }
+        if (v.y < c.mny) { c.mny = v.y; ci.mny = k; }
+        if (v.y > c.mxy) { c.mxy = v.y; ci.mxy = k; }
+    } else {
+        c.mnx = v.x < c.mnx ? v.x : c.mnx;
+        c.mxx = v.x > c.mxx ? v.x : c.mxx;
+        c.mny = v.y < c.mny ? v.y : c.mny;
+        c.mxy = v.y > c.mxy ? v.y : c.mxy;
+    }
+}
+template <bool ARG>
+__device__ __forceinline__ Corner fold_staged(const double2* base, int V, CornerIdx& ci) {
+    constexpr int P = DYD_K1_PIPE;
+    const double2 f = base[0];
+    Corner c{f.x, f.y, f.x, f.y};
+    ci = CornerIdx{0, 0, 0, 0};
+    double2 a[P], b[P];                            // two register buffers used alternately: no copies
+#pragma unroll
+    for (int u = 0; u < P; ++u) a[u] = base[1 + u];
+    int k = 1;
+    for (; k + 2 * P <= V; k += 2 * P) {
+#pragma unroll
+        for (int u = 0; u < P; ++u) b[u] = base[k + P + u];
+#pragma unroll
+        for (int u = 0; u < P; ++u) fold_step<ARG>(c, ci, a[u], k + u);
+#pragma unroll
+        for (int u = 0; u < P; ++u) a[u] = base[k + 2 * P + u];
+#pragma unroll
+        for (int u = 0; u < P; ++u) fold_step<ARG>(c, ci, b[u], k + P + u);
+    }
+    // fewer than 2 P vertices left; a[] holds base[k .. k+P-1]
+    if (k + P < V) {
+#pragma unroll
+        for (int u = 0; u < P; ++u) b[u] = base[k + P + u];
+    }
+#pragma unroll
+    for (int u = 0; u < P; ++u) if (k + u < V) fold_step<ARG>(c, ci, a[u], k + u);
+#pragma unroll
+    for (int u = 0; u < P - 1; ++u) if (k + P + u < V) fold_step<ARG>(c, ci, b[u], k + P + u);
+    return c;
+}
+
 template <bool ARG>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off,
@@ -291,7 +344,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
                 const long long a = st.poly[pshift + pl], b = st.poly[pshift + pl + 1];
                 V = (int)(b - a);
                 const double2* base = st.vert + (a - v0);
-                if (V > 0) c = fold_sequential<ARG>([&](int kk) { return base[kk]; }, V, ci);
+                if (V > 0) c = fold_staged<ARG>(base, V, ci);
             } else {
                 const int64_t a = __ldg(poly_off + p), b = __ldg(poly_off + p + 1);
                 const int64_t Vl = b - a;
