@@ -42,7 +42,18 @@ UNIT = "images/s"
 IMAGES_PER_GPU = 10_000_000
 SEED = 0
 MIN_BOXES, THR = 2, 0.7
-KERNELS_PER_STEP = 6       # tile_desc, fused_tma, iou_crowd, hash_strings, dedup_insert, dedup_lookup (+3 exchange kernels at N>1)
+
+
+def kernels_per_step(n_rows: int, world: int) -> int:
+    """tile_desc, fused_tma, iou_crowd, hash_strings + dedup insert / lookup (each runs once per half of
+    a hash table above 256 MB, csrc/hash_dedup.cu) + bucket / pack_reply / unpack at N > 1; checked
+    against the ncu launch list in profiles/."""
+    cap = 1024
+    while cap < 2 * n_rows:
+        cap *= 2
+    passes = 2 if cap * 16 > (256 << 20) else 1
+    return 4 + 2 * passes + (3 if world > 1 else 0)
+
 
 
 def peaks():
@@ -385,7 +396,7 @@ def main():
                    "parallelism": f"{world} rank(s), rows partitioned by image; dedup keys hash-partitioned by all-to-all" if world > 1 else "1 GPU",
                    "results": {"high_iou_images": n_high, "duplicate_rows_rank0": n_dup}},
         "clocks": clocks,
-        "gpu_launches": (KERNELS_PER_STEP + (3 if world > 1 else 0)) * args.steps,
+        "gpu_launches": kernels_per_step(n_img, world) * args.steps,
         "roofline": {"bound": "hbm", "kernel": "fused_tma_kernel (+ tile_desc pre-pass and crowd worklist kernel, timed together)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_kind, "algorithmic_bytes_per_launch": fused_bytes,
