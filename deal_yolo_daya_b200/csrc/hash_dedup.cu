@@ -26,8 +26,9 @@ struct TableHeader {                 // 64 bytes in front of the slots
 };
 
 static inline uint64_t table_capacity(int64_t n) {
-    uint64_t cap = 1024;
-    while (cap < (uint64_t)(n > 0 ? n : 0) * 2) cap <<= 1;
+    static const int x4 = [] { const char* e = getenv("DYD_TABLE_X4"); const int v = e ? atoi(e) : 0; return v >= 5 && v <= 64 ? v : 8; }();
+    uint64_t cap = 1024;                           // smallest power of two >= n * x4 / 4
+    while (cap * 4 < (uint64_t)(n > 0 ? n : 0) * (uint64_t)x4) cap <<= 1;
     return cap;
 }
 static inline int log2u(uint64_t v) { int k = 0; while ((1ULL << k) < v) ++k; return k; }
