@@ -56,6 +56,7 @@ PROTOTYPES = {
     "dyd_egress_ptlist": (_int, [_p, _p, _p, _p, _p, _p, _p, _int]),
     "dyd_csv_write": (_int, [_p, _p, _p, _p, _i32, _i64, _p, _p, _int]),
     "dyd_py_float_repr": (_int, [_f64, C.c_char_p]),
+    "dyd_yolo_format": (_int, [_p, _p, _p, _p, _i64, _p, _p, _int]),
     "dyd_csv_open": (_int, [_p, _i64, _p, _p, _i32, _i32, _p]),
     "dyd_csv_info": (_int, [_p, _p, _p, _p, _p, _p]),
     "dyd_csv_measure": (_int, [_p, _i64, _p, _p, _p, _p, _i32]),

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <charconv>
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -725,5 +726,51 @@ extern "C" int dyd_csv_write(const int32_t* kinds, const int64_t* const* offs, c
             *o++ = '\n';
         }
     });
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// YOLO label text (processor.py:1045-1052): per image, one line per kept box
+//     f"{cls} {cx:.6f} {cy:.6f} {bw:.6f} {bh:.6f}"      joined by "\n" (no trailing newline)
+// from the device-computed cx/cy/w/h (dyd_yolo_normalise).  "%.6f" of glibc and of CPython are both
+// the correctly rounded decimal expansion; nan / inf are spelled the CPython way.
+// ------------------------------------------------------------------------------------------------
+namespace {
+inline char* put_f6(char* o, double v) {
+    if (std::isnan(v)) { memcpy(o, "nan", 3); return o + 3; }
+    if (std::isinf(v)) { if (v < 0) *o++ = '-'; memcpy(o, "inf", 3); return o + 3; }
+    return o + snprintf(o, 330, "%.6f", v);
+}
+}  // namespace
+
+extern "C" int dyd_yolo_format(const int64_t* img_off, const int32_t* class_id, const double* cxcywh, const uint8_t* ok,
+                               int64_t n_img, int64_t* out_off, uint8_t* out, int n_threads) {
+    if (n_img < 0 || (n_img > 0 && (!img_off || !out_off)) ) return DYD_E_ARG;
+    if (n_img == 0) { if (out_off) out_off[0] = 0; return 0; }
+    if (img_off[n_img] > img_off[0] && (!class_id || !cxcywh || !ok)) return DYD_E_ARG;
+    auto image = [&](int64_t i, char* dst) -> int64_t {          // writes (dst != NULL) or measures one image
+        char line[4 * 340 + 32];
+        int64_t total = 0;
+        bool first = true;
+        for (int64_t q = img_off[i]; q < img_off[i + 1]; ++q) {
+            if (!ok[q]) continue;
+            char* o = line;
+            if (!first) *o++ = '\n';
+            first = false;
+            o += snprintf(o, 16, "%d", (int)class_id[q]);
+            for (int k = 0; k < 4; ++k) { *o++ = ' '; o = put_f6(o, cxcywh[4 * q + k]); }
+            const int64_t len = o - line;
+            if (dst) memcpy(dst + total, line, (size_t)len);
+            total += len;
+        }
+        return total;
+    };
+    if (!out) {
+        out_off[0] = 0;
+        parallel_rows(n_img, n_threads, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) out_off[i + 1] = image(i, nullptr); });
+        for (int64_t i = 0; i < n_img; ++i) out_off[i + 1] += out_off[i];
+        return 0;
+    }
+    parallel_rows(n_img, n_threads, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) image(i, (char*)out + out_off[i]); });
     return 0;
 }

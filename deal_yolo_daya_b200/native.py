@@ -201,6 +201,22 @@ def to_csv(df, path, encoding="utf-8-sig") -> None:
         f.write(body.tobytes() if body.size < (1 << 20) else memoryview(body))
 
 
+def yolo_label_texts(img_off, class_id, cxcywh, ok):
+    """Label-file texts of processor.py:1045-1052 for every image: (text uint8[], off int64[n_img+1]).
+    Inputs are host arrays: img_off int64[n_img+1], class_id int32[n_box], cxcywh float64[4*n_box]
+    (dyd_yolo_normalise's output), ok uint8[n_box]."""
+    img_off = np.ascontiguousarray(img_off, np.int64); class_id = np.ascontiguousarray(class_id, np.int32)
+    cxcywh = np.ascontiguousarray(cxcywh, np.float64).reshape(-1); ok = np.ascontiguousarray(ok, np.uint8)
+    n_img = len(img_off) - 1
+    lib = _lib.load()
+    off = np.empty(n_img + 1, np.int64)
+    a = (_p(img_off), _p(class_id), _p(cxcywh), _p(ok), n_img, _p(off))
+    _lib.check(lib.dyd_yolo_format(*a, None, _threads()), "dyd_yolo_format(size)")
+    out = np.empty(max(int(off[-1]), 1), np.uint8)
+    _lib.check(lib.dyd_yolo_format(*a, _p(out), _threads()), "dyd_yolo_format(write)")
+    return out[:int(off[-1])], off
+
+
 # ------------------------------------------------------------------------------------------------
 # CSV ingest: pd.read_csv(path, encoding="utf-8[-sig]") with the text columns tokenised natively
 # ------------------------------------------------------------------------------------------------

@@ -215,3 +215,28 @@ def image_ranges(vertex_prefix, world: int):
     for r in range(1, len(cuts)):
         cuts[r] = max(cuts[r], cuts[r - 1])
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def split_category_bases(local_counts, group=None):
+    """K6 across ranks: rows are sharded by image in rank order, so category c's expanded
+    rows of rank r start at  cat_off[c] + sum over ranks r' < r of counts[r'][c]  in the global,
+    category-grouped order the reference builds (processor.py:760-775 appends in row order).
+
+    local_counts int64[n_cat] = this rank's expanded rows per category (dyd_split_count's totals).
+    Returns (base int64[n_cat], cat_off int64[n_cat+1]): this rank's first global position per
+    category and the global category offsets.  One all_gather of n_cat integers; no data moves."""
+    import torch.distributed as dist
+    counts = local_counts.to(torch.int64).contiguous()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        all_counts = counts[None]
+    else:
+        bufs = [torch.empty_like(counts) for _ in range(world)]
+        dist.all_gather(bufs, counts, group=group)
+        all_counts = torch.stack(bufs)
+    totals = all_counts.sum(0)
+    cat_off = torch.zeros(len(counts) + 1, dtype=torch.int64, device=counts.device)
+    cat_off[1:] = torch.cumsum(totals, 0)
+    base = cat_off[:-1] + all_counts[:rank].sum(0)
+    return base, cat_off

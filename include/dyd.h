@@ -227,6 +227,12 @@ int dyd_csv_write(const int32_t* kinds, const int64_t* const* offs, const uint8_
                   uint8_t* out, int n_threads);
 int dyd_py_float_repr(double v, char* out40);     /* CPython repr(float); used by the canonical-form check */
 
+/* YOLO label text of processor.py:1045-1052 from dyd_yolo_normalise's output: per image the lines
+ * f"{cls} {cx:.6f} {cy:.6f} {bw:.6f} {bh:.6f}" of the boxes with ok != 0, joined by "\n" (host buffers).
+ * out == NULL: fill out_off[n_img+1]; else write the text at those offsets.                        */
+int dyd_yolo_format(const int64_t* img_off, const int32_t* class_id, const double* cxcywh, const uint8_t* ok,
+                    int64_t n_img, int64_t* out_off, uint8_t* out, int n_threads);
+
 /* ------------------------------------------------------- CSV ingest (§8f-2) ---
  * The tokenizer behind pd.read_csv(path, encoding="utf-8[-sig]") (processor.py:124-128, 181-182, 235,
  * 379, 424, 530, 678) for the text columns of the pipeline: pandas' C tokenizer state machine for the

@@ -56,3 +56,26 @@ def test_falls_back_to_pandas_for_uncovered_frames(tmp_path):
     for df in (one, mixed, dt, i32):
         x, y = both(df, tmp_path)
         assert x == y
+
+
+def test_yolo_label_text_matches_python_formatting():
+    """dyd_yolo_format vs the reference's f-string (processor.py:1052), incl. rounding ties, tiny,
+    huge, signed zero, nan and inf values."""
+    import numpy as np
+    from deal_yolo_daya_b200 import native
+    rng = np.random.RandomState(3)
+    special = [0.0, -0.0, 0.5e-6, 1.5e-6, 2.5e-6, 0.1234565, 0.1234575, 1e-7, 0.9999995, 0.99999949999, 1.0, 123456.7890125,
+               1e22, -3.25, float("nan"), float("inf"), float("-inf"), 5e-324, 0.0000005, 0.0000015]
+    vals = np.concatenate([np.array(special), rng.rand(4000), rng.rand(200) * 1e6, np.round(rng.rand(800), 6) + 5e-7])
+    vals = vals[: len(vals) // 4 * 4]
+    n_box = len(vals) // 4
+    counts = rng.randint(0, 5, size=n_box)
+    counts = counts[np.cumsum(counts) <= n_box]
+    img_off = np.zeros(len(counts) + 2, np.int64); img_off[1:-1] = np.cumsum(counts); img_off[-1] = n_box
+    cls = rng.randint(0, 90, size=n_box).astype(np.int32)
+    ok = (rng.rand(n_box) < 0.8).astype(np.uint8)
+    text, off = native.yolo_label_texts(img_off, cls, vals, ok)
+    for i in range(len(img_off) - 1):
+        want = "\n".join(f"{cls[q]} {vals[4*q]:.6f} {vals[4*q+1]:.6f} {vals[4*q+2]:.6f} {vals[4*q+3]:.6f}"
+                         for q in range(img_off[i], img_off[i + 1]) if ok[q])
+        assert bytes(text[off[i]:off[i + 1]]).decode() == want

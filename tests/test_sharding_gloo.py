@@ -108,3 +108,49 @@ def test_image_ranges_balance_vertices():
         assert all(rngs[i][1] == rngs[i + 1][0] for i in range(world - 1))
         loads = [vp[b] - vp[a] for a, b in rngs]
         assert max(loads) <= vp[-1] / world + 20000
+
+
+# ---- K6 across ranks: per-category base offsets from one all_gather ------------------------------
+def _split_table():
+    rng = np.random.RandomState(5)
+    n_img, n_vocab, n_cat = 300, 12, 4
+    counts = rng.randint(0, 7, size=n_img)
+    img_off = np.zeros(n_img + 1, np.int64); img_off[1:] = np.cumsum(counts)
+    label = rng.randint(-1, n_vocab, size=int(img_off[-1])).astype(np.int32)
+    cat_of_label = rng.randint(-1, n_cat, size=n_vocab).astype(np.int32)
+    return img_off, label, cat_of_label, n_cat
+
+
+def _split_worker(rank, world, port, out):
+    from oracle import oracle_np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        img_off, label, cat_of_label, n_cat = _split_table()
+        n_img = len(img_off) - 1
+        i0, i1 = sharding.image_ranges(img_off, world)[rank]
+        q0 = int(img_off[i0])
+        loc_off = img_off[i0:i1 + 1] - q0
+        e_img, e_box, e_cat, loc_cat_off = oracle_np.split_expand(loc_off, label[q0:int(img_off[i1])], cat_of_label, n_cat)
+        base, cat_off = sharding.split_category_bases(torch.from_numpy(np.diff(loc_cat_off)))
+        # global position of every local expanded row: base of its category + its rank inside the local group
+        pos = base.numpy()[e_cat] + (np.arange(len(e_cat)) - loc_cat_off[e_cat])
+        out[rank] = (pos, e_img + i0, e_box + q0, e_cat, cat_off.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_split_bases_reassemble_the_single_table_order(world):
+    from oracle import oracle_np
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_split_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    img_off, label, cat_of_label, n_cat = _split_table()
+    w_img, w_box, w_cat, w_off = oracle_np.split_expand(img_off, label, cat_of_label, n_cat)
+    g_img = np.full(len(w_img), -1, np.int64); g_box = g_img.copy(); g_cat = np.full(len(w_img), -1, np.int32)
+    for r in range(world):
+        pos, e_img, e_box, e_cat, cat_off = out[r]
+        assert np.array_equal(cat_off, w_off)
+        g_img[pos] = e_img; g_box[pos] = e_box; g_cat[pos] = e_cat
+    assert np.array_equal(g_img, w_img) and np.array_equal(g_box, w_box) and np.array_equal(g_cat, w_cat)
