@@ -45,15 +45,17 @@ MIN_BOXES, THR = 2, 0.7
 
 
 def kernels_per_step(n_rows: int, world: int) -> int:
-    """tile_desc, fused_tma, iou_crowd, hash_strings + dedup insert / lookup (each runs once per half of
-    a hash table above 256 MB, csrc/hash_dedup.cu) + bucket / pack_reply / unpack at N > 1; checked
-    against the ncu launch list in profiles/."""
+    """tile_desc, fused_tma, iou_crowd, hash_strings + dedup (csrc/hash_dedup.cu): partition + resolve +
+    the gated global-table fallback (fill, insert / lookup once per half of a table above 256 MB), which
+    is launched every time and exits at once unless a partition overflowed; at N > 1 bucket / pack_reply
+    / unpack and the padding sweep in addition.  Checked against the ncu launch list in profiles/."""
     cap = 1024
     while cap < 2 * n_rows:
         cap *= 2
     passes = 2 if cap * 16 > (256 << 20) else 1
-    return 4 + 2 * passes + (3 if world > 1 else 0)
-
+    if n_rows < (1 << 21):
+        return 4 + 2 * passes + (3 if world > 1 else 0)
+    return 4 + 2 + 1 + 2 * passes + (4 if world > 1 else 0)
 
 
 def peaks():

@@ -195,9 +195,15 @@ def test_hash_strings(cuda_device):
     assert_bits(host(got), want, "hash")
 
 
+@pytest.fixture
+def small_partitions(monkeypatch):
+    """The partitioned dedup path normally starts at 2 M rows; let 64 K-row inputs take it."""
+    monkeypatch.setenv("DYD_DEDUP_PARTITION_MIN", "65536")
+
+
 @pytest.mark.parametrize("keep", ["first", "last", False])
 @pytest.mark.parametrize("n,groups,pnull", [(1, 1, 0.0), (5000, 700, 0.02), (200000, 150000, 0.001), (3000, 3000, 1.0)])
-def test_dedup(cuda_device, keep, n, groups, pnull):
+def test_dedup(cuda_device, small_partitions, keep, n, groups, pnull):
     d = cuda_device
     rng = np.random.RandomState(n + groups)
     pool = rng.randint(0, 2 ** 63, size=groups, dtype=np.int64).astype(np.uint64)
@@ -224,6 +230,43 @@ def test_dedup_with_row_ids(cuda_device):
         first[k] = min(first.get(k, 1 << 62), i)
     want_rep = np.array([first[k] for k in keys], np.int64)
     assert_bits(host(rep), want_rep); assert_bits(host(keep), (want_rep == ids).astype(np.uint8))
+
+
+@pytest.mark.parametrize("keep", ["first", "last", False])
+def test_dedup_partition_overflow_falls_back_on_device(cuda_device, small_partitions, keep):
+    """Large inputs go through the partitioned path; one key repeated thousands of times overflows its
+    partition and the gated global-table kernels must produce the answer inside the same call."""
+    d = cuda_device
+    rng = np.random.RandomState(77)
+    n = 300000
+    keys = rng.randint(0, 2 ** 63, size=n, dtype=np.int64).astype(np.uint64)
+    hot = rng.choice(n, size=6000, replace=False)
+    keys[hot] = np.uint64(0x1234567890ABCDEF)
+    keys[rng.choice(n, size=20000)] = keys[rng.choice(n, size=20000)]
+    null = (rng.rand(n) < 0.003).astype(np.uint8)
+    want_keep, want_rep = oracle_c.dedup(keys, null, keep)
+    got_keep, got_rep = ops.dedup(dev(keys, d), dev(null, d), keep)
+    assert_bits(host(got_keep), want_keep, "keep"); assert_bits(host(got_rep), want_rep, "rep")
+
+
+@pytest.mark.parametrize("keep", ["first", "last", False])
+def test_dedup_with_row_ids_partitioned(cuda_device, small_partitions, keep):
+    d = cuda_device
+    rng = np.random.RandomState(41)
+    n = 150000
+    keys = rng.randint(0, 40000, size=n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    ids = rng.permutation(n).astype(np.int64) * 5 + (1 << 33)
+    ids[rng.choice(n, size=500, replace=False)] = -1                  # bucket padding
+    got_keep, got_rep = ops.dedup(dev(keys, d), None, keep, row_id=dev(ids, d))
+    live = ids >= 0
+    first, last, cnt = {}, {}, {}
+    for k, i in zip(keys[live], ids[live]):
+        first[k] = min(first.get(k, 1 << 62), i); last[k] = max(last.get(k, -1), i); cnt[k] = cnt.get(k, 0) + 1
+    want_rep = np.full(n, -1, np.int64); want_keep = np.zeros(n, np.uint8)
+    pick = last if keep == "last" else first
+    want_rep[live] = [pick[k] for k in keys[live]]
+    want_keep[live] = [cnt[k] == 1 for k in keys[live]] if keep is False else (want_rep[live] == ids[live])
+    assert_bits(host(got_rep), want_rep, "rep"); assert_bits(host(got_keep), want_keep, "keep")
 
 
 @pytest.mark.parametrize("n,nr", [(4000, 0), (4000, 900), (100000, 60000)])
@@ -337,7 +380,7 @@ def test_host_entry_points(cuda_device):
     assert_bits(keep, wk); assert_bits(rep, wr)
 
 
-def test_exchange_kernels_single_rank_roundtrip(cuda_device):
+def test_exchange_kernels_single_rank_roundtrip(cuda_device, small_partitions):
     """bucket -> (identity exchange) -> dedup on records -> reply -> unpack equals plain dedup;
     world=4 bucket layout is exercised by treating the 4 buckets as arriving from 4 ranks."""
     import ctypes as C
