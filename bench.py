@@ -395,7 +395,8 @@ def main():
         "config": {"workload": f"C2: {n_img} images / {n_poly} polygons / {n_vert} vertices per GPU, fused ptList->bbox + IoU flag "
                                f"(thr {THR}, min_boxes {MIN_BOXES}) + URL hash + first-occurrence dedup (5% dupes)",
                    "seed": SEED, "l2": f"inputs ({16 * n_vert / 1e9:.1f} GB of vertices per step) are far larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"{world} rank(s), rows partitioned by image; dedup keys hash-partitioned by all-to-all" if world > 1 else "1 GPU",
+                   "parallelism": (f"{world} rank(s), rows partitioned by image; dedup keys hash-partitioned to owner ranks, "
+                                   f"exchange transport: {xch.transport}") if world > 1 else "1 GPU",
                    "results": {"high_iou_images": n_high, "duplicate_rows_rank0": n_dup}},
         "clocks": clocks,
         "gpu_launches": kernels_per_step(n_img, world) * args.steps,

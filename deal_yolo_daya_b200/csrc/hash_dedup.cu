@@ -362,6 +362,44 @@ shard_bucket_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
     rec[0] = (long long)key; rec[1] = row_base + r;
 }
 
+// The same scatter straight into the owners' receive buffers over NVLink peer memory: rank `me`
+// owns region `me` of every peer's buffer, so the bucket step IS the all-to-all (no separate collective).
+__global__ void __launch_bounds__(HT_THREADS)
+shard_bucket_p2p_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t row_base,
+                        int64_t n, int world, int me, int64_t cap, long long* const* __restrict__ peer_records,
+                        unsigned long long* cursors, int* overflow) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    const bool live = r < n && (null == nullptr || null[r] == 0);
+    const unsigned long long key = live ? keys[r] : 0ULL;
+    const int own = live ? owner_of(key, world) : -1;
+    const unsigned peers = __match_any_sync(FULL, own);          // one atomic per (warp, owner)
+    if (!live) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&cursors[own], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const unsigned long long slot = base + __popc(peers & ((1u << lane) - 1u));
+    if (slot >= (unsigned long long)cap) { *overflow = 1; return; }
+    longlong2* rec = reinterpret_cast<longlong2*>(peer_records[own]) + ((int64_t)me * cap + (int64_t)slot);
+    *rec = make_longlong2((long long)key, row_base + r);           // one 16-byte store per record
+}
+
+// owner side, peer-memory form: the answer for a record that came from rank s goes straight into
+// region `me` of rank s's reply buffer
+__global__ void __launch_bounds__(HT_THREADS)
+shard_pack_reply_p2p_kernel(const long long* __restrict__ records, const uint8_t* __restrict__ keep,
+                            const int64_t* __restrict__ rep, int64_t m, int64_t cap, int me,
+                            long long* const* __restrict__ peer_reply) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= m) return;
+    const int src = (int)(r / cap);
+    const int64_t slot = r - (int64_t)src * cap;
+    const long long id = records[2 * r + 1];
+    longlong2* out = reinterpret_cast<longlong2*>(peer_reply[src]) + ((int64_t)me * cap + slot);
+    *out = make_longlong2(id, id < 0 ? -1 : (rep[r] | ((long long)(keep[r] ? 1 : 0) << 62)));
+}
+
 // owner side: (id, rep | keep << 62) per received record
 __global__ void __launch_bounds__(HT_THREADS)
 shard_pack_reply_kernel(const long long* __restrict__ records, const uint8_t* __restrict__ keep,
@@ -531,6 +569,31 @@ extern "C" int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, i
                                                           world, cap, reinterpret_cast<long long*>(d_records),
                                                           reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
     return launch_check("shard_bucket_kernel");
+}
+
+extern "C" int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
+                                    int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint64_t* d_cursors,
+                                    int32_t* d_overflow, void* stream) {
+    DYD_REQUIRE(n >= 0 && world >= 1 && cap >= 0 && my_rank >= 0 && my_rank < world, DYD_E_ARG, "bad arguments");
+    DYD_REQUIRE(d_peer_records && d_cursors && d_overflow && (n == 0 || d_keys), DYD_E_ARG, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    DYD_CUDA(cudaMemsetAsync(d_cursors, 0, sizeof(uint64_t) * world, s));
+    DYD_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
+    if (n == 0) return 0;
+    shard_bucket_p2p_kernel<<<grid_for(n), HT_THREADS, 0, s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
+                                                              world, my_rank, cap, reinterpret_cast<long long* const*>(d_peer_records),
+                                                              reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
+    return launch_check("shard_bucket_p2p_kernel");
+}
+
+extern "C" int dyd_shard_pack_reply_p2p(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m, int64_t cap,
+                                        int32_t my_rank, int64_t* const* d_peer_reply, void* stream) {
+    DYD_REQUIRE(m >= 0 && cap > 0 && my_rank >= 0 && m % cap == 0, DYD_E_ARG, "bad arguments");
+    if (m == 0) return 0;
+    DYD_REQUIRE(d_records && d_keep && d_rep && d_peer_reply, DYD_E_ARG, "null pointer");
+    shard_pack_reply_p2p_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_records), d_keep, d_rep,
+                                                                                    m, cap, my_rank, reinterpret_cast<long long* const*>(d_peer_reply));
+    return launch_check("shard_pack_reply_p2p_kernel");
 }
 
 extern "C" int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,

@@ -104,23 +104,42 @@ def dedup_global(keys: torch.Tensor, null: torch.Tensor | None, row_base: int, k
 class DedupExchange:
     """Sync-free sharded dedup (the production multi-GPU form of K4).
 
-    Fixed-capacity buckets make every all-to-all equal-sized, so nothing has to come back to the host
-    between kernels: bucket kernel -> NCCL all-to-all -> dedup on the received records -> reply
-    pack -> reverse all-to-all -> unpack.  The one host read is the overflow flag at the end; if a
-    bucket overflowed (heavily skewed keys) the exact-size path `dedup_global` redoes the step.
-    Buffers are allocated once and reused across calls.
+    Fixed-capacity buckets make every exchange equal-sized, so nothing has to come back to the host
+    between kernels.  Two transports:
+
+    * ``p2p`` (default when the ranks can map each other's memory): the receive and reply buffers live
+      in symmetric memory (torch.distributed._symmetric_memory, NVLink peer access).  The bucket kernel
+      stores every record straight into its owner's receive buffer and the owner's pack kernel stores
+      every answer straight into the origin's reply buffer -- the compute kernels are the all-to-all;
+      three device-side barriers per step order them (after the padding fill, after the scatter, after
+      the replies).
+    * ``nccl``: bucket kernel -> all_to_all_single -> dedup -> reply pack -> reverse all_to_all_single
+      -> unpack (DYD_EXCHANGE=nccl forces it).
+
+    The one host read is the overflow flag at the end; if a bucket overflowed (heavily skewed keys)
+    the exact-size path `dedup_global` redoes the step.  Buffers are allocated once and reused.
     """
 
-    def __init__(self, n_local: int, world: int, device, slack: float = 1.10):
+    def __init__(self, n_local: int, world: int, device, slack: float = 1.10, group=None):
+        import os
         from . import _lib
         self.lib = _lib.load()
         self.n, self.world, self.dev = n_local, world, device
         self.cap = int(n_local / world * slack) + 4096
         m = world * self.cap
-        self.send = torch.empty(2 * m, dtype=torch.int64, device=device)
-        self.recv = torch.empty(2 * m, dtype=torch.int64, device=device)
-        self.reply = torch.empty(2 * m, dtype=torch.int64, device=device)
-        self.back = torch.empty(2 * m, dtype=torch.int64, device=device)
+        self.transport = "nccl"
+        want = os.environ.get("DYD_EXCHANGE", "p2p")
+        if want == "p2p" and world > 1 and dist.is_initialized() and torch.device(device).type == "cuda":
+            try:
+                self._init_p2p(m, group)
+                self.transport = "p2p"
+            except Exception as e:  # noqa: BLE001 - no peer access / no symmetric memory in this build
+                self.p2p_error = repr(e)
+        if self.transport == "nccl":
+            self.send = torch.empty(2 * m, dtype=torch.int64, device=device)
+            self.recv = torch.empty(2 * m, dtype=torch.int64, device=device)
+            self.reply = torch.empty(2 * m, dtype=torch.int64, device=device)
+            self.back = torch.empty(2 * m, dtype=torch.int64, device=device)
         self.cursors = torch.empty(world, dtype=torch.uint64, device=device)
         self.overflow = torch.empty(1, dtype=torch.int32, device=device)
         self.keep_r = torch.empty(m, dtype=torch.uint8, device=device)
@@ -129,6 +148,19 @@ class DedupExchange:
         self.keep = torch.empty(n_local, dtype=torch.uint8, device=device)
         self.rep = torch.empty(n_local, dtype=torch.int64, device=device)
 
+    def _init_p2p(self, m: int, group):
+        import torch.distributed._symmetric_memory as symm
+        grp = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(grp)
+        self.recv = symm.empty(2 * m, dtype=torch.int64, device=self.dev)
+        self.back = symm.empty(2 * m, dtype=torch.int64, device=self.dev)
+        self.h_recv = symm.rendezvous(self.recv, grp)
+        self.h_back = symm.rendezvous(self.back, grp)
+        assert self.h_recv.world_size == self.world and self.h_recv.rank == self.rank
+        self.peer_recv = torch.tensor(list(self.h_recv.buffer_ptrs), dtype=torch.int64, device=self.dev)
+        self.peer_back = torch.tensor(list(self.h_back.buffer_ptrs), dtype=torch.int64, device=self.dev)
+        self.back.fill_(-1)
+
     def run(self, keys: torch.Tensor, row_base: int, keep="first", group=None, check_overflow=True):
         from . import _lib
         from .ops import KEEP_MODES, _ptr, _stream
@@ -136,14 +168,27 @@ class DedupExchange:
         assert keys.numel() == self.n and keys.dtype == torch.uint64
         with torch.cuda.device(dev):
             s = _stream(dev)
-            _lib.check(lib.dyd_shard_bucket(_ptr(keys), None, row_base, self.n, self.world, self.cap, _ptr(self.send),
-                                            _ptr(self.cursors), _ptr(self.overflow), s), "dyd_shard_bucket")
-            dist.all_to_all_single(self.recv, self.send, group=group)
+            if self.transport == "p2p":
+                self.recv.fill_(-1)                               # padding: key = EMPTY, id = -1
+                self.h_recv.barrier(channel=0)                    # every receive buffer is clean before anyone writes
+                _lib.check(lib.dyd_shard_bucket_p2p(_ptr(keys), None, row_base, self.n, self.world, self.rank, self.cap,
+                                                    _ptr(self.peer_recv), _ptr(self.cursors), _ptr(self.overflow), s),
+                           "dyd_shard_bucket_p2p")
+                self.h_recv.barrier(channel=1)                    # all records have landed
+            else:
+                _lib.check(lib.dyd_shard_bucket(_ptr(keys), None, row_base, self.n, self.world, self.cap, _ptr(self.send),
+                                                _ptr(self.cursors), _ptr(self.overflow), s), "dyd_shard_bucket")
+                dist.all_to_all_single(self.recv, self.send, group=group)
             _lib.check(lib.dyd_dedup_records(_ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_r), _ptr(self.rep_r),
                                              _ptr(self.ws), self.ws.numel(), s), "dyd_dedup_records")
-            _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, _ptr(self.reply), s),
-                       "dyd_shard_pack_reply")
-            dist.all_to_all_single(self.back, self.reply, group=group)
+            if self.transport == "p2p":
+                _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, self.cap, self.rank,
+                                                        _ptr(self.peer_back), s), "dyd_shard_pack_reply_p2p")
+                self.h_back.barrier(channel=0)                    # all answers have landed
+            else:
+                _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, _ptr(self.reply), s),
+                           "dyd_shard_pack_reply")
+                dist.all_to_all_single(self.back, self.reply, group=group)
             _lib.check(lib.dyd_shard_unpack(_ptr(self.back), m, row_base, self.n, _ptr(self.keep), _ptr(self.rep), s),
                        "dyd_shard_unpack")
         if check_overflow:
