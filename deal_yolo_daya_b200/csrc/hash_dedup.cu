@@ -364,22 +364,40 @@ shard_bucket_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
 
 // The same scatter straight into the owners' receive buffers over NVLink peer memory: rank `me`
 // owns region `me` of every peer's buffer, so the bucket step IS the all-to-all (no separate collective).
+constexpr int P2P_MAX_WORLD = 64;                 // block-aggregated cursors up to this many ranks
 __global__ void __launch_bounds__(HT_THREADS)
 shard_bucket_p2p_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t row_base,
                         int64_t n, int world, int me, int64_t cap, long long* const* __restrict__ peer_records,
                         unsigned long long* cursors, int* overflow) {
+    // One global atomic per (block, owner): the block counts its records per owner in shared memory,
+    // claims a contiguous run of slots in each owner's region and fills it -- runs of ~256 / world
+    // records (16 bytes each) keep the NVLink stores wide and the cursor traffic negligible.
+    __shared__ unsigned scnt[P2P_MAX_WORLD];
+    __shared__ unsigned long long sbase[P2P_MAX_WORLD];
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     const bool live = r < n && (null == nullptr || null[r] == 0);
     const unsigned long long key = live ? keys[r] : 0ULL;
     const int own = live ? owner_of(key, world) : -1;
-    const unsigned peers = __match_any_sync(FULL, own);          // one atomic per (warp, owner)
-    if (!live) return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(&cursors[own], (unsigned long long)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const unsigned long long slot = base + __popc(peers & ((1u << lane) - 1u));
+    unsigned long long slot;
+    if (world <= P2P_MAX_WORLD) {
+        if (threadIdx.x < world) scnt[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned rank_in_block = live ? atomicAdd(&scnt[own], 1u) : 0u;
+        __syncthreads();
+        if (threadIdx.x < world && scnt[threadIdx.x]) sbase[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long)scnt[threadIdx.x]);
+        __syncthreads();
+        if (!live) return;
+        slot = sbase[own] + rank_in_block;
+    } else {                                           // one atomic per (warp, owner)
+        const unsigned peers = __match_any_sync(FULL, own);
+        if (!live) return;
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&cursors[own], (unsigned long long)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        slot = base + __popc(peers & ((1u << lane) - 1u));
+    }
     if (slot >= (unsigned long long)cap) { *overflow = 1; return; }
     longlong2* rec = reinterpret_cast<longlong2*>(peer_records[own]) + ((int64_t)me * cap + (int64_t)slot);
     *rec = make_longlong2((long long)key, row_base + r);           // one 16-byte store per record
