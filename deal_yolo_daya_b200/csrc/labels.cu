@@ -199,6 +199,68 @@ split_fill_kernel(const int64_t* __restrict__ img_off, int64_t n_img, const int3
     }
 }
 
+// The same scatter with the rows of each category staged in shared memory and written out 32 at a
+// time: three fully coalesced stores per 32 rows instead of a few 8-byte pieces per step (the plain
+// kernel spends 70 % of its time in those partial-sector writes).  Up to ST_CAT categories.
+constexpr int ST_CAT = 16, ST_WARPS = 4, ST_RING = 64;
+__global__ void __launch_bounds__(32 * ST_WARPS)
+split_fill_staged_kernel(const int64_t* __restrict__ img_off, int64_t n_img, const int32_t* __restrict__ label_id,
+                         const int32_t* __restrict__ cat_of_label, int32_t n_vocab, int32_t n_cat,
+                         const int64_t* __restrict__ cat_off, const unsigned long long* __restrict__ chunk_excl, int64_t n_chunks,
+                         int64_t* __restrict__ exp_img, int64_t* __restrict__ exp_box, int32_t* __restrict__ exp_cat) {
+    __shared__ uint2 ring[ST_WARPS][ST_CAT][ST_RING];          // (image - i0, object - q0) of rows waiting to be written
+    __shared__ unsigned long long cur[ST_WARPS][ST_CAT];       // next global row of each category
+    __shared__ int fill[ST_WARPS][ST_CAT];
+    __shared__ int64_t soff[ST_WARPS][IMG_PER_WARP + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t chunk = blockIdx.x * (int64_t)ST_WARPS + w;
+    if (chunk >= n_chunks) return;
+    const int64_t i0 = chunk * IMG_PER_WARP, i1 = min(i0 + IMG_PER_WARP, n_img);
+    const int ni = (int)(i1 - i0);
+    if (lane < n_cat) { cur[w][lane] = (unsigned long long)cat_off[lane] + chunk_excl[chunk * n_cat + lane]; fill[w][lane] = 0; }
+    for (int k = lane; k <= ni; k += 32) soff[w][k] = img_off[i0 + k];
+    __syncwarp();
+    const int64_t q0 = soff[w][0], q1 = soff[w][ni];
+    auto flush = [&](int c, int count) {                       // writes ring[c][0 .. count) (count <= 32), keeps the rest
+        const unsigned long long dst = cur[w][c];
+        const int have = fill[w][c];
+        if (lane < count) {
+            const uint2 e = ring[w][c][lane];
+            exp_img[dst + lane] = i0 + e.x; exp_box[dst + lane] = q0 + e.y; exp_cat[dst + lane] = c;
+        }
+        uint2 keep = make_uint2(0, 0);
+        if (count + lane < have) keep = ring[w][c][count + lane];
+        __syncwarp();
+        if (count + lane < have) ring[w][c][lane] = keep;
+        if (lane == 0) { cur[w][c] = dst + count; fill[w][c] = have - count; }
+        __syncwarp();
+    };
+    for (int64_t base = q0; base < q1; base += 32) {
+        const int64_t q = base + lane;
+        int c = -1;
+        if (q < q1) { c = category_of(label_id, cat_of_label, n_vocab, q); if (c >= n_cat) c = -1; }
+        const unsigned peers = __match_any_sync(FULL, c);
+        bool leader = false;
+        if (c >= 0) {
+            const int rank = __popc(peers & ((1u << lane) - 1));
+            int lo = 0, hi = ni;                               // image of object q: largest k with soff[k] <= q
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (soff[w][mid] <= q) lo = mid; else hi = mid; }
+            ring[w][c][fill[w][c] + rank] = make_uint2((unsigned)lo, (unsigned)(q - q0));
+            leader = lane == __ffs(peers) - 1;
+        }
+        __syncwarp();
+        int now = 0;
+        if (leader) { now = fill[w][c] + __popc(peers); fill[w][c] = now; }
+        unsigned full = __reduce_or_sync(FULL, (leader && now >= 32) ? (1u << c) : 0u);
+        __syncwarp();
+        for (; full; full &= full - 1) flush(__ffs(full) - 1, 32);
+    }
+    for (int c = 0; c < n_cat; ++c) {
+        const int have = fill[w][c];                           // < 32 here
+        if (have > 0) flush(c, have);
+    }
+}
+
 __global__ void __launch_bounds__(LB_THREADS)
 split_assign_kernel(const int64_t* __restrict__ cat_off, int32_t n_cat, const int64_t* __restrict__ perm, int64_t n_exp,
                     const int64_t* __restrict__ n_train, const int64_t* __restrict__ n_val,
@@ -319,6 +381,13 @@ extern "C" int dyd_split_fill(const int64_t* d_img_off, int64_t n_img, const int
     DYD_REQUIRE(d_img_off && d_label_id && d_cat_of_label && d_cat_off && d_exp_img && d_exp_box && d_exp_cat && ws, DYD_E_ARG, "null pointer");
     DYD_REQUIRE(ws_bytes >= dyd_split_workspace_bytes(n_img, n_cat), DYD_E_WORKSPACE, "workspace too small");
     const int64_t nch = n_chunks_of(n_img);
+    if (n_cat <= ST_CAT) {
+        const int64_t grid = (nch + ST_WARPS - 1) / ST_WARPS;
+        split_fill_staged_kernel<<<(unsigned)grid, 32 * ST_WARPS, 0, as_stream(stream)>>>(
+            d_img_off, n_img, d_label_id, d_cat_of_label, n_vocab, n_cat, d_cat_off,
+            reinterpret_cast<const unsigned long long*>(ws), nch, d_exp_img, d_exp_box, d_exp_cat);
+        return launch_check("split_fill_staged_kernel");
+    }
     const int64_t grid = (nch + LB_THREADS / 32 - 1) / (LB_THREADS / 32);
     split_fill_kernel<<<(unsigned)grid, LB_THREADS, 0, as_stream(stream)>>>(
         d_img_off, n_img, d_label_id, d_cat_of_label, n_vocab, n_cat, d_cat_off,

@@ -325,7 +325,7 @@ def test_label_lut(cuda_device):
     assert np.array_equal(w2, want_new[:t.img_off[199]])
 
 
-@pytest.mark.parametrize("n_img,n_cat", [(1, 1), (300, 4), (70000, 20), (5000, 256)])
+@pytest.mark.parametrize("n_img,n_cat", [(1, 1), (300, 4), (70000, 20), (5000, 256), (60000, 16), (40000, 3), (9000, 1)])
 def test_split_expand_and_assign(cuda_device, n_img, n_cat):
     d = cuda_device
     t = synth.make_table(n_cat, 0, n_img)

@@ -117,7 +117,7 @@ def main():
                 print(f"    {pairs / (ms * 1e-3) / 1e9:.1f} G pairs/s over {nc} images, {nb} boxes", flush=True)
     if "labels" in which:
         import numpy as np
-        nv, ncat = 100, 20
+        nv, ncat = 100, 4                         # BASELINE config C5: 4 categories
         rng = np.random.RandomState(0)
         lut_new = torch.from_numpy(rng.randint(0, nv, nv).astype(np.int32)).to(dev)
         lut_ntok = torch.from_numpy(np.ones(nv, np.int32)).to(dev)
@@ -130,6 +130,10 @@ def main():
         ei, eb, ec, co = ops.split_expand(t.img_off, t.label_id, cat, ncat)
         ms, best = time_ms(lambda: ops.split_expand(t.img_off, t.label_id, cat, ncat), max(3, args.reps // 2))
         report("K6 split expand (2 passes)", ms, best, 8 * n_poly + 8 * n_img + 20 * ei.numel(), n_poly, "objects")
+        cat20 = torch.from_numpy(rng.randint(-1, 20, nv).astype(np.int32)).to(dev)
+        ei, eb, ec, co = ops.split_expand(t.img_off, t.label_id, cat20, 20)
+        ms, best = time_ms(lambda: ops.split_expand(t.img_off, t.label_id, cat20, 20), max(3, args.reps // 2))
+        report("K6 split expand, 20 categories", ms, best, 8 * n_poly + 8 * n_img + 20 * ei.numel(), n_poly, "objects")
         pts, valid, _ = ops.bbox_minmax(t.poly_off, t.xy)
         wh = torch.tensor([1920.0, 1080.0], dtype=torch.float64, device=dev).repeat(n_img)
         ms, best = time_ms(lambda: ops.yolo_normalise(t.img_off, pts, valid, wh), args.reps)
