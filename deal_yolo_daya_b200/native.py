@@ -28,11 +28,18 @@ def _threads() -> int:
 
 
 def pack_cells(cells):
-    """list / Series of str-or-missing -> (text uint8[], off int64[n+1], is_text uint8[n])."""
+    """list / Series of str-or-missing -> (text uint8[], off int64[n+1], is_text uint8[n]).
+    An Arrow-backed pandas column is taken as it is (no Python string is created)."""
     n = len(cells)
     try:
         import pyarrow as pa
-        arr = pa.array(cells, type=pa.large_string(), from_pandas=True)
+        pa_arr = getattr(getattr(cells, "array", None), "_pa_array", None)      # pandas str column (pyarrow storage)
+        if pa_arr is not None and str(pa_arr.type) in ("large_string", "string"):
+            arr = pa_arr.combine_chunks() if pa_arr.num_chunks != 1 else pa_arr.chunk(0)
+            if str(arr.type) != "large_string":
+                arr = arr.cast(pa.large_string())
+        else:
+            arr = pa.array(cells, type=pa.large_string(), from_pandas=True)
         if arr.offset != 0:
             arr = pa.concat_arrays([arr])
         bufs = arr.buffers()
@@ -67,6 +74,7 @@ class Ingest:
         self.n = len(cells)
         self.mode = mode
         self.text, self.off, self.is_text, self._keep = pack_cells(cells)
+        self.arrow_input = not isinstance(self._keep, list)          # valid UTF-8 by construction
         h = C.c_void_p()
         _lib.check(self.lib.dyd_ingest_cells(_p(self.text), _p(self.off), _p(self.is_text), self.n, mode, _threads(), C.byref(h)),
                    "dyd_ingest_cells")
@@ -122,6 +130,26 @@ class Ingest:
         lit = bytes(self.text[a:a + int(self.wh_len[i])]).decode("ascii")
         return int(lit) if k == K_INT else float(lit)
 
+    def int_columns(self):
+        """(width int64[n], height int64[n]) when every row has both as plain JSON integers that fit
+        int64 (what pandas turns a list of Python ints into), else None."""
+        if self.n == 0 or not (self.wh_kind == K_INT).all() or (self.wh_off < 0).any() or (self.wh_len > 18).any():
+            return None
+        start = np.repeat(self.off[:-1], 2) + self.wh_off
+        length = self.wh_len.astype(np.int64)
+        out = np.zeros(2 * self.n, np.int64)
+        for L in np.unique(length):                     # a handful of distinct literal lengths
+            idx = np.nonzero(length == L)[0]
+            chars = self.text[start[idx][:, None] + np.arange(L)[None, :]].astype(np.int64)
+            neg = chars[:, 0] == ord("-")
+            digits = chars - ord("0")
+            digits[neg, 0] = 0
+            if ((digits < 0) | (digits > 9)).any():
+                return None
+            val = digits @ (10 ** np.arange(L - 1, -1, -1, dtype=np.int64))
+            out[idx] = np.where(neg, -val, val)
+        return out[0::2].copy(), out[1::2].copy()
+
     # ---- step 5 ----
     def boxes(self):
         n = self.n
@@ -132,6 +160,21 @@ class Ingest:
         _lib.check(self.lib.dyd_ingest_export_boxes(self.h, _p(self.status), _p(self.img_off), _p(self.pts), _p(self.valid), _threads()),
                    "dyd_ingest_export_boxes")
         return self
+
+
+def arrow_strings(data: np.ndarray, off: np.ndarray):
+    """(bytes, offsets int64[n+1]) -> pandas string array over the same buffers (the dtype pd.read_csv
+    infers for text: ``str`` where pandas has it, else a list of Python strings)."""
+    import pandas as pd
+    n = len(off) - 1
+    if not _pandas_infers_arrow_str():
+        blob = data.tobytes()
+        return [blob[off[r]:off[r + 1]].decode("utf-8", "surrogatepass") for r in range(n)]
+    import pyarrow as pa
+    from pandas.arrays import ArrowStringArray
+    arr = pa.Array.from_buffers(pa.large_string(), n, [None, pa.py_buffer(np.ascontiguousarray(off, np.int64)),
+                                                        pa.py_buffer(data if data.size else np.zeros(1, np.uint8))], null_count=0)
+    return ArrowStringArray(pa.chunked_array([arr]), dtype=pd.StringDtype(storage="pyarrow", na_value=np.nan))
 
 
 # ------------------------------------------------------------------------------------------------

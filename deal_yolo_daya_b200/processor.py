@@ -288,10 +288,10 @@ def replace_ptlist_cells(cells):
     below (json.loads / json.dumps), which is also the whole path when DYD_NATIVE_INGEST=0.
     """
     from . import native
-    cells = list(cells)
-    if not native.enabled() or not cells:
-        return _replace_ptlist_cells_python(cells)
-    ing = native.Ingest(cells, 0).polygons()
+    if not native.enabled() or len(cells) == 0:
+        return _replace_ptlist_cells_python(list(cells))
+    ing = native.Ingest(cells, 0).polygons()              # an Arrow-backed column goes in without a copy
+    cell_at = cells.iloc.__getitem__ if hasattr(cells, "iloc") else cells.__getitem__
     try:
         STATS["native_rows"] = int((ing.status == native.ROW_OK).sum())
         if ing.n_obj:
@@ -299,6 +299,11 @@ def replace_ptlist_cells(cells):
         else:
             valid = np.zeros(0, np.uint8); arg = np.zeros(0, np.int32)
         out_bytes, out_off = ing.egress_ptlist(arg, valid)
+        if ing.n and ing.arrow_input and bool((ing.status == native.ROW_OK).all()):
+            wh = ing.int_columns()
+            if wh is not None:                         # every row native, width / height plain ints: no per-row Python
+                STATS["hostlane_objects"] = 0; STATS["slow_rows"] = 0
+                return native.arrow_strings(out_bytes, out_off), wh[0], wh[1]
         blob = out_bytes.tobytes()
         out, widths, heights = [None] * ing.n, [None] * ing.n, [None] * ing.n
         slow = []
@@ -313,7 +318,7 @@ def replace_ptlist_cells(cells):
         ing.close()
     STATS["hostlane_objects"] = 0
     if slow:                                   # CPython lane for the rows the native parser declined
-        o2, w2, h2 = _replace_ptlist_cells_python([cells[r] for r in slow])
+        o2, w2, h2 = _replace_ptlist_cells_python([cell_at(r) for r in slow])
         for i, r in enumerate(slow):
             out[r], widths[r], heights[r] = o2[i], w2[i], h2[i]
     STATS["slow_rows"] = len(slow)
@@ -361,8 +366,11 @@ def replace_ptlist_df(df: pd.DataFrame):
     """DataFrame core of step 4 -> (result frame with the reference's column subset, excluded frame)."""
     kept = df.dropna(subset=[COL_ANN]).copy()
     excluded = df[df[COL_ANN].isna()].copy()
-    new, w, h = replace_ptlist_cells(kept[COL_ANN].tolist())
-    kept[COL_NEW] = pd.Series(new, index=kept.index, dtype=object) if len(new) else pd.Series([], index=kept.index, dtype=object)
+    new, w, h = replace_ptlist_cells(kept[COL_ANN])
+    if isinstance(new, list):
+        kept[COL_NEW] = pd.Series(new, index=kept.index, dtype=object) if len(new) else pd.Series([], index=kept.index, dtype=object)
+    else:
+        kept[COL_NEW] = pd.Series(new, index=kept.index)
     kept["width"] = w
     kept["height"] = h
     cols = [c for c in (COL_SRC, COL_ANN, COL_NEW, "width", "height") if c in kept.columns]
@@ -405,10 +413,10 @@ def high_iou_mask(cells, min_boxes: int = 2, iou_threshold: float = 0.98) -> np.
     parsed by the CPython lane; rows holding values fp64 cannot carry are evaluated by _hostlane.
     """
     from . import native
-    cells = list(cells)
     n = len(cells)
     if n == 0:
         return np.zeros(0, bool)
+    cell_at = cells.iloc.__getitem__ if hasattr(cells, "iloc") else cells.__getitem__
     mask = np.zeros(n, bool)
     slow = list(range(n))
     if native.enabled():
@@ -424,7 +432,7 @@ def high_iou_mask(cells, min_boxes: int = 2, iou_threshold: float = 0.98) -> np.
     STATS["slow_rows"] = len(slow)
     STATS["hostlane_rows"] = 0
     if slow:
-        sub = [cells[r] for r in slow]
+        sub = [cell_at(r) for r in slow]
         batch = ingest.parse_boxes(sub)
         STATS["hostlane_rows"] = len(batch.host_rows)
         high, _ = KERNELS.iou(batch.img_off, batch.pts, batch.valid, min_boxes, iou_threshold)
@@ -437,7 +445,7 @@ def high_iou_mask(cells, min_boxes: int = 2, iou_threshold: float = 0.98) -> np.
 
 def filter_by_box_count_and_iou_df(df: pd.DataFrame, min_boxes: int = 2, iou_threshold: float = 0.98):
     """DataFrame core of step 5 -> (high_iou frame, other frame); all columns, original order."""
-    m = pd.Series(high_iou_mask(df[COL_NEW].tolist(), min_boxes, iou_threshold), index=df.index, dtype=bool)
+    m = pd.Series(high_iou_mask(df[COL_NEW], min_boxes, iou_threshold), index=df.index, dtype=bool)
     return df[m], df[~m]
 
 

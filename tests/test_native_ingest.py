@@ -29,12 +29,22 @@ def _oracle_facade(monkeypatch):
     monkeypatch.setattr(P, "KERNELS", OracleKernels())
 
 
+def _as_lists(res):
+    """(cells, widths, heights) as plain lists: the native lane answers with an Arrow string array and
+    int64 arrays when every row took it (what pandas makes of the lists anyway)."""
+    cells, w, h = res
+    un = lambda v: [x.item() if isinstance(x, np.generic) else x for x in v]   # noqa: E731
+    return [c if isinstance(c, str) else None for c in list(cells)], un(list(w)), un(list(h))
+
+
 def both_lanes_replace(cells, monkeypatch):
     monkeypatch.setenv("DYD_NATIVE_INGEST", "1")
-    a = P.replace_ptlist_cells(cells)
+    a = _as_lists(P.replace_ptlist_cells(cells))
     stats = dict(P.STATS)
+    a_series = _as_lists(P.replace_ptlist_cells(pd.Series(cells)))            # Arrow-backed column in
+    assert a_series[0] == a[0] and a_series[1] == a[1] and a_series[2] == a[2]
     monkeypatch.setenv("DYD_NATIVE_INGEST", "0")
-    b = P.replace_ptlist_cells(cells)
+    b = _as_lists(P.replace_ptlist_cells(cells))
     return a, b, stats
 
 
