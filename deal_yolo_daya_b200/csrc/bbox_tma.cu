@@ -10,13 +10,14 @@
 //   1. lane 0 issues cp.async.bulk (TMA, SASS UBLKCP) copies of the tile's vertex range, poly_off
 //      slice and img_off slice into the stage; completion is counted in bytes on the mbarrier;
 //   2. K1: one lane per polygon folds its vertices straight out of shared memory with the
-//      reference's own left fold (strict comparisons from the first vertex on), which is
-//      CPython's min()/max() bit for bit -- ties, signed zeros and NaN order need no special
-//      cases -- and writes the two corner points to HBM once and the normalised box to the stage;
+//      reference's own left fold (strict comparisons from the first vertex on, software-pipelined
+//      over two register buffers), which is CPython's min()/max() bit for bit -- ties, signed
+//      zeros and NaN order need no special cases -- and writes the two corner points to HBM once
+//      and the normalised box to the stage;
 //   3. the next tile's copies are issued (the vertex buffer is free again), so they land during
-//   4. K2: per-image box counts in parallel lanes, then all pairs of all images of the tile
-//      flattened over the lanes: exact overlap pre-test, survivors compacted into a small ring and
-//      evaluated densely with the full IoU arithmetic.
+//   4. K2 (k2_tile.cuh): per-image box counts in parallel lanes; then lane b owns box b and meets the
+//      boxes of its image at circular distances 1 .. n/2 (every pair once) with an overlap pre-test;
+//      survivors are spread over a small queue and evaluated densely with the full IoU arithmetic.
 //
 // Warps never synchronise with each other; while one waits for its copy the others compute, so the
 // copy engine keeps tens of KB per SM in flight without any register cost.  A single image that
