@@ -48,14 +48,14 @@ def kernels_per_step(n_rows: int, world: int) -> int:
     """tile_desc, fused_tma, iou_crowd, hash_strings + dedup (csrc/hash_dedup.cu): partition + resolve +
     the gated global-table fallback (fill, insert / lookup once per half of a table above 256 MB), which
     is launched every time and exits at once unless a partition overflowed; at N > 1 bucket / pack_reply
-    / unpack and the padding sweep in addition.  Checked against the ncu launch list in profiles/."""
+    / unpack in addition.  Checked against the ncu launch list in profiles/."""
     cap = 1024
     while cap < 2 * n_rows:
         cap *= 2
     passes = 2 if cap * 16 > (256 << 20) else 1
     if n_rows < (1 << 21):
         return 4 + 2 * passes + (3 if world > 1 else 0)
-    return 4 + 2 + 1 + 2 * passes + (4 if world > 1 else 0)
+    return 4 + 2 + 1 + 2 * passes + (3 if world > 1 else 0)
 
 
 def peaks():

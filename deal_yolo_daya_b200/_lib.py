@@ -34,7 +34,8 @@ PROTOTYPES = {
     "dyd_dedup_ids": (_int, [_p, _p, _i64, _int, _p, _p, _p, _sz, _p]),
     "dyd_shard_bucket": (_int, [_p, _p, _i64, _i64, _i32, _i64, _p, _p, _p, _p]),
     "dyd_dedup_records": (_int, [_p, _i64, _int, _p, _p, _p, _sz, _p]),
-    "dyd_shard_bucket_p2p": (_int, [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p]),
+    "dyd_shard_bucket_p2p": (_int, [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p]),
+    "dyd_shard_unpack_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _p]),
     "dyd_shard_pack_reply_p2p": (_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p]),
     "dyd_shard_pack_reply": (_int, [_p, _p, _p, _i64, _p, _p]),
     "dyd_shard_unpack": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),

@@ -198,7 +198,8 @@ template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
 dedup_partition_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
                        const int64_t* __restrict__ row_id, int64_t n, TableHeader* hdr, unsigned* cursors, int* overflow,
-                       ulonglong2* __restrict__ kv, unsigned* __restrict__ rr, int pshift, unsigned pcap) {
+                       ulonglong2* __restrict__ kv, unsigned* __restrict__ rr, int pshift, unsigned pcap,
+                       uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     const bool live = r < n;
     constexpr bool IDS = KIND != 0;
@@ -211,7 +212,7 @@ dedup_partition_kernel(const unsigned long long* __restrict__ keys, const uint8_
     }
     if (!live || isnull) return;
     const long long id = KIND == 2 ? (long long)keys[2 * r + 1] : (KIND == 1 ? row_id[r] : r);
-    if (IDS && id < 0) return;                          // padding of a fixed-capacity exchange bucket
+    if (IDS && id < 0) { rep[r] = -1; keep[r] = 0; return; }   // padding of a fixed-capacity exchange bucket: answered here
     const unsigned long long key = norm_key(KIND == 2 ? keys[2 * r] : keys[r]);
     const unsigned p = pshift >= 64 ? 0u : (unsigned)((key * GOLD) >> pshift);
     const unsigned slot = atomicAdd(&cursors[p], 1u);
@@ -277,7 +278,7 @@ dedup_resolve_kernel(const unsigned* __restrict__ cursors, const int* __restrict
     }
 }
 
-// rows the partitions never saw: null cells (KIND 0) and bucket padding (KIND 1 / 2)
+// rows the partitions never saw: null cells of KIND 0 (bucket padding of KIND 1 / 2 is answered by the partition kernel)
 template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
 dedup_leftover_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
@@ -368,7 +369,7 @@ constexpr int P2P_MAX_WORLD = 64;                 // block-aggregated cursors up
 __global__ void __launch_bounds__(HT_THREADS)
 shard_bucket_p2p_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t row_base,
                         int64_t n, int world, int me, int64_t cap, long long* const* __restrict__ peer_records,
-                        unsigned long long* cursors, int* overflow) {
+                        unsigned* __restrict__ sent_row, unsigned long long* cursors, int* overflow) {
     // One global atomic per (block, owner): the block counts its records per owner in shared memory,
     // claims a contiguous run of slots in each owner's region and fills it -- runs of ~256 / world
     // records (16 bytes each) keep the NVLink stores wide and the cursor traffic negligible.
@@ -401,6 +402,7 @@ shard_bucket_p2p_kernel(const unsigned long long* __restrict__ keys, const uint8
     if (slot >= (unsigned long long)cap) { *overflow = 1; return; }
     longlong2* rec = reinterpret_cast<longlong2*>(peer_records[own]) + ((int64_t)me * cap + (int64_t)slot);
     *rec = make_longlong2((long long)key, row_base + r);           // one 16-byte store per record
+    sent_row[(int64_t)own * cap + (int64_t)slot] = (unsigned)r;    // local: which row the answer in that slot belongs to
 }
 
 // owner side, peer-memory form: the answer for a record that came from rank s goes straight into
@@ -414,8 +416,25 @@ shard_pack_reply_p2p_kernel(const long long* __restrict__ records, const uint8_t
     const int src = (int)(r / cap);
     const int64_t slot = r - (int64_t)src * cap;
     const long long id = records[2 * r + 1];
-    longlong2* out = reinterpret_cast<longlong2*>(peer_reply[src]) + ((int64_t)me * cap + slot);
-    *out = make_longlong2(id, id < 0 ? -1 : (rep[r] | ((long long)(keep[r] ? 1 : 0) << 62)));
+    // 8 bytes per answer: the origin remembers which of its rows sits in (owner, slot)
+    peer_reply[src][(int64_t)me * cap + slot] = id < 0 ? -1 : (rep[r] | ((long long)(keep[r] ? 1 : 0) << 62));
+}
+
+// origin side, peer-memory form: slot s of owner o's region holds the answer for row sent_row[o][s]
+__global__ void __launch_bounds__(HT_THREADS)
+shard_unpack_p2p_kernel(const long long* __restrict__ reply, const unsigned* __restrict__ sent_row,
+                        const unsigned long long* __restrict__ cursors, int world, int64_t cap, int64_t n,
+                        uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
+    const int64_t t = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (t >= (int64_t)world * cap) return;
+    const int own = (int)(t / cap);
+    const int64_t slot = t - (int64_t)own * cap;
+    if ((unsigned long long)slot >= cursors[own]) return;           // never filled
+    const long long v = reply[t];
+    const int64_t row = sent_row[t];
+    if (v < 0 || row >= n) return;
+    keep[row] = (uint8_t)((v >> 62) & 1);
+    rep[row] = v & ((1LL << 62) - 1);
 }
 
 // owner side: (id, rep | keep << 62) per received record
@@ -523,7 +542,8 @@ static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64
     DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
     DYD_CUDA(cudaMemsetAsync(cursors, 0, L.kv - L.cursors, s));                       // cursors + overflow flag
     const int pshift = 64 - L.log2_np;
-    dedup_partition_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(k64, d_null, d_row_id, n, hdr, cursors, overflow, kv, rr, pshift, L.pcap);
+    dedup_partition_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(k64, d_null, d_row_id, n, hdr, cursors, overflow, kv, rr, pshift, L.pcap,
+                                                                     d_keep, d_rep);
     if (int rc = launch_check("dedup_partition_kernel")) return rc;
     {
         const unsigned np = 1u << L.log2_np;
@@ -533,7 +553,7 @@ static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64
         else dedup_resolve_kernel<KIND, 2, R32><<<np, PT_THREADS, 0, s>>>(cursors, overflow, kv, rr, pshift, L.pcap, d_keep, d_rep);
         if (int rc = launch_check("dedup_resolve_kernel")) return rc;
     }
-    if (KIND != 0 || d_null != nullptr) {
+    if (KIND == 0 && d_null != nullptr) {               // null cells: their answer needs the finished null statistics
         dedup_leftover_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(k64, d_null, d_row_id, n, keep_mode, hdr, overflow, d_keep, d_rep);
         if (int rc = launch_check("dedup_leftover_kernel")) return rc;
     }
@@ -590,17 +610,17 @@ extern "C" int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, i
 }
 
 extern "C" int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
-                                    int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint64_t* d_cursors,
-                                    int32_t* d_overflow, void* stream) {
-    DYD_REQUIRE(n >= 0 && world >= 1 && cap >= 0 && my_rank >= 0 && my_rank < world, DYD_E_ARG, "bad arguments");
-    DYD_REQUIRE(d_peer_records && d_cursors && d_overflow && (n == 0 || d_keys), DYD_E_ARG, "null pointer");
+                                    int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
+                                    uint64_t* d_cursors, int32_t* d_overflow, void* stream) {
+    DYD_REQUIRE(n >= 0 && n < (1LL << 32) && world >= 1 && cap >= 0 && my_rank >= 0 && my_rank < world, DYD_E_ARG, "bad arguments");
+    DYD_REQUIRE(d_peer_records && d_sent_row && d_cursors && d_overflow && (n == 0 || d_keys), DYD_E_ARG, "null pointer");
     cudaStream_t s = as_stream(stream);
     DYD_CUDA(cudaMemsetAsync(d_cursors, 0, sizeof(uint64_t) * world, s));
     DYD_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
     if (n == 0) return 0;
     shard_bucket_p2p_kernel<<<grid_for(n), HT_THREADS, 0, s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
                                                               world, my_rank, cap, reinterpret_cast<long long* const*>(d_peer_records),
-                                                              reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
+                                                              d_sent_row, reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
     return launch_check("shard_bucket_p2p_kernel");
 }
 
@@ -612,6 +632,16 @@ extern "C" int dyd_shard_pack_reply_p2p(const int64_t* d_records, const uint8_t*
     shard_pack_reply_p2p_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_records), d_keep, d_rep,
                                                                                     m, cap, my_rank, reinterpret_cast<long long* const*>(d_peer_reply));
     return launch_check("shard_pack_reply_p2p_kernel");
+}
+
+extern "C" int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
+                                    int64_t cap, int64_t n, uint8_t* d_keep, int64_t* d_rep, void* stream) {
+    DYD_REQUIRE(world >= 1 && cap >= 0 && n >= 0, DYD_E_ARG, "bad arguments");
+    if (cap == 0 || n == 0) return 0;
+    DYD_REQUIRE(d_reply && d_sent_row && d_cursors && d_keep && d_rep, DYD_E_ARG, "null pointer");
+    shard_unpack_p2p_kernel<<<grid_for((int64_t)world * cap), HT_THREADS, 0, as_stream(stream)>>>(
+        reinterpret_cast<const long long*>(d_reply), d_sent_row, reinterpret_cast<const unsigned long long*>(d_cursors), world, cap, n, d_keep, d_rep);
+    return launch_check("shard_unpack_p2p_kernel");
 }
 
 extern "C" int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,

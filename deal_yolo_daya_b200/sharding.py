@@ -152,8 +152,9 @@ class DedupExchange:
         import torch.distributed._symmetric_memory as symm
         grp = group if group is not None else dist.group.WORLD
         self.rank = dist.get_rank(grp)
-        self.recv = symm.empty(2 * m, dtype=torch.int64, device=self.dev)
-        self.back = symm.empty(2 * m, dtype=torch.int64, device=self.dev)
+        self.recv = symm.empty(2 * m, dtype=torch.int64, device=self.dev)      # (key, id) records, region per sender
+        self.back = symm.empty(m, dtype=torch.int64, device=self.dev)          # 8-byte answers, region per owner
+        self.sent_row = torch.empty(m, dtype=torch.int32, device=self.dev)     # which local row went into (owner, slot)
         self.h_recv = symm.rendezvous(self.recv, grp)
         self.h_back = symm.rendezvous(self.back, grp)
         assert self.h_recv.world_size == self.world and self.h_recv.rank == self.rank
@@ -172,8 +173,8 @@ class DedupExchange:
                 self.recv.fill_(-1)                               # padding: key = EMPTY, id = -1
                 self.h_recv.barrier(channel=0)                    # every receive buffer is clean before anyone writes
                 _lib.check(lib.dyd_shard_bucket_p2p(_ptr(keys), None, row_base, self.n, self.world, self.rank, self.cap,
-                                                    _ptr(self.peer_recv), _ptr(self.cursors), _ptr(self.overflow), s),
-                           "dyd_shard_bucket_p2p")
+                                                    _ptr(self.peer_recv), _ptr(self.sent_row), _ptr(self.cursors),
+                                                    _ptr(self.overflow), s), "dyd_shard_bucket_p2p")
                 self.h_recv.barrier(channel=1)                    # all records have landed
             else:
                 _lib.check(lib.dyd_shard_bucket(_ptr(keys), None, row_base, self.n, self.world, self.cap, _ptr(self.send),
@@ -185,12 +186,14 @@ class DedupExchange:
                 _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, self.cap, self.rank,
                                                         _ptr(self.peer_back), s), "dyd_shard_pack_reply_p2p")
                 self.h_back.barrier(channel=0)                    # all answers have landed
+                _lib.check(lib.dyd_shard_unpack_p2p(_ptr(self.back), _ptr(self.sent_row), _ptr(self.cursors), self.world, self.cap,
+                                                    self.n, _ptr(self.keep), _ptr(self.rep), s), "dyd_shard_unpack_p2p")
             else:
                 _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, _ptr(self.reply), s),
                            "dyd_shard_pack_reply")
                 dist.all_to_all_single(self.back, self.reply, group=group)
-            _lib.check(lib.dyd_shard_unpack(_ptr(self.back), m, row_base, self.n, _ptr(self.keep), _ptr(self.rep), s),
-                       "dyd_shard_unpack")
+                _lib.check(lib.dyd_shard_unpack(_ptr(self.back), m, row_base, self.n, _ptr(self.keep), _ptr(self.rep), s),
+                           "dyd_shard_unpack")
         if check_overflow:
             flag = self.overflow.clone()
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)

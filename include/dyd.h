@@ -114,17 +114,21 @@ int dyd_dedup_ids(const uint64_t* d_keys, const int64_t* d_row_id, int64_t n, in
 int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
                      int64_t cap, int64_t* d_records, uint64_t* d_cursors, int32_t* d_overflow, void* stream);
 int dyd_dedup_records(const int64_t* d_records, int64_t m, int keep_mode, uint8_t* d_keep, int64_t* d_rep,
-                      void* d_workspace, size_t workspace_bytes, void* stream);   /* Peer-memory forms of the two exchange steps (NVLink P2P, buffers mapped into every rank, e.g. by
+                      void* d_workspace, size_t workspace_bytes, void* stream);   /* Peer-memory forms of the exchange steps (NVLink P2P, buffers mapped into every rank, e.g. by
  * torch.distributed._symmetric_memory): the scatter writes each record straight into region `my_rank` of
- * its owner's receive buffer, and the owner writes each answer straight into region `my_rank` of the
- * origin's reply buffer, so the compute kernels ARE the all-to-all.  d_peer_records / d_peer_reply:
+ * its owner's receive buffer (and notes locally, in d_sent_row[world*cap], which row went into which
+ * slot); the owner writes each 8-byte answer (rep | keep << 62, -1 for padding) straight into region
+ * `my_rank` of the origin's reply buffer (int64[world*cap]); the origin places the answers with
+ * d_sent_row and its own cursors.  The compute kernels ARE the all-to-all.  d_peer_records / d_peer_reply:
  * device arrays of `world` pointers (own buffer included); the receive buffers must be pre-filled with
  * 0xFF padding and the ranks must synchronise before and after each step (sharding.DedupExchange).   */
 int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
-                         int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint64_t* d_cursors,
-                         int32_t* d_overflow, void* stream);
+                         int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
+                         uint64_t* d_cursors, int32_t* d_overflow, void* stream);
 int dyd_shard_pack_reply_p2p(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m, int64_t cap,
                              int32_t my_rank, int64_t* const* d_peer_reply, void* stream);
+int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
+                         int64_t cap, int64_t n, uint8_t* d_keep, int64_t* d_rep, void* stream);
 /* K4 on received (key, id) records */
 int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,
                          int64_t* d_reply, void* stream);
