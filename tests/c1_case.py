@@ -53,3 +53,21 @@ def steps(mod, td: Path, paths: dict):
         ("iou_0.98", lambda: mod.filter_by_box_count_and_iou(str(p["rep"]), str(p["hi98"]), str(p["other98"]), 2, 0.98),
          {"hi98": p["hi98"], "other98": p["other98"]}),
     ]
+
+
+# ---- label remap + split on the C1 chain's `other70.csv` (BASELINE config C5's rules at C1 size) ----
+def mapping_frame() -> pd.DataFrame:
+    """80 -> 20: cls{i} -> grp{i % 20}; a few labels left unmapped on purpose."""
+    rows = [(synth.label_name(i), f"grp{i % 20:02d}") for i in range(synth.N_LABELS) if i % 17 != 5]
+    return pd.DataFrame(rows, columns=["原标签", "新标签"])
+
+
+def rules_frame() -> pd.DataFrame:
+    """wide rules: 4 categories x 5 groups; grp19 undefined on purpose (unclassified rows)."""
+    cats = {f"类别{c}": [f"grp{g:02d}" for g in range(c * 5, c * 5 + 5) if g != 19] for c in range(4)}
+    n = max(len(v) for v in cats.values())
+    return pd.DataFrame({k: v + [None] * (n - len(v)) for k, v in cats.items()})
+
+
+def frame_digest(df: pd.DataFrame) -> str:
+    return hashlib.sha256(df.to_csv(index=False).encode("utf-8")).hexdigest()

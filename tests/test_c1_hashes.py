@@ -1,11 +1,14 @@
 """BASELINE.json config C1 (10 k rows as real CSV files) replayed through the oracle port (CPU) and
 through the CUDA drop-in (GPU): every output file must have the SHA-256 the UNMODIFIED REFERENCE
-produced for it (tests/golden/c1_hashes.json, written by tests/golden/make_c1_hashes.py)."""
+produced for it (tests/golden/c1_hashes.json, written by tests/golden/make_c1_hashes.py), and so must every
+frame of the label remap and the split that follow (the port's turn at those takes five minutes and runs
+with DYD_SLOW_TESTS=1; the drop-in's runs with the GPU tests)."""
 from __future__ import annotations
 
 import contextlib
 import io
 import json
+import os
 from pathlib import Path
 
 import pandas as pd
@@ -27,6 +30,33 @@ def _replay(mod, tmp_path):
             fn()
         for key, p in produced.items():
             assert c1_case.sha256(p) == PINS["files"][key], f"step {name}: {key}.csv differs from the reference's output"
+    return tmp_path / "other70.csv"
+
+
+def _replay_labels(mod, other70, tmp_path):
+    """Label remap + split on the chain's other70.csv: every frame the reference wrote (to CSV or to an
+    Excel sheet) must have the reference's digest, and the summaries must be equal."""
+    df = pd.read_csv(other70, encoding="utf-8-sig")
+    out, summary, diffs, unmatched = mod.remap_df(df, mod.mapping_from_frame(c1_case.mapping_frame()))
+    remapped = tmp_path / "remapped.csv"
+    out.to_csv(remapped, index=False, encoding="utf-8-sig")
+    assert c1_case.sha256(remapped) == PINS["files"]["remapped"]
+    assert {k: summary[k] for k in PINS["remap_summary"]} == PINS["remap_summary"]
+    assert c1_case.frame_digest(pd.DataFrame(diffs)) == PINS["frames"]["remap_diff"]
+    um = pd.DataFrame([{"标签": k, "数量": v} for k, v in unmatched.items()]).sort_values("数量", ascending=False)
+    assert c1_case.frame_digest(um) == PINS["frames"]["remap_unmatched"]
+    res = mod.split_df(pd.read_csv(remapped, encoding="utf-8-sig"), mod.rules_from_frame(c1_case.rules_frame()))
+    assert json.loads(json.dumps(res["summary"], default=int, ensure_ascii=False)) == PINS["split_summary"]
+    from deal_yolo_daya_b200.processor import _safe_filename as safe       # sheet files are named by it (utils.py:525-529)
+    seen = set()
+    for cat, parts in res["categories"].items():
+        for name, part in parts.items():
+            key = f"split/{safe(cat)}/{name}"
+            assert c1_case.frame_digest(part) == PINS["frames"][key], key
+            seen.add(key)
+    assert c1_case.frame_digest(res["unclassified"]) == PINS["frames"]["split/unclassified/Sheet1"]
+    assert c1_case.frame_digest(res["split_counts"]) == PINS["frames"]["split/split_counts/Sheet1"]
+    assert seen == {k for k in PINS["frames"] if k.startswith("split/") and k.split("/")[1] not in ("unclassified", "split_counts")}
 
 
 def test_oracle_port_reproduces_reference_files(tmp_path):
@@ -53,7 +83,9 @@ def test_oracle_port_reproduces_reference_files(tmp_path):
         def filter_by_box_count_and_iou(src, hi, other, min_boxes, thr):
             h, o = pipeline_port.iou_split_df(pd.read_csv(src, encoding=enc), min_boxes, thr)
             h.to_csv(hi, index=False, encoding=enc); o.to_csv(other, index=False, encoding=enc)
-    _replay(Port, tmp_path)
+    other70 = _replay(Port, tmp_path)
+    if os.environ.get("DYD_SLOW_TESTS") == "1":      # the port expands rows one by one like the reference: ~5 minutes
+        _replay_labels(pipeline_port, other70, tmp_path)
 
 
 @pytest.mark.gpu
@@ -63,4 +95,6 @@ def test_cuda_dropin_reproduces_reference_files(tmp_path, cuda_device, monkeypat
     monkeypatch.setattr(P, "KERNELS", P.CudaKernels(cuda_device.index))
     if io == "pandas-io":
         monkeypatch.setenv("DYD_NATIVE_INGEST", "0")
-    _replay(P, tmp_path)
+    other70 = _replay(P, tmp_path)
+    if io == "native-io":
+        _replay_labels(P, other70, tmp_path)
