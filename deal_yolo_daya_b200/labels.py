@@ -185,6 +185,7 @@ def remap_df(df: pd.DataFrame, label_map: dict, json_columns=None):
         exotic_set.setdefault(ci, set()).add(k)
     # ---- egress: rewrite names, re-serialise, collect diff rows ----
     diff_rows = []
+    touched_cols = set()
     sources = df["source"].tolist() if "source" in df.columns else [None] * n_rows
     for ci, (r, c, doc, objs) in enumerate(cells):
         q = int(cell_off[ci])
@@ -220,10 +221,14 @@ def remap_df(df: pd.DataFrame, label_map: dict, json_columns=None):
         if cell_rep[ci]:
             row_touched[r] = True
         doc["objects"] = objs
-        df.iat[r, df.columns.get_loc(c)] = json.dumps(doc, ensure_ascii=False)
+        col_values[c][r] = json.dumps(doc, ensure_ascii=False)     # columns are assigned once below: a per-cell
+        touched_cols.add(c)                                         # setitem on an Arrow string column copies the column
         if pairs:
             diff_rows.append({"source": sources[r], "column": c,
                               "before": "；".join(p[0] for p in pairs), "after": "；".join(p[1] for p in pairs)})
+    for c in cols:
+        if c in touched_cols:
+            df[c] = pd.Series(col_values[c], index=df.index, dtype=df[c].dtype)
     summary = {
         "total_rows": n_rows, "replaced_rows": int(row_touched.sum()), "total_objects": cnt["total_objects"],
         "replaced_objects": cnt["replaced_objects"], "total_labels": cnt["total_labels"],
