@@ -11,7 +11,6 @@ reference: processor.py:516-652 (remap), :654-831 (split); utils.py:635-679 (str
 """
 from __future__ import annotations
 
-import copy
 import json
 import re
 
@@ -344,7 +343,7 @@ def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
         for e, r in zip(exp_entry[a:b][order], rows_idx):
             doc, combo = row_info[int(r)]
             lab = vocab.names[int(labels[e])]
-            one = copy.deepcopy(entry_obj[int(e)]); one["name"] = lab
+            one = dict(entry_obj[int(e)]); one["name"] = lab      # serialised at once: a shallow copy is enough
             nd = {k: v for k, v in doc.items() if k != "objects"}
             nd["objects"] = [one]
             cells.append(json.dumps(nd, ensure_ascii=False)); labs.append(lab); combos.append(combo)

@@ -88,6 +88,27 @@ def test_oracle_port_reproduces_reference_files(tmp_path):
         _replay_labels(pipeline_port, other70, tmp_path)
 
 
+def test_dropin_label_host_logic_reproduces_reference_frames(tmp_path, monkeypatch):
+    """The drop-in's remap / split host logic (dictionary encoding, LUTs, frame assembly) with the kernels
+    emulated by the C oracle, on the reference's own C1 `other70.csv`: all 18 frame digests."""
+    from deal_yolo_daya_b200 import processor as P
+    from oracle import pipeline_port
+    from tests.oracle_kernels import OracleKernels
+    if pd.__version__ != PINS["pandas"]:
+        pytest.skip(f"pins were made with pandas {PINS['pandas']}")
+    monkeypatch.setattr(P, "KERNELS", OracleKernels())
+    paths = c1_case.write_inputs(tmp_path)
+    enc = "utf-8-sig"
+    d = pipeline_port.dedup_df(pd.read_csv(paths["merged"], encoding=enc, parse_dates=False))
+    f = pipeline_port.ref_filter_df(d, pd.read_csv(paths["ref"], encoding=enc, parse_dates=False))
+    r, _ = pipeline_port.replace_ptlist_df(f)
+    r.to_csv(tmp_path / "rep.csv", index=False, encoding=enc)
+    _, other = pipeline_port.iou_split_df(pd.read_csv(tmp_path / "rep.csv", encoding=enc), 2, 0.7)
+    other.to_csv(tmp_path / "other70.csv", index=False, encoding=enc)
+    assert c1_case.sha256(tmp_path / "other70.csv") == PINS["files"]["other70"]
+    _replay_labels(P, tmp_path / "other70.csv", tmp_path)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("io", ["native-io", "pandas-io"])
 def test_cuda_dropin_reproduces_reference_files(tmp_path, cuda_device, monkeypatch, io):
