@@ -55,7 +55,10 @@ struct RowOut {
     // step 5
     std::vector<double> boxes;           // 4 per box
     std::vector<uint8_t> bvalid;
+    // step 5.5 (mode 2): per dict object the span of its "name" string contents (len -1: None / absent)
+    std::vector<Span> names;
 };
+enum RowStatus2 : uint8_t { ROW_NO_LIST = 4 };      // mode 2: "objects" absent or not a list -> the cell is left as it is
 
 struct Fail {};
 
@@ -443,10 +446,53 @@ static void parse_box_row(const char* text, size_t len, RowOut& out) {
     out.status = ROW_OK;
 }
 
+// ---------------------------------------------------------------- step 5.5: object names
+// replace_labels_by_mapping (processor.py:560-604) re-serialises every cell it can parse, so the native
+// lane only takes cells that are already in json.dumps form (strict): the output is then the input with
+// some "name" strings replaced.  Names that are not plain strings / None go to the Python lane.
+static void parse_names_row(const char* text, size_t len, RowOut& out) {
+    Parser ps{text, text, text + len, true};
+    ps.need(ps.p < ps.end && *ps.p == '{');             // doc.get on a non-dict raises in the reference
+    ++ps.p;
+    bool have_list = false;
+    KeySet top_keys;
+    if (ps.p < ps.end && *ps.p == '}') { ++ps.p; }
+    else do {
+        bool plain; Span k = ps.str(&plain); ps.check_dup(top_keys, k); ps.colon();
+        if (plain && ps.key_is(k, "objects")) {
+            ps.need(ps.p < ps.end);
+            if (*ps.p != '[') { ps.skip(); continue; }   // not a list: the cell is skipped by the reference
+            have_list = true;
+            ++ps.p;
+            if (ps.p < ps.end && *ps.p == ']') { ++ps.p; continue; }
+            do {
+                ps.need(ps.p < ps.end);
+                if (*ps.p != '{') { ps.skip(); continue; }               // non-dict elements are not counted
+                ++ps.p;
+                Span name{0, (uint32_t)-1};
+                KeySet okeys;
+                if (ps.p < ps.end && *ps.p == '}') { ++ps.p; out.names.push_back(name); continue; }
+                do {
+                    bool pl2; Span ok = ps.str(&pl2); ps.check_dup(okeys, ok); ps.colon();
+                    if (pl2 && ps.key_is(ok, "name")) {
+                        ps.need(ps.p < ps.end);
+                        if (*ps.p == '"') { bool pl3; name = ps.str(&pl3); ps.need(pl3); }     // escapes: Python lane
+                        else { Span sp; double v; ps.need(ps.scalar(&sp, &v) == K_NULL); }     // None; anything else: Python lane
+                    } else ps.skip();
+                } while (ps.more('}'));
+                out.names.push_back(name);
+            } while (ps.more(']'));
+        } else ps.skip();
+    } while (ps.more('}'));
+    ps.need(ps.p == ps.end);
+    out.status = have_list ? ROW_OK : (uint8_t)ROW_NO_LIST;
+    if (!have_list) out.names.clear();
+}
+
 }  // namespace
 
 struct dyd_ingest {
-    int mode = 0;                            // 0 polygons (step 4), 1 boxes (step 5)
+    int mode = 0;                            // 0 polygons (step 4), 1 boxes (step 5), 2 object names (step 5.5)
     int64_t n_rows = 0;
     std::vector<RowOut> rows;
     std::vector<int64_t> obj_base, vert_base;    // exclusive prefix over rows
@@ -499,7 +545,7 @@ inline size_t wrap_len(const Poly& p) {      // extra bytes around the value for
 
 extern "C" int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const uint8_t* is_text, int64_t n_rows,
                                 int mode, int n_threads, dyd_ingest** out) {
-    if (!out || n_rows < 0 || (n_rows > 0 && (!text || !off)) || (mode != 0 && mode != 1)) return DYD_E_ARG;
+    if (!out || n_rows < 0 || (n_rows > 0 && (!text || !off)) || (mode < 0 || mode > 2)) return DYD_E_ARG;
     dyd_ingest* h = new dyd_ingest();
     h->mode = mode; h->n_rows = n_rows;
     h->rows.resize((size_t)n_rows);
@@ -511,7 +557,8 @@ extern "C" int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const u
             const size_t len = (size_t)(off[r + 1] - off[r]);
             try {
                 if (len >= (1ull << 31)) throw Fail{};
-                if (mode == 0) parse_polygon_row(s, len, true, ro); else parse_box_row(s, len, ro);
+                if (mode == 2 && len == 0) { ro.status = ROW_NOT_TEXT; continue; }     // an empty cell is skipped like a missing one
+                if (mode == 0) parse_polygon_row(s, len, true, ro); else if (mode == 1) parse_box_row(s, len, ro); else parse_names_row(s, len, ro);
             } catch (const Fail&) {
                 ro = RowOut(); ro.status = ROW_SLOW;
             } catch (const std::bad_alloc&) {
@@ -525,7 +572,7 @@ extern "C" int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const u
         const RowOut& ro = h->rows[(size_t)r];
         h->obj_base[(size_t)r] = no; h->vert_base[(size_t)r] = nv;
         if (ro.status == ROW_SLOW) ++ns;
-        no += mode == 0 ? (int64_t)ro.polys.size() : (int64_t)ro.bvalid.size();
+        no += mode == 0 ? (int64_t)ro.polys.size() : (mode == 1 ? (int64_t)ro.bvalid.size() : (int64_t)ro.names.size());
         nv += (int64_t)ro.verts.size();
     }
     h->obj_base[(size_t)n_rows] = no; h->vert_base[(size_t)n_rows] = nv;
@@ -726,6 +773,64 @@ extern "C" int dyd_csv_write(const int32_t* kinds, const int64_t* const* offs, c
             *o++ = '\n';
         }
     });
+    return 0;
+}
+
+// mode 2: status[n], cell_off[n+1] (objects per cell), name_off[n_obj] (byte offset inside the cell's text) /
+// name_len[n_obj] (-1: the object has no name or None)
+extern "C" int dyd_ingest_export_names(const dyd_ingest* h, uint8_t* status, int64_t* cell_off, int64_t* name_off, int32_t* name_len,
+                                       int n_threads) {
+    if (!h || h->mode != 2 || !status || !cell_off) return DYD_E_ARG;
+    const int64_t n = h->n_rows;
+    cell_off[n] = h->n_obj;
+    parallel_rows(n, n_threads, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            const RowOut& ro = h->rows[(size_t)r];
+            status[r] = ro.status;
+            int64_t q = h->obj_base[(size_t)r];
+            cell_off[r] = q;
+            for (const Span& sp : ro.names) { if (name_off) name_off[q] = sp.off; if (name_len) name_len[q] = (int32_t)sp.len; ++q; }
+        }
+    });
+    return 0;
+}
+
+// New cell texts of step 5.5: the input text with the name of every object whose flag is set replaced by
+// vocab entry obj_new[q] (bytes already JSON-escaped by the caller, without the quotes).  Cells that are
+// not ROW_OK get length 0.  out == NULL: fill out_off[n+1]; else write.
+extern "C" int dyd_egress_names(const dyd_ingest* h, const uint8_t* text, const int64_t* off, const uint8_t* obj_flag,
+                                const int32_t* obj_new, const uint8_t* vocab_bytes, const int64_t* vocab_off, int64_t n_vocab,
+                                int64_t* out_off, uint8_t* out, int n_threads) {
+    if (!h || h->mode != 2 || !text || !off || !out_off || (h->n_obj > 0 && (!obj_flag || !obj_new || !vocab_bytes || !vocab_off))) return DYD_E_ARG;
+    const int64_t n = h->n_rows;
+    auto cell = [&](int64_t r, uint8_t* dst) -> int64_t {
+        const RowOut& ro = h->rows[(size_t)r];
+        if (ro.status != ROW_OK) return 0;
+        const uint8_t* src = text + off[r];
+        const int64_t len = off[r + 1] - off[r];
+        int64_t q = h->obj_base[(size_t)r], pos = 0, total = 0;
+        for (const Span& sp : ro.names) {
+            if (obj_flag[q] && sp.len != (uint32_t)-1) {
+                const int32_t v = obj_new[q];
+                if (v < 0 || v >= n_vocab) return -1;
+                const int64_t nl = vocab_off[v + 1] - vocab_off[v];
+                if (dst) { memcpy(dst + total, src + pos, (size_t)(sp.off - pos)); memcpy(dst + total + (sp.off - pos), vocab_bytes + vocab_off[v], (size_t)nl); }
+                total += (sp.off - pos) + nl;
+                pos = (int64_t)sp.off + sp.len;
+            }
+            ++q;
+        }
+        if (dst) memcpy(dst + total, src + pos, (size_t)(len - pos));
+        return total + (len - pos);
+    };
+    bool bad = false;
+    if (!out) {
+        out_off[0] = 0;
+        parallel_rows(n, n_threads, [&](int64_t a, int64_t b) { for (int64_t r = a; r < b; ++r) { const int64_t l = cell(r, nullptr); if (l < 0) bad = true; out_off[r + 1] = l < 0 ? 0 : l; } });
+        for (int64_t r = 0; r < n; ++r) out_off[r + 1] += out_off[r];
+        return bad ? DYD_E_ARG : 0;
+    }
+    parallel_rows(n, n_threads, [&](int64_t a, int64_t b) { for (int64_t r = a; r < b; ++r) cell(r, out + out_off[r]); });
     return 0;
 }
 

@@ -20,6 +20,7 @@ import pandas as pd
 COL_ANN = "结果字段-目标检测标签配置"
 COL_NEW = "新_结果字段-目标检测标签配置"
 _SEP = re.compile(r"[,，;；|]")
+LAST = {"remap_lane": None}          # observability: which lane the last remap_df call took
 
 
 def _kernels():
@@ -101,12 +102,146 @@ class _Vocab:
         return i
 
 
+def _remap_tables(vocab, label_map):
+    """Per-vocabulary tables with the reference's string rules (utils.py:659-679): tokens, normalised
+    new name, and the three LUTs K3 reads (new id, token count, replaced-token count)."""
+    n_raw = len(vocab.names)
+    toks_of, norm_of = [], []
+    for v in range(n_raw):
+        raw = vocab.names[v]
+        toks = split_labels(raw)
+        toks_of.append(toks)
+        norm_of.append(raw if not raw else ",".join(sorted(set(label_map.get(t, t) for t in toks))))
+    lut_ntok = np.array([0 if not vocab.names[v] else len(toks_of[v]) for v in range(n_raw)], np.int32)
+    lut_nrep = np.array([0 if not vocab.names[v] else sum(1 for t in toks_of[v] if t in label_map) for v in range(n_raw)], np.int32)
+    lut_new = np.array([vocab.get(norm_of[v]) for v in range(n_raw)], np.int32)       # may append new names
+    n_vocab = len(vocab.names)
+    pad = n_vocab - n_raw
+    lut_new = np.concatenate([lut_new, np.arange(n_raw, n_vocab, dtype=np.int32)])
+    lut_ntok = np.concatenate([lut_ntok, np.zeros(pad, np.int32)])
+    lut_nrep = np.concatenate([lut_nrep, np.zeros(pad, np.int32)])
+    return n_raw, n_vocab, toks_of, norm_of, lut_new, lut_ntok, lut_nrep
+
+
+def _unmatched_from_hist(vocab, n_raw, toks_of, hist, label_map):
+    """Unmatched labels in first-encounter order with their object counts (processor.py:591-593)."""
+    unmatched = {}
+    for v in range(n_raw):
+        h = int(hist[v]) if v < len(hist) else 0
+        if h == 0 or not vocab.names[v]:
+            continue
+        for t in toks_of[v]:
+            if t not in label_map:
+                unmatched[t] = unmatched.get(t, 0) + h
+    return unmatched
+
+
+def _remap_native(df, label_map, cols):
+    """Native lane of remap_df: every text cell of the JSON columns is already in json.dumps form (what
+    step 4 / step 5 wrote), so the names are taken from the text by csrc/ingest.cpp (mode 2), K3 decides
+    on the dictionary-encoded ids and the new texts are the old ones with names spliced.  Returns None
+    when any cell needs CPython's json (the caller then runs the Python lane for the whole frame: the
+    vocabulary order depends on every cell)."""
+    from . import native
+    n = len(df)
+    if not native.enabled() or not cols or n == 0 or not native._pandas_infers_arrow_str():
+        return None
+    if any(getattr(df[c].array, "_pa_array", None) is None for c in cols):
+        return None
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    ings = []
+    try:
+        for c in cols:
+            ing = native.Ingest(df[c], 2)
+            ings.append(ing)
+            if ing.n_slow:
+                return None
+            ing.names()
+        ncols = len(cols)
+        counts = np.stack([np.diff(i.cell_off) for i in ings], axis=1)              # objects per (row, column) cell
+        cell_off = np.zeros(n * ncols + 1, np.int64)
+        np.cumsum(counts.reshape(-1), out=cell_off[1:])
+        total = int(cell_off[-1])
+        dests = []                                                                   # column-major object -> traversal position
+        for ci, ing in enumerate(ings):
+            dst_start = cell_off[np.arange(n, dtype=np.int64) * ncols + ci]
+            dests.append(np.repeat(dst_start - ing.cell_off[:-1], counts[:, ci]) + np.arange(ing.n_obj, dtype=np.int64))
+        dest = np.concatenate(dests) if dests else np.zeros(0, np.int64)
+        perm = np.empty(total, np.int64); perm[dest] = np.arange(total, dtype=np.int64)
+        if total:
+            enc = pc.dictionary_encode(pa.concat_arrays([i.name_array() for i in ings]).take(pa.array(perm)))
+            ids = np.asarray(enc.indices.fill_null(-1)).astype(np.int32)
+            raw_names = enc.dictionary.to_pylist()
+        else:
+            ids = np.zeros(0, np.int32); raw_names = []
+        vocab = _Vocab()
+        for nm in raw_names:
+            vocab.get(nm)
+        n_raw, n_vocab, toks_of, norm_of, lut_new, lut_ntok, lut_nrep = _remap_tables(vocab, label_map)
+        if total:
+            new_id, cell_rep, cnt, hist = _kernels().label_lut(cell_off, ids, lut_new, lut_ntok, lut_nrep)
+        else:
+            new_id = np.zeros(0, np.int32); cell_rep = np.zeros(n * ncols, np.uint8); hist = np.zeros(n_vocab, np.uint64)
+            cnt = dict(total_objects=0, missing_name_objects=0, total_labels=0, replaced_labels=0, replaced_objects=0, replaced_rows=0)
+        unmatched = _unmatched_from_hist(vocab, n_raw, toks_of, hist, label_map)
+        # ---- egress: splice the new names, one pass per column ----
+        safe = np.where(ids >= 0, ids, 0)
+        flags = ((ids >= 0) & (lut_nrep[safe] > 0)).astype(np.uint8) if total else np.zeros(0, np.uint8)
+        esc = [json.dumps(nm, ensure_ascii=False)[1:-1].encode("utf-8") for nm in vocab.names]
+        v_off = np.zeros(len(esc) + 1, np.int64)
+        if esc:
+            np.cumsum([len(e) for e in esc], out=v_off[1:])
+        v_bytes = np.frombuffer(b"".join(esc) or b"\0", dtype=np.uint8)
+        for ci, (c, ing) in enumerate(zip(cols, ings)):
+            out, out_off = ing.egress_names(flags[dests[ci]], np.asarray(new_id)[dests[ci]], v_bytes, v_off)
+            ok = ing.status == native.ROW_OK
+            if ok.all():
+                df[c] = pd.Series(native.arrow_strings(out, out_off), index=df.index)
+            elif ok.any():
+                vals = df[c].tolist()
+                blob = out.tobytes()
+                for r in np.nonzero(ok)[0]:
+                    vals[r] = blob[out_off[r]:out_off[r + 1]].decode("utf-8")
+                df[c] = pd.Series(vals, index=df.index, dtype=df[c].dtype)
+        # ---- diff rows in traversal order ----
+        diff_rows = []
+        if total:
+            changed_v = np.array([vocab.names[v] != norm_of[v] for v in range(n_raw)] + [False] * (n_vocab - n_raw), bool)
+            obj_changed = (ids >= 0) & changed_v[safe]
+            cell_of_obj = np.repeat(np.arange(n * ncols, dtype=np.int64), counts.reshape(-1))
+            has = np.bincount(cell_of_obj[obj_changed], minlength=n * ncols) > 0
+            sources = df["source"].tolist() if "source" in df.columns else [None] * n
+            names = vocab.names
+            for ci in np.nonzero(has)[0]:
+                a, b = int(cell_off[ci]), int(cell_off[ci + 1])
+                sel = ids[a:b][obj_changed[a:b]]
+                diff_rows.append({"source": sources[ci // ncols], "column": cols[ci % ncols],
+                                  "before": "；".join(names[v] for v in sel), "after": "；".join(norm_of[v] for v in sel)})
+        row_touched = np.asarray(cell_rep).reshape(n, ncols).any(axis=1) if n else np.zeros(0, bool)
+    finally:
+        for ing in ings:
+            ing.close()
+    summary = {
+        "total_rows": n, "replaced_rows": int(row_touched.sum()), "total_objects": cnt["total_objects"],
+        "replaced_objects": cnt["replaced_objects"], "total_labels": cnt["total_labels"],
+        "replaced_labels": cnt["replaced_labels"], "invalid_json_rows": 0,
+        "missing_name_objects": cnt["missing_name_objects"], "mapping_size": len(label_map),
+        "unmatched_labels": len(unmatched),
+    }
+    return df, summary, diff_rows, unmatched
+
+
 def remap_df(df: pd.DataFrame, label_map: dict, json_columns=None):
     """DataFrame core of replace_labels_by_mapping -> (frame, summary, diff_rows, unmatched counter)."""
     df = df.copy()
     if json_columns is None:
         json_columns = default_json_columns(df)
     cols = [c for c in json_columns if c in df.columns]
+    fast = _remap_native(df, label_map, cols)
+    LAST["remap_lane"] = "native" if fast is not None else "python"
+    if fast is not None:
+        return fast
     n_rows = len(df)
     invalid_json_rows = 0
     # ---- ingest: decode cells, dictionary-encode names in reference traversal order ----
@@ -142,21 +277,7 @@ def remap_df(df: pd.DataFrame, label_map: dict, json_columns=None):
                 n += 1
             cells.append((r, c, doc, objs)); cell_cnt.append(n)
     # ---- per-vocabulary tables (string rules of utils.py:659-679) ----
-    n_raw = len(vocab.names)
-    toks_of, norm_of = [], []
-    for v in range(n_raw):
-        raw = vocab.names[v]
-        toks = split_labels(raw)
-        toks_of.append(toks)
-        norm_of.append(raw if not raw else ",".join(sorted(set(label_map.get(t, t) for t in toks))))
-    lut_ntok = np.array([0 if not vocab.names[v] else len(toks_of[v]) for v in range(n_raw)], np.int32)
-    lut_nrep = np.array([0 if not vocab.names[v] else sum(1 for t in toks_of[v] if t in label_map) for v in range(n_raw)], np.int32)
-    lut_new = np.array([vocab.get(norm_of[v]) for v in range(n_raw)], np.int32)       # may append new names
-    n_vocab = len(vocab.names)
-    pad = n_vocab - n_raw
-    lut_new = np.concatenate([lut_new, np.arange(n_raw, n_vocab, dtype=np.int32)])
-    lut_ntok = np.concatenate([lut_ntok, np.zeros(pad, np.int32)])
-    lut_nrep = np.concatenate([lut_nrep, np.zeros(pad, np.int32)])
+    n_raw, n_vocab, toks_of, norm_of, lut_new, lut_ntok, lut_nrep = _remap_tables(vocab, label_map)
     # ---- device: rewrite decisions, counters, histogram ----
     cell_off = np.zeros(len(cells) + 1, np.int64)
     np.cumsum(np.array(cell_cnt, np.int64), out=cell_off[1:])
@@ -169,14 +290,7 @@ def remap_df(df: pd.DataFrame, label_map: dict, json_columns=None):
         cnt = dict(total_objects=0, missing_name_objects=0, total_labels=0, replaced_labels=0, replaced_objects=0, replaced_rows=0)
     cnt["missing_name_objects"] -= len(exotic)                    # they were sent as "no name"; corrected here
     # ---- unmatched labels in first-encounter order (processor.py:591-593) ----
-    unmatched = {}
-    for v in range(n_raw):
-        h = int(hist[v]) if v < len(hist) else 0
-        if h == 0 or not vocab.names[v]:
-            continue
-        for t in toks_of[v]:
-            if t not in label_map:
-                unmatched[t] = unmatched.get(t, 0) + h
+    unmatched = _unmatched_from_hist(vocab, n_raw, toks_of, hist, label_map)
     # ---- host lane: names that are not strings (numbers, lists ...) follow CPython semantics ----
     row_touched = np.zeros(n_rows, bool)
     exotic_set = {}

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 
-ROW_OK, ROW_SLOW, ROW_NOT_TEXT = 0, 1, 2
+ROW_OK, ROW_SLOW, ROW_NOT_TEXT, ROW_NO_LIST = 0, 1, 2, 4
 K_INT, K_FLT, K_TRUE, K_FALSE, K_NULL = 3, 4, 5, 6, 7
 
 
@@ -129,6 +129,44 @@ class Ingest:
         a = int(self.off[r]) + o
         lit = bytes(self.text[a:a + int(self.wh_len[i])]).decode("ascii")
         return int(lit) if k == K_INT else float(lit)
+
+    # ---- step 5.5 ----
+    def names(self):
+        n = self.n
+        self.status = np.empty(n, np.uint8)
+        self.cell_off = np.empty(n + 1, np.int64)
+        self.name_off = np.empty(self.n_obj, np.int64)
+        self.name_len = np.empty(self.n_obj, np.int32)
+        _lib.check(self.lib.dyd_ingest_export_names(self.h, _p(self.status), _p(self.cell_off), _p(self.name_off), _p(self.name_len),
+                                                    _threads()), "dyd_ingest_export_names")
+        return self
+
+    def name_array(self):
+        """Arrow large_string array of the objects' names (null where the object has none)."""
+        import pyarrow as pa
+        cnt = np.diff(self.cell_off)
+        start = np.repeat(self.off[:-1], cnt) + self.name_off                  # absolute byte offset of each name
+        ln = np.where(self.name_len < 0, 0, self.name_len).astype(np.int64)
+        o = np.zeros(self.n_obj + 1, np.int64); np.cumsum(ln, out=o[1:])
+        total = int(o[-1])
+        if total:
+            idx = np.repeat(start - o[:-1], ln) + np.arange(total, dtype=np.int64)
+            data = self.text[idx]
+        else:
+            data = np.zeros(1, np.uint8)
+        valid = np.packbits(self.name_len >= 0, bitorder="little")
+        return pa.Array.from_buffers(pa.large_string(), self.n_obj, [pa.py_buffer(valid), pa.py_buffer(o), pa.py_buffer(data)])
+
+    def egress_names(self, obj_flag, obj_new, vocab_bytes, vocab_off):
+        """-> (out bytes uint8[], out_off int64[n+1]): new texts of the ROW_OK cells (length 0 for the others)."""
+        obj_flag = np.ascontiguousarray(obj_flag, np.uint8); obj_new = np.ascontiguousarray(obj_new, np.int32)
+        vocab_bytes = np.ascontiguousarray(vocab_bytes, np.uint8); vocab_off = np.ascontiguousarray(vocab_off, np.int64)
+        out_off = np.empty(self.n + 1, np.int64)
+        a = (self.h, _p(self.text), _p(self.off), _p(obj_flag), _p(obj_new), _p(vocab_bytes), _p(vocab_off), len(vocab_off) - 1, _p(out_off))
+        _lib.check(self.lib.dyd_egress_names(*a, None, _threads()), "dyd_egress_names(size)")
+        out = np.empty(max(int(out_off[-1]), 1), np.uint8)
+        _lib.check(self.lib.dyd_egress_names(*a, _p(out), _threads()), "dyd_egress_names(write)")
+        return out[:int(out_off[-1])], out_off
 
     def int_columns(self):
         """(width int64[n], height int64[n]) when every row has both as plain JSON integers that fit

@@ -230,6 +230,16 @@ int dyd_ingest_sizes(const dyd_ingest* h, int64_t* n_obj, int64_t* n_vert, int64
 int dyd_ingest_export_polygons(const dyd_ingest* h, uint8_t* status, int64_t* img_off, int64_t* poly_off, double* xy,
                                int64_t* wh_off, int32_t* wh_len, uint8_t* wh_kind, int n_threads);
 int dyd_ingest_export_boxes(const dyd_ingest* h, uint8_t* status, int64_t* img_off, double* pts, uint8_t* valid, int n_threads);
+/* mode 2 (step 5.5, replace_labels_by_mapping processor.py:560-604): per dict object of "objects" the span
+ * of its "name" string inside the cell's text (name_len -1: None / absent).  Only cells already in
+ * json.dumps form are taken (status 0); status 4: "objects" absent or not a list (the reference leaves the
+ * cell alone); status 1: the caller's CPython lane.  dyd_egress_names writes the new cell texts: the input
+ * with the flagged objects' names replaced by JSON-escaped vocabulary entries.                        */
+int dyd_ingest_export_names(const dyd_ingest* h, uint8_t* status, int64_t* cell_off, int64_t* name_off, int32_t* name_len,
+                            int n_threads);
+int dyd_egress_names(const dyd_ingest* h, const uint8_t* text, const int64_t* off, const uint8_t* obj_flag,
+                     const int32_t* obj_new, const uint8_t* vocab_bytes, const int64_t* vocab_off, int64_t n_vocab,
+                     int64_t* out_off, uint8_t* out, int n_threads);
 /* Output cells of step 4: input text with every ptList value replaced by the two corner points built
  * from the original number literals selected by K1's arg indices.  Call with out == NULL to get the
  * offsets (out_off int64[n_rows+1]), then again with the buffer.                                  */

@@ -237,3 +237,48 @@ def test_boxes_mode_matches_cpython_lane(monkeypatch):
     got2 = P.high_iou_mask(rows, 2, 0.02)
     assert np.array_equal(got, want) and np.array_equal(got2, want)
     assert native_slow < 0.2 * len(rows) and want.sum() > 20
+
+
+def test_remap_native_lane_equals_python_lane(monkeypatch):
+    """Step 5.5 on json.dumps-form cells: names spliced by csrc/ingest.cpp (mode 2) vs the CPython lane --
+    same frame, summary, diff rows and unmatched counter; awkward cells send the whole frame to CPython."""
+    from deal_yolo_daya_b200 import labels
+    from oracle import pipeline_port as port
+    t = synth.make_table(5, 0, 400)
+    df = pd.DataFrame(synth.table_to_rows(t), columns=["source", ANN])
+    rep, _ = port.replace_ptlist_df(df)
+    rep = pd.read_csv(io.StringIO(rep.to_csv(index=False)))                 # as step 5.5 reads it: Arrow-backed str columns
+    # a few name shapes: multi-token, unknown, empty, None, missing key, unicode
+    docs = [json.loads(x) for x in rep[NEW]]
+    docs[0]["objects"][0]["name"] = "cls01,cls02；cls01"
+    docs[1]["objects"][0]["name"] = "未知标签"
+    docs[2]["objects"][0]["name"] = ""
+    docs[3]["objects"][0]["name"] = None
+    docs[4]["objects"][0].pop("name", None)
+    docs[5]["objects"] = []
+    docs[6].pop("objects")
+    rep[NEW] = [json.dumps(d, ensure_ascii=False) for d in docs]
+    rep.loc[7, NEW] = np.nan
+    rep = pd.read_csv(io.StringIO(rep.to_csv(index=False)))
+    lm = {synth.label_name(i): f"grp{i % 20:02d}" for i in range(synth.N_LABELS) if i % 7}
+    lm["cls02"] = "cls01"
+
+    def run(native_on):
+        monkeypatch.setenv("DYD_NATIVE_INGEST", "1" if native_on else "0")
+        out = labels.remap_df(rep, lm)
+        return out, labels.LAST["remap_lane"]
+    (a, lane_a), (b, lane_b) = run(True), run(False)
+    assert (lane_a, lane_b) == ("native", "python")
+    pd.testing.assert_frame_equal(a[0], b[0])
+    assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and list(a[3]) == list(b[3])
+    # one non-canonical cell (extra space) -> the whole call takes the CPython lane, same answer as all-python
+    rep2 = rep.copy()
+    rep2[NEW] = rep2[NEW].astype(object)
+    rep2.loc[9, NEW] = rep2.loc[9, NEW].replace('{"', '{ "', 1)
+    rep2 = pd.read_csv(io.StringIO(rep2.to_csv(index=False)))
+    monkeypatch.setenv("DYD_NATIVE_INGEST", "1")
+    c = labels.remap_df(rep2, lm)
+    assert labels.LAST["remap_lane"] == "python"
+    monkeypatch.setenv("DYD_NATIVE_INGEST", "0")
+    d = labels.remap_df(rep2, lm)
+    pd.testing.assert_frame_equal(c[0], d[0]); assert c[1:] == d[1:]
