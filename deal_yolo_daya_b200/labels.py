@@ -389,6 +389,15 @@ def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
     cat_ids, cat_names = {}, []
     entry_cnt = np.zeros(n_rows, np.int64)
     entry_label, entry_obj = [], []          # per entry: label id / (row, object) payload
+    labs_cache = {}
+
+    def labs_of(name):                       # split_labels per distinct name string
+        if type(name) is str:
+            got = labs_cache.get(name)
+            if got is None:
+                got = labs_cache[name] = split_labels(name)
+            return got
+        return split_labels(name)
     row_info = [None] * n_rows               # (doc, combo) for classifiable rows
     events = []                              # unclassified rows & split_counts rows in reference order
     for r in range(n_rows):
@@ -404,7 +413,7 @@ def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
         labset = set()
         for obj in objs:
             if isinstance(obj, dict) and obj.get("name"):
-                labset.update(split_labels(obj.get("name")))
+                labset.update(labs_of(obj.get("name")))
         combo = "，".join(sorted(labset)) if labset else ""
         row_info[r] = (doc, combo)
         n = 0
@@ -412,7 +421,7 @@ def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
         for obj in objs:
             if not isinstance(obj, dict):
                 continue
-            labs = split_labels(obj.get("name"))
+            labs = labs_of(obj.get("name"))
             per_obj.append((obj, labs))
             for lab in labs:
                 v = vocab.get(lab)
@@ -452,7 +461,8 @@ def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
         order = np.empty(b - a, np.int64)
         order[pos[a:b]] = np.arange(b - a)             # shuffled position -> original expanded row
         rows_idx = exp_row[a:b][order]
-        frame = df.iloc[rows_idx].reset_index(drop=True)
+        keep_cols = [c for c in df.columns if c not in json_columns]        # the JSON columns are rewritten below:
+        frame = df[keep_cols].iloc[rows_idx].reset_index(drop=True)         # do not gather their old texts first
         cells, labs, combos = [], [], []
         for e, r in zip(exp_entry[a:b][order], rows_idx):
             doc, combo = row_info[int(r)]
@@ -464,6 +474,7 @@ def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
         for c in json_columns:
             if c in df.columns:
                 frame[c] = cells
+        frame = frame[list(df.columns)]                                      # original column order
         frame["分类标签"] = labs
         frame["分类类别"] = cat
         frame["原始标签组合"] = combos
