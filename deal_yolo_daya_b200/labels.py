@@ -186,8 +186,8 @@ def _remap_native(df, label_map, cols):
             cnt = dict(total_objects=0, missing_name_objects=0, total_labels=0, replaced_labels=0, replaced_objects=0, replaced_rows=0)
         unmatched = _unmatched_from_hist(vocab, n_raw, toks_of, hist, label_map)
         # ---- egress: splice the new names, one pass per column ----
-        safe = np.where(ids >= 0, ids, 0)
-        flags = ((ids >= 0) & (lut_nrep[safe] > 0)).astype(np.uint8) if total else np.zeros(0, np.uint8)
+        safe = np.where(ids >= 0, ids, n_vocab)                                     # objects without a name index a padding slot
+        flags = (np.append(lut_nrep, 0)[safe] > 0).astype(np.uint8) if total else np.zeros(0, np.uint8)
         esc = [json.dumps(nm, ensure_ascii=False)[1:-1].encode("utf-8") for nm in vocab.names]
         v_off = np.zeros(len(esc) + 1, np.int64)
         if esc:
@@ -207,8 +207,8 @@ def _remap_native(df, label_map, cols):
         # ---- diff rows in traversal order ----
         diff_rows = []
         if total:
-            changed_v = np.array([vocab.names[v] != norm_of[v] for v in range(n_raw)] + [False] * (n_vocab - n_raw), bool)
-            obj_changed = (ids >= 0) & changed_v[safe]
+            changed_v = np.array([vocab.names[v] != norm_of[v] for v in range(n_raw)] + [False] * (n_vocab - n_raw + 1), bool)
+            obj_changed = changed_v[safe]
             cell_of_obj = np.repeat(np.arange(n * ncols, dtype=np.int64), counts.reshape(-1))
             has = np.bincount(cell_of_obj[obj_changed], minlength=n * ncols) > 0
             sources = df["source"].tolist() if "source" in df.columns else [None] * n

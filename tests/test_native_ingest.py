@@ -282,3 +282,75 @@ def test_remap_native_lane_equals_python_lane(monkeypatch):
     monkeypatch.setenv("DYD_NATIVE_INGEST", "0")
     d = labels.remap_df(rep2, lm)
     pd.testing.assert_frame_equal(c[0], d[0]); assert c[1:] == d[1:]
+
+
+def test_remap_lanes_agree_on_random_documents(monkeypatch):
+    """Random documents (shuffled keys, missing / non-list "objects", objects without names, odd name
+    values, junk members, missing cells): the native lane, where it applies, and the CPython lane give the
+    same frame / summary / diff rows / unmatched counter, or raise the same exception."""
+    from deal_yolo_daya_b200 import labels
+    rng = random.Random(99)
+    names_pool = ["cat", "dog", "cat,dog", "猫", "cat；bird", " cat ", "", "x|y", "bird", "a,b,a"]
+    odd_names = [None, 5, 2.5, True, ["cat"], {"a": 1}, 'q"uote', "back\\slash", "new\nline"]
+
+    def val(d=0):
+        t = rng.random()
+        if t < 0.3: return rng.randint(-5, 2000)
+        if t < 0.5: return round(rng.uniform(-10, 3000), rng.randint(0, 6))
+        if t < 0.6: return rng.choice([None, True, False])
+        if t < 0.8: return rng.choice(["s", "中文", "", "a b"])
+        if d > 1: return 1
+        if t < 0.9: return [val(d + 1) for _ in range(rng.randint(0, 3))]
+        return {rng.choice("abcxyz"): val(d + 1) for _ in range(rng.randint(0, 3))}
+
+    def obj(clean):
+        if not clean and rng.random() < 0.1:
+            return rng.choice([1, "str", None, [1]])
+        o, keys = {}, ["name", "polygon", "id", "score"]
+        rng.shuffle(keys)
+        for k in keys:
+            if k == "name":
+                if rng.random() < 0.85:
+                    o["name"] = rng.choice(names_pool) if (clean or rng.random() < 0.8) else rng.choice(odd_names)
+            elif rng.random() < 0.6:
+                o[k] = val()
+        return o
+
+    def doc(clean):
+        d, keys = {}, ["width", "objects", "height", "meta"]
+        rng.shuffle(keys)
+        for k in keys:
+            if k == "objects":
+                r = rng.random()
+                if r < 0.85: d[k] = [obj(clean) for _ in range(rng.randint(0, 5))]
+                elif r < 0.92: d[k] = val()
+            elif rng.random() < 0.7:
+                d[k] = val()
+        return d
+    lm = {"cat": "animal", "dog": "animal", "猫": "animal", "bird": "bird2", "x": "y"}
+    lanes = {"native": 0, "python": 0}
+    for _ in range(120):
+        clean = rng.random() < 0.7
+        n = rng.randint(1, 10)
+        col_new = [json.dumps(doc(clean), ensure_ascii=False) if rng.random() < 0.93 else rng.choice([None, ""] if clean else [None, "", "not json", "[1, 2]"])
+                   for _ in range(n)]
+        col_ann = [json.dumps(doc(clean), ensure_ascii=False) if rng.random() < 0.9 else None for _ in range(n)]
+        df = pd.read_csv(io.StringIO(pd.DataFrame({"source": [f"u{i}" for i in range(n)], ANN: col_ann, NEW: col_new}).to_csv(index=False)))
+        for c in (ANN, NEW):
+            if str(df[c].dtype) != "str" and df[c].notna().any():
+                df[c] = df[c].astype("str")
+        res = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("DYD_NATIVE_INGEST", mode)
+            try:
+                res[mode] = (labels.remap_df(df, lm), None)
+            except Exception as e:  # noqa: BLE001
+                res[mode] = (None, type(e).__name__)
+            if mode == "1":
+                lanes[labels.LAST["remap_lane"]] += 1
+        (a, ea), (b, eb) = res["1"], res["0"]
+        assert ea == eb
+        if ea is None:
+            pd.testing.assert_frame_equal(a[0], b[0])
+            assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and list(a[3]) == list(b[3])
+    assert lanes["native"] > 40 and lanes["python"] > 10
