@@ -193,7 +193,7 @@ __device__ __forceinline__ Corner fold_sequential(LoadFn load, int V, CornerIdx&
 // ~30 cycles, one group of compares ~50).  `base` may be read up to 3 * DYD_K1_PIPE entries past the
 // polygon's end: that is still inside the stage (the caller guarantees it) and the values are not used.
 #ifndef DYD_K1_PIPE
-#define DYD_K1_PIPE 4
+#define DYD_K1_PIPE 2
 #endif
 template <bool ARG>
 __device__ __forceinline__ void fold_step(Corner& c, CornerIdx& ci, const double2 v, int k) {

@@ -29,12 +29,12 @@ inline size_t crowd_list_bytes(int64_t n_img) {
 #define DYD_TILE_MAX_IMAGES 6
 #endif
 #ifndef DYD_TILE_CAP_V
-#define DYD_TILE_CAP_V 600
+#define DYD_TILE_CAP_V 616
 #endif
 constexpr int SEG_IMAGES = DYD_SEG_IMAGES;
 constexpr int TILE_LANES = 32;
 constexpr int TILE_MAX_IMAGES = DYD_TILE_MAX_IMAGES;
-constexpr int TILE_CAP_V = DYD_TILE_CAP_V;   // vertices staged per tile (9.4 KB)
+constexpr int TILE_CAP_V = DYD_TILE_CAP_V;   // vertices staged per tile (9.6 KB)
 struct TileDesc {                            // 32 bytes
     long long q0;                            // first object  img_off[i0]
     long long v0;                            // first vertex  poly_off[q0]
