@@ -57,6 +57,8 @@ PROTOTYPES = {
     "dyd_ingest_export_polygons": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _int]),
     "dyd_ingest_export_boxes": (_int, [_p, _p, _p, _p, _p, _int]),
     "dyd_ingest_export_names": (_int, [_p, _p, _p, _p, _p, _int]),
+    "dyd_ingest_export_objects": (_int, [_p, _p, _p, _p, _int]),
+    "dyd_egress_split": (_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _int]),
     "dyd_egress_names": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _int]),
     "dyd_egress_ptlist": (_int, [_p, _p, _p, _p, _p, _p, _p, _int]),
     "dyd_csv_write": (_int, [_p, _p, _p, _p, _i32, _i64, _p, _p, _int]),

@@ -55,10 +55,14 @@ struct RowOut {
     // step 5
     std::vector<double> boxes;           // 4 per box
     std::vector<uint8_t> bvalid;
-    // step 5.5 (mode 2): per dict object the span of its "name" string contents (len -1: None / absent)
-    std::vector<Span> names;
+    // step 5.5 / 6 (mode 2): per dict object the span of its "name" string contents (len -1: None / absent)
+    // and of the object itself; the "objects" member (key .. value) and how it sits among its siblings
+    std::vector<Span> names, objspans;
+    Span member{0, 0};
+    uint8_t member_first = 0, member_has_next = 0;
+    int32_t list_len = 0;                // elements of the "objects" list, dicts or not
 };
-enum RowStatus2 : uint8_t { ROW_NO_LIST = 4 };      // mode 2: "objects" absent or not a list -> the cell is left as it is
+enum RowStatus2 : uint8_t { ROW_NO_LIST = 4, ROW_NOT_A_LIST = 5 };   // mode 2: "objects" absent / present but not a list
 
 struct Fail {};
 
@@ -454,25 +458,30 @@ static void parse_names_row(const char* text, size_t len, RowOut& out) {
     Parser ps{text, text, text + len, true};
     ps.need(ps.p < ps.end && *ps.p == '{');             // doc.get on a non-dict raises in the reference
     ++ps.p;
-    bool have_list = false;
+    bool have_list = false, not_a_list = false, first_member = true;
     KeySet top_keys;
     if (ps.p < ps.end && *ps.p == '}') { ++ps.p; }
     else do {
+        const uint32_t key_at = ps.at();
         bool plain; Span k = ps.str(&plain); ps.check_dup(top_keys, k); ps.colon();
+        const bool is_first = first_member;
+        first_member = false;
         if (plain && ps.key_is(k, "objects")) {
             ps.need(ps.p < ps.end);
-            if (*ps.p != '[') { ps.skip(); continue; }   // not a list: the cell is skipped by the reference
+            if (*ps.p != '[') { ps.skip(); not_a_list = true; continue; }   // not a list: the cell is skipped by the reference
             have_list = true;
             ++ps.p;
-            if (ps.p < ps.end && *ps.p == ']') { ++ps.p; continue; }
-            do {
+            if (ps.p < ps.end && *ps.p == ']') { ++ps.p; }
+            else do {
+                ++out.list_len;
                 ps.need(ps.p < ps.end);
                 if (*ps.p != '{') { ps.skip(); continue; }               // non-dict elements are not counted
+                const uint32_t obj_at = ps.at();
                 ++ps.p;
                 Span name{0, (uint32_t)-1};
                 KeySet okeys;
-                if (ps.p < ps.end && *ps.p == '}') { ++ps.p; out.names.push_back(name); continue; }
-                do {
+                if (ps.p < ps.end && *ps.p == '}') { ++ps.p; }
+                else do {
                     bool pl2; Span ok = ps.str(&pl2); ps.check_dup(okeys, ok); ps.colon();
                     if (pl2 && ps.key_is(ok, "name")) {
                         ps.need(ps.p < ps.end);
@@ -481,12 +490,16 @@ static void parse_names_row(const char* text, size_t len, RowOut& out) {
                     } else ps.skip();
                 } while (ps.more('}'));
                 out.names.push_back(name);
+                out.objspans.push_back(Span{obj_at, ps.at() - obj_at});
             } while (ps.more(']'));
+            out.member = Span{key_at, ps.at() - key_at};                 // from the key's opening quote to the end of the value
+            out.member_first = is_first;
+            out.member_has_next = ps.p < ps.end && *ps.p == ',';
         } else ps.skip();
     } while (ps.more('}'));
     ps.need(ps.p == ps.end);
-    out.status = have_list ? ROW_OK : (uint8_t)ROW_NO_LIST;
-    if (!have_list) out.names.clear();
+    out.status = have_list ? ROW_OK : (uint8_t)(not_a_list ? ROW_NOT_A_LIST : ROW_NO_LIST);
+    if (!have_list) { out.names.clear(); out.objspans.clear(); out.list_len = 0; }
 }
 
 }  // namespace
@@ -831,6 +844,72 @@ extern "C" int dyd_egress_names(const dyd_ingest* h, const uint8_t* text, const 
         return bad ? DYD_E_ARG : 0;
     }
     parallel_rows(n, n_threads, [&](int64_t a, int64_t b) { for (int64_t r = a; r < b; ++r) cell(r, out + out_off[r]); });
+    return 0;
+}
+
+// mode 2, for the split (step 6): list_len[n] (elements of "objects", dicts or not), obj_off / obj_len [n_obj]
+// (span of every dict object inside its cell's text)
+extern "C" int dyd_ingest_export_objects(const dyd_ingest* h, int32_t* list_len, int64_t* obj_off, int32_t* obj_len, int n_threads) {
+    if (!h || h->mode != 2 || !list_len) return DYD_E_ARG;
+    parallel_rows(h->n_rows, n_threads, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            const RowOut& ro = h->rows[(size_t)r];
+            list_len[r] = ro.list_len;
+            int64_t q = h->obj_base[(size_t)r];
+            for (const Span& sp : ro.objspans) { if (obj_off) obj_off[q] = sp.off; if (obj_len) obj_len[q] = (int32_t)sp.len; ++q; }
+        }
+    });
+    return 0;
+}
+
+// Cells of the split's expanded rows (processor.py:760-775): json.dumps of the document with "objects" replaced
+// by the single object exp_obj[i] (global dict-object index) renamed to label exp_tok[i] -- in text form: the
+// document without its "objects" member, then `"objects": [` + the object with its name spliced + `]}`.
+// Labels are passed JSON-escaped.  out == NULL: fill out_off[n_exp+1]; else write.
+extern "C" int dyd_egress_split(const dyd_ingest* h, const uint8_t* text, const int64_t* off, int64_t n_exp,
+                                const int64_t* exp_cell, const int64_t* exp_obj, const int32_t* exp_tok,
+                                const uint8_t* tok_bytes, const int64_t* tok_off, int64_t n_tok,
+                                int64_t* out_off, uint8_t* out, int n_threads) {
+    if (!h || h->mode != 2 || n_exp < 0 || !out_off || (n_exp > 0 && (!text || !off || !exp_cell || !exp_obj || !exp_tok || !tok_bytes || !tok_off)))
+        return DYD_E_ARG;
+    static const char kOpen[] = "\"objects\": [";
+    bool bad = false;
+    auto one = [&](int64_t i, uint8_t* dst) -> int64_t {
+        const int64_t r = exp_cell[i];
+        if (r < 0 || r >= h->n_rows) return -1;
+        const RowOut& ro = h->rows[(size_t)r];
+        const int64_t k = exp_obj[i] - h->obj_base[(size_t)r];
+        const int32_t t = exp_tok[i];
+        if (ro.status != ROW_OK || k < 0 || k >= (int64_t)ro.objspans.size() || t < 0 || t >= n_tok) return -1;
+        const Span os = ro.objspans[(size_t)k], ns = ro.names[(size_t)k];
+        if (ns.len == (uint32_t)-1) return -1;                       // an object without a name has no labels
+        const uint8_t* src = text + off[r];
+        const int64_t len = off[r + 1] - off[r];
+        // the document without the "objects" member and without its closing brace
+        int64_t cut_a = ro.member.off, cut_b = (int64_t)ro.member.off + ro.member.len;
+        if (!ro.member_first) cut_a -= 2; else if (ro.member_has_next) cut_b += 2;
+        const bool others = !(ro.member_first && !ro.member_has_next);
+        const int64_t tl = tok_off[t + 1] - tok_off[t];
+        uint8_t* o = dst;
+        int64_t total = 0;
+        auto put = [&](const void* p, int64_t n) { if (o) { memcpy(o + total, p, (size_t)n); } total += n; };
+        put(src, cut_a);
+        put(src + cut_b, (len - 1) - cut_b);
+        if (others) put(", ", 2);
+        put(kOpen, (int64_t)sizeof(kOpen) - 1);
+        put(src + os.off, (int64_t)ns.off - os.off);
+        put(tok_bytes + tok_off[t], tl);
+        put(src + ns.off + ns.len, ((int64_t)os.off + os.len) - ((int64_t)ns.off + ns.len));
+        put("]}", 2);
+        return total;
+    };
+    if (!out) {
+        out_off[0] = 0;
+        parallel_rows(n_exp, n_threads, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) { const int64_t l = one(i, nullptr); if (l < 0) bad = true; out_off[i + 1] = l < 0 ? 0 : l; } });
+        for (int64_t i = 0; i < n_exp; ++i) out_off[i + 1] += out_off[i];
+        return bad ? DYD_E_ARG : 0;
+    }
+    parallel_rows(n_exp, n_threads, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) one(i, out + out_off[i]); });
     return 0;
 }
 

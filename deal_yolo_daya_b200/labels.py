@@ -20,7 +20,7 @@ import pandas as pd
 COL_ANN = "结果字段-目标检测标签配置"
 COL_NEW = "新_结果字段-目标检测标签配置"
 _SEP = re.compile(r"[,，;；|]")
-LAST = {"remap_lane": None}          # observability: which lane the last remap_df call took
+LAST = {"remap_lane": None, "split_lane": None}          # observability: which lane the last call took
 
 
 def _kernels():
@@ -371,6 +371,188 @@ def _parse_objects(text):
         return None, [], str(e)
 
 
+def _split_native(df, l2c, json_columns, train_ratio, val_ratio, random_seed):
+    """Native lane of split_df: the JSON column every row uses holds json.dumps-form text, so the objects'
+    names and spans come from csrc/ingest.cpp (mode 2), the (object, label) entries, label sets and the
+    unclassified / split_counts bookkeeping are built on arrays, K6 groups and assigns, and the one-object
+    cells are spliced natively (dyd_egress_split).  Returns None when a row needs CPython's json or picks a
+    different JSON column: the caller then runs the Python lane for the whole frame."""
+    from . import native
+    n = len(df)
+    if not native.enabled() or n == 0 or not native._pandas_infers_arrow_str():
+        return None
+    c0 = next((c for c in json_columns if c in df.columns), None)
+    if c0 is None:
+        return None
+    pa_arr = getattr(df[c0].array, "_pa_array", None)
+    if pa_arr is None or pa_arr.null_count:
+        return None
+    import pyarrow.compute as pc
+    if not pc.all(pc.greater(pc.binary_length(pa_arr), 0)).as_py():
+        return None                                            # some row would fall through to the next JSON column
+    ing = native.Ingest(df[c0], 2)
+    try:
+        if ing.n_slow:
+            return None
+        ing.names().objects()
+        st = ing.status
+        cnt_obj = np.diff(ing.cell_off)
+        n_obj = ing.n_obj
+        obj_row = np.repeat(np.arange(n, dtype=np.int64), cnt_obj)
+        # ---- names -> label tokens (string rules on the distinct names only) ----
+        if n_obj:
+            enc = pc.dictionary_encode(ing.name_array())
+            ids = np.asarray(enc.indices.fill_null(-1)).astype(np.int64)
+            uniq = enc.dictionary.to_pylist()
+        else:
+            ids = np.zeros(0, np.int64); uniq = []
+        tok_ids, tok_names, flat, name_off = {}, [], [], [0]
+        for nm in uniq:
+            for t in split_labels(nm):
+                i = tok_ids.get(t)
+                if i is None:
+                    i = tok_ids[t] = len(tok_names); tok_names.append(t)
+                flat.append(i)
+            name_off.append(len(flat))
+        n_tok = len(tok_names)
+        name_off = np.array(name_off, np.int64); flat = np.array(flat, np.int64)
+        ntok_name = np.diff(name_off)
+        ntok_obj = np.where(ids >= 0, np.append(ntok_name, 0)[np.where(ids >= 0, ids, len(ntok_name))], 0).astype(np.int64)
+        n_ent = int(ntok_obj.sum())
+        ent_obj = np.repeat(np.arange(n_obj, dtype=np.int64), ntok_obj)
+        ent_first = np.cumsum(ntok_obj) - ntok_obj
+        ent_tok = flat[name_off[ids[ent_obj]] + (np.arange(n_ent, dtype=np.int64) - ent_first[ent_obj])] if n_ent else np.zeros(0, np.int64)
+        ent_row = obj_row[ent_obj]
+        row_off = np.zeros(n + 1, np.int64)
+        np.cumsum(np.bincount(ent_row, minlength=n), out=row_off[1:])
+        # ---- categories in first-encounter order over the entries ----
+        tok_cat = [l2c.get(t) for t in tok_names]
+        known_tok = np.array([c is not None for c in tok_cat], bool) if n_tok else np.zeros(0, bool)
+        first_of_tok = np.full(n_tok, n_ent, np.int64)
+        if n_ent:
+            np.minimum.at(first_of_tok, ent_tok, np.arange(n_ent, dtype=np.int64))
+        cat_first = {}
+        for t in range(n_tok):
+            if tok_cat[t] is not None:
+                cat_first[tok_cat[t]] = min(cat_first.get(tok_cat[t], n_ent), int(first_of_tok[t]))
+        cat_names = sorted(cat_first, key=cat_first.get)
+        cat_ids = {c: i for i, c in enumerate(cat_names)}
+        n_cat = len(cat_names)
+        cat_of_label = np.array([cat_ids[c] if c is not None else -1 for c in tok_cat], np.int32) if n_tok else np.zeros(0, np.int32)
+        # ---- label-set string of every row: sorted distinct tokens joined by the full-width comma ----
+        combo = [""] * n
+        if n_ent:
+            by_name = sorted(range(n_tok), key=tok_names.__getitem__)
+            rank = np.empty(n_tok, np.int64); rank[by_name] = np.arange(n_tok)
+            names_by_rank = [tok_names[t] for t in by_name]
+            uk = np.unique(ent_row * n_tok + rank[ent_tok])
+            urow, urank = uk // n_tok, uk % n_tok
+            cut = np.searchsorted(urow, np.arange(n + 1))
+            for r in np.nonzero(np.diff(cut))[0]:
+                combo[r] = "，".join(names_by_rank[k] for k in urank[cut[r]:cut[r + 1]])
+        # ---- device: stable grouping by category, split ids from the host permutation ----
+        labels = ent_tok.astype(np.int32)
+        if n_cat and n_ent:
+            exp_row, exp_entry, exp_cat, cat_off = _kernels().split_expand(row_off, labels, cat_of_label, n_cat)
+        else:
+            exp_row = np.zeros(0, np.int64); exp_entry = np.zeros(0, np.int64); cat_off = np.zeros(n_cat + 1, np.int64)
+        sizes = np.diff(cat_off)
+        n_train = np.array([int(k * train_ratio) for k in sizes], np.int64)
+        n_val = np.array([int(k * val_ratio) for k in sizes], np.int64)
+        perms = [np.random.RandomState(random_seed).permutation(int(k)) for k in sizes]
+        perm = np.concatenate(perms).astype(np.int64) if perms else np.zeros(0, np.int64)
+        if len(perm):
+            split_id, pos = _kernels().split_assign(cat_off, perm, n_train, n_val)
+        else:
+            split_id = np.zeros(0, np.uint8); pos = np.zeros(0, np.int64)
+        # ---- egress: per-category frames, cells spliced natively ----
+        esc = [json.dumps(t, ensure_ascii=False)[1:-1].encode("utf-8") for t in tok_names]
+        t_off = np.zeros(n_tok + 1, np.int64)
+        if esc:
+            np.cumsum([len(e) for e in esc], out=t_off[1:])
+        t_bytes = np.frombuffer(b"".join(esc) or b"\0", dtype=np.uint8)
+        keep_cols = [c for c in df.columns if c not in json_columns]
+        categories, cat_counts = {}, {}
+        for ci, cat in enumerate(cat_names):
+            a, b = int(cat_off[ci]), int(cat_off[ci + 1])
+            if b == a:
+                continue
+            cat_counts[cat] = b - a
+            order = np.empty(b - a, np.int64)
+            order[pos[a:b]] = np.arange(b - a)             # shuffled position -> original expanded row
+            rows_idx = np.asarray(exp_row[a:b])[order]
+            ents = np.asarray(exp_entry[a:b])[order]
+            out, out_off = ing.egress_split(rows_idx, ent_obj[ents], ent_tok[ents], t_bytes, t_off)
+            cells = native.arrow_strings(out, out_off)
+            frame = df[keep_cols].iloc[rows_idx].reset_index(drop=True)
+            for c in json_columns:
+                if c in df.columns:
+                    frame[c] = cells
+            frame = frame[list(df.columns)]
+            frame["分类标签"] = [tok_names[t] for t in ent_tok[ents]]
+            frame["分类类别"] = cat
+            frame["原始标签组合"] = [combo[r] for r in rows_idx]
+            sp = np.asarray(split_id[a:b])[order]
+            categories[cat] = {"train": frame[sp == 0], "val": frame[sp == 1], "test": frame[sp == 2]}
+        # ---- unclassified rows and split_counts in reference order, on arrays ----
+        bad = (st != native.ROW_OK) | (ing.list_len == 0)
+        bad_reason = np.where(st == native.ROW_NOT_A_LIST, "objects不是列表", "标注字段objects为空")
+        ent_known = known_tok[ent_tok] if n_ent else np.zeros(0, bool)
+        n_ok_row = np.bincount(ent_row[ent_known], minlength=n) if n_ent else np.zeros(n, np.int64)
+        reason_tok = [f"标签{t}未在规则中定义" for t in tok_names]
+        b_ent = np.nonzero(~ent_known)[0]
+        row_reasons = [""] * n                                  # "；".join(sorted(set(reasons))) per row
+        has_reason = np.zeros(n, bool)
+        if len(b_ent):
+            by_reason = sorted(range(n_tok), key=reason_tok.__getitem__)
+            rrank = np.empty(n_tok, np.int64); rrank[by_reason] = np.arange(n_tok)
+            reason_by_rank = [reason_tok[t] for t in by_reason]
+            uk = np.unique(ent_row[b_ent] * n_tok + rrank[ent_tok[b_ent]])
+            urow, urank = uk // n_tok, uk % n_tok
+            cut = np.searchsorted(urow, np.arange(n + 1))
+            for r in np.nonzero(np.diff(cut))[0]:
+                row_reasons[r] = "；".join(reason_by_rank[k] for k in urank[cut[r]:cut[r + 1]])
+                has_reason[r] = True
+        a_obj = np.nonzero(ntok_obj == 0)[0]
+        c_row = np.nonzero(~bad & (n_ok_row == 0))[0]
+        d_row = np.nonzero(bad)[0]
+        ev_row = np.concatenate([d_row, obj_row[a_obj], ent_row[b_ent], c_row])
+        ev_k2 = np.concatenate([np.full(len(d_row), -1, np.int64), a_obj, ent_obj[b_ent], np.full(len(c_row), n_obj + 1, np.int64)])
+        ev_k3 = np.concatenate([np.zeros(len(d_row), np.int64), np.full(len(a_obj), -1, np.int64), b_ent, np.zeros(len(c_row), np.int64)])
+        ev_reason = ([str(x) for x in bad_reason[d_row]] + ["标注框缺少name字段"] * len(a_obj) + [reason_tok[t] for t in ent_tok[b_ent]] +
+                     [row_reasons[r] if has_reason[r] else "标签无法匹配规则" for r in c_row])
+        ev_label = [None] * (len(d_row) + len(a_obj)) + [tok_names[t] for t in ent_tok[b_ent]] + [None] * len(c_row)
+        o = np.lexsort((ev_k3, ev_k2, ev_row))
+        unc_rows = ev_row[o]
+        unc_reason = [ev_reason[i] for i in o]
+        unc_label = [ev_label[i] for i in o]
+        if len(unc_rows):
+            unc = df.iloc[unc_rows].reset_index(drop=True)
+            unc["无法分类原因"] = unc_reason
+            if len(b_ent):
+                unc["无法分类标签"] = pd.Series(unc_label, dtype=object).where(pd.Series([x is not None for x in unc_label]), np.nan)
+        else:
+            unc = pd.DataFrame()
+        sources = df["source"].tolist() if "source" in df.columns else [None] * n
+        status = np.where(bad | (n_ok_row == 0), "否", np.where(has_reason, "部分可分类", "是"))
+        counts = pd.DataFrame({
+            "source": sources,
+            "原始标签组合": [("" if bad[r] else combo[r]) for r in range(n)],
+            "拆分条数": np.where(bad, 0, n_ok_row).astype(np.int64),
+            "是否可分类": [str(x) for x in status],
+            "无法分类原因": [(str(bad_reason[r]) if bad[r] else row_reasons[r]) for r in range(n)],
+        }) if n else pd.DataFrame([])
+    finally:
+        ing.close()
+    return {
+        "categories": categories,
+        "unclassified": unc,
+        "split_counts": counts,
+        "summary": {"categories": n_cat, "classified": int(sum(cat_counts.values())), "unclassified": int(len(unc_rows)),
+                    "category_counts": cat_counts},
+    }
+
+
 def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
              train_ratio=0.8, val_ratio=0.1, test_ratio=0.1, random_seed=42):
     """DataFrame core of split_dataset_by_rules -> dict(categories={cat: {train,val,test}}, unclassified,
@@ -380,6 +562,10 @@ def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
     train_ratio /= tot; val_ratio /= tot; test_ratio /= tot
     if json_columns is None:
         json_columns = default_json_columns(df)
+    fast = _split_native(df, l2c, list(json_columns), train_ratio, val_ratio, random_seed)
+    LAST["split_lane"] = "native" if fast is not None else "python"
+    if fast is not None:
+        return fast
     jcols_present = [c for c in json_columns if c in df.columns]
     n_rows = len(df)
     col_values = {c: df[c].tolist() for c in jcols_present}

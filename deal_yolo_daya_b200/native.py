@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 
-ROW_OK, ROW_SLOW, ROW_NOT_TEXT, ROW_NO_LIST = 0, 1, 2, 4
+ROW_OK, ROW_SLOW, ROW_NOT_TEXT, ROW_NO_LIST, ROW_NOT_A_LIST = 0, 1, 2, 4, 5
 K_INT, K_FLT, K_TRUE, K_FALSE, K_NULL = 3, 4, 5, 6, 7
 
 
@@ -156,6 +156,28 @@ class Ingest:
             data = np.zeros(1, np.uint8)
         valid = np.packbits(self.name_len >= 0, bitorder="little")
         return pa.Array.from_buffers(pa.large_string(), self.n_obj, [pa.py_buffer(valid), pa.py_buffer(o), pa.py_buffer(data)])
+
+    def objects(self):
+        """list_len int32[n] (elements of "objects"), obj_off int64 / obj_len int32 [n_obj] (dict-object spans)."""
+        self.list_len = np.empty(self.n, np.int32)
+        self.obj_off = np.empty(self.n_obj, np.int64)
+        self.obj_len = np.empty(self.n_obj, np.int32)
+        _lib.check(self.lib.dyd_ingest_export_objects(self.h, _p(self.list_len), _p(self.obj_off), _p(self.obj_len), _threads()),
+                   "dyd_ingest_export_objects")
+        return self
+
+    def egress_split(self, exp_cell, exp_obj, exp_tok, tok_bytes, tok_off):
+        """-> (out bytes uint8[], out_off int64[n_exp+1]): the one-object cells of the split's expanded rows."""
+        exp_cell = np.ascontiguousarray(exp_cell, np.int64); exp_obj = np.ascontiguousarray(exp_obj, np.int64)
+        exp_tok = np.ascontiguousarray(exp_tok, np.int32)
+        tok_bytes = np.ascontiguousarray(tok_bytes, np.uint8); tok_off = np.ascontiguousarray(tok_off, np.int64)
+        n_exp = len(exp_cell)
+        out_off = np.empty(n_exp + 1, np.int64)
+        a = (self.h, _p(self.text), _p(self.off), n_exp, _p(exp_cell), _p(exp_obj), _p(exp_tok), _p(tok_bytes), _p(tok_off), len(tok_off) - 1, _p(out_off))
+        _lib.check(self.lib.dyd_egress_split(*a, None, _threads()), "dyd_egress_split(size)")
+        out = np.empty(max(int(out_off[-1]), 1), np.uint8)
+        _lib.check(self.lib.dyd_egress_split(*a, _p(out), _threads()), "dyd_egress_split(write)")
+        return out[:int(out_off[-1])], out_off
 
     def egress_names(self, obj_flag, obj_new, vocab_bytes, vocab_off):
         """-> (out bytes uint8[], out_off int64[n+1]): new texts of the ROW_OK cells (length 0 for the others)."""

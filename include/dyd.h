@@ -237,6 +237,14 @@ int dyd_ingest_export_boxes(const dyd_ingest* h, uint8_t* status, int64_t* img_o
  * with the flagged objects' names replaced by JSON-escaped vocabulary entries.                        */
 int dyd_ingest_export_names(const dyd_ingest* h, uint8_t* status, int64_t* cell_off, int64_t* name_off, int32_t* name_len,
                             int n_threads);
+/* mode 2 for the split (step 6, processor.py:741-775): status 5 = "objects" present but not a list; list_len =
+ * elements of the list (dicts or not); obj_off / obj_len = span of every dict object.  dyd_egress_split writes
+ * the cells of the expanded rows: the document with "objects" replaced by one object renamed to one label.   */
+int dyd_ingest_export_objects(const dyd_ingest* h, int32_t* list_len, int64_t* obj_off, int32_t* obj_len, int n_threads);
+int dyd_egress_split(const dyd_ingest* h, const uint8_t* text, const int64_t* off, int64_t n_exp,
+                     const int64_t* exp_cell, const int64_t* exp_obj, const int32_t* exp_tok,
+                     const uint8_t* tok_bytes, const int64_t* tok_off, int64_t n_tok,
+                     int64_t* out_off, uint8_t* out, int n_threads);
 int dyd_egress_names(const dyd_ingest* h, const uint8_t* text, const int64_t* off, const uint8_t* obj_flag,
                      const int32_t* obj_new, const uint8_t* vocab_bytes, const int64_t* vocab_off, int64_t n_vocab,
                      int64_t* out_off, uint8_t* out, int n_threads);

@@ -354,3 +354,89 @@ def test_remap_lanes_agree_on_random_documents(monkeypatch):
             pd.testing.assert_frame_equal(a[0], b[0])
             assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and list(a[3]) == list(b[3])
     assert lanes["native"] > 40 and lanes["python"] > 10
+
+
+def test_split_lanes_agree_on_random_documents(monkeypatch):
+    """split_df: the native / array lane (names and spans from csrc/ingest.cpp, cells spliced by
+    dyd_egress_split, bookkeeping on arrays) against the CPython lane on random documents -- same category
+    frames (values, dtypes, index), unclassified sheet, split_counts sheet and summary, or the same exception."""
+    from deal_yolo_daya_b200 import labels
+    rng = random.Random(4242)
+    names_pool = ["cat", "dog", "cat,dog", "猫", "cat；bird", " cat ", "", "x|y", "bird", "a,b,a", "ab", "a"]
+    odd_names = [None, 5, 2.5, True, ["cat"], {"a": 1}, 'q"uote', "back\\slash", "new\nline"]
+
+    def val(d=0):
+        t = rng.random()
+        if t < 0.3: return rng.randint(-5, 2000)
+        if t < 0.5: return round(rng.uniform(-10, 3000), rng.randint(0, 6))
+        if t < 0.6: return rng.choice([None, True, False])
+        if t < 0.8: return rng.choice(["s", "中文", "", "a b"])
+        if d > 1: return 1
+        if t < 0.9: return [val(d + 1) for _ in range(rng.randint(0, 3))]
+        return {rng.choice("abcxyz"): val(d + 1) for _ in range(rng.randint(0, 3))}
+
+    def obj(clean):
+        if rng.random() < (0.05 if clean else 0.1):
+            return rng.choice([1, "str", None, [1]])
+        o, keys = {}, ["name", "polygon", "id", "score"]
+        rng.shuffle(keys)
+        for k in keys:
+            if k == "name":
+                if rng.random() < 0.85:
+                    o["name"] = rng.choice(names_pool) if (clean or rng.random() < 0.8) else rng.choice(odd_names)
+                    if clean and rng.random() < 0.05:
+                        o["name"] = None
+            elif rng.random() < 0.6:
+                o[k] = val()
+        return o
+
+    def doc(clean):
+        d, keys = {}, ["width", "objects", "height", "meta"]
+        rng.shuffle(keys)
+        for k in keys:
+            if k == "objects":
+                r = rng.random()
+                if r < 0.85: d[k] = [obj(clean) for _ in range(rng.randint(0, 5))]
+                elif r < 0.92: d[k] = val()
+            elif rng.random() < 0.7:
+                d[k] = val()
+        return d
+
+    def same_frame(a, b):
+        if len(a) == 0 and len(b) == 0:
+            return
+        pd.testing.assert_frame_equal(a.reset_index(drop=True), b.reset_index(drop=True))
+        assert list(a.index) == list(b.index)
+    l2c = {"cat": "动物", "dog": "动物", "猫": "动物", "bird": "鸟类", "x": "其它", "a": "其它"}
+    lanes = {"native": 0, "python": 0}
+    for _ in range(150):
+        clean = rng.random() < 0.75
+        n = rng.randint(1, 14)
+        col_new = [json.dumps(doc(clean), ensure_ascii=False) if (clean or rng.random() < 0.93) else rng.choice([None, "", "not json", "[1, 2]"])
+                   for _ in range(n)]
+        col_ann = [json.dumps(doc(clean), ensure_ascii=False) if rng.random() < 0.9 else None for _ in range(n)]
+        cols = {"source": [f"u{i}" for i in range(n)], ANN: col_ann, NEW: col_new}
+        if rng.random() < 0.3:
+            cols["width"] = [rng.randint(1, 9) for _ in range(n)]
+        df = pd.read_csv(io.StringIO(pd.DataFrame(cols).to_csv(index=False)))
+        for c in (ANN, NEW):
+            if str(df[c].dtype) != "str" and df[c].notna().any():
+                df[c] = df[c].astype("str")
+        res = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("DYD_NATIVE_INGEST", mode)
+            try:
+                res[mode] = (labels.split_df(df, l2c), None)
+            except Exception as e:  # noqa: BLE001
+                res[mode] = (None, type(e).__name__)
+            if mode == "1":
+                lanes[labels.LAST["split_lane"]] += 1
+        (a, ea), (b, eb) = res["1"], res["0"]
+        assert ea == eb
+        if ea is None:
+            assert a["summary"] == b["summary"] and list(a["categories"]) == list(b["categories"])
+            for cat in a["categories"]:
+                for part in ("train", "val", "test"):
+                    same_frame(a["categories"][cat][part], b["categories"][cat][part])
+            same_frame(a["unclassified"], b["unclassified"]); same_frame(a["split_counts"], b["split_counts"])
+    assert lanes["native"] > 60 and lanes["python"] > 15
