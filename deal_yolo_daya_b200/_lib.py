@@ -56,6 +56,8 @@ PROTOTYPES = {
     "dyd_ingest_sizes": (_int, [_p, _p, _p, _p]),
     "dyd_ingest_export_polygons": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _int]),
     "dyd_ingest_export_boxes": (_int, [_p, _p, _p, _p, _p, _int]),
+    "dyd_ingest_effective_text": (_int, [_p, _p, _p, _p, _p, _p, _int]),
+    "dyd_json_canonical": (_i64, [_p, _i64, _p, _i64]),
     "dyd_ingest_export_names": (_int, [_p, _p, _p, _p, _p, _int]),
     "dyd_ingest_export_objects": (_int, [_p, _p, _p, _p, _int]),
     "dyd_egress_split": (_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _int]),

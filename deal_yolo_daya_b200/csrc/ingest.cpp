@@ -58,6 +58,8 @@ struct RowOut {
     // step 5.5 / 6 (mode 2): per dict object the span of its "name" string contents (len -1: None / absent)
     // and of the object itself; the "objects" member (key .. value) and how it sits among its siblings
     std::vector<Span> names, objspans;
+    std::string canon;                   // json.dumps(json.loads(text)) when the text was valid JSON in another style:
+                                         // every span of this row then refers to `canon`, not to the input text
     Span member{0, 0};
     uint8_t member_first = 0, member_has_next = 0;
     int32_t list_len = 0;                // elements of the "objects" list, dicts or not
@@ -266,6 +268,152 @@ struct Parser {
     }
     bool key_is(Span k, const char* s) const { size_t n = strlen(s); return k.len == n && memcmp(base + k.off, s, n) == 0; }
 };
+
+// ---------------------------------------------------------------- canonical form
+// json.dumps(json.loads(text), ensure_ascii=False) without CPython: any valid JSON text (other separators,
+// indentation, \u escapes, "1.50", "1E5" ...) is rewritten in the one style the splicing lanes work on.
+// The parsed VALUE is untouched by construction (same ints, same floats, same strings), so whatever the
+// reference computes from json.loads(text) it also computes from json.loads(canonical text).  Documents
+// this file is not certain about (duplicate keys, escaped keys, lone surrogates, nesting deeper than 200,
+// anything json.loads rejects) fail and stay with the CPython lane.
+static void canon_string(Parser& ps, std::string& o, bool is_key) {
+    ps.need(ps.p < ps.end && *ps.p == '"'); ++ps.p;
+    o.push_back('"');
+    auto put_cp = [&](unsigned cp) {
+        switch (cp) {
+            case '"': o += "\\\""; return;
+            case '\\': o += "\\\\"; return;
+            case '\n': o += "\\n"; return;
+            case '\r': o += "\\r"; return;
+            case '\t': o += "\\t"; return;
+            case '\b': o += "\\b"; return;
+            case '\f': o += "\\f"; return;
+            default: break;
+        }
+        if (cp < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", cp); o += b; return; }
+        if (cp < 0x80) o.push_back((char)cp);
+        else if (cp < 0x800) { o.push_back((char)(0xC0 | (cp >> 6))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+        else if (cp < 0x10000) { o.push_back((char)(0xE0 | (cp >> 12))); o.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+        else { o.push_back((char)(0xF0 | (cp >> 18))); o.push_back((char)(0x80 | ((cp >> 12) & 0x3F))); o.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+    };
+    auto hex4 = [&](const char* q) {
+        unsigned cp = 0;
+        for (int i = 0; i < 4; ++i) {
+            const char h = q[i]; unsigned d;
+            if (h >= '0' && h <= '9') d = h - '0';
+            else if (h >= 'a' && h <= 'f') d = h - 'a' + 10;
+            else if (h >= 'A' && h <= 'F') d = h - 'A' + 10;
+            else Parser::fail();
+            cp = cp * 16 + d;
+        }
+        return cp;
+    };
+    for (;;) {
+        ps.need(ps.p < ps.end);
+        const unsigned char c = (unsigned char)*ps.p;
+        if (c == '"') { ++ps.p; break; }
+        if (c == '\\') {
+            ps.need(ps.p + 1 < ps.end);
+            const char e = ps.p[1];
+            if (e == 'u') {
+                ps.need(ps.p + 5 < ps.end);
+                unsigned cp = hex4(ps.p + 2);
+                ps.p += 6;
+                if (cp >= 0xD800 && cp <= 0xDBFF) {
+                    ps.need(ps.p + 5 < ps.end && ps.p[0] == '\\' && ps.p[1] == 'u');
+                    const unsigned lo = hex4(ps.p + 2);
+                    ps.need(lo >= 0xDC00 && lo <= 0xDFFF);               // a lone surrogate cannot be written as UTF-8
+                    ps.p += 6;
+                    cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                } else ps.need(!(cp >= 0xDC00 && cp <= 0xDFFF));
+                put_cp(cp);
+            } else {
+                unsigned cp;
+                switch (e) {
+                    case '"': cp = '"'; break;  case '\\': cp = '\\'; break;  case '/': cp = '/'; break;
+                    case 'b': cp = '\b'; break; case 'f': cp = '\f'; break; case 'n': cp = '\n'; break;
+                    case 'r': cp = '\r'; break; case 't': cp = '\t'; break;
+                    default: Parser::fail();
+                }
+                ps.p += 2;
+                put_cp(cp);
+            }
+            continue;
+        }
+        ps.need(c >= 0x20);                         // raw control characters are not valid JSON
+        o.push_back((char)c);
+        ++ps.p;
+    }
+    o.push_back('"');
+    (void)is_key;
+}
+
+static void canon_value(Parser& ps, std::string& o, int depth) {
+    ps.need(depth < 200);
+    ps.ws();
+    ps.need(ps.p < ps.end);
+    const char c = *ps.p;
+    if (c == '{') {
+        ++ps.p; ps.ws();
+        o.push_back('{');
+        if (ps.p < ps.end && *ps.p == '}') { ++ps.p; o.push_back('}'); return; }
+        // duplicate keys (json.loads keeps the last value at the first position) are left to CPython; keys are
+        // compared in their canonical spelling, which is unique per string
+        size_t key_at[KeySet::CAP], key_len[KeySet::CAP];
+        int n_keys = 0;
+        for (;;) {
+            ps.ws();
+            const size_t o_at = o.size();
+            canon_string(ps, o, true);
+            const size_t kl = o.size() - o_at;
+            for (int i = 0; i < n_keys; ++i) ps.need(!(key_len[i] == kl && memcmp(o.data() + key_at[i], o.data() + o_at, kl) == 0));
+            ps.need(n_keys < KeySet::CAP);
+            key_at[n_keys] = o_at; key_len[n_keys] = kl; ++n_keys;
+            ps.colon();
+            o += ": ";
+            canon_value(ps, o, depth + 1);
+            if (!ps.more('}')) break;
+            o += ", ";
+        }
+        o.push_back('}');
+        return;
+    }
+    if (c == '[') {
+        ++ps.p; ps.ws();
+        o.push_back('[');
+        if (ps.p < ps.end && *ps.p == ']') { ++ps.p; o.push_back(']'); return; }
+        for (;;) {
+            canon_value(ps, o, depth + 1);
+            if (!ps.more(']')) break;
+            o += ", ";
+        }
+        o.push_back(']');
+        return;
+    }
+    if (c == '"') { canon_string(ps, o, false); return; }
+    Span sp; double v;
+    const Kind k = ps.scalar(&sp, &v);
+    switch (k) {
+        case K_TRUE: o += "true"; break;
+        case K_FALSE: o += "false"; break;
+        case K_NULL: o += "null"; break;
+        case K_FLT: { char b[40]; const int n = py_float_repr(v, b); o.append(b, (size_t)n); break; }
+        default: {                                  // int: the digits as written; int("-0") is 0
+            const char* q = ps.base + sp.off;
+            if (sp.len >= 2 && q[0] == '-' && q[1] == '0') o.push_back('0'); else o.append(q, sp.len);
+        }
+    }
+}
+
+// whole document; fails (throws) unless the text is exactly one JSON value surrounded by whitespace
+static void canonicalize(const char* text, size_t len, std::string& o) {
+    Parser ps{text, text, text + len, false};
+    o.clear();
+    o.reserve(len + len / 8);
+    canon_value(ps, o, 0);
+    ps.ws();
+    ps.need(ps.p == ps.end);
+}
 
 // ---------------------------------------------------------------- step 4: polygons
 static void parse_point(Parser& ps, RowOut& out, bool& valid_point) {
@@ -509,7 +657,7 @@ struct dyd_ingest {
     int64_t n_rows = 0;
     std::vector<RowOut> rows;
     std::vector<int64_t> obj_base, vert_base;    // exclusive prefix over rows
-    int64_t n_obj = 0, n_vert = 0, n_slow = 0;
+    int64_t n_obj = 0, n_vert = 0, n_slow = 0, n_canon = 0;
 };
 
 namespace {
@@ -571,7 +719,18 @@ extern "C" int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const u
             try {
                 if (len >= (1ull << 31)) throw Fail{};
                 if (mode == 2 && len == 0) { ro.status = ROW_NOT_TEXT; continue; }     // an empty cell is skipped like a missing one
-                if (mode == 0) parse_polygon_row(s, len, true, ro); else if (mode == 1) parse_box_row(s, len, ro); else parse_names_row(s, len, ro);
+                if (mode == 1) { parse_box_row(s, len, ro); continue; }
+                try {
+                    if (mode == 0) parse_polygon_row(s, len, true, ro); else parse_names_row(s, len, ro);
+                } catch (const Fail&) {
+                    // not in json.dumps form (or not acceptable at all): rewrite it canonically and try again
+                    ro = RowOut();
+                    std::string canon;
+                    canonicalize(s, len, canon);
+                    if (canon.size() >= (1ull << 31)) throw Fail{};
+                    if (mode == 0) parse_polygon_row(canon.data(), canon.size(), true, ro); else parse_names_row(canon.data(), canon.size(), ro);
+                    ro.canon = std::move(canon);
+                }
             } catch (const Fail&) {
                 ro = RowOut(); ro.status = ROW_SLOW;
             } catch (const std::bad_alloc&) {
@@ -585,6 +744,7 @@ extern "C" int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const u
         const RowOut& ro = h->rows[(size_t)r];
         h->obj_base[(size_t)r] = no; h->vert_base[(size_t)r] = nv;
         if (ro.status == ROW_SLOW) ++ns;
+        if (!ro.canon.empty()) ++h->n_canon;
         no += mode == 0 ? (int64_t)ro.polys.size() : (mode == 1 ? (int64_t)ro.bvalid.size() : (int64_t)ro.names.size());
         nv += (int64_t)ro.verts.size();
     }
@@ -595,6 +755,52 @@ extern "C" int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const u
 }
 
 extern "C" void dyd_ingest_free(dyd_ingest* h) { delete h; }
+
+// Rows that were valid JSON in another style have been rewritten canonically; their spans refer to the
+// rewritten text.  n_canon = how many; with new_text == NULL new_off[n+1] receives the offsets of the
+// effective texts (rewritten where rewritten, input otherwise), with new_text they are written.  The caller
+// passes these buffers, not the input, to every export / egress call that takes `text` and `off`.
+extern "C" int dyd_ingest_effective_text(const dyd_ingest* h, const uint8_t* text, const int64_t* off, int64_t* n_canon,
+                                         int64_t* new_off, uint8_t* new_text, int n_threads) {
+    if (!h) return DYD_E_ARG;
+    if (n_canon) *n_canon = h->n_canon;
+    if (!new_off) return 0;
+    if (!off || (!text && h->n_rows > 0)) return DYD_E_ARG;
+    const int64_t n = h->n_rows;
+    if (!new_text) {
+        new_off[0] = 0;
+        for (int64_t r = 0; r < n; ++r) {
+            const RowOut& ro = h->rows[(size_t)r];
+            new_off[r + 1] = new_off[r] + (ro.canon.empty() ? off[r + 1] - off[r] : (int64_t)ro.canon.size());
+        }
+        return 0;
+    }
+    parallel_rows(n, n_threads, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            const RowOut& ro = h->rows[(size_t)r];
+            if (ro.canon.empty()) memcpy(new_text + new_off[r], text + off[r], (size_t)(off[r + 1] - off[r]));
+            else memcpy(new_text + new_off[r], ro.canon.data(), ro.canon.size());
+        }
+    });
+    return 0;
+}
+
+// json.dumps(json.loads(text), ensure_ascii=False) of one document (test hook of the canonical rewriter).
+// Returns the length, -1 if this file leaves the document to CPython, -2 if `cap` is too small.
+extern "C" int64_t dyd_json_canonical(const uint8_t* text, int64_t len, uint8_t* out, int64_t cap) {
+    if (!text || len < 0) return -1;
+    try {
+        std::string o;
+        canonicalize(reinterpret_cast<const char*>(text), (size_t)len, o);
+        if ((int64_t)o.size() > cap || !out) return -2;
+        memcpy(out, o.data(), o.size());
+        return (int64_t)o.size();
+    } catch (const Fail&) {
+        return -1;
+    } catch (const std::bad_alloc&) {
+        return -1;
+    }
+}
 
 extern "C" int dyd_ingest_sizes(const dyd_ingest* h, int64_t* n_obj, int64_t* n_vert, int64_t* n_slow) {
     if (!h) return DYD_E_ARG;

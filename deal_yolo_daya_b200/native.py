@@ -82,6 +82,18 @@ class Ingest:
         no, nv, ns = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self.lib.dyd_ingest_sizes(self.h, C.byref(no), C.byref(nv), C.byref(ns)), "dyd_ingest_sizes")
         self.n_obj, self.n_vert, self.n_slow = no.value, nv.value, ns.value
+        # cells that were valid JSON in another style were rewritten as json.dumps would write them and parsed
+        # from that form: every later call must see the rewritten texts
+        nc = C.c_int64()
+        _lib.check(self.lib.dyd_ingest_effective_text(self.h, None, None, C.byref(nc), None, None, 0), "dyd_ingest_effective_text(count)")
+        self.n_canon = nc.value
+        if self.n_canon:
+            new_off = np.empty(self.n + 1, np.int64)
+            a = (self.h, _p(self.text), _p(self.off), None, _p(new_off))
+            _lib.check(self.lib.dyd_ingest_effective_text(*a, None, _threads()), "dyd_ingest_effective_text(size)")
+            new_text = np.empty(max(int(new_off[-1]), 1), np.uint8)
+            _lib.check(self.lib.dyd_ingest_effective_text(*a, _p(new_text), _threads()), "dyd_ingest_effective_text(write)")
+            self.text, self.off = new_text, new_off
 
     def close(self):
         if getattr(self, "h", None):

@@ -227,6 +227,14 @@ int dyd_ingest_cells(const uint8_t* text, const int64_t* off, const uint8_t* is_
                      int mode, int n_threads, dyd_ingest** out);
 void dyd_ingest_free(dyd_ingest* h);
 int dyd_ingest_sizes(const dyd_ingest* h, int64_t* n_obj, int64_t* n_vert, int64_t* n_slow);
+/* Cells of modes 0 and 2 that are valid JSON in another style than json.dumps' are rewritten canonically
+ * (= json.dumps(json.loads(text), ensure_ascii=False), same parsed value) and parsed from that form; every span
+ * of such a row refers to the rewritten text.  n_canon = how many rows; new_off / new_text = the effective
+ * texts (call with new_text == NULL for the offsets first) to pass to the export / egress calls instead of the
+ * input.  dyd_json_canonical rewrites one document (test hook; -1: left to CPython, -2: buffer too small).   */
+int dyd_ingest_effective_text(const dyd_ingest* h, const uint8_t* text, const int64_t* off, int64_t* n_canon,
+                              int64_t* new_off, uint8_t* new_text, int n_threads);
+int64_t dyd_json_canonical(const uint8_t* text, int64_t len, uint8_t* out, int64_t cap);
 int dyd_ingest_export_polygons(const dyd_ingest* h, uint8_t* status, int64_t* img_off, int64_t* poly_off, double* xy,
                                int64_t* wh_off, int32_t* wh_len, uint8_t* wh_kind, int n_threads);
 int dyd_ingest_export_boxes(const dyd_ingest* h, uint8_t* status, int64_t* img_off, double* pts, uint8_t* valid, int n_threads);

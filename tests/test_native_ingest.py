@@ -139,12 +139,21 @@ def test_edge_documents_both_lanes_agree(monkeypatch):
     assert a[0] == [port.replace_cell(c) for c in cells]
 
 
-def test_non_canonical_rows_fall_to_the_cpython_lane(monkeypatch):
+def test_non_canonical_rows(monkeypatch):
+    """Documents that differ from json.dumps form only in style (first seven) are rewritten canonically inside the
+    library and take the native lane; the others (dropped objects, duplicate keys, values fp64 cannot carry,
+    invalid JSON) go to the CPython lane.  Either way the cell equals the reference's."""
     from oracle import pipeline_port as port
     ok = [t for t in SLOW_TEXTS if t not in ('[1, 2]',)]                       # a list document crashes the reference
     a, b, stats = both_lanes_replace(ok, monkeypatch)
-    assert stats["native_rows"] == 0 and stats["slow_rows"] == len(ok)
     assert a[0] == b[0] == [port.replace_cell(c) for c in ok]
+    style_only = SLOW_TEXTS[:7]
+    a, b, stats = both_lanes_replace(style_only, monkeypatch)
+    assert stats["native_rows"] == len(style_only) and stats["slow_rows"] == 0
+    assert a[0] == b[0] == [port.replace_cell(c) for c in style_only]
+    rest = [t for t in SLOW_TEXTS[7:] if t != '[1, 2]']
+    a, b, stats = both_lanes_replace(rest, monkeypatch)
+    assert stats["native_rows"] == 0 and stats["slow_rows"] == len(rest)
     with pytest.raises(AttributeError):
         monkeypatch.setenv("DYD_NATIVE_INGEST", "1")
         P.replace_ptlist_cells(['[1, 2]'])
@@ -271,17 +280,29 @@ def test_remap_native_lane_equals_python_lane(monkeypatch):
     assert (lane_a, lane_b) == ("native", "python")
     pd.testing.assert_frame_equal(a[0], b[0])
     assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and list(a[3]) == list(b[3])
-    # one non-canonical cell (extra space) -> the whole call takes the CPython lane, same answer as all-python
+    # a cell in another style (extra space) is rewritten canonically inside the library: still the native lane
     rep2 = rep.copy()
     rep2[NEW] = rep2[NEW].astype(object)
     rep2.loc[9, NEW] = rep2.loc[9, NEW].replace('{"', '{ "', 1)
     rep2 = pd.read_csv(io.StringIO(rep2.to_csv(index=False)))
     monkeypatch.setenv("DYD_NATIVE_INGEST", "1")
     c = labels.remap_df(rep2, lm)
-    assert labels.LAST["remap_lane"] == "python"
+    assert labels.LAST["remap_lane"] == "native"
     monkeypatch.setenv("DYD_NATIVE_INGEST", "0")
     d = labels.remap_df(rep2, lm)
     pd.testing.assert_frame_equal(c[0], d[0]); assert c[1:] == d[1:]
+    # a name that needs an escape when written -> the whole call takes the CPython lane, same answer
+    docs3 = [json.loads(x) if isinstance(x, str) else None for x in rep[NEW]]
+    docs3[11]["objects"][0]["name"] = 'say "cheese"'
+    rep3 = rep.copy()
+    rep3[NEW] = [json.dumps(x, ensure_ascii=False) if x is not None else np.nan for x in docs3]
+    rep3 = pd.read_csv(io.StringIO(rep3.to_csv(index=False)))
+    monkeypatch.setenv("DYD_NATIVE_INGEST", "1")
+    e = labels.remap_df(rep3, lm)
+    assert labels.LAST["remap_lane"] == "python"
+    monkeypatch.setenv("DYD_NATIVE_INGEST", "0")
+    f = labels.remap_df(rep3, lm)
+    pd.testing.assert_frame_equal(e[0], f[0]); assert e[1:] == f[1:]
 
 
 def test_remap_lanes_agree_on_random_documents(monkeypatch):
@@ -440,3 +461,120 @@ def test_split_lanes_agree_on_random_documents(monkeypatch):
                     same_frame(a["categories"][cat][part], b["categories"][cat][part])
             same_frame(a["unclassified"], b["unclassified"]); same_frame(a["split_counts"], b["split_counts"])
     assert lanes["native"] > 60 and lanes["python"] > 15
+
+
+def test_canonical_rewriter_equals_cpython_json():
+    """dyd_json_canonical(text) == json.dumps(json.loads(text), ensure_ascii=False) on random values written in
+    random styles (compact / padded separators, indentation, \\u escapes, alternative number spellings,
+    truncations); documents json.loads rejects must be declined, and nothing valid may be declined here."""
+    import ctypes as C
+    import re
+    from deal_yolo_daya_b200 import _lib
+    lib = _lib.load()
+    rng = random.Random(2718)
+
+    def canon(text):
+        b = text.encode("utf-8")
+        out = C.create_string_buffer(len(b) * 6 + 64)
+        n = lib.dyd_json_canonical(b, len(b), out, len(out))
+        return None if n < 0 else out.raw[:n].decode("utf-8")
+    chars = ["a", "b", " ", "中", "é", "😀", '"', "\\", "\n", "\t", "\r", "\b", "\f", "\x01", "\x1f", "\x7f", "/", "x", "1", "{", "}", "[", ","]
+
+    def rstr():
+        return "".join(rng.choice(chars) for _ in range(rng.randint(0, 8)))
+
+    def rnum():
+        t = rng.random()
+        if t < 0.25: return rng.randint(-10**6, 10**6)
+        if t < 0.3: return rng.choice([0, -0.0, 0.0, 10**20, -10**25, 2**53, 2**53 + 1, 1e16, 1e15, 123456789012345678])
+        if t < 0.6: return round(rng.uniform(-5000, 5000), rng.randint(0, 10))
+        if t < 0.7: return rng.uniform(-1, 1) * 10 ** rng.randint(-320, 308)
+        if t < 0.75: return rng.choice([float("inf"), float("-inf"), float("nan"), 5e-324, 1.7976931348623157e308])
+        return rng.random()
+
+    def rval(d=0):
+        t = rng.random()
+        if d > 3 or t < 0.35: return rnum()
+        if t < 0.5: return rstr()
+        if t < 0.6: return rng.choice([True, False, None])
+        if t < 0.8: return [rval(d + 1) for _ in range(rng.randint(0, 4))]
+        return {rstr() if rng.random() < 0.3 else rng.choice(["x", "y", "name", "objects", "k1", "键"]): rval(d + 1) for _ in range(rng.randint(0, 4))}
+
+    def style(v):
+        t, kw = rng.random(), {}
+        if t < 0.3: kw["separators"] = (",", ":")
+        elif t < 0.5: kw["indent"] = rng.choice([1, 2, 4, "\t"])
+        elif t < 0.6: kw["separators"] = (" , ", " : ")
+        kw["ensure_ascii"] = rng.random() < 0.5
+        s = json.dumps(v, **kw)
+        if rng.random() < 0.3:
+            s = rng.choice([" ", "\n", "\t\r\n"]) + s + rng.choice(["", " ", "\n"])
+        return s
+
+    def respell(m):
+        lit, r = m.group(0), rng.random()
+        plain_int = "." not in lit and "e" not in lit.lower()
+        if r < 0.2 and "." in lit and "e" not in lit.lower(): return lit + "0"
+        if r < 0.3 and plain_int and len(lit) < 8: return lit + "E0"
+        if r < 0.4 and "e" in lit: return lit.replace("e", "E")
+        if r < 0.45 and plain_int: return lit + ".0"
+        return lit
+    n_equal = n_invalid = 0
+    for _ in range(4000):
+        v = rval()
+        text = style(v)
+        if '"' not in text and rng.random() < 0.5:
+            text = re.sub(r"-?\d+(?:\.\d+)?(?:[eE][+-]?\d+)?", respell, text)
+        if rng.random() < 0.03:
+            text = text[:rng.randint(0, len(text))]
+        try:
+            want = json.dumps(json.loads(text), ensure_ascii=False)
+        except (json.JSONDecodeError, RecursionError):
+            want = None
+        got = canon(text)
+        assert got == want, (text, want, got)
+        n_equal += want is not None; n_invalid += want is None
+    assert n_equal > 3500 and n_invalid > 20
+    # what it must leave to CPython: duplicate keys (also when spelled differently), lone surrogates
+    for text in ('{"a": 1, "a": 2}', '{"a": 1, "\\u0061": 2}', '"\\ud800"', '"\\udc00x"', '{"a": }', "[1, 2", "01", "- 1", "'a'"):
+        assert canon(text) is None, text
+
+
+def test_other_json_styles_take_the_native_lanes(monkeypatch):
+    """Cells written compactly, indented, or with \\u escapes (what an annotation platform exports) are rewritten
+    canonically inside the library and take the native lanes of steps 4, 5.5 and 6, with the CPython lanes'
+    (and the oracle port's) results."""
+    from deal_yolo_daya_b200 import labels
+    from oracle import pipeline_port as port
+    t = synth.make_table(3, 0, 240)
+    rows = synth.table_to_rows(t)
+    docs = [json.loads(r[1]) for r in rows]
+    for d in docs[:40]:
+        d["objects"][0]["name"] = "猫,狗"
+    styles = [lambda d: json.dumps(d, separators=(",", ":"), ensure_ascii=True), lambda d: json.dumps(d, indent=2, ensure_ascii=False),
+              lambda d: json.dumps(d, ensure_ascii=False)]
+    cells = [styles[i % 3](d) for i, d in enumerate(docs)]
+    df = pd.read_csv(io.StringIO(pd.DataFrame({"source": [r[0] for r in rows], ANN: cells}).to_csv(index=False)))
+
+    def both(fn):
+        out = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("DYD_NATIVE_INGEST", mode)
+            out[mode] = fn()
+        return out["1"], out["0"]
+    (a, sa), (b, _) = both(lambda: (P.replace_ptlist_df(df)[0], dict(P.STATS)))
+    assert sa["native_rows"] == len(df) and sa["slow_rows"] == 0
+    assert a.to_csv(index=False) == b.to_csv(index=False) == port.replace_ptlist_df(df)[0].to_csv(index=False)
+    rep = pd.read_csv(io.StringIO(a.to_csv(index=False)))
+    lm = {synth.label_name(i): f"grp{i % 20:02d}" for i in range(synth.N_LABELS)}
+    lm["猫"] = "animal"
+    (ra, lane_a), (rb, lane_b) = both(lambda: (labels.remap_df(rep, lm), labels.LAST["remap_lane"]))
+    assert (lane_a, lane_b) == ("native", "python")
+    pd.testing.assert_frame_equal(ra[0], rb[0]); assert ra[1:] == rb[1:]
+    l2c = {f"grp{g:02d}": f"cat{g // 5}" for g in range(20)}
+    (xa, lane_a), (xb, lane_b) = both(lambda: (labels.split_df(ra[0], l2c), labels.LAST["split_lane"]))
+    assert (lane_a, lane_b) == ("native", "python") and xa["summary"] == xb["summary"]
+    for c in xa["categories"]:
+        for part in ("train", "val", "test"):
+            pd.testing.assert_frame_equal(xa["categories"][c][part], xb["categories"][c][part])
+    pd.testing.assert_frame_equal(xa["split_counts"], xb["split_counts"])
