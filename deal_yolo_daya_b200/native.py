@@ -420,8 +420,9 @@ def read_csv(path, encoding="utf-8", **kwargs):
         if not col_utf8.all():
             return fallback()                  # pandas raises UnicodeDecodeError
         uncertain = [j for j in range(n_cols) if not col_text[j]]
-        if uncertain and n_rows > window:
-            return fallback()                  # per-chunk inference of mixed columns: pandas' own business
+        # pandas infers dtypes per chunk of `window` rows and concatenates the chunks; columns that are not
+        # certainly text in every chunk are inferred by pandas itself, chunk by chunk, from the same tokens
+        windows = [(a, min(a + window, n_rows)) for a in range(0, n_rows, window)]
         sel = list(range(n_cols))              # every column's cell texts, one parallel pass
         offs = [np.empty(n_rows + 1, np.int64) for _ in sel]
         datas = [np.empty(max(int(col_bytes[j]), 1), np.uint8) for j in sel]
@@ -446,12 +447,16 @@ def read_csv(path, encoding="utf-8", **kwargs):
             ls = pa.large_string()
             lines = pc.binary_join_element_wise(pa.scalar('"', ls), pc.replace_substring(pc.fill_null(arr, pa.scalar("", ls)), '"', '""'),
                                                 pa.scalar('"\n', ls), pa.scalar("", ls))
-            lo, hi = lines.offset, lines.offset + len(lines)
-            o = np.frombuffer(lines.buffers()[1], dtype=np.int64)
-            text = lines.buffers()[2].slice(int(o[lo]), int(o[hi] - o[lo])).to_pybytes()      # the cells' lines, back to back
-            one = pd.read_csv(io.BytesIO(text), header=None, encoding="utf-8", skip_blank_lines=False)
-            if one.shape != (n_rows, 1):
-                return fallback()
+            o = np.frombuffer(lines.buffers()[1], dtype=np.int64)[lines.offset:lines.offset + len(lines) + 1]
+            buf = lines.buffers()[2]
+            parts = []
+            for a, b in windows:                                   # the cells' lines of one chunk, back to back
+                text = buf.slice(int(o[a]), int(o[b] - o[a])).to_pybytes()
+                one = pd.read_csv(io.BytesIO(text), header=None, encoding="utf-8", skip_blank_lines=False)
+                if one.shape != (b - a, 1):
+                    return fallback()
+                parts.append(one.iloc[:, 0])
+            one = parts[0].to_frame() if len(parts) == 1 else pd.concat(parts, ignore_index=True).to_frame()
             columns[j] = one.iloc[:, 0].array
             _READ_STATS["delegated_columns"] += 1
     finally:

@@ -134,18 +134,50 @@ def test_fuzz_against_pandas(tmp_path):
 
 
 def test_chunked_dtype_inference_boundary(tmp_path):
-    """pandas infers dtypes per chunk of _buffer_lines(n_cols) rows; a column that is numeric for a
-    whole chunk and text later comes back mixed.  The native reader must hand exactly those files to
-    pandas and keep the ones whose text columns are text in every chunk."""
+    """pandas infers dtypes per chunk of _buffer_lines(n_cols) rows and concatenates the chunks: a column that
+    is numeric for a whole chunk and text later comes back mixed.  The native reader hands exactly those
+    columns to pandas chunk by chunk and must return the very same frame."""
     ncols = 16
     w = native._buffer_lines(ncols)
     assert w == 32768
     head = ",".join(f"c{k}" for k in range(ncols))
-    for k_numeric, expect_native in ((w, False), (0, True)):
+    for k_numeric in (w, w - 1, 0):
         rows = [head]
         for r in range(w + 5):
             rows.append(",".join(["http://t"] * (ncols - 1) + ["1" if r < k_numeric else "word"]))
-        assert _both(tmp_path, "\n".join(rows) + "\n", name=f"chunk{k_numeric}.csv") == expect_native
+        assert _both(tmp_path, "\n".join(rows) + "\n", name=f"chunk{k_numeric}.csv") is True
+
+
+def test_mixed_columns_across_chunks_match_pandas(tmp_path):
+    """A wide file (400 columns -> 2048-row chunks) whose typed columns change character from chunk to chunk:
+    int -> float, int -> text, a missing chunk, bool -> int, text starting with 't' ...: same dtypes and the same
+    Python element types as pd.read_csv, chunk for chunk."""
+    ncols = 400
+    w = native._buffer_lines(ncols)
+    n = 3 * w + 37
+    kinds = {
+        "text": lambda i: f"http://t/{i}", "int": lambda i: str(i), "float": lambda i: f"{i / 7:.3f}",
+        "int_then_float": lambda i: str(i) if i < w else f"{i:.1f}", "int_then_text": lambda i: str(i) if i < 2 * w else f"word{i}",
+        "text_then_int": lambda i: f"word{i}" if i < w else str(i), "int_with_na_chunk": lambda i: "" if w <= i < 2 * w else str(i),
+        "bool_then_int": lambda i: ("True" if i % 2 else "False") if i < w else str(i), "all_na": lambda i: "",
+        "na_then_text": lambda i: "" if i < w else "word", "text_t": lambda i: f"text{i}",
+        "float_na_text": lambda i: "1.5" if i < w else ("" if i < 2 * w else "zz"),
+    }
+    names = list(kinds)
+    cols = {f"c{k}": ([kinds[names[k % len(names)]](i) for i in range(n)] if k < 2 * len(names) else ["x"] * n) for k in range(ncols)}
+    p = tmp_path / "wide.csv"
+    pd.DataFrame(cols).to_csv(p, index=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exp = pd.read_csv(p)
+        before = native._READ_STATS["native"]
+        got = native.read_csv(str(p))
+    assert native._READ_STATS["native"] == before + 1
+    pd.testing.assert_frame_equal(got, exp)
+    assert [str(a) for a in got.dtypes] == [str(a) for a in exp.dtypes]
+    for k in range(len(names)):
+        a, b = got[f"c{k}"], exp[f"c{k}"]
+        assert [type(x) for x in a.iloc[[0, w, 2 * w, n - 1]]] == [type(x) for x in b.iloc[[0, w, 2 * w, n - 1]]], names[k]
 
 
 def test_parallel_stitch_with_quoted_newlines(tmp_path, monkeypatch):
