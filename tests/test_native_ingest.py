@@ -578,3 +578,35 @@ def test_other_json_styles_take_the_native_lanes(monkeypatch):
         for part in ("train", "val", "test"):
             pd.testing.assert_frame_equal(xa["categories"][c][part], xb["categories"][c][part])
     pd.testing.assert_frame_equal(xa["split_counts"], xb["split_counts"])
+
+
+def test_split_egress_cells_equal_json_dumps():
+    """dyd_egress_split at the ABI level: for every position of the "objects" member (first, middle, last,
+    only) and for cells rewritten from another style, the spliced one-object cell equals json.dumps of the
+    document with "objects" replaced by the renamed object (processor.py:760-775)."""
+    docs = [{"width": 10, "objects": [{"name": "a,b", "id": 1}, {"id": 2}, {"name": "c", "polygon": {"ptList": []}}], "height": 5},
+            {"objects": [{"name": "x"}]},
+            {"objects": [{"name": "y", "k": [1, 2]}], "w": 1},
+            {"w": 1, "objects": [{"k": 0, "name": "z"}, 7, {"name": "中"}]}]
+    texts = [json.dumps(docs[0], ensure_ascii=False), json.dumps(docs[1], separators=(",", ":")),
+             json.dumps(docs[2], indent=2), json.dumps(docs[3], ensure_ascii=True)]
+    ing = native.Ingest(pd.Series(texts), 2).names().objects()
+    try:
+        assert list(ing.status) == [0, 0, 0, 0] and ing.n_canon == 3 and list(ing.list_len) == [3, 1, 1, 3]
+        labels_ = ["L0", 'q"uote', "标签"]
+        esc = [json.dumps(t, ensure_ascii=False)[1:-1].encode() for t in labels_]
+        off = np.zeros(len(esc) + 1, np.int64); off[1:] = np.cumsum([len(e) for e in esc])
+        exp = []                                    # (cell, global dict-object index, label)
+        for r, d in enumerate(docs):
+            dict_objs = [o for o in d["objects"] if isinstance(o, dict)]
+            for k, o in enumerate(dict_objs):
+                if o.get("name"):
+                    exp.append((r, int(ing.cell_off[r]) + k, (r + k) % 3, dict_objs[k]))
+        out, oo = ing.egress_split([e[0] for e in exp], [e[1] for e in exp], [e[2] for e in exp], np.frombuffer(b"".join(esc), np.uint8), off)
+        blob = out.tobytes()
+        for i, (r, q, t, obj) in enumerate(exp):
+            one = dict(obj); one["name"] = labels_[t]
+            nd = {k: v for k, v in docs[r].items() if k != "objects"}; nd["objects"] = [one]
+            assert blob[oo[i]:oo[i + 1]].decode() == json.dumps(nd, ensure_ascii=False)
+    finally:
+        ing.close()
