@@ -1,24 +1,31 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: ptList -> bbox + IoU filter + URL dedup, images/sec.
+"""Benchmark of the hot path: ptList -> bbox + IoU filter + URL dedup + reference filter, images/sec.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic input.  At N=1 the batch
-is BASELINE.json configs[1]: 10 M images / ~80 M polygons (SURVEY §8d generator), fused
-polygon->bbox + IoU flag (thr 0.7, min_boxes 2) plus hash + first-occurrence dedup of the
-10 M `source` URLs (5 % duplicates).  At N>1 every rank holds its own 10 M-image shard
-(weak scaling): bbox/IoU need no communication, dedup hash-partitions its keys with one
-all-to-all each way (deal_yolo_daya_b200/sharding.py).
+One "step" = one pass of the hot path over one batch of synthetic input.  At N=1 the batch is
+BASELINE.json configs[1] (C2): 10 M images / ~80 M polygons (SURVEY §8d generator), fused polygon->bbox +
+IoU flag (thr 0.7, min_boxes 2), plus the URL chain of configs[2] (C3) on the same rows: hash of the 10 M
+`source` URLs (5 % duplicates) and of a 5 M-row reference set (10 % of it inside the main id range),
+first-occurrence dedup and the reference-set anti-join.  At N>1 every rank holds its own 10 M-image /
+5 M-reference-row shard (weak scaling; N=8 is C3's 100 M-vs-50 M shape at 80 M / 40 M): bbox/IoU need no
+communication; dedup and the anti-join hash-partition their keys to owner ranks over NVLink peer memory
+(deal_yolo_daya_b200/sharding.py).  The URL chain depends on the `source` column only, so it runs on a second
+stream next to the fused kernel, which leaves it a few SMs (dyd_bbox_iou_fused_ex); a step ends when both
+streams are done.
 
-Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM;
-`e2e` = the same metric through the host-buffer C-ABI entry points (H2D and D2H inside the
-timed region); `roofline` describes the fused kernel; `cpu_baseline` is the CPU port of the
-reference timed on this box's host cores on a bounded sample.
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
+work through the host-buffer entry points (H2D and D2H inside the timed region, cross-rank exchange
+included); `roofline` describes the fused kernel; `results` carries the global duplicate / filtered counts
+and `exchange_verified` -- the sharded answers compared bit for bit, after the timed region, with a
+sort-based ground truth on the generator's integer url ids (deal_yolo_daya_b200/verify.py); `cpu_baseline`
+is the reference's own CPU path timed on this box's host cores on a bounded sample; `c4` / `c5` are the
+dense-crowd and remap+split legs (BASELINE.json configs[3], configs[4]).
 
-`--impl reference` times the reference's CPU path.  The reference is pure Python and cannot
-travel to the GPU box, so this arm runs oracle/pipeline_port.py -- the row-level port held
-byte-for-byte to the real reference's outputs by tests/test_oracle_golden.py -- through CSV
-files with every host core (kind "port").
+`--impl reference` times the reference's CPU path: the UNMODIFIED reference step functions staged in
+oracle/_ref by oracle/make_ref.py (kind "reference"), or -- when no staged copy travelled -- the row-level
+port oracle/pipeline_port.py, held byte-for-byte to the reference's outputs by tests/test_oracle_golden.py
+(kind "port"); through CSV files, all host cores.
 """
 from __future__ import annotations
 
@@ -42,20 +49,7 @@ UNIT = "images/s"
 IMAGES_PER_GPU = 10_000_000
 SEED = 0
 MIN_BOXES, THR = 2, 0.7
-
-
-def kernels_per_step(n_rows: int, world: int) -> int:
-    """tile_desc, fused_tma, iou_crowd, hash_strings + dedup (csrc/hash_dedup.cu): partition + resolve +
-    the gated global-table fallback (fill, insert / lookup once per half of a table above 256 MB), which
-    is launched every time and exits at once unless a partition overflowed; at N > 1 bucket / pack_reply
-    / unpack in addition.  Checked against the ncu launch list in profiles/."""
-    cap = 1024
-    while cap < 2 * n_rows:
-        cap *= 2
-    passes = 2 if cap * 16 > (256 << 20) else 1
-    if n_rows < (1 << 21):
-        return 4 + 2 * passes + (3 if world > 1 else 0)
-    return 4 + 2 + 1 + 2 * passes + (3 if world > 1 else 0)
+URL_SMS = 8                      # SMs the fused kernel leaves to the URL stream (tools/overlap_sweep.py)
 
 
 def peaks():
@@ -63,6 +57,16 @@ def peaks():
     if p.exists():
         return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_config(world: int, n_img: int):
+    """The workload both arms are quoted on (the reference arm times a bounded sample of it)."""
+    return {"workload": f"C2 + C3 URL chain: {n_img} images (~{8 * n_img} polygons, 4-32 vertices each) and {n_img // 2} reference rows per GPU; "
+                        f"dedup by source (5% dupes) -> reference filter (10% of the reference set inside the main ids) -> ptList->bbox -> "
+                        f"IoU filter (thr {THR}, min_boxes {MIN_BOXES})",
+            "seed": SEED, "images_per_gpu": n_img, "reference_rows_per_gpu": n_img // 2,
+            "l2": "inputs (23 GB of vertices per step at 10 M images) are far larger than the 126 MB L2; no flush needed",
+            "parallelism": f"{world} rank(s), rows partitioned by image; dedup / anti-join keys hash-partitioned to owner ranks" if world > 1 else "1 GPU"}
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -109,41 +113,71 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# --------------------------------------------------------------------------------------- CPU port legs
-def _port_worker(args):
-    """One process: the row-level port through CSV files on its own sample (single-threaded like the reference)."""
-    seed, first, n_rows, reps = args
-    import contextlib
-    import io
+# --------------------------------------------------------------------------------------- CPU legs
+def _write_sample(td: Path, seed, first, n_rows):
+    """Reference-format CSVs of one bounded sample: merged.csv (rows [first, first+n)) and ref.csv (n/2 rows, 10 % of
+    them sources of the sample)."""
+    import numpy as np
     import pandas as pd
     from deal_yolo_daya_b200 import synth
     from oracle import pipeline_port as port
     t = synth.make_table(seed, first, n_rows)
     rows = synth.table_to_rows(t)
+    merged, ref = td / "merged.csv", td / "ref.csv"
+    pd.DataFrame(rows, columns=[port.COL_SRC, port.COL_ANN]).to_csv(merged, index=False, encoding="utf-8-sig")
+    n_ref = n_rows // 2
+    inside = [int(i) for i in t.url_id[::20]][: max(1, n_ref // 10)]
+    ref_ids = inside + [10 ** 12 + first + k for k in range(n_ref - len(inside))]
+    ref_ids = [ref_ids[i] for i in np.random.RandomState(seed).permutation(len(ref_ids))]
+    pd.DataFrame({port.COL_SRC: [synth.url_of(i) for i in ref_ids]}).to_csv(ref, index=False, encoding="utf-8-sig")
+    return merged, ref
+
+
+def _cpu_worker(args):
+    """One process: the reference's step functions through CSV files on its own sample (single-threaded like the reference)."""
+    seed, first, n_rows, reps, kind = args
+    import contextlib
+    import io
+    if kind == "reference":
+        from oracle import ref_loader as impl
+    else:
+        from oracle import pipeline_port as impl
     best = float("inf")
     with tempfile.TemporaryDirectory() as td:
-        merged = Path(td) / "merged.csv"
-        pd.DataFrame(rows, columns=[port.COL_SRC, port.COL_ANN]).to_csv(merged, index=False, encoding="utf-8-sig")
+        td = Path(td)
+        merged, ref = _write_sample(td, seed, first, n_rows)
         for _ in range(reps):
             t0 = time.perf_counter()
             with contextlib.redirect_stdout(io.StringIO()):
-                port.run_hot_path_files(td, merged, None, MIN_BOXES, THR)
+                impl.run_hot_path_files(td, merged, ref, MIN_BOXES, THR)
             best = min(best, time.perf_counter() - t0)
     return n_rows, best
 
 
-def port_throughput(rows_per_proc: int, procs: int, reps: int = 1, first: int = 0):
-    """images/s of the CPU port with `procs` worker processes, each on its own row range."""
-    jobs = [(SEED, first + i * rows_per_proc, rows_per_proc, reps) for i in range(procs)]
+def cpu_kind():
+    from oracle import ref_loader
+    return "reference" if ref_loader.available() else "port"
+
+
+def cpu_throughput(rows_per_proc: int, procs: int, kind: str, reps: int = 1, first: int = 0):
+    """images/s of the CPU path with `procs` worker processes, each on its own row range."""
+    jobs = [(SEED, first + i * rows_per_proc, rows_per_proc, reps, kind) for i in range(procs)]
     t0 = time.perf_counter()
     if procs == 1:
-        res = [_port_worker(jobs[0])]
+        res = [_cpu_worker(jobs[0])]
     else:
         with mp.get_context("spawn").Pool(procs) as pool:
-            res = pool.map(_port_worker, jobs)
+            res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
     slowest = max(r[1] for r in res)
     return sum(r[0] for r in res) / slowest, slowest, wall
+
+
+def cpu_sample_text(kind, rows, procs):
+    what = ("the unmodified reference step functions (oracle/_ref via oracle/ref_loader.run_hot_path_files)" if kind == "reference"
+            else "oracle/pipeline_port.run_hot_path_files")
+    return (f"{rows} synthetic C2 rows (+ {rows // 2} reference rows) per process as reference-format CSV, {procs} process(es): {what}: "
+            f"dedup -> reference filter -> ptList->bbox -> IoU filter through CSV files")
 
 
 def csr_port_throughput(n_img: int):
@@ -154,43 +188,47 @@ def csr_port_throughput(n_img: int):
     t = synth.make_table(SEED, 0, n_img)
     urls = [synth.url_of(i) for i in t.url_id]
     off, data = oracle_c.pack_strings(urls)
+    rurls = [synth.url_of(i) for i in synth.ref_ids_of(SEED, np.arange(n_img // 2), n_img)]
+    roff, rdata = oracle_c.pack_strings(rurls)
     best = float("inf")
     for _ in range(3):
         t0 = time.perf_counter()
         pts, valid, _ = oracle_c.bbox_fold(t.poly_off, t.xy, want_arg=False)
         oracle_c.iou_filter(t.img_off, pts, valid, MIN_BOXES, THR)
         keys = oracle_c.hash_strings_buf(off, data)
+        rkeys = oracle_c.hash_strings_buf(roff, rdata)
         oracle_c.dedup(keys, np.zeros(n_img, np.uint8), "first")
+        oracle_c.antijoin(keys, np.zeros(n_img, np.uint8), rkeys, np.zeros(len(rkeys), np.uint8))
         best = min(best, time.perf_counter() - t0)
     return n_img / best, oracle_c.num_threads()
 
 
 def dropin_files_throughput(n_rows: int, device: int):
-    """images/s of the drop-in's own step functions on CSV files (dedup -> ptList->bbox -> IoU filter),
-    the same chain and file contract the reference arm runs."""
+    """images/s of the drop-in's own step functions on CSV files (dedup -> reference filter -> ptList->bbox -> IoU
+    filter), the same chain and file contract the reference arm runs."""
     import contextlib
     import io
-    import pandas as pd
     from deal_yolo_daya_b200 import processor as P, synth
     os.environ["DYD_DEVICE"] = str(device)
-    t = synth.make_table(SEED, 0, n_rows)
-    rows = synth.table_to_rows(t)
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
-        merged = td / "merged.csv"
-        pd.DataFrame(rows, columns=[P.COL_SRC, P.COL_ANN]).to_csv(merged, index=False, encoding="utf-8-sig")
+        merged, ref = _write_sample(td, SEED, 0, n_rows)
         best, steps = float("inf"), None
-        for _ in range(2):
+        for _ in range(3):
             with contextlib.redirect_stdout(io.StringIO()):
                 t0 = time.perf_counter()
                 P.deduplicate_csv_by_source(str(merged), str(td / "dedup.csv"))
                 t1 = time.perf_counter()
-                P.process_csv_replace_ptlist(str(td / "dedup.csv"), str(td / "rep.csv"), str(td / "exc.csv"))
+                P.remove_duplicates_between_csv(str(td / "dedup.csv"), str(ref), str(td / "filtered.csv"))
                 t2 = time.perf_counter()
-                P.filter_by_box_count_and_iou(str(td / "rep.csv"), str(td / "hi.csv"), str(td / "other.csv"), MIN_BOXES, THR)
+                P.process_csv_replace_ptlist(str(td / "filtered.csv"), str(td / "rep.csv"), str(td / "exc.csv"))
                 t3 = time.perf_counter()
-            if t3 - t0 < best:
-                best, steps = t3 - t0, {"dedup_s": t1 - t0, "replace_ptlist_s": t2 - t1, "iou_filter_s": t3 - t2}
+                P.filter_by_box_count_and_iou(str(td / "rep.csv"), str(td / "hi.csv"), str(td / "other.csv"), MIN_BOXES, THR)
+                t4 = time.perf_counter()
+            if t4 - t0 < best:
+                best = t4 - t0
+                steps = {"dedup_s": t1 - t0, "ref_filter_s": t2 - t1, "replace_ptlist_s": t3 - t2, "iou_filter_s": t4 - t3,
+                         "phases": dict(getattr(P, "PHASES", {}))}
         # steps 5.5 / 6 on what the chain left over (informational; not part of `value`)
         try:
             from deal_yolo_daya_b200 import labels as L
@@ -214,12 +252,13 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    rows = 1500
+    kind = cpu_kind()
+    rows = 1000 if kind == "reference" else 1500
     vals = []
     for _ in range(args.warmup):
-        port_throughput(200, min(cores, 8))
+        cpu_throughput(200, min(cores, 8), kind)
     for _ in range(args.steps):
-        v, slow, wall = port_throughput(rows, cores)
+        v, slow, wall = cpu_throughput(rows, cores, kind)
         vals.append((v, slow))
     vals.sort()
     v, slow = vals[len(vals) // 2]
@@ -227,14 +266,47 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": slow * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2 rows as reference-format CSV: {rows} rows x {cores} processes per step, dedup -> ptList->bbox -> IoU filter "
-                               f"(thr {THR}, min_boxes {MIN_BOXES}) through CSV files", "seed": SEED},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{rows} rows per process, {cores} processes, oracle/pipeline_port.run_hot_path_files"},
+        "config": make_config(world, args.images),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_text(kind, rows, cores) + " per step"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# --------------------------------------------------------------------------------------- NUMA
+def bind_to_gpu_numa_node(local: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned allocation: cudaHostAlloc
+    places pages on the allocating thread's node, and a pinned buffer on the far socket halves H2D bandwidth once
+    several ranks copy at the same time.  No-op when the box exposes one node."""
+    info = {"bound": False}
+    try:
+        pci = None
+        out = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        if out:
+            pci = out.lower()
+            if pci.startswith("00000000:"):
+                pci = pci[4:]
+        nodes = sorted(p.name for p in Path("/sys/devices/system/node").glob("node[0-9]*"))
+        info["nodes"] = len(nodes)
+        node = -1
+        if pci and Path(f"/sys/bus/pci/devices/{pci}/numa_node").exists():
+            node = int(Path(f"/sys/bus/pci/devices/{pci}/numa_node").read_text().strip())
+        info["gpu_numa_node"] = node
+        if len(nodes) > 1 and node >= 0:
+            cpus = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+            ids = set()
+            for part in cpus.split(","):
+                a, _, b = part.partition("-")
+                ids.update(range(int(a), int(b or a) + 1))
+            ids &= os.sched_getaffinity(0)
+            if ids:
+                os.sched_setaffinity(0, ids)
+                info["bound"] = True
+                info["cpus"] = cpus
+    except Exception as e:  # noqa: BLE001
+        info["error"] = str(e)[:120]
+    return info
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -245,9 +317,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=IMAGES_PER_GPU, help="images per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--url-sms", type=int, default=URL_SMS, help="SMs left to the URL stream by the fused kernel (0: one stream, no overlap)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = --steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the C4 / C5 legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -267,12 +341,13 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from deal_yolo_daya_b200 import _lib, build, ops, sharding, synth_device
+    from deal_yolo_daya_b200 import _lib, build, ops, sharding, synth_device, verify
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     if rank == 0:
         build.build()
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -282,30 +357,62 @@ def main():
     peak, peak_kind = peaks()
 
     n = args.images
-    first = rank * n
+    n_ref = n // 2
+    first, ref_first = rank * n, rank * n_ref
     t = synth_device.make_table(SEED, first, n, dev)
     url_id, uoff, udata = synth_device.make_urls(SEED, first, n, dev)
-    del url_id
+    ref_id, roff, rdata = synth_device.make_urls(SEED, ref_first, n_ref, dev, n_main_for_ref=world * n)
     n_img, n_poly, n_vert = t.n_img, t.n_poly, t.n_vert
     buf = ops.FusedBuffers(n_img, n_poly, dev)
-    dws = torch.empty(lib.dyd_dedup_workspace_bytes(int(n_img * (1.3 if world > 1 else 1.0))), dtype=torch.uint8, device=dev)
     fused_bytes = 16 * n_vert + 8 * (n_poly + 1) + 33 * n_poly + 8 * (n_img + 1) + 5 * n_img
-    ev_f0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev_f1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    url_bytes = int(udata.numel() + rdata.numel()) + 16 * (n_img + n_ref) + 18 * n_img + 8 * n_ref + 17 * n_img   # K0 (both) + K4 + K5
+    overlap = args.url_sms > 0
+    max_ctas = 148 - args.url_sms if overlap else 0
+    s_poly = torch.cuda.current_stream(dev)
+    s_url = torch.cuda.Stream(dev, priority=-1) if overlap else s_poly
+    K = args.steps
+    mk = lambda: [torch.cuda.Event(enable_timing=True) for _ in range(K)]   # noqa: E731
+    ev_f0, ev_f1, ev_u0, ev_u1, ev_a0 = mk(), mk(), mk(), mk(), mk()
     state = {}
-    xch = sharding.DedupExchange(n_img, world, dev) if world > 1 else None
+    if world > 1:
+        xd = sharding.DedupExchange(n_img, world, dev)
+        xa = sharding.AntiJoinExchange(n_img, n_ref, world, dev)
+    else:
+        dws = torch.empty(max(lib.dyd_dedup_workspace_bytes(n_img), lib.dyd_antijoin_workspace_bytes(n_ref)), dtype=torch.uint8, device=dev)
 
-    def step(i=None):
+    def url_chain(i):
         if i is not None:
-            ev_f0[i].record()
-        ops.bbox_iou_fused(t.img_off, t.poly_off, t.xy, MIN_BOXES, THR, out=buf)
-        if i is not None:
-            ev_f1[i].record()
+            ev_u0[i].record()
         keys = ops.hash_strings(uoff, udata)
+        rkeys = ops.hash_strings(roff, rdata)
         if world == 1:
             state["keep"], state["rep"] = ops.dedup(keys, None, "first", workspace=dws)
         else:
-            state["keep"], state["rep"] = xch.run(keys, first, "first", check_overflow=False)
+            state["keep"], state["rep"] = xd.run(keys, first, "first", check_overflow=False)
+        if i is not None:
+            ev_a0[i].record()
+        if world == 1:
+            state["keep_ref"], state["ref_row"] = ops.antijoin(keys, None, rkeys, None, workspace=dws)
+        else:
+            state["keep_ref"], state["ref_row"] = xa.run(keys, first, rkeys, ref_first, check_overflow=False)
+        if i is not None:
+            ev_u1[i].record()
+        state["keys"] = keys
+
+    def step(i=None):
+        if overlap:
+            s_url.wait_stream(s_poly)               # a step starts on both streams together ...
+        if i is not None:
+            ev_f0[i].record()
+        ops.bbox_iou_fused(t.img_off, t.poly_off, t.xy, MIN_BOXES, THR, out=buf, max_ctas=max_ctas)
+        if i is not None:
+            ev_f1[i].record()
+        if overlap:
+            with torch.cuda.stream(s_url):
+                url_chain(i)
+            s_poly.wait_stream(s_url)               # ... and ends when both are done
+        else:
+            url_chain(i)
 
     for _ in range(max(args.warmup, 1)):
         step()
@@ -317,27 +424,66 @@ def main():
     if world > 1:
         dist.barrier()                      # every rank enters the timed region together
     torch.cuda.synchronize()
+    launches0 = int(lib.dyd_launch_count())
     e0.record()
-    for i in range(args.steps):
+    for i in range(K):
         step(i)
     e1.record()
     torch.cuda.synchronize()
+    launches = int(lib.dyd_launch_count()) - launches0
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
-    fused_ms = sum(a.elapsed_time(b) for a, b in zip(ev_f0, ev_f1)) / args.steps
+    fused_ms = sum(a.elapsed_time(b) for a, b in zip(ev_f0, ev_f1)) / K
+    url_ms = sum(a.elapsed_time(b) for a, b in zip(ev_u0, ev_u1)) / K
+    anti_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a0, ev_u1)) / K
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
-    ms_step = ms_total / args.steps
-    value = world * n_img / (ms_step * 1e-3)
-    if xch is not None:
-        assert int(xch.overflow.item()) == 0, "exchange bucket overflow: rerun with exact-size splits"
-    n_high = int(buf.high.sum().item()); n_dup = int(n_img - state["keep"].sum().item())
 
-    # ---------------- end to end through the host-buffer C ABI (H2D + D2H inside the timed region) ----------------
+    def allmax(v):
+        if world == 1:
+            return float(v)
+        tt = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    ms_total = allmax(ms_total)
+    ms_step = ms_total / K
+    value = world * n_img / (ms_step * 1e-3)
+    url_ms_max, anti_ms_max = allmax(url_ms), allmax(anti_ms)
+
+    # ---------------- results + verification against the url-id ground truth (after the timed region) ----------------
+    overflowed = 0
+    if world > 1:
+        fl = torch.cat([xd.overflow, xa.overflow]).max().reshape(1).clone()
+        dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+        overflowed = int(fl.item())
+    assert overflowed == 0, "exchange bucket overflow: rerun with exact-size splits"
+    n_high = int(buf.high.sum().item())
+    ek, er = verify.expected_dedup_first(url_id, first)
+    ak, ar = verify.expected_antijoin(url_id, ref_id, ref_first)
+    ok = [torch.equal(ek, state["keep"]), torch.equal(er, state["rep"]), torch.equal(ak, state["keep_ref"]), torch.equal(ar, state["ref_row"])]
+    okt = torch.tensor([int(all(ok))], device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    verified = bool(okt.item())
+    dup_global = verify.global_counts(state["keep"])
+    filt_global = verify.global_counts(state["keep_ref"])
+    dup_expected = verify.global_counts(ek); filt_expected = verify.global_counts(ak)
+    dropped_either = verify.global_counts(state["keep"] & state["keep_ref"])
+    high_t = torch.tensor([n_high], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(high_t)
+    del ek, er, ak, ar
+    results = {"high_iou_images_global": int(high_t.item()), "duplicate_rows_global": dup_global, "duplicate_rows_expected": dup_expected,
+               "duplicate_rows_rank0": int(n_img - state["keep"].sum().item()),
+               "reference_filtered_rows_global": filt_global, "reference_filtered_rows_expected": filt_expected,
+               "rows_dropped_by_either_global": dropped_either, "exchange_verified": verified,
+               "verified_how": "keep / rep of the sharded dedup and keep / ref_row of the sharded anti-join of the LAST timed step compared bit for bit, on "
+                               "every rank, with a torch sort-based ground truth over the all-gathered integer url ids (deal_yolo_daya_b200/verify.py)",
+               "exchange_transport": (xd.transport if world > 1 else "none (1 GPU)")}
+    assert verified, f"sharded dedup / anti-join differs from the url-id ground truth: {ok}"
+
+    # ---------------- end to end through the host-buffer entry points (H2D + D2H inside the timed region) ----------------
     e2e = None
     if not args.no_e2e:
         ne = n_img
@@ -345,11 +491,16 @@ def main():
             avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
         except Exception:  # noqa: BLE001
             avail = 0
-        need = 16 * n_vert + 8 * n_poly + 37 * n_poly + 60 * n_img
+        need = 16 * n_vert + 8 * n_poly + 37 * n_poly + 120 * n_img
         frac = 1.0
         if avail and need * world > 0.6 * avail:
             frac = max(0.05, 0.6 * avail / (need * world))
             ne = int(n_img * frac)
+        if world > 1:                               # every rank must hold the same number of rows (global row ids)
+            tt = torch.tensor([ne], dtype=torch.int64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            ne = int(tt.item())
+        ne_ref = ne // 2
 
         def pinned(src, count=None):
             src = src if count is None else src[:count]
@@ -359,39 +510,77 @@ def main():
 
         q_e = int(t.img_off[ne].item()); v_e = int(t.poly_off[q_e].item())
         h_img = pinned(t.img_off, ne + 1); h_poly = pinned(t.poly_off, q_e + 1); h_xy = pinned(t.xy, 2 * v_e)
-        ub = int(uoff[ne].item())
-        h_uoff = pinned(uoff, ne + 1); h_udata = pinned(udata, ub)
+        # the URL columns of this leg's table: rows [rank*ne, rank*ne + ne) and reference rows [rank*ne_ref, ...)
+        e_uid, e_uoff, e_udata = synth_device.make_urls(SEED, rank * ne, ne, dev)
+        e_rid, e_roff, e_rdata = synth_device.make_urls(SEED, rank * ne_ref, ne_ref, dev, n_main_for_ref=world * ne)
+        h_uoff = pinned(e_uoff); h_udata = pinned(e_udata); h_roff = pinned(e_roff); h_rdata = pinned(e_rdata)
         out = {"pts": torch.empty(4 * q_e, dtype=torch.float64, pin_memory=True).numpy(),
                "valid": torch.empty(q_e, dtype=torch.uint8, pin_memory=True).numpy(),
                "high": torch.empty(ne, dtype=torch.uint8, pin_memory=True).numpy(),
                "count": torch.empty(ne, dtype=torch.int32, pin_memory=True).numpy()}
-        h2d = h_img.nbytes + h_poly.nbytes + h_xy.nbytes + h_uoff.nbytes + h_udata.nbytes
-        d2h = out["pts"].nbytes + out["valid"].nbytes + out["high"].nbytes + out["count"].nbytes + ne * 9
+        url = sharding.ShardedUrlFilter(ne, ne_ref, h_udata.nbytes, h_rdata.nbytes, world, dev)
+        h2d_poly = h_img.nbytes + h_poly.nbytes + h_xy.nbytes
+        h2d = h2d_poly + h_uoff.nbytes + h_udata.nbytes + h_roff.nbytes + h_rdata.nbytes
+        d2h = out["pts"].nbytes + out["valid"].nbytes + out["high"].nbytes + out["count"].nbytes + 18 * ne
+        t_poly = [0.0]
 
         def e2e_step():
-            ops.bbox_iou_host(h_img, h_poly, h_xy, MIN_BOXES, THR, want_pts=True, out=out, device=local)
-            return ops.dedup_host(h_uoff, h_udata, None, "first", device=local)
+            a = time.perf_counter()
+            r = ops.bbox_iou_host(h_img, h_poly, h_xy, MIN_BOXES, THR, want_pts=True, out=out, device=local, tile_modes=True)
+            t_poly[0] += time.perf_counter() - a
+            u = url.run(h_uoff, h_udata, h_roff, h_rdata, rank * ne, rank * ne_ref, "first")
+            return r, u
 
         e2e_step()
+        esteps = args.e2e_steps or K
+        t_poly[0] = 0.0
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            k_e, _ = e2e_step()
+        for _ in range(esteps):
+            r_e, u_e = e2e_step()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt_own = time.perf_counter() - t0
+        dt = allmax(dt_own)
+        gbs = torch.tensor([h2d_poly * esteps / t_poly[0] / 1e9, (h2d + d2h) * esteps / dt_own / 1e9], dtype=torch.float64, device=dev)
         if world > 1:
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        e2e = {"value": world * ne * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": args.e2e_steps, "images_per_step_per_gpu": ne,
-               "note": "dyd_bbox_iou_host + dyd_dedup_host on pinned host CSR/Arrow buffers; chunked H2D/kernel/D2H overlap inside the library"
-                       + ("" if frac == 1.0 else f"; host memory allowed only {frac:.2f} of the shard") +
-                       ("" if world == 1 else "; per-rank dedup (no cross-rank exchange on the host path)")}
+            allg = [torch.empty_like(gbs) for _ in range(world)]
+            dist.all_gather(allg, gbs)
+        else:
+            allg = [gbs]
+        # the host path must give the device-resident answers: polygons directly, the URL columns against the same ground truth
         assert int(out["high"].sum()) == int(buf.high[:ne].sum().item()), "host-path result differs from the device-resident path"
-        del h_xy, h_poly, h_img, out
+        ek, er = verify.expected_dedup_first(e_uid, rank * ne)
+        ak, ar = verify.expected_antijoin(e_uid, e_rid, rank * ne_ref)
+        e_ok = (torch.equal(ek.cpu(), u_e[0]) and torch.equal(er.cpu(), u_e[1]) and torch.equal(ak.cpu(), u_e[2]) and torch.equal(ar.cpu(), u_e[3]))
+        okt = torch.tensor([int(e_ok)], device=dev)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        assert bool(okt.item()), "host-path dedup / anti-join differs from the url-id ground truth"
+        e2e = {"value": world * ne * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": esteps, "images_per_step_per_gpu": ne, "verified": True, "tile_modes": r_e.get("tile_modes"),
+               "per_rank_polygon_h2d_gbs": [round(float(g[0]), 2) for g in allg],
+               "per_rank_total_pcie_gbs": [round(float(g[1]), 2) for g in allg],
+               "numa": numa,
+               "note": "dyd_bbox_iou_host on pinned host CSR buffers (chunked H2D / kernel / D2H overlap inside the library), then "
+                       "sharding.ShardedUrlFilter on pinned host Arrow buffers (H2D, hash, dedup + anti-join"
+                       + (" with the cross-rank exchange" if world > 1 else "") + ", D2H)"
+                       + ("" if frac == 1.0 else f"; host memory allowed only {frac:.2f} of the shard")}
+        del h_xy, h_poly, h_img, out, url, e_uid, e_rid
+
+    # ---------------- C4 / C5 legs (every rank takes part; rank 0 reports) ----------------
+    legs = {}
+    if not args.no_legs:
+        import bench_legs
+        try:
+            legs["c4"] = bench_legs.c4_leg(dev, rank, world, peak)
+        except Exception as e:  # noqa: BLE001
+            legs["c4"] = {"error": repr(e)[:300]}
+        try:
+            legs["c5"] = bench_legs.c5_leg(dev, rank, world, t, peak)
+        except Exception as e:  # noqa: BLE001
+            legs["c5"] = {"error": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -406,39 +595,45 @@ def main():
             traffic = tj.get("dram_bytes_per_launch")
     achieved = fused_bytes / (fused_ms * 1e-3) / 1e9
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: {n_img} images / {n_poly} polygons / {n_vert} vertices per GPU, fused ptList->bbox + IoU flag "
-                               f"(thr {THR}, min_boxes {MIN_BOXES}) + URL hash + first-occurrence dedup (5% dupes)",
-                   "seed": SEED, "l2": f"inputs ({16 * n_vert / 1e9:.1f} GB of vertices per step) are far larger than the 126 MB L2; no flush needed",
-                   "parallelism": (f"{world} rank(s), rows partitioned by image; dedup keys hash-partitioned to owner ranks, "
-                                   f"exchange transport: {xch.transport}") if world > 1 else "1 GPU",
-                   "results": {"high_iou_images": n_high, "duplicate_rows_rank0": n_dup}},
+        "config": make_config(world, n_img),
+        "results": results,
         "clocks": clocks,
-        "gpu_launches": kernels_per_step(n_img, world) * args.steps,
+        "gpu_launches": launches,
+        "gpu_launches_how": "dyd_launch_count() before / after the timed region: every kernel launch of libdyd.so increments it",
+        "streams": {"overlap": overlap, "fused_ctas": max_ctas or 148, "url_stream_sms": args.url_sms,
+                    "fused_ms": fused_ms, "url_chain_ms": url_ms_max, "antijoin_ms": anti_ms_max,
+                    "note": "per-step CUDA-event times on each stream (max over ranks for the URL chain); a step ends when both streams are done"},
         "roofline": {"bound": "hbm", "kernel": "fused_tma_kernel (+ tile_desc pre-pass and crowd worklist kernel, timed together)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_kind, "algorithmic_bytes_per_launch": fused_bytes,
-                     "bytes_per_image": fused_bytes / n_img, "ms_per_launch": fused_ms},
+                     "bytes_per_image": fused_bytes / n_img, "ms_per_launch": fused_ms,
+                     "concurrent": "timed while the URL stream runs beside it" if overlap else "timed alone"},
+        "url_chain": {"rows_per_s_per_gpu": (n_img + n_ref) / (url_ms_max * 1e-3), "antijoin_main_rows_per_s_per_gpu": n_img / (anti_ms_max * 1e-3),
+                      "algorithmic_bytes": url_bytes, "achieved_gbs": url_bytes / (url_ms_max * 1e-3) / 1e9,
+                      "frac_of_peak": url_bytes / (url_ms_max * 1e-3) / 1e9 / peak,
+                      "note": "K0 hash of main + reference URLs, K4 dedup, K5 anti-join" + (" incl. both cross-rank exchanges" if world > 1 else "")
+                              + "; runs on the SMs the fused kernel leaves free, so its own fraction of peak is not the optimisation target"},
     }
     if e2e:
         line["e2e"] = e2e
+    line.update(legs)
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        rows = 1200
-        v1, slow1, _ = port_throughput(rows, 1)
-        vall, slow, wall = port_throughput(rows, cores)
-        line["cpu_baseline"] = {"value": vall, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{rows} synthetic C2 rows per process as reference-format CSV, {cores} processes "
-                                          f"(oracle/pipeline_port.run_hot_path_files: dedup -> ptList->bbox -> IoU filter through CSV files)",
+        kind = cpu_kind()
+        rows = 800 if kind == "reference" else 1200
+        v1, slow1, _ = cpu_throughput(rows, 1, kind)
+        vall, slow, wall = cpu_throughput(rows, cores, kind)
+        line["cpu_baseline"] = {"value": vall, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_text(kind, rows, cores),
                                 "one_core_value": v1}
         try:
             vd, dsteps = dropin_files_throughput(20_000, local)
             line["dropin_files"] = {"value": vd, "unit": UNIT, "rows": 20_000, "seconds": dsteps,
                                     "note": "this repo's processor.py step functions on CSV files, one process (native CSV reader/writer, native JSON "
-                                            "ingest/egress, CUDA kernels); value = rows / (dedup + ptList->bbox + IoU filter seconds); "
+                                            "ingest/egress, CUDA kernels); value = rows / (dedup + reference filter + ptList->bbox + IoU filter seconds); "
                                             "seconds.labels = label remap + split of the rows that remain (not in value); "
-                                            "compare with cpu_baseline.one_core_value"}
+                                            "the like-for-like figure against cpu_baseline (same files, same chain)"}
         except Exception as e:  # noqa: BLE001
             line["dropin_files"] = {"error": str(e)[:200]}
         try:

@@ -23,6 +23,7 @@ _sz = C.c_size_t
 # name -> (restype, argtypes); mirrors include/dyd.h one to one
 PROTOTYPES = {
     "dyd_version": (_int, []),
+    "dyd_launch_count": (_u64, []),
     "dyd_last_error": (_sz, [C.c_char_p, _sz]),
     "dyd_bbox_minmax": (_int, [_p, _p, _i64, _p, _p, _p, _p]),
     "dyd_iou_workspace_bytes": (_sz, [_i64]),
@@ -35,10 +36,14 @@ PROTOTYPES = {
     "dyd_shard_bucket": (_int, [_p, _p, _i64, _i64, _i32, _i64, _p, _p, _p, _p]),
     "dyd_dedup_records": (_int, [_p, _i64, _int, _p, _p, _p, _sz, _p]),
     "dyd_shard_bucket_p2p": (_int, [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p]),
-    "dyd_shard_unpack_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _p]),
-    "dyd_shard_pack_reply_p2p": (_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p]),
-    "dyd_shard_pack_reply": (_int, [_p, _p, _p, _i64, _p, _p]),
-    "dyd_shard_unpack": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
+    "dyd_shard_unpack_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _i32, _p]),
+    "dyd_shard_pack_reply_p2p": (_int, [_p, _p, _p, _i64, _i64, _i32, _p, _i32, _i32, _p]),
+    "dyd_shard_pack_reply": (_int, [_p, _p, _p, _i64, _p, _i32, _p]),
+    "dyd_shard_unpack": (_int, [_p, _i64, _i64, _i64, _p, _p, _i32, _p]),
+    "dyd_antijoin_records": (_int, [_p, _i64, _p, _i64, _p, _p, _p, _sz, _i32, _p]),
+    "dyd_bbox_iou_fused_ex": (_int, [_p, _p, _p, _i64, _i64, _i64, _f64, _p, _p, _p, _p, _p, _p, _sz, _i32, _p]),
+    "dyd_fused_tile_modes": (_int, [_p, _i64, _p, _p]),
+    "dyd_bbox_iou_host_ex": (_int, [_p, _p, _p, _i64, _i64, _f64, _p, _p, _p, _p, _p, _i64, _p]),
     "dyd_antijoin_workspace_bytes": (_sz, [_i64]),
     "dyd_antijoin": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "dyd_label_lut": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
@@ -50,6 +55,7 @@ PROTOTYPES = {
     "dyd_yolo_normalise": (_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
     "dyd_bbox_iou_host": (_int, [_p, _p, _p, _i64, _i64, _f64, _p, _p, _p, _p, _p, _i64]),
     "dyd_dedup_host": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
+    "dyd_antijoin_host": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p]),
     "dyd_host_release": (_int, []),
     "dyd_ingest_cells": (_int, [_p, _p, _p, _i64, _int, _int, _p]),
     "dyd_ingest_free": (None, [_p]),
@@ -71,6 +77,10 @@ PROTOTYPES = {
     "dyd_csv_measure": (_int, [_p, _i64, _p, _p, _p, _p, _i32]),
     "dyd_csv_fill": (_int, [_p, _i32, _p, _p, _p, _p, _i32]),
     "dyd_csv_close": (None, [_p]),
+}
+
+# libdyd_synth.so (include/dyd_synth.h): the synthetic-table generator of bench.py / the GPU tests, not product code
+SYNTH_PROTOTYPES = {
     "dyd_synth_counts": (_int, [_u64, _i64, _i64, _p, _i32, _p, _p]),
     "dyd_synth_nvert": (_int, [_u64, _i64, _i64, _p, _p, _p]),
     "dyd_synth_fill": (_int, [_u64, _i64, _i64, _p, _p, _p, _p, _p]),
@@ -78,9 +88,11 @@ PROTOTYPES = {
     "dyd_synth_url_bytes": (_int, [_p, _p, _i64, _p, _p]),
     "dyd_synth_crowd": (_int, [_u64, _i64, _i64, _i32, _i32, _p, _p, _p, _p]),
 }
+SYNTH_LIB_PATH = PKG / "libdyd_synth.so"
 
 _lock = threading.Lock()
 _lib = None
+_synth = None
 
 
 class DydError(RuntimeError):
@@ -103,6 +115,22 @@ def load() -> C.CDLL:
                 fn.argtypes = args
             _lib = lib
     return _lib
+
+
+def load_synth() -> C.CDLL:
+    """Load libdyd_synth.so (the generator used by bench.py and the tests)."""
+    global _synth
+    with _lock:
+        if _synth is None:
+            if not SYNTH_LIB_PATH.exists():
+                raise DydError(f"{SYNTH_LIB_PATH} is missing: run `python -m deal_yolo_daya_b200.build`")
+            lib = C.CDLL(str(SYNTH_LIB_PATH))
+            for name, (res, args) in SYNTH_PROTOTYPES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _synth = lib
+    return _synth
 
 
 def last_error() -> str:

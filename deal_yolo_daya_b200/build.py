@@ -16,7 +16,9 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libdyd.so"
-SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "synth.cu", "host_pipeline.cu", "ingest.cpp", "csv_read.cpp"]
+SYNTH_OUT = PKG / "libdyd_synth.so"          # synthetic-table generator (bench / tests), kept out of the product library
+SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "host_pipeline.cu", "ingest.cpp", "csv_read.cpp"]
+SYNTH_SOURCES = ["api.cu", "synth.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -32,10 +34,10 @@ def sources():
 
 
 def needs_build() -> bool:
-    if not OUT.exists():
+    if not OUT.exists() or not SYNTH_OUT.exists():
         return True
-    t = OUT.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) + [PKG.parent / "include" / "dyd.h"]
+    t = min(OUT.stat().st_mtime, SYNTH_OUT.stat().st_mtime)
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) + list((PKG.parent / "include").glob("*.h"))
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -47,12 +49,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += os.environ.get("DYD_NVCC_FLAGS", "").split()          # tuning experiments: -DDYD_NW=.. -DDYD_TILE_CAP_V=..
-    cmd += ["-o", str(OUT)] + [str(s) for s in sources()]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libdyd.so")
+    jobs = [(OUT, sources()), (SYNTH_OUT, [CSRC / s for s in SYNTH_SOURCES])]
+    procs = [(out, subprocess.Popen(cmd + ["-o", str(out)] + [str(s) for s in srcs], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+             for out, srcs in jobs]
+    for out, pr in procs:
+        log, _ = pr.communicate()
+        if verbose or pr.returncode != 0:
+            sys.stderr.write(log)
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed building {out.name}")
     return OUT
 
 

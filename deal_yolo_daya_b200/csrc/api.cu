@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace dyd {
@@ -15,6 +17,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// Kernel launches issued by this library since it was loaded (a statistic, read by bench.py for `gpu_launches`).
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
     return (int)e;
@@ -23,6 +29,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace dyd
 
 extern "C" int dyd_version(void) { return DYD_VERSION; }
+
+extern "C" uint64_t dyd_launch_count(void) { return dyd::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" size_t dyd_last_error(char* buf, size_t cap) {
     size_t n = strlen(dyd::g_err);

@@ -83,13 +83,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
     return ok != 0;
 }
 __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
-    const long long t0 = clock64();
+#ifdef DYD_DEBUG_WATCHDOG                      // debug builds only: under time-slicing / MPS / a debugger a legitimate
+    const long long t0 = clock64();            // wait can be arbitrarily long, and a trap poisons the caller's context
     while (!mbar_try_wait(addr, parity)) {
-        if (clock64() - t0 > 6000000000LL) {                                 // ~3 s: a protocol bug, not load
+        if (clock64() - t0 > 6000000000LL) {
             printf("dyd: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }
     }
+#else
+    while (!mbar_try_wait(addr, parity)) {}
+#endif
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -258,8 +262,15 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
     __syncthreads();
 
     const bool zero_hits = 0.0 >= thr;
-    const int64_t stride = (int64_t)gridDim.x * NW;
     uint32_t phase = 0;
+    // Segments are claimed dynamically: every warp starts on segment (block, warp) and takes further ones from
+    // an atomic counter (CrowdList::next_seg, zeroed by the entry point).  A CTA that becomes resident late --
+    // another stream's kernels held its SM -- or that runs slower simply claims fewer segments, so the kernel
+    // tolerates concurrent work on the GPU and skewed tables.  The claim for the segment after next is issued
+    // one segment ahead; its latency is hidden behind a whole segment of tiles.
+    unsigned long long* const seg_counter = &reinterpret_cast<CrowdList*>(ws)->next_seg;
+    const int64_t dyn_base = (int64_t)gridDim.x * NW;
+    int64_t claimed = 0;
 
     // Lane 0 walks the descriptors of this warp's segments two tiles ahead of the tile being
     // processed: the load issued while one tile is filled is consumed a full tile later.
@@ -277,8 +288,14 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
     Cursor c_nxt{(int64_t)blockIdx.x * NW + warp, 0, 0}, c_far{0, 0, 0};
     Raw nxt{}, far{};
     bool has_nxt = false, has_far = false;
-    auto advance = [&](const Cursor& c) { return c.j + 1 < c.cnt ? Cursor{c.seg, c.j + 1, c.cnt} : Cursor{c.seg + stride, 0, 0}; };
+    auto advance = [&](const Cursor& c) {
+        if (c.j + 1 < c.cnt) return Cursor{c.seg, c.j + 1, c.cnt};
+        const Cursor r{claimed, 0, 0};
+        if (claimed < n_seg) claimed = dyn_base + (int64_t)atomicAdd(seg_counter, 1ULL);
+        return r;
+    };
     if (lane == 0) {
+        claimed = dyn_base + (int64_t)atomicAdd(seg_counter, 1ULL);
         has_nxt = c_nxt.seg < n_seg;
         if (has_nxt) {
             nxt = load_raw(c_nxt.seg * SEG_IMAGES);
@@ -391,17 +408,35 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
     }
 }
 
+// Diagnostics: how many tiles of each mode the pre-pass produced (the descriptors stay in the workspace).
+__global__ void tile_modes_kernel(const TileDesc* __restrict__ desc, int64_t n_seg, unsigned long long* counts) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const int cnt = desc[s * SEG_IMAGES].cnt;
+    unsigned c[3] = {0, 0, 0};
+    for (int j = 0; j < cnt; ++j) { const int m = desc[s * SEG_IMAGES + j].mode; if (m < 3) ++c[m]; }
+    for (int m = 0; m < 3; ++m) if (c[m]) atomicAdd(&counts[m], (unsigned long long)c[m]);
+}
+int launch_tile_modes(const void* ws, int64_t n_img, unsigned long long* d_counts3, cudaStream_t s) {
+    const int64_t n_seg = n_segments_of(n_img);
+    if (n_seg == 0) return 0;
+    const TileDesc* desc = tile_descs(const_cast<void*>(ws), n_img);
+    tile_modes_kernel<<<(unsigned)((n_seg + 255) / 256), 256, 0, s>>>(desc, n_seg, d_counts3);
+    return launch_check("tile_modes_kernel");
+}
+
 int launch_fused_tma(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
                      int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
                      double* d_pts, uint8_t* d_valid, int32_t* d_arg, uint8_t* d_high, int32_t* d_count,
-                     void* ws, cudaStream_t s) {
+                     void* ws, int max_ctas, cudaStream_t s) {
     const int64_t n_seg = n_segments_of(n_img);
     TileDesc* desc = tile_descs(ws, n_img);
     tile_desc_kernel<<<(unsigned)((n_seg + DESC_WARPS - 1) / DESC_WARPS), 32 * DESC_WARPS, 0, s>>>(d_img_off, d_poly_off, n_img, n_poly, n_seg, desc);
     if (int rc = launch_check("tile_desc_kernel")) return rc;
     const size_t smem = sizeof(Smem);
     const int64_t want = (n_seg + NW - 1) / NW;
-    const unsigned grid = (unsigned)(want < NUM_SMS ? want : NUM_SMS);
+    const int64_t cap = max_ctas > 0 && max_ctas < NUM_SMS ? max_ctas : NUM_SMS;   // < 148: leave SMs to concurrent streams
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     const double2* xy2 = reinterpret_cast<const double2*>(d_xy);
     if (d_arg) {
         DYD_CUDA(cudaFuncSetAttribute(fused_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

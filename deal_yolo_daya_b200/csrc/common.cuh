@@ -25,7 +25,9 @@ int cuda_fail(cudaError_t e, const char* what);
         if (!(cond)) { ::dyd::set_error("%s: %s", __func__, msg); return (code); } \
     } while (0)
 
-inline int launch_check(const char* what) {
+void count_launch();
+inline int launch_check(const char* what) {           // called once after every kernel launch of the library
+    count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, what);
 }

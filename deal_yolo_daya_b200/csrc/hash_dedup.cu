@@ -299,20 +299,34 @@ dedup_leftover_kernel(const unsigned long long* __restrict__ keys, const uint8_t
 }
 
 // ------------------------------------------------------------------------------- K5
+// KIND 0: plain key arrays (row = index, null flags honoured); KIND 2: interleaved (key, id) records as they arrive
+// from the exchange (id < 0 = padding of a fixed-capacity bucket; `null` unused).  With `reset` the build kernel,
+// the last reader of the reference records, turns every record back into padding for the next exchange step.
+template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
-antijoin_build_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t n,
-                      Slot* tab, int shift, uint64_t mask) {
+antijoin_build_kernel(unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t n,
+                      Slot* tab, int shift, uint64_t mask, bool reset) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
-    if (r >= n || (null != nullptr && null[r] != 0)) return;      // ref.dropna()
-    const unsigned long long key = norm_key(keys[r]);
+    if (r >= n) return;
+    unsigned long long key, row;
+    if (KIND == 0) {
+        if (null != nullptr && null[r] != 0) return;               // ref.dropna()
+        key = norm_key(keys[r]); row = (unsigned long long)r;
+    } else {
+        const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(keys)[r];
+        if ((long long)rec.y < 0) return;
+        key = norm_key(rec.x); row = rec.y;
+        if (reset) keys[2 * r + 1] = ~0ULL;
+    }
     uint64_t s = home_slot(key, shift);
     for (;;) {
         unsigned long long prev = atomicCAS(&tab[s].key, EMPTY, key);
-        if (prev == EMPTY || prev == key) { atomicMin(&tab[s].row, (unsigned long long)r); return; }
+        if (prev == EMPTY || prev == key) { atomicMin(&tab[s].row, row); return; }
         s = (s + 1) & mask;
     }
 }
 
+template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
 antijoin_probe_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t n,
                       const Slot* __restrict__ tab, int shift, uint64_t mask,
@@ -320,8 +334,12 @@ antijoin_probe_kernel(const unsigned long long* __restrict__ keys, const uint8_t
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= n) return;
     uint8_t k = 1; long long rr = -1;
-    if (null == nullptr || null[r] == 0) {             // a NaN main cell never matches
-        const unsigned long long key = norm_key(keys[r]);
+    bool live;
+    unsigned long long key;
+    if (KIND == 0) { live = null == nullptr || null[r] == 0; key = live ? keys[r] : 0ULL; }   // a NaN main cell never matches
+    else { const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(keys)[r]; live = (long long)rec.y >= 0; key = rec.x; if (!live) k = 0; }
+    if (live) {
+        key = norm_key(key);
         uint64_t s = home_slot(key, shift);
         for (;;) {
             const unsigned long long cur = tab[s].key;
@@ -402,29 +420,38 @@ shard_bucket_p2p_kernel(const unsigned long long* __restrict__ keys, const uint8
     if (slot >= (unsigned long long)cap) { *overflow = 1; return; }
     longlong2* rec = reinterpret_cast<longlong2*>(peer_records[own]) + ((int64_t)me * cap + (int64_t)slot);
     *rec = make_longlong2((long long)key, row_base + r);           // one 16-byte store per record
-    sent_row[(int64_t)own * cap + (int64_t)slot] = (unsigned)r;    // local: which row the answer in that slot belongs to
+    if (sent_row != nullptr) sent_row[(int64_t)own * cap + (int64_t)slot] = (unsigned)r;   // local: which row the answer in that slot belongs to
 }
 
 // owner side, peer-memory form: the answer for a record that came from rank s goes straight into
 // region `me` of rank s's reply buffer
+// mode 0 (dedup): answer = rep | keep << 62; mode 1 (anti-join): answer = kept ? 1 << 62 : first matching reference row.
+// This kernel is the last reader of the received records: with `reset` it turns each one back into padding (id = -1),
+// so the next step needs no separate fill of the receive buffer and no "buffers are clean" barrier.
+__device__ __forceinline__ long long reply_word(int mode, long long id, uint8_t keep, long long rep) {
+    if (id < 0) return -1;
+    if (mode == 1) return keep ? (1LL << 62) : rep;
+    return rep | ((long long)(keep ? 1 : 0) << 62);
+}
 __global__ void __launch_bounds__(HT_THREADS)
-shard_pack_reply_p2p_kernel(const long long* __restrict__ records, const uint8_t* __restrict__ keep,
+shard_pack_reply_p2p_kernel(long long* __restrict__ records, const uint8_t* __restrict__ keep,
                             const int64_t* __restrict__ rep, int64_t m, int64_t cap, int me,
-                            long long* const* __restrict__ peer_reply) {
+                            long long* const* __restrict__ peer_reply, int mode, bool reset) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= m) return;
     const int src = (int)(r / cap);
     const int64_t slot = r - (int64_t)src * cap;
     const long long id = records[2 * r + 1];
+    if (reset && id >= 0) records[2 * r + 1] = -1;
     // 8 bytes per answer: the origin remembers which of its rows sits in (owner, slot)
-    peer_reply[src][(int64_t)me * cap + slot] = id < 0 ? -1 : (rep[r] | ((long long)(keep[r] ? 1 : 0) << 62));
+    peer_reply[src][(int64_t)me * cap + slot] = reply_word(mode, id, keep[r], rep[r]);
 }
 
 // origin side, peer-memory form: slot s of owner o's region holds the answer for row sent_row[o][s]
 __global__ void __launch_bounds__(HT_THREADS)
 shard_unpack_p2p_kernel(const long long* __restrict__ reply, const unsigned* __restrict__ sent_row,
                         const unsigned long long* __restrict__ cursors, int world, int64_t cap, int64_t n,
-                        uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
+                        uint8_t* __restrict__ keep, int64_t* __restrict__ rep, int mode) {
     const int64_t t = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (t >= (int64_t)world * cap) return;
     const int own = (int)(t / cap);
@@ -433,25 +460,26 @@ shard_unpack_p2p_kernel(const long long* __restrict__ reply, const unsigned* __r
     const long long v = reply[t];
     const int64_t row = sent_row[t];
     if (v < 0 || row >= n) return;
-    keep[row] = (uint8_t)((v >> 62) & 1);
-    rep[row] = v & ((1LL << 62) - 1);
+    const uint8_t k = (uint8_t)((v >> 62) & 1);
+    keep[row] = k;
+    rep[row] = (mode == 1 && k) ? -1 : (v & ((1LL << 62) - 1));
 }
 
 // owner side: (id, rep | keep << 62) per received record
 __global__ void __launch_bounds__(HT_THREADS)
 shard_pack_reply_kernel(const long long* __restrict__ records, const uint8_t* __restrict__ keep,
-                        const int64_t* __restrict__ rep, int64_t m, long long* __restrict__ reply) {
+                        const int64_t* __restrict__ rep, int64_t m, long long* __restrict__ reply, int mode) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= m) return;
     const long long id = records[2 * r + 1];
     reply[2 * r] = id;
-    reply[2 * r + 1] = id < 0 ? -1 : (rep[r] | ((long long)(keep[r] ? 1 : 0) << 62));
+    reply[2 * r + 1] = reply_word(mode, id, keep[r], rep[r]);
 }
 
 // origin side: place the answers at the rows they belong to
 __global__ void __launch_bounds__(HT_THREADS)
 shard_unpack_kernel(const long long* __restrict__ reply, int64_t m, int64_t row_base, int64_t n,
-                    uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
+                    uint8_t* __restrict__ keep, int64_t* __restrict__ rep, int mode) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= m) return;
     const long long id = reply[2 * r];
@@ -459,8 +487,9 @@ shard_unpack_kernel(const long long* __restrict__ reply, int64_t m, int64_t row_
     const long long local = id - row_base;
     if (local < 0 || local >= n) return;
     const long long v = reply[2 * r + 1];
-    keep[local] = (uint8_t)((v >> 62) & 1);
-    rep[local] = v & ((1LL << 62) - 1);
+    const uint8_t k = (uint8_t)((v >> 62) & 1);
+    keep[local] = k;
+    rep[local] = (mode == 1 && k) ? -1 : (v & ((1LL << 62) - 1));
 }
 
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + HT_THREADS - 1) / HT_THREADS); }
@@ -613,7 +642,7 @@ extern "C" int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_nul
                                     int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
                                     uint64_t* d_cursors, int32_t* d_overflow, void* stream) {
     DYD_REQUIRE(n >= 0 && n < (1LL << 32) && world >= 1 && cap >= 0 && my_rank >= 0 && my_rank < world, DYD_E_ARG, "bad arguments");
-    DYD_REQUIRE(d_peer_records && d_sent_row && d_cursors && d_overflow && (n == 0 || d_keys), DYD_E_ARG, "null pointer");
+    DYD_REQUIRE(d_peer_records && d_cursors && d_overflow && (n == 0 || d_keys), DYD_E_ARG, "null pointer");
     cudaStream_t s = as_stream(stream);
     DYD_CUDA(cudaMemsetAsync(d_cursors, 0, sizeof(uint64_t) * world, s));
     DYD_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
@@ -624,42 +653,43 @@ extern "C" int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_nul
     return launch_check("shard_bucket_p2p_kernel");
 }
 
-extern "C" int dyd_shard_pack_reply_p2p(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m, int64_t cap,
-                                        int32_t my_rank, int64_t* const* d_peer_reply, void* stream) {
-    DYD_REQUIRE(m >= 0 && cap > 0 && my_rank >= 0 && m % cap == 0, DYD_E_ARG, "bad arguments");
+extern "C" int dyd_shard_pack_reply_p2p(int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m, int64_t cap,
+                                        int32_t my_rank, int64_t* const* d_peer_reply, int32_t mode, int32_t reset_records, void* stream) {
+    DYD_REQUIRE(m >= 0 && cap > 0 && my_rank >= 0 && m % cap == 0 && (mode == 0 || mode == 1), DYD_E_ARG, "bad arguments");
     if (m == 0) return 0;
     DYD_REQUIRE(d_records && d_keep && d_rep && d_peer_reply, DYD_E_ARG, "null pointer");
-    shard_pack_reply_p2p_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_records), d_keep, d_rep,
-                                                                                    m, cap, my_rank, reinterpret_cast<long long* const*>(d_peer_reply));
+    shard_pack_reply_p2p_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<long long*>(d_records), d_keep, d_rep,
+                                                                                    m, cap, my_rank, reinterpret_cast<long long* const*>(d_peer_reply),
+                                                                                    mode, reset_records != 0);
     return launch_check("shard_pack_reply_p2p_kernel");
 }
 
 extern "C" int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
-                                    int64_t cap, int64_t n, uint8_t* d_keep, int64_t* d_rep, void* stream) {
-    DYD_REQUIRE(world >= 1 && cap >= 0 && n >= 0, DYD_E_ARG, "bad arguments");
+                                    int64_t cap, int64_t n, uint8_t* d_keep, int64_t* d_rep, int32_t mode, void* stream) {
+    DYD_REQUIRE(world >= 1 && cap >= 0 && n >= 0 && (mode == 0 || mode == 1), DYD_E_ARG, "bad arguments");
     if (cap == 0 || n == 0) return 0;
     DYD_REQUIRE(d_reply && d_sent_row && d_cursors && d_keep && d_rep, DYD_E_ARG, "null pointer");
     shard_unpack_p2p_kernel<<<grid_for((int64_t)world * cap), HT_THREADS, 0, as_stream(stream)>>>(
-        reinterpret_cast<const long long*>(d_reply), d_sent_row, reinterpret_cast<const unsigned long long*>(d_cursors), world, cap, n, d_keep, d_rep);
+        reinterpret_cast<const long long*>(d_reply), d_sent_row, reinterpret_cast<const unsigned long long*>(d_cursors), world, cap, n, d_keep, d_rep, mode);
     return launch_check("shard_unpack_p2p_kernel");
 }
 
 extern "C" int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,
-                                    int64_t* d_reply, void* stream) {
-    DYD_REQUIRE(m >= 0, DYD_E_ARG, "negative count");
+                                    int64_t* d_reply, int32_t mode, void* stream) {
+    DYD_REQUIRE(m >= 0 && (mode == 0 || mode == 1), DYD_E_ARG, "bad arguments");
     if (m == 0) return 0;
     DYD_REQUIRE(d_records && d_keep && d_rep && d_reply, DYD_E_ARG, "null pointer");
     shard_pack_reply_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_records), d_keep, d_rep, m,
-                                                                                reinterpret_cast<long long*>(d_reply));
+                                                                                reinterpret_cast<long long*>(d_reply), mode);
     return launch_check("shard_pack_reply_kernel");
 }
 
 extern "C" int dyd_shard_unpack(const int64_t* d_reply, int64_t m, int64_t row_base, int64_t n,
-                                uint8_t* d_keep, int64_t* d_rep, void* stream) {
-    DYD_REQUIRE(m >= 0 && n >= 0, DYD_E_ARG, "negative count");
+                                uint8_t* d_keep, int64_t* d_rep, int32_t mode, void* stream) {
+    DYD_REQUIRE(m >= 0 && n >= 0 && (mode == 0 || mode == 1), DYD_E_ARG, "bad arguments");
     if (m == 0) return 0;
     DYD_REQUIRE(d_reply && d_keep && d_rep, DYD_E_ARG, "null pointer");
-    shard_unpack_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_reply), m, row_base, n, d_keep, d_rep);
+    shard_unpack_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_reply), m, row_base, n, d_keep, d_rep, mode);
     return launch_check("shard_unpack_kernel");
 }
 
@@ -667,13 +697,14 @@ extern "C" size_t dyd_antijoin_workspace_bytes(int64_t n_ref) {
     return table_capacity(n_ref) * sizeof(Slot);
 }
 
-extern "C" int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
-                            const uint64_t* d_ref_keys, const uint8_t* d_ref_null, int64_t n_ref,
-                            uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, void* stream) {
+template <int KIND>
+static int antijoin_impl(uint64_t* d_ref, const uint8_t* d_ref_null, int64_t n_ref, const uint64_t* d_main, const uint8_t* d_main_null,
+                         int64_t n_main, uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, bool reset_ref, void* stream) {
     DYD_REQUIRE(n_main >= 0 && n_ref >= 0, DYD_E_ARG, "negative count");
-    if (n_main == 0) return 0;
-    DYD_REQUIRE(d_main_keys && d_keep && d_ref_row && ws && (n_ref == 0 || d_ref_keys), DYD_E_ARG, "null pointer");
+    if (n_main == 0 && !(KIND == 2 && reset_ref)) return 0;
+    DYD_REQUIRE((n_main == 0 || (d_main && d_keep && d_ref_row)) && ws && (n_ref == 0 || d_ref), DYD_E_ARG, "null pointer");
     DYD_REQUIRE(((uintptr_t)ws & 15) == 0, DYD_E_ALIGN, "workspace must be 16-byte aligned");
+    DYD_REQUIRE(KIND == 0 || ((((uintptr_t)d_ref | (uintptr_t)d_main) & 15) == 0), DYD_E_ALIGN, "records must be 16-byte aligned");
     DYD_REQUIRE(ws_bytes >= dyd_antijoin_workspace_bytes(n_ref), DYD_E_WORKSPACE, "workspace too small");
     const uint64_t cap = table_capacity(n_ref);
     const int shift = 64 - log2u(cap);
@@ -681,11 +712,25 @@ extern "C" int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_n
     Slot* tab = reinterpret_cast<Slot*>(ws);
     DYD_CUDA(cudaMemsetAsync(ws, 0xFF, cap * sizeof(Slot), s));
     if (n_ref > 0) {
-        antijoin_build_kernel<<<grid_for(n_ref), HT_THREADS, 0, s>>>(
-            reinterpret_cast<const unsigned long long*>(d_ref_keys), d_ref_null, n_ref, tab, shift, cap - 1);
+        antijoin_build_kernel<KIND><<<grid_for(n_ref), HT_THREADS, 0, s>>>(
+            reinterpret_cast<unsigned long long*>(d_ref), d_ref_null, n_ref, tab, shift, cap - 1, reset_ref);
         if (int rc = launch_check("antijoin_build_kernel")) return rc;
     }
-    antijoin_probe_kernel<<<grid_for(n_main), HT_THREADS, 0, s>>>(
-        reinterpret_cast<const unsigned long long*>(d_main_keys), d_main_null, n_main, tab, shift, cap - 1, d_keep, d_ref_row);
+    if (n_main == 0) return 0;
+    antijoin_probe_kernel<KIND><<<grid_for(n_main), HT_THREADS, 0, s>>>(
+        reinterpret_cast<const unsigned long long*>(d_main), d_main_null, n_main, tab, shift, cap - 1, d_keep, d_ref_row);
     return launch_check("antijoin_probe_kernel");
+}
+
+extern "C" int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
+                            const uint64_t* d_ref_keys, const uint8_t* d_ref_null, int64_t n_ref,
+                            uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, void* stream) {
+    return antijoin_impl<0>(const_cast<uint64_t*>(d_ref_keys), d_ref_null, n_ref, d_main_keys, d_main_null, n_main, d_keep, d_ref_row,
+                            ws, ws_bytes, false, stream);
+}
+
+extern "C" int dyd_antijoin_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main,
+                                    uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, int32_t reset_ref, void* stream) {
+    return antijoin_impl<2>(reinterpret_cast<uint64_t*>(d_ref_records), nullptr, m_ref, reinterpret_cast<const uint64_t*>(d_main_records), nullptr,
+                            m_main, d_keep, d_ref_row, ws, ws_bytes, reset_ref != 0, stream);
 }

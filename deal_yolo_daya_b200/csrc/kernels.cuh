@@ -8,8 +8,8 @@ namespace dyd {
 // ---- workspace layout of the K2 / fused entry points -------------------------------------
 //   [CrowdList header 16 B][int32 image ids, n_img][pad to 16 B][TileDesc, n_tiles]
 struct CrowdList {
-    unsigned long long count;   // number of deferred images
-    unsigned long long pad;
+    unsigned long long count;      // number of deferred images
+    unsigned long long next_seg;   // fused kernel: dynamic segment counter (both zeroed by the entry point)
 };
 __host__ __device__ __forceinline__ int* crowd_ids(void* ws) {
     return reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + sizeof(CrowdList));
@@ -56,7 +56,10 @@ inline TileDesc* tile_descs(void* ws, int64_t n_img) {
 int launch_fused_tma(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
                      int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
                      double* d_pts, uint8_t* d_valid, int32_t* d_arg, uint8_t* d_high, int32_t* d_count,
-                     void* ws, cudaStream_t s);
+                     void* ws, int max_ctas, cudaStream_t s);
+
+// [fast, direct, defer] tile counts of the descriptors a fused call left in its workspace (diagnostics)
+int launch_tile_modes(const void* ws, int64_t n_img, unsigned long long* d_counts3, cudaStream_t s);
 
 int launch_crowd(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid, int64_t min_boxes,
                  double thr, uint8_t* d_high, int32_t* d_count, void* ws, cudaStream_t s);

@@ -3,6 +3,7 @@
 // only (the library is compiled with -fmad=false), so the output is bit-identical to the numpy
 // generator and any slice can be re-created on the host for parity checks.
 #include "common.cuh"
+#include "../../include/dyd_synth.h"
 
 namespace dyd {
 

@@ -95,8 +95,12 @@ class FusedBuffers:
         self.ws = _ws(lib.dyd_iou_workspace_bytes(n_img), device)
 
 
-def bbox_iou_fused(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_arg=False, out: FusedBuffers | None = None):
-    """Fused K1+K2 over a device-resident CSR table.  Returns a FusedBuffers."""
+def bbox_iou_fused(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_arg=False, out: FusedBuffers | None = None,
+                   max_ctas: int = 0):
+    """Fused K1+K2 over a device-resident CSR table.  Returns a FusedBuffers.
+
+    ``max_ctas`` (0 = every SM) caps the persistent grid so that a second stream -- the URL hash / dedup /
+    exchange chain -- finds free SMs while this kernel runs (dyd_bbox_iou_fused_ex)."""
     _need_cuda(img_off, poly_off, xy)
     lib = _lib.load()
     img_off = _chk(img_off, torch.int64, "img_off"); poly_off = _chk(poly_off, torch.int64, "poly_off")
@@ -107,11 +111,21 @@ def bbox_iou_fused(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_arg=False,
     if out is None:
         out = FusedBuffers(n_img, n_poly, dev, want_arg)
     with torch.cuda.device(dev):
-        _lib.check(lib.dyd_bbox_iou_fused(_ptr(img_off), _ptr(poly_off), _ptr(xy), n_img, n_poly, int(min_boxes),
-                                          float(thr), _ptr(out.pts), _ptr(out.valid), _ptr(out.arg), _ptr(out.high),
-                                          _ptr(out.count), _ptr(out.ws), out.ws.numel(), _stream(dev)),
-                   "dyd_bbox_iou_fused")
+        _lib.check(lib.dyd_bbox_iou_fused_ex(_ptr(img_off), _ptr(poly_off), _ptr(xy), n_img, n_poly, int(min_boxes),
+                                             float(thr), _ptr(out.pts), _ptr(out.valid), _ptr(out.arg), _ptr(out.high),
+                                             _ptr(out.count), _ptr(out.ws), out.ws.numel(), int(max_ctas), _stream(dev)),
+                   "dyd_bbox_iou_fused_ex")
     return out
+
+
+def fused_tile_modes(buf: FusedBuffers, n_img: int):
+    """(staged, direct, deferred) tile counts of the last fused call that used ``buf`` (diagnostics)."""
+    lib = _lib.load()
+    dev = buf.ws.device
+    counts = torch.empty(3, dtype=torch.uint64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_fused_tile_modes(_ptr(buf.ws), n_img, _ptr(counts), _stream(dev)), "dyd_fused_tile_modes")
+    return tuple(int(v) for v in counts.cpu().numpy())
 
 
 # ------------------------------------------------------------------ K0 / K4 / K5
@@ -279,7 +293,7 @@ def _hp(a):
 
 
 def bbox_iou_host(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_pts=True, want_arg=False,
-                  chunk_images=0, out=None, device=0):
+                  chunk_images=0, out=None, device=0, tile_modes=False):
     """Host CSR in -> host results out, H2D / kernels / D2H pipelined inside the library.
 
     Returns dict(pts, valid, arg, high, count) of numpy arrays (pinned if ``out`` supplies them).
@@ -304,23 +318,41 @@ def bbox_iou_host(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_pts=True, w
         out["count"] = np.empty(n_img, np.int32)
     pts = _np(out.get("pts"), np.float64, "pts") if want_pts else None
     arg = _np(out.get("arg"), np.int32, "arg") if want_arg else None
+    modes = np.zeros(3, np.int64) if tile_modes else None
     with torch.cuda.device(device):
-        _lib.check(lib.dyd_bbox_iou_host(_hp(img_off), _hp(poly_off), _hp(xy), n_img, int(min_boxes), float(thr),
-                                         _hp(pts), _hp(_np(out["valid"], np.uint8, "valid")), _hp(arg),
-                                         _hp(_np(out["high"], np.uint8, "high")), _hp(_np(out["count"], np.int32, "count")),
-                                         int(chunk_images)), "dyd_bbox_iou_host")
+        _lib.check(lib.dyd_bbox_iou_host_ex(_hp(img_off), _hp(poly_off), _hp(xy), n_img, int(min_boxes), float(thr),
+                                            _hp(pts), _hp(_np(out["valid"], np.uint8, "valid")), _hp(arg),
+                                            _hp(_np(out["high"], np.uint8, "high")), _hp(_np(out["count"], np.int32, "count")),
+                                            int(chunk_images), _hp(modes)), "dyd_bbox_iou_host_ex")
+    if tile_modes:
+        out["tile_modes"] = {"staged": int(modes[0]), "direct": int(modes[1]), "deferred": int(modes[2])}
     return out
 
 
-def dedup_host(off, data, null=None, keep="first", device=0):
-    """Host Arrow string buffers in -> (keep uint8, rep int64) numpy arrays out."""
+def dedup_host(off, data, null=None, keep="first", device=0, out=None):
+    """Host Arrow string buffers in -> (keep uint8, rep int64) numpy arrays out (``out`` = preallocated, e.g. pinned, pair)."""
     lib = _lib.load()
     if not torch.cuda.is_available():
         raise _lib.DydError("no CUDA device: the hot path has no CPU fallback")
     off = _np(off, np.int64, "off"); data = _np(data, np.uint8, "data"); null = _np(null, np.uint8, "null")
     n = len(off) - 1
-    km = np.empty(n, np.uint8); rep = np.empty(n, np.int64)
+    km, rep = out if out is not None else (np.empty(n, np.uint8), np.empty(n, np.int64))
     with torch.cuda.device(device):
         _lib.check(lib.dyd_dedup_host(_hp(off), _hp(data), _hp(null), n, KEEP_MODES[keep], _hp(km), _hp(rep)),
                    "dyd_dedup_host")
     return km, rep
+
+
+def antijoin_host(off, data, null, ref_off, ref_data, ref_null, device=0, out=None):
+    """Host Arrow string buffers of the main and the reference `source` columns in -> (keep uint8, ref_row int64) out."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.DydError("no CUDA device: the hot path has no CPU fallback")
+    off = _np(off, np.int64, "off"); data = _np(data, np.uint8, "data"); null = _np(null, np.uint8, "null")
+    ref_off = _np(ref_off, np.int64, "ref_off"); ref_data = _np(ref_data, np.uint8, "ref_data"); ref_null = _np(ref_null, np.uint8, "ref_null")
+    n, n_ref = len(off) - 1, len(ref_off) - 1
+    km, rr = out if out is not None else (np.empty(n, np.uint8), np.empty(n, np.int64))
+    with torch.cuda.device(device):
+        _lib.check(lib.dyd_antijoin_host(_hp(off), _hp(data), _hp(null), n, _hp(ref_off), _hp(ref_data), _hp(ref_null), n_ref,
+                                         _hp(km), _hp(rr)), "dyd_antijoin_host")
+    return km, rr

@@ -101,8 +101,30 @@ def dedup_global(keys: torch.Tensor, null: torch.Tensor | None, row_base: int, k
     return keep_out, rep_out
 
 
+def _want_p2p(world, device):
+    import os
+    return (os.environ.get("DYD_EXCHANGE", "p2p") == "p2p" and world > 1 and dist.is_initialized()
+            and torch.device(device).type == "cuda")
+
+
+class _Region:
+    """One direction of the peer-memory exchange: a symmetric receive buffer of `world` regions of `cap`
+    (key, id) records (region s is written by rank s), plus this rank's cursors / slot map for what it sent."""
+
+    def __init__(self, cap, world, device, group, want_sent_row):
+        import torch.distributed._symmetric_memory as symm
+        m = world * cap
+        self.cap, self.m = cap, m
+        self.recv = symm.empty(2 * m, dtype=torch.int64, device=device)
+        self.h = symm.rendezvous(self.recv, group)
+        self.peers = torch.tensor(list(self.h.buffer_ptrs), dtype=torch.int64, device=device)
+        self.cursors = torch.empty(world, dtype=torch.uint64, device=device)
+        self.sent_row = torch.empty(m, dtype=torch.int32, device=device) if want_sent_row else None
+        self.recv.fill_(-1)                     # padding once; afterwards the last reader of a record resets it
+
+
 class DedupExchange:
-    """Sync-free sharded dedup (the production multi-GPU form of K4).
+    """Sync-free sharded dedup (the production multi-GPU form of K4, processor.py:140-144 over all ranks' rows).
 
     Fixed-capacity buckets make every exchange equal-sized, so nothing has to come back to the host
     between kernels.  Two transports:
@@ -110,26 +132,26 @@ class DedupExchange:
     * ``p2p`` (default when the ranks can map each other's memory): the receive and reply buffers live
       in symmetric memory (torch.distributed._symmetric_memory, NVLink peer access).  The bucket kernel
       stores every record straight into its owner's receive buffer and the owner's pack kernel stores
-      every answer straight into the origin's reply buffer -- the compute kernels are the all-to-all;
-      three device-side barriers per step order them (after the padding fill, after the scatter, after
-      the replies).
+      every answer straight into the origin's reply buffer -- the compute kernels are the all-to-all.
+      Two device-side barriers per step order them (records landed, answers landed); the pack kernel, the
+      last reader of a received record, turns it back into padding, so no fill and no third barrier.
     * ``nccl``: bucket kernel -> all_to_all_single -> dedup -> reply pack -> reverse all_to_all_single
       -> unpack (DYD_EXCHANGE=nccl forces it).
 
     The one host read is the overflow flag at the end; if a bucket overflowed (heavily skewed keys)
     the exact-size path `dedup_global` redoes the step.  Buffers are allocated once and reused.
+    Null cells (``null`` uint8[n]) never travel: they form one global group resolved by two all-reduces.
     """
+    MODE = 0
 
     def __init__(self, n_local: int, world: int, device, slack: float = 1.10, group=None):
-        import os
         from . import _lib
         self.lib = _lib.load()
         self.n, self.world, self.dev = n_local, world, device
         self.cap = int(n_local / world * slack) + 4096
         m = world * self.cap
         self.transport = "nccl"
-        want = os.environ.get("DYD_EXCHANGE", "p2p")
-        if want == "p2p" and world > 1 and dist.is_initialized() and torch.device(device).type == "cuda":
+        if _want_p2p(world, device):
             try:
                 self._init_p2p(m, group)
                 self.transport = "p2p"
@@ -140,29 +162,65 @@ class DedupExchange:
             self.recv = torch.empty(2 * m, dtype=torch.int64, device=device)
             self.reply = torch.empty(2 * m, dtype=torch.int64, device=device)
             self.back = torch.empty(2 * m, dtype=torch.int64, device=device)
-        self.cursors = torch.empty(world, dtype=torch.uint64, device=device)
-        self.overflow = torch.empty(1, dtype=torch.int32, device=device)
+            self.cursors = torch.empty(world, dtype=torch.uint64, device=device)
+        self.overflow = torch.zeros(2, dtype=torch.int32, device=device)
         self.keep_r = torch.empty(m, dtype=torch.uint8, device=device)
         self.rep_r = torch.empty(m, dtype=torch.int64, device=device)
-        self.ws = torch.empty(self.lib.dyd_dedup_workspace_bytes(m), dtype=torch.uint8, device=device)
+        self.ws = torch.empty(self._workspace_bytes(m), dtype=torch.uint8, device=device)
         self.keep = torch.empty(n_local, dtype=torch.uint8, device=device)
         self.rep = torch.empty(n_local, dtype=torch.int64, device=device)
+
+    def _workspace_bytes(self, m):
+        return self.lib.dyd_dedup_workspace_bytes(m)
 
     def _init_p2p(self, m: int, group):
         import torch.distributed._symmetric_memory as symm
         grp = group if group is not None else dist.group.WORLD
         self.rank = dist.get_rank(grp)
-        self.recv = symm.empty(2 * m, dtype=torch.int64, device=self.dev)      # (key, id) records, region per sender
+        self.main = _Region(self.cap, self.world, self.dev, grp, True)
         self.back = symm.empty(m, dtype=torch.int64, device=self.dev)          # 8-byte answers, region per owner
-        self.sent_row = torch.empty(m, dtype=torch.int32, device=self.dev)     # which local row went into (owner, slot)
-        self.h_recv = symm.rendezvous(self.recv, grp)
         self.h_back = symm.rendezvous(self.back, grp)
-        assert self.h_recv.world_size == self.world and self.h_recv.rank == self.rank
-        self.peer_recv = torch.tensor(list(self.h_recv.buffer_ptrs), dtype=torch.int64, device=self.dev)
+        assert self.main.h.world_size == self.world and self.main.h.rank == self.rank
         self.peer_back = torch.tensor(list(self.h_back.buffer_ptrs), dtype=torch.int64, device=self.dev)
         self.back.fill_(-1)
+        self.recv, self.cursors = self.main.recv, self.main.cursors
+        torch.cuda.synchronize(self.dev)
+        self.main.h.barrier(channel=0)                                         # every buffer is padded before anyone writes
 
-    def run(self, keys: torch.Tensor, row_base: int, keep="first", group=None, check_overflow=True):
+    # ---- steps shared with AntiJoinExchange -------------------------------------------------------------
+    def _scatter_p2p(self, region, keys, null, row_base, overflow, s):
+        from . import _lib
+        from .ops import _ptr
+        _lib.check(self.lib.dyd_shard_bucket_p2p(_ptr(keys), _ptr(null), row_base, keys.numel(), self.world, self.rank, region.cap,
+                                                 _ptr(region.peers), _ptr(region.sent_row), _ptr(region.cursors),
+                                                 _ptr(overflow), s), "dyd_shard_bucket_p2p")
+
+    def _reply_p2p(self, s):
+        from . import _lib
+        from .ops import _ptr
+        lib, m = self.lib, self.world * self.cap
+        _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, self.cap, self.rank,
+                                                _ptr(self.peer_back), self.MODE, 1, s), "dyd_shard_pack_reply_p2p")
+        self.h_back.barrier(channel=0)                    # all answers have landed (and every rank is done with its records)
+        _lib.check(lib.dyd_shard_unpack_p2p(_ptr(self.back), _ptr(self.main.sent_row), _ptr(self.cursors), self.world, self.cap,
+                                            self.n, _ptr(self.keep), _ptr(self.rep), self.MODE, s), "dyd_shard_unpack_p2p")
+
+    def _reply_nccl(self, row_base, group, s):
+        from . import _lib
+        from .ops import _ptr
+        lib, m = self.lib, self.world * self.cap
+        _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, _ptr(self.reply), self.MODE, s),
+                   "dyd_shard_pack_reply")
+        dist.all_to_all_single(self.back, self.reply, group=group)
+        _lib.check(lib.dyd_shard_unpack(_ptr(self.back), m, row_base, self.n, _ptr(self.keep), _ptr(self.rep), self.MODE, s),
+                   "dyd_shard_unpack")
+
+    def _overflowed(self, group):
+        flag = self.overflow.clone()
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        return bool(flag.max().item())
+
+    def run(self, keys: torch.Tensor, row_base: int, keep="first", group=None, check_overflow=True, null=None):
         from . import _lib
         from .ops import KEEP_MODES, _ptr, _stream
         lib, dev, m = self.lib, self.dev, self.world * self.cap
@@ -170,35 +228,111 @@ class DedupExchange:
         with torch.cuda.device(dev):
             s = _stream(dev)
             if self.transport == "p2p":
-                self.recv.fill_(-1)                               # padding: key = EMPTY, id = -1
-                self.h_recv.barrier(channel=0)                    # every receive buffer is clean before anyone writes
-                _lib.check(lib.dyd_shard_bucket_p2p(_ptr(keys), None, row_base, self.n, self.world, self.rank, self.cap,
-                                                    _ptr(self.peer_recv), _ptr(self.sent_row), _ptr(self.cursors),
-                                                    _ptr(self.overflow), s), "dyd_shard_bucket_p2p")
-                self.h_recv.barrier(channel=1)                    # all records have landed
+                self._scatter_p2p(self.main, keys, null, row_base, self.overflow, s)
+                self.main.h.barrier(channel=1)                    # all records have landed
             else:
-                _lib.check(lib.dyd_shard_bucket(_ptr(keys), None, row_base, self.n, self.world, self.cap, _ptr(self.send),
+                _lib.check(lib.dyd_shard_bucket(_ptr(keys), _ptr(null), row_base, self.n, self.world, self.cap, _ptr(self.send),
                                                 _ptr(self.cursors), _ptr(self.overflow), s), "dyd_shard_bucket")
                 dist.all_to_all_single(self.recv, self.send, group=group)
             _lib.check(lib.dyd_dedup_records(_ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_r), _ptr(self.rep_r),
                                              _ptr(self.ws), self.ws.numel(), s), "dyd_dedup_records")
             if self.transport == "p2p":
-                _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, self.cap, self.rank,
-                                                        _ptr(self.peer_back), s), "dyd_shard_pack_reply_p2p")
-                self.h_back.barrier(channel=0)                    # all answers have landed
-                _lib.check(lib.dyd_shard_unpack_p2p(_ptr(self.back), _ptr(self.sent_row), _ptr(self.cursors), self.world, self.cap,
-                                                    self.n, _ptr(self.keep), _ptr(self.rep), s), "dyd_shard_unpack_p2p")
+                self._reply_p2p(s)
             else:
-                _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, _ptr(self.reply), s),
-                           "dyd_shard_pack_reply")
-                dist.all_to_all_single(self.back, self.reply, group=group)
-                _lib.check(lib.dyd_shard_unpack(_ptr(self.back), m, row_base, self.n, _ptr(self.keep), _ptr(self.rep), s),
-                           "dyd_shard_unpack")
-        if check_overflow:
-            flag = self.overflow.clone()
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-            if int(flag.item()):
-                return dedup_global(keys, None, row_base, keep, group)
+                self._reply_nccl(row_base, group, s)
+            if null is not None:
+                _resolve_null_group(self.keep, self.rep, null, row_base, keep, group)
+        if check_overflow and self._overflowed(group):
+            return dedup_global(keys, null, row_base, keep, group)
+        return self.keep, self.rep
+
+
+def _resolve_null_group(keep_out, rep_out, null, row_base, keep, group):
+    """Null (NaN) cells are one global group (drop_duplicates treats NaN == NaN): first / last / count across ranks."""
+    dev = null.device
+    nidx = torch.nonzero(null != 0).squeeze(1)
+    big = torch.iinfo(torch.int64).max
+    gid = nidx + row_base
+    stats = torch.stack([gid.min() if nidx.numel() else torch.tensor(big, device=dev),
+                         -gid.max() if nidx.numel() else torch.tensor(big, device=dev)]).to(torch.int64)
+    dist.all_reduce(stats, op=dist.ReduceOp.MIN, group=group)
+    cnt = torch.tensor([nidx.numel()], dtype=torch.int64, device=dev)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    if nidx.numel():
+        first, last = stats[0], -stats[1]
+        if keep == "first":
+            rep_out[nidx] = first; keep_out[nidx] = (gid == first).to(torch.uint8)
+        elif keep == "last":
+            rep_out[nidx] = last; keep_out[nidx] = (gid == last).to(torch.uint8)
+        else:
+            rep_out[nidx] = first; keep_out[nidx] = (cnt[0] == 1).to(torch.uint8)
+
+
+class AntiJoinExchange(DedupExchange):
+    """Sync-free sharded anti-join (the production multi-GPU form of K5, processor.py:194-199 with the main
+    table AND the reference set sharded by row across the ranks).
+
+    Both tables are hash-partitioned to owner ranks with the same peer-memory scatter as the dedup: reference
+    records (key, global reference row) and main records (key, global row) land in the owner's two receive
+    buffers, the owner builds its table from the reference records, probes the main records and stores each
+    8-byte answer (kept, or the smallest global reference row holding the key -- what the host needs for the
+    string check of a dropped row) straight into the origin's reply buffer.  Two device-side barriers per step;
+    the build / pack kernels reset the records they consumed.  ``DYD_EXCHANGE=nccl`` (or ranks without peer
+    access) uses bucket -> all_to_all_single for each table and the reverse all_to_all_single for the answers.
+    A bucket overflow falls back to `antijoin_global`.  Null main cells are kept (never match); null reference
+    cells are dropped (``dropna``)."""
+    MODE = 1
+
+    def __init__(self, n_main_local: int, n_ref_local: int, world: int, device, slack: float = 1.10, group=None):
+        self.n_ref = n_ref_local
+        self.cap_ref = int(n_ref_local / world * slack) + 4096
+        super().__init__(n_main_local, world, device, slack, group)
+        m_ref = world * self.cap_ref
+        if self.transport == "p2p":
+            grp = group if group is not None else dist.group.WORLD
+            self.ref = _Region(self.cap_ref, world, device, grp, False)
+            torch.cuda.synchronize(device)
+            self.ref.h.barrier(channel=0)
+            self.recv_ref, self.cursors_ref = self.ref.recv, self.ref.cursors
+        else:
+            self.send_ref = torch.empty(2 * m_ref, dtype=torch.int64, device=device)
+            self.recv_ref = torch.empty(2 * m_ref, dtype=torch.int64, device=device)
+            self.cursors_ref = torch.empty(world, dtype=torch.uint64, device=device)
+
+    def _workspace_bytes(self, m):
+        return self.lib.dyd_antijoin_workspace_bytes(self.world * self.cap_ref)
+
+    def run(self, main_keys, row_base: int, ref_keys, ref_row_base: int, group=None, check_overflow=True,
+            main_null=None, ref_null=None):
+        from . import _lib
+        from .ops import _ptr, _stream
+        lib, dev = self.lib, self.dev
+        m, m_ref = self.world * self.cap, self.world * self.cap_ref
+        assert main_keys.numel() == self.n and ref_keys.numel() == self.n_ref
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            if self.transport == "p2p":
+                self._scatter_p2p(self.ref, ref_keys, ref_null, ref_row_base, self.overflow[1:], s)
+                self._scatter_p2p(self.main, main_keys, main_null, row_base, self.overflow[:1], s)
+                self.main.h.barrier(channel=1)                    # both tables' records have landed
+            else:
+                _lib.check(lib.dyd_shard_bucket(_ptr(ref_keys), _ptr(ref_null), ref_row_base, self.n_ref, self.world, self.cap_ref,
+                                                _ptr(self.send_ref), _ptr(self.cursors_ref), _ptr(self.overflow[1:]), s), "dyd_shard_bucket")
+                dist.all_to_all_single(self.recv_ref, self.send_ref, group=group)
+                _lib.check(lib.dyd_shard_bucket(_ptr(main_keys), _ptr(main_null), row_base, self.n, self.world, self.cap,
+                                                _ptr(self.send), _ptr(self.cursors), _ptr(self.overflow[:1]), s), "dyd_shard_bucket")
+                dist.all_to_all_single(self.recv, self.send, group=group)
+            _lib.check(lib.dyd_antijoin_records(_ptr(self.recv_ref), m_ref, _ptr(self.recv), m, _ptr(self.keep_r), _ptr(self.rep_r),
+                                                _ptr(self.ws), self.ws.numel(), 1 if self.transport == "p2p" else 0, s),
+                       "dyd_antijoin_records")
+            if main_null is not None:                         # rows that never travel: a NaN cell never matches
+                self.keep.fill_(1); self.rep.fill_(-1)
+            if self.transport == "p2p":
+                self._reply_p2p(s)
+            else:
+                self._reply_nccl(row_base, group, s)
+        if check_overflow and self._overflowed(group):
+            return antijoin_global(main_keys, main_null, ref_keys, ref_null, ref_row_base, group)
         return self.keep, self.rep
 
 
@@ -288,3 +422,54 @@ def split_category_bases(local_counts, group=None):
     cat_off[1:] = torch.cumsum(totals, 0)
     base = cat_off[:-1] + all_counts[:rank].sum(0)
     return base, cat_off
+
+
+class ShardedUrlFilter:
+    """Steps 2 + 3 (dedup by `source`, then the reference filter; processor.py:140-144, 194-199) for a row-sharded
+    table whose `source` columns live in HOST memory on every rank -- the N-GPU form of dyd_dedup_host /
+    dyd_antijoin_host.  Per call: H2D of the Arrow buffers (pinned memory gives full PCIe speed), K0 hash of both
+    columns, `DedupExchange` and `AntiJoinExchange` across the ranks (plain K4 / K5 on one GPU), D2H of the four
+    result columns into pinned host arrays.  Device buffers are allocated once for the stated capacities."""
+
+    def __init__(self, n_local: int, n_ref_local: int, max_bytes: int, max_ref_bytes: int, world: int, device, group=None):
+        from . import _lib
+        self.lib = _lib.load()
+        self.n, self.n_ref, self.world, self.dev, self.group = n_local, n_ref_local, world, device, group
+        d = device
+        self.d_off = torch.empty(n_local + 1, dtype=torch.int64, device=d)
+        self.d_data = torch.empty(max_bytes + 8, dtype=torch.uint8, device=d)
+        self.d_roff = torch.empty(n_ref_local + 1, dtype=torch.int64, device=d)
+        self.d_rdata = torch.empty(max_ref_bytes + 8, dtype=torch.uint8, device=d)
+        if world > 1:
+            self.dedup = DedupExchange(n_local, world, d, group=group)
+            self.anti = AntiJoinExchange(n_local, n_ref_local, world, d, group=group)
+        else:
+            self.ws = torch.empty(max(self.lib.dyd_dedup_workspace_bytes(n_local), self.lib.dyd_antijoin_workspace_bytes(n_ref_local)),
+                                  dtype=torch.uint8, device=d)
+        pin = lambda n, dt: torch.empty(n, dtype=dt, pin_memory=True)   # noqa: E731
+        self.h_keep, self.h_rep = pin(n_local, torch.uint8), pin(n_local, torch.int64)
+        self.h_keep_ref, self.h_ref_row = pin(n_local, torch.uint8), pin(n_local, torch.int64)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 18 * n_local
+
+    def run(self, h_off, h_data, h_ref_off, h_ref_data, row_base: int, ref_row_base: int, keep="first"):
+        from . import ops
+        t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(a)   # noqa: E731
+        h_off, h_data, h_ref_off, h_ref_data = t(h_off), t(h_data), t(h_ref_off), t(h_ref_data)
+        nb, nrb = h_data.numel(), h_ref_data.numel()
+        self.h2d_bytes = 8 * (h_off.numel() + h_ref_off.numel()) + nb + nrb
+        with torch.cuda.device(self.dev):
+            self.d_off.copy_(h_off, non_blocking=True); self.d_data[:nb].copy_(h_data, non_blocking=True)
+            self.d_roff.copy_(h_ref_off, non_blocking=True); self.d_rdata[:nrb].copy_(h_ref_data, non_blocking=True)
+            keys = ops.hash_strings(self.d_off, self.d_data[:nb])
+            rkeys = ops.hash_strings(self.d_roff, self.d_rdata[:nrb])
+            if self.world > 1:
+                k, r = self.dedup.run(keys, row_base, keep, group=self.group)
+                k2, r2 = self.anti.run(keys, row_base, rkeys, ref_row_base, group=self.group)
+            else:
+                k, r = ops.dedup(keys, None, keep, workspace=self.ws)
+                k2, r2 = ops.antijoin(keys, None, rkeys, None, workspace=self.ws)
+            self.h_keep.copy_(k, non_blocking=True); self.h_rep.copy_(r, non_blocking=True)
+            self.h_keep_ref.copy_(k2, non_blocking=True); self.h_ref_row.copy_(r2, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+        return self.h_keep, self.h_rep, self.h_keep_ref, self.h_ref_row

@@ -44,7 +44,7 @@ def _excl_offsets(counts: torch.Tensor) -> torch.Tensor:
 
 
 def make_table(seed: int, first_img: int, n_img: int, device="cuda") -> DeviceTable:
-    lib = _lib.load()
+    lib = _lib.load_synth()
     dev = torch.device(device)
     thr = torch.from_numpy(synth.poisson8_thresholds()).to(dev)
     with torch.cuda.device(dev):
@@ -68,7 +68,7 @@ def make_table(seed: int, first_img: int, n_img: int, device="cuda") -> DeviceTa
 
 def make_urls(seed: int, first_row: int, n: int, device="cuda", n_main_for_ref: int = -1):
     """URL column as Arrow buffers on the device: (url_id int64[n], off int64[n+1], bytes uint8)."""
-    lib = _lib.load()
+    lib = _lib.load_synth()
     dev = torch.device(device)
     with torch.cuda.device(dev):
         s = _stream(dev)
@@ -85,7 +85,7 @@ def make_urls(seed: int, first_row: int, n: int, device="cuda", n_main_for_ref: 
 
 def make_crowd(seed: int, first_img: int, n_img: int, lo: int = 200, hi: int = 500, device="cuda"):
     """Dense-crowd boxes (config C4): (img_off int64[n_img+1], pts float64[4*n_box])."""
-    lib = _lib.load()
+    lib = _lib.load_synth()
     dev = torch.device(device)
     with torch.cuda.device(dev):
         s = _stream(dev)

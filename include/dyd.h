@@ -17,7 +17,9 @@
  *     sized by the matching dyd_*_workspace_bytes() query;
  *   - return value: 0 ok; <0 invalid argument (DYD_E_*); >0 a cudaError_t.
  *     dyd_last_error() gives the thread-local message of the last failure;
- *   - re-entrant: no mutable globals, callable from any host thread.
+ *   - re-entrant and callable from any host thread.  The only library-owned state is the per-device
+ *     CUDA memory pool behind the host-buffer entry points (created on first use under a mutex,
+ *     returned to the driver by dyd_host_release()); everything else lives in caller memory.
  *
  * Data layout: a ragged CSR annotation table
  *   img_off  int64[n_img+1]   object range of each image (row)
@@ -42,6 +44,9 @@ extern "C" {
 #define DYD_E_WORKSPACE (-3)     /* workspace too small */
 
 int dyd_version(void);
+/* Number of CUDA kernels this library has launched in the calling process so far (statistic; bench.py reports the
+ * difference over its timed region as `gpu_launches`).                                                  */
+uint64_t dyd_launch_count(void);
 /* Copies the calling thread's last error message (NUL terminated) into buf. */
 size_t dyd_last_error(char* buf, size_t cap);
 
@@ -82,6 +87,19 @@ int dyd_bbox_iou_fused(const int64_t* d_img_off, const int64_t* d_poly_off, cons
                        double* d_pts, uint8_t* d_valid, int32_t* d_arg,
                        uint8_t* d_high, int32_t* d_count,
                        void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Same call restricted to at most `max_ctas` persistent CTAs (one per SM; <= 0 or >= 148: all SMs).  The
+ * kernel claims its image segments dynamically, so a caller that runs another stream next to it -- the URL
+ * hash / dedup / exchange chain of the pipeline, which depends on the `source` column only -- can leave that
+ * stream a few SMs and have both finish together (bench.py).                           */
+int dyd_bbox_iou_fused_ex(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
+                          int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
+                          double* d_pts, uint8_t* d_valid, int32_t* d_arg,
+                          uint8_t* d_high, int32_t* d_count,
+                          void* d_workspace, size_t workspace_bytes, int32_t max_ctas, void* stream);
+/* Diagnostics: tiles of each staging mode (0 bulk-copy staged, 1 direct loads, 2 deferred crowded image) that the
+ * last fused call on this workspace produced; d_counts3 uint64[3].                                   */
+int dyd_fused_tile_modes(const void* d_workspace, int64_t n_img, uint64_t* d_counts3, void* stream);
 
 /* ---------------------------------------------------------------- K0 ------
  * 64-bit hash of each string of an Arrow-style (offsets, bytes) column; the
@@ -125,15 +143,19 @@ int dyd_dedup_records(const int64_t* d_records, int64_t m, int keep_mode, uint8_
 int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
                          int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
                          uint64_t* d_cursors, int32_t* d_overflow, void* stream);
-int dyd_shard_pack_reply_p2p(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m, int64_t cap,
-                             int32_t my_rank, int64_t* const* d_peer_reply, void* stream);
+/* mode 0: dedup answers (rep | keep << 62); mode 1: anti-join answers (kept ? 1 << 62 : first matching
+ * reference row; _unpack then writes ref_row = -1 for kept rows).  reset_records != 0: the pack kernel, the
+ * last reader of the received records, turns each one back into padding (id = -1) so the next step needs no
+ * fill of the receive buffer.                                                                           */
+int dyd_shard_pack_reply_p2p(int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m, int64_t cap,
+                             int32_t my_rank, int64_t* const* d_peer_reply, int32_t mode, int32_t reset_records, void* stream);
 int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
-                         int64_t cap, int64_t n, uint8_t* d_keep, int64_t* d_rep, void* stream);
-/* K4 on received (key, id) records */
+                         int64_t cap, int64_t n, uint8_t* d_keep, int64_t* d_rep, int32_t mode, void* stream);
+/* NCCL-transport forms: (id, answer) pairs */
 int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,
-                         int64_t* d_reply, void* stream);
+                         int64_t* d_reply, int32_t mode, void* stream);
 int dyd_shard_unpack(const int64_t* d_reply, int64_t m, int64_t row_base, int64_t n,
-                     uint8_t* d_keep, int64_t* d_rep, void* stream);
+                     uint8_t* d_keep, int64_t* d_rep, int32_t mode, void* stream);
 
 /* ---------------------------------------------------------------- K5 ------
  * Anti-join of processor.py:194-199: keep[r] = main value not in
@@ -144,6 +166,14 @@ int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_
                  const uint64_t* d_ref_keys, const uint8_t* d_ref_null, int64_t n_ref,
                  uint8_t* d_keep, int64_t* d_ref_row,
                  void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Sharded form (owner side of the exchange): both tables arrive as (key, id) records in fixed-capacity buckets
+ * (id < 0 = padding).  d_keep / d_ref_row are indexed by main record; d_ref_row = smallest reference id holding the
+ * key (global reference row), -1 when kept; padding records get keep 0.  reset_ref != 0 turns the reference
+ * records back into padding after they were read.  Workspace: dyd_antijoin_workspace_bytes(m_ref).      */
+int dyd_antijoin_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main,
+                         uint8_t* d_keep, int64_t* d_ref_row, void* d_workspace, size_t workspace_bytes,
+                         int32_t reset_ref, void* stream);
 
 /* ---------------------------------------------------------------- K3 ------
  * Object-name rewrite through a lookup table, processor.py:582-602 with the
@@ -205,6 +235,13 @@ int dyd_bbox_iou_host(const int64_t* h_img_off, const int64_t* h_poly_off, const
                       double* h_pts, uint8_t* h_valid, int32_t* h_arg,
                       uint8_t* h_high, int32_t* h_count, int64_t chunk_images);
 
+/* Same call, also reporting how the staged kernel handled the chunks: h_tile_modes int64[3] = tiles that were
+ * bulk-copy staged / read with direct loads / deferred to the block-per-image kernel (may be NULL).        */
+int dyd_bbox_iou_host_ex(const int64_t* h_img_off, const int64_t* h_poly_off, const double* h_xy,
+                         int64_t n_img, int64_t min_boxes, double thr,
+                         double* h_pts, uint8_t* h_valid, int32_t* h_arg,
+                         uint8_t* h_high, int32_t* h_count, int64_t chunk_images, int64_t* h_tile_modes);
+
 /* The two host entry points cache their transient device buffers in a library-owned CUDA memory
  * pool (per device); this returns the cached blocks of the current device to the driver. */
 int dyd_host_release(void);
@@ -213,6 +250,11 @@ int dyd_host_release(void);
  * Arrow buffers to host masks.  h_ref_* may be NULL when n_ref == 0.              */
 int dyd_dedup_host(const int64_t* h_off, const uint8_t* h_bytes, const uint8_t* h_null, int64_t n,
                    int keep_mode, uint8_t* h_keep, int64_t* h_rep);
+/* Anti-join (processor.py:194-199) from host Arrow buffers of both `source` columns to the host keep mask and the
+ * first matching reference row (-1 when kept): H2D, hash of both columns, build + probe, D2H.           */
+int dyd_antijoin_host(const int64_t* h_off, const uint8_t* h_bytes, const uint8_t* h_null, int64_t n,
+                      const int64_t* h_ref_off, const uint8_t* h_ref_bytes, const uint8_t* h_ref_null, int64_t n_ref,
+                      uint8_t* h_keep, int64_t* h_ref_row);
 
 /* ------------------------------------------------ native ingest / egress (host) ---
  * Multi-threaded C++ replacement of the per-row json.loads / Python loops of processor.py:262-296
@@ -292,21 +334,6 @@ int dyd_csv_measure(void* handle, int64_t window, int64_t* col_bytes, int64_t* c
 int dyd_csv_fill(void* handle, int32_t n_sel, const int32_t* cols, int64_t* const* off_out, uint8_t* const* data_out,
                  uint8_t* const* bitmap_out, int32_t threads);
 void dyd_csv_close(void* handle);
-
-/* ------------------------------------------------ synthetic tables (§8d) ---
- * Device-side twin of deal_yolo_daya_b200/synth.py (bit-identical output).       */
-int dyd_synth_counts(uint64_t seed, int64_t first_img, int64_t n_img, const uint64_t* d_pois_thr,
-                     int32_t n_thr, int64_t* d_npoly /* [n_img] */, void* stream);
-int dyd_synth_nvert(uint64_t seed, int64_t first_img, int64_t n_img, const int64_t* d_img_off,
-                    int64_t* d_nvert /* [n_poly] */, void* stream);
-int dyd_synth_fill(uint64_t seed, int64_t first_img, int64_t n_img, const int64_t* d_img_off,
-                   const int64_t* d_poly_off, double* d_xy, int32_t* d_label_id, void* stream);
-int dyd_synth_urls(uint64_t seed, int64_t first_row, int64_t n, int64_t n_main_for_ref /* <0: main table */,
-                   int64_t* d_url_id, int64_t* d_len /* [n] byte length of each URL */, void* stream);
-int dyd_synth_url_bytes(const int64_t* d_url_id, const int64_t* d_off, int64_t n, uint8_t* d_bytes, void* stream);
-int dyd_synth_crowd(uint64_t seed, int64_t first_img, int64_t n_img, int32_t lo, int32_t hi,
-                    const int64_t* d_img_off /* NULL: write counts to d_nbox */, int64_t* d_nbox,
-                    double* d_pts, void* stream);
 
 #ifdef __cplusplus
 }

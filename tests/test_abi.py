@@ -11,8 +11,8 @@ from deal_yolo_daya_b200 import _lib, build
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def declared_symbols():
-    text = (ROOT / "include" / "dyd.h").read_text()
+def declared_symbols(header="dyd.h"):
+    text = (ROOT / "include" / header).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(dyd_[a-z0-9_]+)\s*\(", text)))
 
@@ -30,6 +30,18 @@ def test_binding_matches_header():
     assert sorted(_lib.PROTOTYPES) == declared_symbols()
     lib = _lib.load()
     assert lib.dyd_version() == 100
+
+
+def test_generator_library_is_separate_from_the_product_library():
+    """The synthetic-table generator (bench / tests) has its own header and library; libdyd.so does not export it."""
+    build.build()
+    names = declared_symbols("dyd_synth.h")
+    assert sorted(_lib.SYNTH_PROTOTYPES) == names and len(names) >= 6
+    synth = ctypes.CDLL(str(_lib.SYNTH_LIB_PATH))
+    product = ctypes.CDLL(str(_lib.LIB_PATH))
+    for n in names:
+        assert hasattr(synth, n)
+        assert not hasattr(product, n), f"{n} leaked into the product ABI"
 
 
 def test_argument_errors_are_reported_without_a_gpu():

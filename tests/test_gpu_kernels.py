@@ -368,16 +368,43 @@ def test_host_entry_points(cuda_device):
     t = synth.make_table(12, 0, 40000)
     want_pts, want_valid, want_arg = oracle_c.bbox_fold(t.poly_off, t.xy)
     want_high, want_count = oracle_c.iou_filter(t.img_off, want_pts, want_valid, 2, 0.7)
-    for chunk in (0, 1777, 100000):
-        out = ops.bbox_iou_host(t.img_off, t.poly_off, t.xy, 2, 0.7, want_pts=True, want_arg=True, chunk_images=chunk)
+    for chunk in (0, 1777, 1111, 100000):
+        out = ops.bbox_iou_host(t.img_off, t.poly_off, t.xy, 2, 0.7, want_pts=True, want_arg=True, chunk_images=chunk, tile_modes=True)
         assert_bits(out["pts"], want_pts); assert_bits(out["valid"], want_valid); assert_bits(out["arg"], want_arg)
         assert_bits(out["high"], want_high); assert_bits(out["count"], want_count)
+        # every chunk -- also those that start at an odd object number or deep inside the table -- takes the bulk-copy staged
+        # kernel: at most the last tile of a chunk may fall back to direct loads (its 16-byte slices would leave the arrays)
+        tm = out["tile_modes"]
+        n_chunks = -(-40000 // (chunk or 16384))
+        assert tm["deferred"] == 0 and tm["direct"] <= 2 * n_chunks and tm["staged"] > 6000, tm
     strs = [synth.url_of(i) for i in synth.url_ids_of(12, np.arange(20000))]
     off, data = oracle_c.pack_strings(strs)
     null = np.zeros(len(strs), np.uint8); null[5] = null[77] = 1
     keep, rep = ops.dedup_host(off, data, null, "first")
     wk, wr = oracle_c.dedup(oracle_c.hash_strings_buf(off, data), null, "first")
     assert_bits(keep, wk); assert_bits(rep, wr)
+    rstrs = [synth.url_of(i) for i in synth.ref_ids_of(12, np.arange(9000), 20000)]
+    roff, rdata = oracle_c.pack_strings(rstrs)
+    rnull = np.zeros(len(rstrs), np.uint8); rnull[3] = 1
+    keep, row = ops.antijoin_host(off, data, null, roff, rdata, rnull)
+    wk, wr = oracle_c.antijoin(oracle_c.hash_strings_buf(off, data), null, oracle_c.hash_strings_buf(roff, rdata), rnull)
+    assert_bits(keep, wk); assert_bits(row, wr)
+    assert 0 < int(wk.sum()) < len(strs)
+
+
+def test_fused_with_fewer_ctas_and_dynamic_segments(cuda_device):
+    """The fused kernel claims its segments dynamically: any CTA cap gives the same bits (dyd_bbox_iou_fused_ex)."""
+    d = cuda_device
+    t = synth.make_table(21, 5, 30000)
+    want_pts, want_valid, _ = oracle_c.bbox_fold(t.poly_off, t.xy)
+    want_high, want_count = oracle_c.iou_filter(t.img_off, want_pts, want_valid, 2, 0.7)
+    io, po, xy = dev(t.img_off, d), dev(t.poly_off, d), dev(t.xy, d)
+    for ctas in (0, 1, 3, 47, 140, 148, 1000):
+        out = ops.bbox_iou_fused(io, po, xy, 2, 0.7, max_ctas=ctas)
+        assert_bits(host(out.pts), want_pts, f"pts ctas={ctas}"); assert_bits(host(out.valid), want_valid)
+        assert_bits(host(out.high), want_high, f"high ctas={ctas}"); assert_bits(host(out.count), want_count)
+    modes = ops.fused_tile_modes(out, 30000)
+    assert modes[0] > 0 and sum(modes) >= 30000 // 6
 
 
 def test_exchange_kernels_single_rank_roundtrip(cuda_device, small_partitions):
@@ -405,9 +432,59 @@ def test_exchange_kernels_single_rank_roundtrip(cuda_device, small_partitions):
         _lib.check(lib.dyd_shard_bucket(_ptr(k), None, 1000, n, world, cap, _ptr(send), _ptr(cursors), _ptr(overflow), s), "bucket")
         assert int(overflow.item()) == 0 and int(cursors.cpu().numpy().astype(np.int64).sum()) == n
         _lib.check(lib.dyd_dedup_records(_ptr(send), m, ops.KEEP_MODES[keep], _ptr(keep_r), _ptr(rep_r), _ptr(ws), ws.numel(), s), "records")
-        _lib.check(lib.dyd_shard_pack_reply(_ptr(send), _ptr(keep_r), _ptr(rep_r), m, _ptr(reply), s), "pack")
-        _lib.check(lib.dyd_shard_unpack(_ptr(reply), m, 1000, n, _ptr(out_keep), _ptr(out_rep), s), "unpack")
+        _lib.check(lib.dyd_shard_pack_reply(_ptr(send), _ptr(keep_r), _ptr(rep_r), m, _ptr(reply), 0, s), "pack")
+        _lib.check(lib.dyd_shard_unpack(_ptr(reply), m, 1000, n, _ptr(out_keep), _ptr(out_rep), 0, s), "unpack")
         assert_bits(host(out_keep), want_keep, f"keep {keep}"); assert_bits(host(out_rep), want_rep, f"rep {keep}")
+        # peer-memory forms with this GPU as all four "ranks": one rank's records fill region 0 of a 4-region buffer
+        # per owner; here world = 1 keeps it a self-exchange (region 0 of the own buffer), run twice so that the
+        # second pass works on records the first pass's pack kernel reset to padding
+        cap1 = n + 512
+        recv, back = torch.full((2 * cap1,), -1, dtype=torch.int64, device=d), torch.full((cap1,), -1, dtype=torch.int64, device=d)
+        sent = t(cap1, dt=torch.int32); cur1 = t(1, dt=torch.uint64)
+        peers_recv = torch.tensor([recv.data_ptr()], dtype=torch.int64, device=d); peers_back = torch.tensor([back.data_ptr()], dtype=torch.int64, device=d)
+        kr1, rr1 = t(cap1, dt=torch.uint8), t(cap1)
+        ws1 = t(lib.dyd_dedup_workspace_bytes(cap1), dt=torch.uint8)
+        for _ in range(2):
+            _lib.check(lib.dyd_shard_bucket_p2p(_ptr(k), None, 1000, n, 1, 0, cap1, _ptr(peers_recv), _ptr(sent), _ptr(cur1), _ptr(overflow), s), "bucket_p2p")
+            _lib.check(lib.dyd_dedup_records(_ptr(recv), cap1, ops.KEEP_MODES[keep], _ptr(kr1), _ptr(rr1), _ptr(ws1), ws1.numel(), s), "records")
+            _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(recv), _ptr(kr1), _ptr(rr1), cap1, cap1, 0, _ptr(peers_back), 0, 1, s), "pack_p2p")
+            out_keep.fill_(7); out_rep.fill_(-7)
+            _lib.check(lib.dyd_shard_unpack_p2p(_ptr(back), _ptr(sent), _ptr(cur1), 1, cap1, n, _ptr(out_keep), _ptr(out_rep), 0, s), "unpack_p2p")
+            assert_bits(host(out_keep), want_keep, f"p2p keep {keep}"); assert_bits(host(out_rep), want_rep, f"p2p rep {keep}")
+            assert bool((recv.view(-1, 2)[:, 1] == -1).all()), "pack kernel must leave the receive buffer padded"
     # overflow is reported, never silent
     _lib.check(lib.dyd_shard_bucket(_ptr(k), None, 0, n, world, 100, _ptr(send), _ptr(cursors), _ptr(overflow), s), "bucket")
     assert int(overflow.item()) == 1
+
+
+def test_antijoin_records_roundtrip(cuda_device):
+    """Sharded anti-join on one GPU: both tables bucketed into 4 fixed-capacity regions of (key, id) records, the owner-side
+    table step on records (dyd_antijoin_records), answers packed in anti-join mode and unpacked -- equals the plain anti-join
+    with global reference rows; the reference records are reset to padding by the build kernel."""
+    from deal_yolo_daya_b200 import _lib
+    from deal_yolo_daya_b200.ops import _ptr, _stream
+    lib = _lib.load(); d = cuda_device
+    rng = np.random.RandomState(11)
+    n, nr, world = 50000, 21000, 4
+    keys = rng.randint(0, 30000, size=n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    ref = rng.randint(20000, 45000, size=nr).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    mnull = (rng.rand(n) < 0.01).astype(np.uint8); rnull = (rng.rand(nr) < 0.03).astype(np.uint8)
+    want_keep, want_row = oracle_c.antijoin(keys, mnull, ref, rnull)
+    want_row = np.where(want_row >= 0, want_row + 500, -1)                   # global reference rows = 500 + row
+    cap, capr = n // world + 2000, nr // world + 2000
+    m, mr = world * cap, world * capr
+    t = lambda *shape, dt=torch.int64: torch.empty(*shape, dtype=dt, device=d)   # noqa: E731
+    send, sendr, reply = t(2 * m), t(2 * mr), t(2 * m)
+    cursors, overflow = t(world, dt=torch.uint64), t(2, dt=torch.int32)
+    keep_r, row_r = t(m, dt=torch.uint8), t(m)
+    ws = t(lib.dyd_antijoin_workspace_bytes(mr), dt=torch.uint8)
+    s = _stream(d)
+    _lib.check(lib.dyd_shard_bucket(_ptr(dev(ref, d)), _ptr(dev(rnull, d)), 500, nr, world, capr, _ptr(sendr), _ptr(cursors), _ptr(overflow[1:]), s), "bucket ref")
+    _lib.check(lib.dyd_shard_bucket(_ptr(dev(keys, d)), _ptr(dev(mnull, d)), 9000, n, world, cap, _ptr(send), _ptr(cursors), _ptr(overflow[:1]), s), "bucket main")
+    assert overflow.cpu().tolist() == [0, 0]
+    _lib.check(lib.dyd_antijoin_records(_ptr(sendr), mr, _ptr(send), m, _ptr(keep_r), _ptr(row_r), _ptr(ws), ws.numel(), 1, s), "antijoin_records")
+    assert bool((sendr.view(-1, 2)[:, 1] == -1).all()), "build kernel must reset the reference records"
+    _lib.check(lib.dyd_shard_pack_reply(_ptr(send), _ptr(keep_r), _ptr(row_r), m, _ptr(reply), 1, s), "pack")
+    out_keep = torch.ones(n, dtype=torch.uint8, device=d); out_row = torch.full((n,), -1, dtype=torch.int64, device=d)   # NaN rows never travel
+    _lib.check(lib.dyd_shard_unpack(_ptr(reply), m, 9000, n, _ptr(out_keep), _ptr(out_row), 1, s), "unpack")
+    assert_bits(host(out_keep), want_keep, "keep"); assert_bits(host(out_row), want_row, "ref_row")
