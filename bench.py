@@ -368,8 +368,14 @@ def main():
     url_bytes = int(udata.numel() + rdata.numel()) + 16 * (n_img + n_ref) + 18 * n_img + 8 * n_ref + 17 * n_img   # K0 (both) + K4 + K5
     overlap = args.url_sms > 0
     max_ctas = 148 - args.url_sms if overlap else 0
-    s_poly = torch.cuda.current_stream(dev)
-    s_url = torch.cuda.Stream(dev, priority=-1) if overlap else s_poly
+    # The polygon stream has the higher priority: when the pre-pass ends its persistent CTAs are placed first and the URL
+    # stream's kernels, released by the same event, fill the SMs that are left (and all of them once the fused kernel is done).
+    s_poly = torch.cuda.Stream(dev, priority=-1) if overlap else torch.cuda.current_stream(dev)
+    s_url = torch.cuda.Stream(dev, priority=0) if overlap else s_poly
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(s_poly)
+    ev_pre = torch.cuda.Event()
+    ev_pre.record()                                 # creates the underlying cudaEvent
     K = args.steps
     mk = lambda: [torch.cuda.Event(enable_timing=True) for _ in range(K)]   # noqa: E731
     ev_f0, ev_f1, ev_u0, ev_u1, ev_a0 = mk(), mk(), mk(), mk(), mk()
@@ -400,17 +406,16 @@ def main():
         state["keys"] = keys
 
     def step(i=None):
-        if overlap:
-            s_url.wait_stream(s_poly)               # a step starts on both streams together ...
         if i is not None:
             ev_f0[i].record()
-        ops.bbox_iou_fused(t.img_off, t.poly_off, t.xy, MIN_BOXES, THR, out=buf, max_ctas=max_ctas)
+        ops.bbox_iou_fused(t.img_off, t.poly_off, t.xy, MIN_BOXES, THR, out=buf, max_ctas=max_ctas, prepass_event=ev_pre if overlap else None)
         if i is not None:
             ev_f1[i].record()
         if overlap:
             with torch.cuda.stream(s_url):
+                s_url.wait_event(ev_pre)            # the URL chain of a step starts when the fused kernel's CTAs are being placed ...
                 url_chain(i)
-            s_poly.wait_stream(s_url)               # ... and ends when both are done
+            s_poly.wait_stream(s_url)               # ... and the step ends when both streams are done
         else:
             url_chain(i)
 
@@ -446,6 +451,11 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
+    ct = ops.fused_cta_times().astype(np.float64)
+    ct = ct[ct[:, 0] > 0]
+    cta_times = {"ctas": int(len(ct)), "start_spread_ms": float((ct[:, 0].max() - ct[:, 0].min()) * 1e-6),
+                 "end_spread_ms": float((ct[:, 1].max() - ct[:, 1].min()) * 1e-6),
+                 "kernel_ms": float((ct[:, 1].max() - ct[:, 0].min()) * 1e-6)} if len(ct) else None
     ms_total = allmax(ms_total)
     ms_step = ms_total / K
     value = world * n_img / (ms_step * 1e-3)
@@ -603,7 +613,7 @@ def main():
         "gpu_launches": launches,
         "gpu_launches_how": "dyd_launch_count() before / after the timed region: every kernel launch of libdyd.so increments it",
         "streams": {"overlap": overlap, "fused_ctas": max_ctas or 148, "url_stream_sms": args.url_sms,
-                    "fused_ms": fused_ms, "url_chain_ms": url_ms_max, "antijoin_ms": anti_ms_max,
+                    "fused_ms": fused_ms, "url_chain_ms": url_ms_max, "antijoin_ms": anti_ms_max, "fused_cta_times_last_launch": cta_times,
                     "note": "per-step CUDA-event times on each stream (max over ranks for the URL chain); a step ends when both streams are done"},
         "roofline": {"bound": "hbm", "kernel": "fused_tma_kernel (+ tile_desc pre-pass and crowd worklist kernel, timed together)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -364,7 +364,7 @@ extern "C" int dyd_iou_filter(const int64_t* d_img_off, const double* d_pts, con
 extern "C" int dyd_bbox_iou_fused_ex(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
                                      int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
                                      double* d_pts, uint8_t* d_valid, int32_t* d_arg, uint8_t* d_high, int32_t* d_count,
-                                     void* d_workspace, size_t workspace_bytes, int32_t max_ctas, void* stream) {
+                                     void* d_workspace, size_t workspace_bytes, int32_t max_ctas, void* prepass_done_event, void* stream) {
     DYD_REQUIRE(n_img >= 0 && n_img <= 0x7fffffff && n_poly >= 0, DYD_E_ARG, "bad count");
     if (n_img == 0) return 0;
     DYD_REQUIRE(d_img_off && d_poly_off && d_pts && d_valid && d_high && d_count && d_workspace, DYD_E_ARG, "null pointer");
@@ -379,7 +379,7 @@ extern "C" int dyd_bbox_iou_fused_ex(const int64_t* d_img_off, const int64_t* d_
     const bool tma_ok = ((uintptr_t)d_img_off & 15) == 0 && ((uintptr_t)d_poly_off & 15) == 0;
     if (!direct && tma_ok) {
         if (int rc = launch_fused_tma(d_img_off, d_poly_off, d_xy, n_img, n_poly, min_boxes, thr, d_pts, d_valid, d_arg,
-                                      d_high, d_count, d_workspace, max_ctas, s)) return rc;
+                                      d_high, d_count, d_workspace, max_ctas, reinterpret_cast<cudaEvent_t>(prepass_done_event), s)) return rc;
     } else {
         const int G = env_int("DYD_GROUP", 4);
         const int64_t want = (n_img + CTA_WARPS - 1) / CTA_WARPS;
@@ -388,8 +388,14 @@ extern "C" int dyd_bbox_iou_fused_ex(const int64_t* d_img_off, const int64_t* d_
         int rc = d_arg ? launch_fused_direct<true>(G, grid, s, d_img_off, d_poly_off, xy2, n_img, min_boxes, thr, d_pts, d_valid, d_arg, d_high, d_count, d_workspace)
                        : launch_fused_direct<false>(G, grid, s, d_img_off, d_poly_off, xy2, n_img, min_boxes, thr, d_pts, d_valid, nullptr, d_high, d_count, d_workspace);
         if (rc) return rc;
+        if (prepass_done_event) DYD_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(prepass_done_event), s));
     }
     return launch_crowd(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, d_workspace, s);
+}
+
+extern "C" int dyd_fused_cta_times(uint64_t* h_times, int32_t n) {
+    DYD_REQUIRE(h_times && n >= 0, DYD_E_ARG, "bad arguments");
+    return fused_cta_times(reinterpret_cast<unsigned long long*>(h_times), n);
 }
 
 extern "C" int dyd_bbox_iou_fused(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
@@ -397,7 +403,7 @@ extern "C" int dyd_bbox_iou_fused(const int64_t* d_img_off, const int64_t* d_pol
                                   double* d_pts, uint8_t* d_valid, int32_t* d_arg, uint8_t* d_high, int32_t* d_count,
                                   void* d_workspace, size_t workspace_bytes, void* stream) {
     return dyd_bbox_iou_fused_ex(d_img_off, d_poly_off, d_xy, n_img, n_poly, min_boxes, thr, d_pts, d_valid, d_arg, d_high, d_count,
-                                 d_workspace, workspace_bytes, 0, stream);
+                                 d_workspace, workspace_bytes, 0, nullptr, stream);
 }
 
 extern "C" int dyd_fused_tile_modes(const void* d_workspace, int64_t n_img, uint64_t* d_counts3, void* stream) {

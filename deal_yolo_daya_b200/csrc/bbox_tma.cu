@@ -245,6 +245,14 @@ __device__ __forceinline__ Corner fold_staged(const double2* base, int V, Corner
     return c;
 }
 
+// Diagnostics: globaltimer at which each CTA of the last fused launch started / finished (2 stores per CTA).
+__device__ unsigned long long g_cta_times[2 * NUM_SMS];
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <bool ARG>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict__ poly_off,
@@ -259,6 +267,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
 
     if (lane == 0) mbar_init(&st.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (threadIdx.x == 0 && blockIdx.x < NUM_SMS) g_cta_times[2 * blockIdx.x] = globaltimer();
     __syncthreads();
 
     const bool zero_hits = 0.0 >= thr;
@@ -406,6 +415,7 @@ fused_tma_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict_
         if (lane < ni) { count[i0 + lane] = my_ne; high[i0 + lane] = (hits >> lane) & 1u; }
         __syncwarp();                              // st.k2 scratch is rewritten by the next tile
     }
+    if (threadIdx.x == 0 && blockIdx.x < NUM_SMS) atomicMax(&g_cta_times[2 * blockIdx.x + 1], globaltimer());
 }
 
 // Diagnostics: how many tiles of each mode the pre-pass produced (the descriptors stay in the workspace).
@@ -416,6 +426,11 @@ __global__ void tile_modes_kernel(const TileDesc* __restrict__ desc, int64_t n_s
     unsigned c[3] = {0, 0, 0};
     for (int j = 0; j < cnt; ++j) { const int m = desc[s * SEG_IMAGES + j].mode; if (m < 3) ++c[m]; }
     for (int m = 0; m < 3; ++m) if (c[m]) atomicAdd(&counts[m], (unsigned long long)c[m]);
+}
+int fused_cta_times(unsigned long long* h_out, int n) {
+    if (n > 2 * NUM_SMS) n = 2 * NUM_SMS;
+    DYD_CUDA(cudaMemcpyFromSymbol(h_out, g_cta_times, sizeof(unsigned long long) * n));
+    return 0;
 }
 int launch_tile_modes(const void* ws, int64_t n_img, unsigned long long* d_counts3, cudaStream_t s) {
     const int64_t n_seg = n_segments_of(n_img);
@@ -428,11 +443,12 @@ int launch_tile_modes(const void* ws, int64_t n_img, unsigned long long* d_count
 int launch_fused_tma(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
                      int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
                      double* d_pts, uint8_t* d_valid, int32_t* d_arg, uint8_t* d_high, int32_t* d_count,
-                     void* ws, int max_ctas, cudaStream_t s) {
+                     void* ws, int max_ctas, cudaEvent_t prepass_done, cudaStream_t s) {
     const int64_t n_seg = n_segments_of(n_img);
     TileDesc* desc = tile_descs(ws, n_img);
     tile_desc_kernel<<<(unsigned)((n_seg + DESC_WARPS - 1) / DESC_WARPS), 32 * DESC_WARPS, 0, s>>>(d_img_off, d_poly_off, n_img, n_poly, n_seg, desc);
     if (int rc = launch_check("tile_desc_kernel")) return rc;
+    if (prepass_done) DYD_CUDA(cudaEventRecord(prepass_done, s));
     const size_t smem = sizeof(Smem);
     const int64_t want = (n_seg + NW - 1) / NW;
     const int64_t cap = max_ctas > 0 && max_ctas < NUM_SMS ? max_ctas : NUM_SMS;   // < 148: leave SMs to concurrent streams

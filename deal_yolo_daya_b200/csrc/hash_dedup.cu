@@ -305,7 +305,8 @@ dedup_leftover_kernel(const unsigned long long* __restrict__ keys, const uint8_t
 template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
 antijoin_build_kernel(unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t n,
-                      Slot* tab, int shift, uint64_t mask, bool reset) {
+                      Slot* tab, int shift, uint64_t mask, bool reset, const int* gate) {
+    if (gate != nullptr && *gate == 0) return;         // fallback of the partitioned path: not needed
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= n) return;
     unsigned long long key, row;
@@ -330,7 +331,8 @@ template <int KIND>
 __global__ void __launch_bounds__(HT_THREADS)
 antijoin_probe_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t n,
                       const Slot* __restrict__ tab, int shift, uint64_t mask,
-                      uint8_t* __restrict__ keep, int64_t* __restrict__ ref_row) {
+                      uint8_t* __restrict__ keep, int64_t* __restrict__ ref_row, const int* gate) {
+    if (gate != nullptr && *gate == 0) return;
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= n) return;
     uint8_t k = 1; long long rr = -1;
@@ -493,6 +495,9 @@ shard_unpack_kernel(const long long* __restrict__ reply, int64_t m, int64_t row_
 }
 
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + HT_THREADS - 1) / HT_THREADS); }
+// EXPERIMENT: dynamic shared memory requested by every URL-chain launch.  A non-zero value keeps these kernels off the SMs
+// whose shared memory the persistent fused kernel owns, i.e. confines them to the SMs that kernel leaves free.
+static inline size_t url_pad() { const char* e = getenv("DYD_URL_SMEM_PAD"); return e ? (size_t)atoi(e) : 0; }
 
 // memset that only happens when *gate != 0 (16-byte units)
 __global__ void gated_fill_kernel(uint4* p, size_t n16, unsigned v, const int* gate) {
@@ -515,10 +520,10 @@ static int dedup_table(const uint64_t* d_keys, const uint8_t* d_null, const int6
         DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
         if (keep_mode == 2) DYD_CUDA(cudaMemsetAsync(cnt, 0, cap * sizeof(unsigned), s));
     } else {
-        gated_fill_kernel<<<NUM_SMS * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(tab), cap * sizeof(Slot) / 16, 0xFFFFFFFFu, gate);
+        gated_fill_kernel<<<NUM_SMS * 8, 256, url_pad(), s>>>(reinterpret_cast<uint4*>(tab), cap * sizeof(Slot) / 16, 0xFFFFFFFFu, gate);
         if (int rc = launch_check("gated_fill_kernel")) return rc;
         if (keep_mode == 2) {
-            gated_fill_kernel<<<NUM_SMS * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(cnt), cap * sizeof(unsigned) / 16, 0u, gate);
+            gated_fill_kernel<<<NUM_SMS * 8, 256, url_pad(), s>>>(reinterpret_cast<uint4*>(cnt), cap * sizeof(unsigned) / 16, 0u, gate);
             if (int rc = launch_check("gated_fill_kernel")) return rc;
         }
         hdr = null_hdr;                                // null statistics were gathered by the partition kernel
@@ -533,13 +538,13 @@ static int dedup_table(const uint64_t* d_keys, const uint8_t* d_null, const int6
     // the gated fallback normally exits at once: a small grid-stride grid keeps that exit cheap
     const unsigned grid = gate == nullptr ? grid_for(n) : std::min(grid_for(n), (unsigned)(NUM_SMS * 8));
     for (unsigned pass = 0; pass < (1u << log2_passes); ++pass) {
-        dedup_insert_kernel<KIND><<<grid, HT_THREADS, 0, s>>>(
+        dedup_insert_kernel<KIND><<<grid, HT_THREADS, url_pad(), s>>>(
             reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1, pass_shift, pass,
             gate, gate == nullptr);
         if (int rc = launch_check("dedup_insert_kernel")) return rc;
     }
     for (unsigned pass = 0; pass < (1u << log2_passes); ++pass) {
-        dedup_lookup_kernel<KIND><<<grid, HT_THREADS, 0, s>>>(
+        dedup_lookup_kernel<KIND><<<grid, HT_THREADS, url_pad(), s>>>(
             reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n, keep_mode, hdr, tab, cnt, shift, cap - 1, pass_shift, pass, d_keep, d_rep,
             gate);
         if (int rc = launch_check("dedup_lookup_kernel")) return rc;
@@ -547,9 +552,285 @@ static int dedup_table(const uint64_t* d_keys, const uint8_t* d_null, const int6
     return 0;
 }
 
+// =============================================================================== radix-partitioned K4 / K5
+// The large-input path of dedup, anti-join and the joint "URL filter" (dedup keep=first + anti-join in one pass).
+//
+//   scatter  one CTA per tile of 16 K records: partition index = top bits of the mixed key; the CTA counts its records per
+//            partition in shared memory, claims one run per partition with ONE global atomic and writes the 16-byte records
+//            {key, pos | id << 32} of a run next to each other -- a few million global atomics and 64-byte runs instead of
+//            one atomic and one isolated 16-byte store per record.  Partitions are fixed-capacity regions (4096 records,
+//            average fill <= 2731); an overflow (one key repeated thousands of times) raises a device flag and the gated
+//            global-table kernels redo the call on the device.
+//   resolve  one CTA per partition: an 8192-slot open-addressing table in shared memory (64-bit CAS for the key, native
+//            32-bit atomics for first / last row, count, smallest reference row), then every main record's answer is
+//            written at its position.  Random accesses never leave the SM.
+//
+// Row ids travel as 32 bits here, so the path is taken for tables below 2^32 - 1 rows (callers of the records form state
+// the bound); anything else keeps the older kernels above.
+constexpr int RP_CAP = 4096;                     // records per partition region
+constexpr int RP_SLOTS = 8192;                   // shared-memory table of one partition
+constexpr int RP_THREADS = 512;
+constexpr int RP_ITEMS = RP_CAP / RP_THREADS;    // records per thread of the resolve kernel
+constexpr int RP_AVG_MAX = 2731;                 // average fill that keeps an overflow ~25 sigma away
+constexpr int SC_THREADS = 512;
+constexpr int SC_ITEMS = 32;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;   // records per scatter CTA
+constexpr int SC_MAX_NP = 8192;                  // partitions the scatter can count in shared memory
+constexpr unsigned RP_NONE = 0xFFFFFFFFu;
+enum { RP_FIRST = 0, RP_LAST = 1, RP_COUNT = 2, RP_ANTI = 3, RP_JOINT = 4 };
+
+struct RpLayout {
+    int log2_np;
+    size_t cursors, flag, kv, fallback, total;   // byte offsets from the workspace start
+};
+static inline RpLayout rp_layout(int64_t n_total, size_t fallback_bytes) {
+    RpLayout L{};
+    int k = 0;
+    while ((n_total >> k) > RP_AVG_MAX) ++k;
+    L.log2_np = k;
+    const uint64_t np = 1ULL << k;
+    size_t o = sizeof(TableHeader);
+    L.cursors = o; o += sizeof(unsigned) * np;
+    L.flag = o; o += 16;
+    o = (o + 255) & ~(size_t)255;
+    L.kv = o; o += sizeof(ulonglong2) * np * RP_CAP;
+    o = (o + 255) & ~(size_t)255;
+    L.fallback = o;
+    L.total = o + fallback_bytes;
+    return L;
+}
+static inline int64_t rp_min_rows() {
+    const char* m = getenv("DYD_DEDUP_PARTITION_MIN");
+    const long long lo = m ? atoll(m) : (1LL << 20);
+    return lo < 4096 ? 4096 : lo;
+}
+static inline bool rp_eligible(int64_t n_total, int64_t id_bound) {
+    const char* e = getenv("DYD_DEDUP_PARTITION");
+    if (e && atoi(e) == 0) return false;
+    return n_total >= rp_min_rows() && n_total < (1LL << 31) && id_bound > 0 && id_bound < (int64_t)RP_NONE && (n_total >> 16) <= RP_AVG_MAX;
+}
+
+struct RpSrc {                                   // one input of the scatter
+    const unsigned long long* data;              // KIND 0: keys; KIND 2: (key, id) records
+    const uint8_t* null;                         // KIND 0 only, may be NULL
+    int64_t n;
+    int64_t id_base;                             // KIND 0: id = id_base + row
+};
+struct RpOut {
+    uint8_t* keep; int64_t* rep;                 // dedup answers (NULL when not wanted)
+    uint8_t* keep2; int64_t* ref_row;            // anti-join answers (NULL when not wanted)
+};
+
+// AGG: block-aggregated cursors (np <= SC_MAX_NP); otherwise one global atomic per record.
+template <int KIND, bool AGG>
+__global__ void __launch_bounds__(SC_THREADS)
+rp_scatter_kernel(RpSrc src, bool is_ref, bool reset, int log2_np, TableHeader* hdr, unsigned* cursors, int* overflow,
+                  ulonglong2* __restrict__ kv, RpOut out) {
+    extern __shared__ unsigned s_hist[];                       // np counters, then the claimed bases
+    const unsigned np = 1u << log2_np;
+    const int pshift = 64 - log2_np;
+    const int64_t tile0 = (int64_t)blockIdx.x * SC_TILE;
+    if (AGG) {
+        for (unsigned p = threadIdx.x; p < np; p += SC_THREADS) s_hist[p] = 0;
+        __syncthreads();
+    }
+    unsigned short lr[SC_ITEMS];                               // rank of the record inside (this CTA, its partition)
+    unsigned gslot[AGG ? 1 : SC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        const int64_t r = tile0 + (int64_t)j * SC_THREADS + threadIdx.x;
+        lr[j] = 0xFFFF;
+        bool live = r < src.n;
+        unsigned long long key = 0;
+        if (KIND == 0) {
+            const bool isnull = live && src.null != nullptr && src.null[r] != 0;
+            if (!is_ref && out.rep != nullptr) {                // null statistics of the dedup (rows ascend with the lane)
+                const unsigned nm = __ballot_sync(FULL, isnull);
+                if (nm) {
+                    const int lane = threadIdx.x & 31;
+                    if (lane == __ffs(nm) - 1) { atomicMin(&hdr->null_first, (unsigned long long)r); atomicAdd(&hdr->null_count, (unsigned long long)__popc(nm)); }
+                    if (lane == 31 - __clz(nm)) atomicMax(&hdr->null_last, (long long)r);
+                }
+            }
+            if (isnull && !is_ref && out.ref_row != nullptr) { out.keep2[r] = 1; out.ref_row[r] = -1; }   // a NaN cell never matches
+            live = live && !isnull;
+            if (live) key = src.data[r];
+        } else if (live) {
+            const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(src.data)[r];
+            if ((long long)rec.y < 0) {                         // padding of a fixed-capacity exchange bucket: answered here
+                live = false;
+                if (!is_ref) {
+                    if (out.rep != nullptr) { out.rep[r] = -1; out.keep[r] = 0; }
+                    if (out.ref_row != nullptr) { out.ref_row[r] = -1; out.keep2[r] = 0; }
+                }
+            } else key = rec.x;
+        }
+        if (live) {
+            const unsigned p = log2_np == 0 ? 0u : (unsigned)((norm_key(key) * GOLD) >> pshift);
+            if (AGG) lr[j] = (unsigned short)atomicAdd(&s_hist[p], 1u);
+            else { gslot[AGG ? 0 : j] = atomicAdd(&cursors[p], 1u); lr[j] = 0; }
+        }
+    }
+    if (AGG) {
+        __syncthreads();
+        for (unsigned p = threadIdx.x; p < np; p += SC_THREADS) {
+            const unsigned c = s_hist[p];
+            if (c) s_hist[p] = atomicAdd(&cursors[p], c);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        if (lr[j] == 0xFFFF) continue;
+        const int64_t r = tile0 + (int64_t)j * SC_THREADS + threadIdx.x;
+        unsigned long long key, id;
+        if (KIND == 0) { key = src.data[r]; id = (unsigned long long)(src.id_base + r); }
+        else {
+            const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(src.data)[r];
+            key = rec.x; id = rec.y;
+            if (reset) const_cast<unsigned long long*>(src.data)[2 * r + 1] = ~0ULL;   // last reader: back to padding
+        }
+        key = norm_key(key);
+        const unsigned p = log2_np == 0 ? 0u : (unsigned)((key * GOLD) >> pshift);
+        const unsigned slot = AGG ? s_hist[p] + lr[j] : gslot[AGG ? 0 : j];
+        if (slot >= (unsigned)RP_CAP) { *overflow = 1; continue; }
+        const unsigned pos = is_ref ? RP_NONE : (unsigned)r;
+        kv[(size_t)p * RP_CAP + slot] = make_ulonglong2(key, (unsigned long long)pos | (id << 32));
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RP_THREADS)
+rp_resolve_kernel(const unsigned* __restrict__ cursors, const int* __restrict__ overflow, const ulonglong2* __restrict__ kv,
+                  int log2_np, RpOut out) {
+    extern __shared__ __align__(16) unsigned char rp_smem[];
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(rp_smem);
+    constexpr bool HAS_A = MODE != RP_ANTI, HAS_B = MODE >= RP_COUNT;
+    unsigned* sa = reinterpret_cast<unsigned*>(skey + RP_SLOTS);           // first / last main row
+    unsigned* sb = HAS_A ? sa + RP_SLOTS : sa;                             // count (RP_COUNT) or smallest reference row
+    if (*overflow) return;                                                 // the gated global-table kernels take over
+    const unsigned p = blockIdx.x;
+    const unsigned cnt = min(cursors[p], (unsigned)RP_CAP);
+    if (cnt == 0) return;
+    for (int i = threadIdx.x; i < RP_SLOTS; i += RP_THREADS) {
+        skey[i] = EMPTY;
+        if (HAS_A) sa[i] = MODE == RP_LAST ? 0u : RP_NONE;
+        if (HAS_B) sb[i] = MODE == RP_COUNT ? 0u : RP_NONE;
+    }
+    __syncthreads();
+    const ulonglong2* mine = kv + (size_t)p * RP_CAP;
+    ulonglong2 rec[RP_ITEMS];
+    unsigned short at[RP_ITEMS];
+#pragma unroll
+    for (int u = 0; u < RP_ITEMS; ++u) {
+        const unsigned i = threadIdx.x + u * RP_THREADS;
+        at[u] = 0xFFFF;
+        if (i >= cnt) continue;
+        rec[u] = mine[i];
+        const unsigned pos = (unsigned)rec[u].y, id = (unsigned)(rec[u].y >> 32);
+        const bool is_ref = pos == RP_NONE;
+        if (MODE == RP_ANTI && !is_ref) continue;                          // main records only probe
+        // the bits just below the partition bits pick the home slot
+        unsigned s = (unsigned)(((rec[u].x * GOLD) << log2_np) >> 51) & (RP_SLOTS - 1);
+        for (;;) {
+            const unsigned long long prev = atomicCAS(&skey[s], EMPTY, rec[u].x);
+            if (prev == EMPTY || prev == rec[u].x) break;
+            s = (s + 1) & (RP_SLOTS - 1);
+        }
+        if (is_ref) atomicMin(&sb[s], id);
+        else {
+            if (MODE == RP_LAST) atomicMax(&sa[s], id); else atomicMin(&sa[s], id);
+            if (MODE == RP_COUNT) atomicAdd(&sb[s], 1u);
+        }
+        at[u] = (unsigned short)s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < RP_ITEMS; ++u) {
+        const unsigned i = threadIdx.x + u * RP_THREADS;
+        if (i >= cnt) continue;
+        const unsigned pos = (unsigned)rec[u].y, id = (unsigned)(rec[u].y >> 32);
+        if (pos == RP_NONE) continue;
+        if (MODE == RP_ANTI) {
+            unsigned s = (unsigned)(((rec[u].x * GOLD) << log2_np) >> 51) & (RP_SLOTS - 1);
+            unsigned rr = RP_NONE;
+            for (;;) {
+                const unsigned long long cur = skey[s];
+                if (cur == rec[u].x) { rr = sb[s]; break; }
+                if (cur == EMPTY) break;
+                s = (s + 1) & (RP_SLOTS - 1);
+            }
+            out.ref_row[pos] = rr == RP_NONE ? -1LL : (long long)rr;
+            out.keep2[pos] = rr == RP_NONE ? 1 : 0;
+            continue;
+        }
+        const unsigned s = at[u];
+        const unsigned rp = sa[s];
+        out.rep[pos] = (long long)rp;
+        out.keep[pos] = MODE == RP_COUNT ? (sb[s] == 1u) : (rp == id);
+        if (MODE == RP_JOINT) {
+            const unsigned rr = sb[s];
+            out.ref_row[pos] = rr == RP_NONE ? -1LL : (long long)rr;
+            out.keep2[pos] = rr == RP_NONE ? 1 : 0;
+        }
+    }
+}
+
+template <int KIND>
+static int rp_scatter(const RpSrc& src, bool is_ref, bool reset, const RpLayout& L, char* base, const RpOut& out, cudaStream_t s) {
+    if (src.n == 0) return 0;
+    TableHeader* hdr = reinterpret_cast<TableHeader*>(base);
+    unsigned* cursors = reinterpret_cast<unsigned*>(base + L.cursors);
+    int* overflow = reinterpret_cast<int*>(base + L.flag);
+    ulonglong2* kv = reinterpret_cast<ulonglong2*>(base + L.kv);
+    const unsigned grid = (unsigned)((src.n + SC_TILE - 1) / SC_TILE);
+    const unsigned np = 1u << L.log2_np;
+    if (np <= (unsigned)SC_MAX_NP)
+        rp_scatter_kernel<KIND, true><<<grid, SC_THREADS, sizeof(unsigned) * np, s>>>(src, is_ref, reset, L.log2_np, hdr, cursors, overflow, kv, out);
+    else
+        rp_scatter_kernel<KIND, false><<<grid, SC_THREADS, 0, s>>>(src, is_ref, reset, L.log2_np, hdr, cursors, overflow, kv, out);
+    return launch_check("rp_scatter_kernel");
+}
+
+template <int MODE>
+static int rp_resolve_launch(const RpLayout& L, char* base, const RpOut& out, cudaStream_t s) {
+    const size_t smem = RP_SLOTS * (sizeof(unsigned long long) + sizeof(unsigned) * ((MODE != RP_ANTI ? 1 : 0) + (MODE >= RP_COUNT ? 1 : 0)));
+    DYD_CUDA(cudaFuncSetAttribute(rp_resolve_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rp_resolve_kernel<MODE><<<1u << L.log2_np, RP_THREADS, smem, s>>>(reinterpret_cast<const unsigned*>(base + L.cursors),
+                                                                       reinterpret_cast<const int*>(base + L.flag),
+                                                                       reinterpret_cast<const ulonglong2*>(base + L.kv), L.log2_np, out);
+    return launch_check("rp_resolve_kernel");
+}
+
+// scatter (main, then reference) + resolve; returns the device overflow flag through *flag for the caller's gated fallback
+template <int KIND>
+static int rp_run(int mode, const RpSrc& main, const RpSrc* ref, bool reset_ref, const RpLayout& L, void* ws, const RpOut& out,
+                  int** flag, cudaStream_t s) {
+    char* base = reinterpret_cast<char*>(ws);
+    TableHeader* hdr = reinterpret_cast<TableHeader*>(base);
+    DYD_CUDA(cudaMemsetAsync(base, 0xFF, sizeof(TableHeader), s));
+    DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
+    DYD_CUDA(cudaMemsetAsync(base + L.cursors, 0, L.kv - L.cursors, s));                 // cursors + overflow flag
+    *flag = reinterpret_cast<int*>(base + L.flag);
+    if (ref != nullptr) if (int rc = rp_scatter<KIND>(*ref, true, reset_ref, L, base, out, s)) return rc;
+    if (int rc = rp_scatter<KIND>(main, false, false, L, base, out, s)) return rc;
+    switch (mode) {
+        case RP_FIRST: return rp_resolve_launch<RP_FIRST>(L, base, out, s);
+        case RP_LAST: return rp_resolve_launch<RP_LAST>(L, base, out, s);
+        case RP_COUNT: return rp_resolve_launch<RP_COUNT>(L, base, out, s);
+        case RP_ANTI: return rp_resolve_launch<RP_ANTI>(L, base, out, s);
+        default: return rp_resolve_launch<RP_JOINT>(L, base, out, s);
+    }
+}
+
+static inline size_t dedup_table_bytes(int64_t n) {
+    const uint64_t cap = table_capacity(n);
+    return sizeof(TableHeader) + cap * sizeof(Slot) + cap * sizeof(unsigned);
+}
+
 template <int KIND>
 static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64_t* d_row_id, int64_t n, int keep_mode,
-                      uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
+                      uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream, int64_t id_bound = 0) {
     DYD_REQUIRE(n >= 0 && n < (1LL << 40), DYD_E_ARG, "bad row count");
     DYD_REQUIRE(keep_mode >= 0 && keep_mode <= 2, DYD_E_ARG, "keep_mode must be 0 (first), 1 (last) or 2 (False)");
     if (n == 0) return 0;
@@ -557,6 +838,25 @@ static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64
     DYD_REQUIRE(((uintptr_t)ws & 15) == 0, DYD_E_ALIGN, "workspace must be 16-byte aligned");
     DYD_REQUIRE(ws_bytes >= dyd_dedup_workspace_bytes(n), DYD_E_WORKSPACE, "workspace too small");
     cudaStream_t s = as_stream(stream);
+    if (KIND == 0) id_bound = n;
+    if (KIND != 1 && rp_eligible(n, id_bound)) {
+        const RpLayout L = rp_layout(n, dedup_table_bytes(n));
+        if (ws_bytes >= L.total) {
+            const RpSrc main{reinterpret_cast<const unsigned long long*>(d_keys), d_null, n, 0};
+            const RpOut out{d_keep, d_rep, nullptr, nullptr};
+            int* flag = nullptr;
+            if (int rc = rp_run<KIND>(keep_mode, main, nullptr, false, L, ws, out, &flag, s)) return rc;
+            char* base = reinterpret_cast<char*>(ws);
+            TableHeader* hdr = reinterpret_cast<TableHeader*>(base);
+            if (KIND == 0 && d_null != nullptr) {           // null cells: their answer needs the finished null statistics
+                dedup_leftover_kernel<KIND><<<grid_for(n), HT_THREADS, url_pad(), s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n,
+                                                                                      keep_mode, hdr, flag, d_keep, d_rep);
+                if (int rc = launch_check("dedup_leftover_kernel")) return rc;
+            }
+            // a partition overflowed (one key repeated thousands of times): the same call falls back on the device
+            return dedup_table<KIND>(d_keys, d_null, d_row_id, n, keep_mode, d_keep, d_rep, base + L.fallback, flag, hdr, s);
+        }
+    }
     if (!use_partitions(n)) return dedup_table<KIND>(d_keys, d_null, d_row_id, n, keep_mode, d_keep, d_rep, ws, nullptr, nullptr, s);
 
     const PartLayout L = part_layout(n, KIND != 0);
@@ -571,19 +871,19 @@ static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64
     DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
     DYD_CUDA(cudaMemsetAsync(cursors, 0, L.kv - L.cursors, s));                       // cursors + overflow flag
     const int pshift = 64 - L.log2_np;
-    dedup_partition_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(k64, d_null, d_row_id, n, hdr, cursors, overflow, kv, rr, pshift, L.pcap,
+    dedup_partition_kernel<KIND><<<grid_for(n), HT_THREADS, url_pad(), s>>>(k64, d_null, d_row_id, n, hdr, cursors, overflow, kv, rr, pshift, L.pcap,
                                                                      d_keep, d_rep);
     if (int rc = launch_check("dedup_partition_kernel")) return rc;
     {
         const unsigned np = 1u << L.log2_np;
         constexpr bool R32 = KIND == 0;                // row ids are 0 .. n-1 < 2^31 on this path
-        if (keep_mode == 0) dedup_resolve_kernel<KIND, 0, R32><<<np, PT_THREADS, 0, s>>>(cursors, overflow, kv, rr, pshift, L.pcap, d_keep, d_rep);
-        else if (keep_mode == 1) dedup_resolve_kernel<KIND, 1, R32><<<np, PT_THREADS, 0, s>>>(cursors, overflow, kv, rr, pshift, L.pcap, d_keep, d_rep);
-        else dedup_resolve_kernel<KIND, 2, R32><<<np, PT_THREADS, 0, s>>>(cursors, overflow, kv, rr, pshift, L.pcap, d_keep, d_rep);
+        if (keep_mode == 0) dedup_resolve_kernel<KIND, 0, R32><<<np, PT_THREADS, url_pad(), s>>>(cursors, overflow, kv, rr, pshift, L.pcap, d_keep, d_rep);
+        else if (keep_mode == 1) dedup_resolve_kernel<KIND, 1, R32><<<np, PT_THREADS, url_pad(), s>>>(cursors, overflow, kv, rr, pshift, L.pcap, d_keep, d_rep);
+        else dedup_resolve_kernel<KIND, 2, R32><<<np, PT_THREADS, url_pad(), s>>>(cursors, overflow, kv, rr, pshift, L.pcap, d_keep, d_rep);
         if (int rc = launch_check("dedup_resolve_kernel")) return rc;
     }
     if (KIND == 0 && d_null != nullptr) {               // null cells: their answer needs the finished null statistics
-        dedup_leftover_kernel<KIND><<<grid_for(n), HT_THREADS, 0, s>>>(k64, d_null, d_row_id, n, keep_mode, hdr, overflow, d_keep, d_rep);
+        dedup_leftover_kernel<KIND><<<grid_for(n), HT_THREADS, url_pad(), s>>>(k64, d_null, d_row_id, n, keep_mode, hdr, overflow, d_keep, d_rep);
         if (int rc = launch_check("dedup_leftover_kernel")) return rc;
     }
     // a partition overflowed (one key repeated hundreds of times): the same call falls back on the device
@@ -598,14 +898,15 @@ extern "C" int dyd_hash_strings(const int64_t* d_off, const uint8_t* d_bytes, in
     DYD_REQUIRE(n >= 0, DYD_E_ARG, "negative count");
     if (n == 0) return 0;
     DYD_REQUIRE(d_off && d_hash, DYD_E_ARG, "null pointer");
-    hash_strings_kernel<<<grid_for(n), HT_THREADS, 0, as_stream(stream)>>>(d_off, d_bytes, n, d_hash);
+    hash_strings_kernel<<<grid_for(n), HT_THREADS, url_pad(), as_stream(stream)>>>(d_off, d_bytes, n, d_hash);
     return launch_check("hash_strings_kernel");
 }
 
 extern "C" size_t dyd_dedup_workspace_bytes(int64_t n) {
-    const uint64_t cap = table_capacity(n);
-    const size_t table = sizeof(TableHeader) + cap * sizeof(Slot) + cap * sizeof(unsigned);
-    return use_partitions(n) ? part_layout(n, true).total : table;
+    const size_t table = dedup_table_bytes(n);
+    size_t need = use_partitions(n) ? part_layout(n, true).total : table;
+    if (rp_eligible(n, n)) need = std::max(need, rp_layout(n, table).total);
+    return need;
 }
 
 extern "C" int dyd_dedup(const uint64_t* d_keys, const uint8_t* d_null, int64_t n, int keep_mode,
@@ -619,8 +920,8 @@ extern "C" int dyd_dedup_ids(const uint64_t* d_keys, const int64_t* d_row_id, in
 }
 
 extern "C" int dyd_dedup_records(const int64_t* d_records, int64_t m, int keep_mode,
-                                 uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
-    return dedup_impl<2>(reinterpret_cast<const uint64_t*>(d_records), nullptr, nullptr, m, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
+                                 uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, int64_t id_bound, void* stream) {
+    return dedup_impl<2>(reinterpret_cast<const uint64_t*>(d_records), nullptr, nullptr, m, keep_mode, d_keep, d_rep, ws, ws_bytes, stream, id_bound);
 }
 
 extern "C" int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
@@ -632,7 +933,7 @@ extern "C" int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, i
     DYD_CUDA(cudaMemsetAsync(d_cursors, 0, sizeof(uint64_t) * world, s));
     DYD_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
     if (n == 0) return 0;
-    shard_bucket_kernel<<<grid_for(n), HT_THREADS, 0, s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
+    shard_bucket_kernel<<<grid_for(n), HT_THREADS, url_pad(), s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
                                                           world, cap, reinterpret_cast<long long*>(d_records),
                                                           reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
     return launch_check("shard_bucket_kernel");
@@ -647,7 +948,7 @@ extern "C" int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_nul
     DYD_CUDA(cudaMemsetAsync(d_cursors, 0, sizeof(uint64_t) * world, s));
     DYD_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
     if (n == 0) return 0;
-    shard_bucket_p2p_kernel<<<grid_for(n), HT_THREADS, 0, s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
+    shard_bucket_p2p_kernel<<<grid_for(n), HT_THREADS, url_pad(), s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
                                                               world, my_rank, cap, reinterpret_cast<long long* const*>(d_peer_records),
                                                               d_sent_row, reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
     return launch_check("shard_bucket_p2p_kernel");
@@ -658,7 +959,7 @@ extern "C" int dyd_shard_pack_reply_p2p(int64_t* d_records, const uint8_t* d_kee
     DYD_REQUIRE(m >= 0 && cap > 0 && my_rank >= 0 && m % cap == 0 && (mode == 0 || mode == 1), DYD_E_ARG, "bad arguments");
     if (m == 0) return 0;
     DYD_REQUIRE(d_records && d_keep && d_rep && d_peer_reply, DYD_E_ARG, "null pointer");
-    shard_pack_reply_p2p_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<long long*>(d_records), d_keep, d_rep,
+    shard_pack_reply_p2p_kernel<<<grid_for(m), HT_THREADS, url_pad(), as_stream(stream)>>>(reinterpret_cast<long long*>(d_records), d_keep, d_rep,
                                                                                     m, cap, my_rank, reinterpret_cast<long long* const*>(d_peer_reply),
                                                                                     mode, reset_records != 0);
     return launch_check("shard_pack_reply_p2p_kernel");
@@ -669,7 +970,7 @@ extern "C" int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_se
     DYD_REQUIRE(world >= 1 && cap >= 0 && n >= 0 && (mode == 0 || mode == 1), DYD_E_ARG, "bad arguments");
     if (cap == 0 || n == 0) return 0;
     DYD_REQUIRE(d_reply && d_sent_row && d_cursors && d_keep && d_rep, DYD_E_ARG, "null pointer");
-    shard_unpack_p2p_kernel<<<grid_for((int64_t)world * cap), HT_THREADS, 0, as_stream(stream)>>>(
+    shard_unpack_p2p_kernel<<<grid_for((int64_t)world * cap), HT_THREADS, url_pad(), as_stream(stream)>>>(
         reinterpret_cast<const long long*>(d_reply), d_sent_row, reinterpret_cast<const unsigned long long*>(d_cursors), world, cap, n, d_keep, d_rep, mode);
     return launch_check("shard_unpack_p2p_kernel");
 }
@@ -679,7 +980,7 @@ extern "C" int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_k
     DYD_REQUIRE(m >= 0 && (mode == 0 || mode == 1), DYD_E_ARG, "bad arguments");
     if (m == 0) return 0;
     DYD_REQUIRE(d_records && d_keep && d_rep && d_reply, DYD_E_ARG, "null pointer");
-    shard_pack_reply_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_records), d_keep, d_rep, m,
+    shard_pack_reply_kernel<<<grid_for(m), HT_THREADS, url_pad(), as_stream(stream)>>>(reinterpret_cast<const long long*>(d_records), d_keep, d_rep, m,
                                                                                 reinterpret_cast<long long*>(d_reply), mode);
     return launch_check("shard_pack_reply_kernel");
 }
@@ -689,37 +990,83 @@ extern "C" int dyd_shard_unpack(const int64_t* d_reply, int64_t m, int64_t row_b
     DYD_REQUIRE(m >= 0 && n >= 0 && (mode == 0 || mode == 1), DYD_E_ARG, "bad arguments");
     if (m == 0) return 0;
     DYD_REQUIRE(d_reply && d_keep && d_rep, DYD_E_ARG, "null pointer");
-    shard_unpack_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(d_reply), m, row_base, n, d_keep, d_rep, mode);
+    shard_unpack_kernel<<<grid_for(m), HT_THREADS, url_pad(), as_stream(stream)>>>(reinterpret_cast<const long long*>(d_reply), m, row_base, n, d_keep, d_rep, mode);
     return launch_check("shard_unpack_kernel");
 }
 
 extern "C" size_t dyd_antijoin_workspace_bytes(int64_t n_ref) {
-    return table_capacity(n_ref) * sizeof(Slot);
+    return table_capacity(n_ref < 0 ? 0 : n_ref) * sizeof(Slot);
+}
+
+__global__ void __launch_bounds__(HT_THREADS) reset_record_ids_kernel(unsigned long long* records, int64_t m) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r < m) records[2 * r + 1] = ~0ULL;
+}
+
+static inline size_t antijoin_table_bytes(int64_t n_ref) { return table_capacity(n_ref) * sizeof(Slot); }
+
+// the global-table anti-join; gate == nullptr: unconditional, else only if *gate != 0
+template <int KIND>
+static int antijoin_table(uint64_t* d_ref, const uint8_t* d_ref_null, int64_t n_ref, const uint64_t* d_main, const uint8_t* d_main_null,
+                          int64_t n_main, uint8_t* d_keep, int64_t* d_ref_row, void* ws, bool reset_ref, const int* gate, cudaStream_t s) {
+    const uint64_t cap = table_capacity(n_ref);
+    const int shift = 64 - log2u(cap);
+    Slot* tab = reinterpret_cast<Slot*>(ws);
+    if (gate == nullptr) DYD_CUDA(cudaMemsetAsync(ws, 0xFF, cap * sizeof(Slot), s));
+    else {
+        gated_fill_kernel<<<NUM_SMS * 8, 256, url_pad(), s>>>(reinterpret_cast<uint4*>(tab), cap * sizeof(Slot) / 16, 0xFFFFFFFFu, gate);
+        if (int rc = launch_check("gated_fill_kernel")) return rc;
+    }
+    if (n_ref > 0) {
+        antijoin_build_kernel<KIND><<<grid_for(n_ref), HT_THREADS, url_pad(), s>>>(
+            reinterpret_cast<unsigned long long*>(d_ref), d_ref_null, n_ref, tab, shift, cap - 1, reset_ref, gate);
+        if (int rc = launch_check("antijoin_build_kernel")) return rc;
+    }
+    if (n_main == 0) return 0;
+    antijoin_probe_kernel<KIND><<<grid_for(n_main), HT_THREADS, url_pad(), s>>>(
+        reinterpret_cast<const unsigned long long*>(d_main), d_main_null, n_main, tab, shift, cap - 1, d_keep, d_ref_row, gate);
+    return launch_check("antijoin_probe_kernel");
 }
 
 template <int KIND>
 static int antijoin_impl(uint64_t* d_ref, const uint8_t* d_ref_null, int64_t n_ref, const uint64_t* d_main, const uint8_t* d_main_null,
-                         int64_t n_main, uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, bool reset_ref, void* stream) {
+                         int64_t n_main, uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, bool reset_ref, void* stream,
+                         int64_t id_bound = 0) {
     DYD_REQUIRE(n_main >= 0 && n_ref >= 0, DYD_E_ARG, "negative count");
     if (n_main == 0 && !(KIND == 2 && reset_ref)) return 0;
     DYD_REQUIRE((n_main == 0 || (d_main && d_keep && d_ref_row)) && ws && (n_ref == 0 || d_ref), DYD_E_ARG, "null pointer");
     DYD_REQUIRE(((uintptr_t)ws & 15) == 0, DYD_E_ALIGN, "workspace must be 16-byte aligned");
     DYD_REQUIRE(KIND == 0 || ((((uintptr_t)d_ref | (uintptr_t)d_main) & 15) == 0), DYD_E_ALIGN, "records must be 16-byte aligned");
     DYD_REQUIRE(ws_bytes >= dyd_antijoin_workspace_bytes(n_ref), DYD_E_WORKSPACE, "workspace too small");
-    const uint64_t cap = table_capacity(n_ref);
-    const int shift = 64 - log2u(cap);
     cudaStream_t s = as_stream(stream);
-    Slot* tab = reinterpret_cast<Slot*>(ws);
-    DYD_CUDA(cudaMemsetAsync(ws, 0xFF, cap * sizeof(Slot), s));
-    if (n_ref > 0) {
-        antijoin_build_kernel<KIND><<<grid_for(n_ref), HT_THREADS, 0, s>>>(
-            reinterpret_cast<unsigned long long*>(d_ref), d_ref_null, n_ref, tab, shift, cap - 1, reset_ref);
-        if (int rc = launch_check("antijoin_build_kernel")) return rc;
+    if (KIND == 0) id_bound = std::max(n_main, n_ref);
+    if (n_main > 0 && rp_eligible(n_main + n_ref, id_bound)) {
+        const RpLayout L = rp_layout(n_main + n_ref, antijoin_table_bytes(n_ref));
+        if (ws_bytes >= L.total) {
+            const RpSrc main{reinterpret_cast<const unsigned long long*>(d_main), d_main_null, n_main, 0};
+            const RpSrc ref{reinterpret_cast<const unsigned long long*>(d_ref), d_ref_null, n_ref, 0};
+            const RpOut out{nullptr, nullptr, d_keep, d_ref_row};
+            int* flag = nullptr;
+            // (the reference records are reset only after the gated fallback, which may have to read them again)
+            if (int rc = rp_run<KIND>(RP_ANTI, main, &ref, false, L, ws, out, &flag, s)) return rc;
+            if (int rc = antijoin_table<KIND>(d_ref, d_ref_null, n_ref, d_main, d_main_null, n_main, d_keep, d_ref_row,
+                                              reinterpret_cast<char*>(ws) + L.fallback, false, flag, s)) return rc;
+            if (KIND == 2 && reset_ref && n_ref > 0) {
+                reset_record_ids_kernel<<<grid_for(n_ref), HT_THREADS, url_pad(), s>>>(reinterpret_cast<unsigned long long*>(d_ref), n_ref);
+                return launch_check("reset_record_ids_kernel");
+            }
+            return 0;
+        }
     }
-    if (n_main == 0) return 0;
-    antijoin_probe_kernel<KIND><<<grid_for(n_main), HT_THREADS, 0, s>>>(
-        reinterpret_cast<const unsigned long long*>(d_main), d_main_null, n_main, tab, shift, cap - 1, d_keep, d_ref_row);
-    return launch_check("antijoin_probe_kernel");
+    return antijoin_table<KIND>(d_ref, d_ref_null, n_ref, d_main, d_main_null, n_main, d_keep, d_ref_row, ws, reset_ref, nullptr, s);
+}
+
+extern "C" size_t dyd_antijoin_fast_workspace_bytes(int64_t n_main, int64_t n_ref) {
+    if (n_main < 0) n_main = 0;
+    if (n_ref < 0) n_ref = 0;
+    const size_t table = antijoin_table_bytes(n_ref);
+    if (!rp_eligible(n_main + n_ref, std::max<int64_t>(std::max(n_main, n_ref), 1))) return table;
+    return rp_layout(n_main + n_ref, table).total;
 }
 
 extern "C" int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
@@ -730,7 +1077,8 @@ extern "C" int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_n
 }
 
 extern "C" int dyd_antijoin_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main,
-                                    uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, int32_t reset_ref, void* stream) {
+                                    uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, int32_t reset_ref, int64_t id_bound,
+                                    void* stream) {
     return antijoin_impl<2>(reinterpret_cast<uint64_t*>(d_ref_records), nullptr, m_ref, reinterpret_cast<const uint64_t*>(d_main_records), nullptr,
-                            m_main, d_keep, d_ref_row, ws, ws_bytes, reset_ref != 0, stream);
+                            m_main, d_keep, d_ref_row, ws, ws_bytes, reset_ref != 0, stream, id_bound);
 }

@@ -56,7 +56,8 @@ inline TileDesc* tile_descs(void* ws, int64_t n_img) {
 int launch_fused_tma(const int64_t* d_img_off, const int64_t* d_poly_off, const double* d_xy,
                      int64_t n_img, int64_t n_poly, int64_t min_boxes, double thr,
                      double* d_pts, uint8_t* d_valid, int32_t* d_arg, uint8_t* d_high, int32_t* d_count,
-                     void* ws, int max_ctas, cudaStream_t s);
+                     void* ws, int max_ctas, cudaEvent_t prepass_done, cudaStream_t s);
+int fused_cta_times(unsigned long long* h_out, int n);
 
 // [fast, direct, defer] tile counts of the descriptors a fused call left in its workspace (diagnostics)
 int launch_tile_modes(const void* ws, int64_t n_img, unsigned long long* d_counts3, cudaStream_t s);

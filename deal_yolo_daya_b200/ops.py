@@ -96,7 +96,7 @@ class FusedBuffers:
 
 
 def bbox_iou_fused(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_arg=False, out: FusedBuffers | None = None,
-                   max_ctas: int = 0):
+                   max_ctas: int = 0, prepass_event=None):
     """Fused K1+K2 over a device-resident CSR table.  Returns a FusedBuffers.
 
     ``max_ctas`` (0 = every SM) caps the persistent grid so that a second stream -- the URL hash / dedup /
@@ -113,9 +113,18 @@ def bbox_iou_fused(img_off, poly_off, xy, min_boxes=2, thr=0.98, want_arg=False,
     with torch.cuda.device(dev):
         _lib.check(lib.dyd_bbox_iou_fused_ex(_ptr(img_off), _ptr(poly_off), _ptr(xy), n_img, n_poly, int(min_boxes),
                                              float(thr), _ptr(out.pts), _ptr(out.valid), _ptr(out.arg), _ptr(out.high),
-                                             _ptr(out.count), _ptr(out.ws), out.ws.numel(), int(max_ctas), _stream(dev)),
+                                             _ptr(out.count), _ptr(out.ws), out.ws.numel(), int(max_ctas),
+                                             C.c_void_p(prepass_event.cuda_event) if prepass_event is not None else None, _stream(dev)),
                    "dyd_bbox_iou_fused_ex")
     return out
+
+
+def fused_cta_times():
+    """(start, end) globaltimer ns of every CTA of the last staged fused launch (diagnostics); rows of never-used CTAs are 0."""
+    lib = _lib.load()
+    a = np.zeros(296, np.uint64)
+    _lib.check(lib.dyd_fused_cta_times(C.c_void_p(a.ctypes.data), 296), "dyd_fused_cta_times")
+    return a.reshape(148, 2)
 
 
 def fused_tile_modes(buf: FusedBuffers, n_img: int):
@@ -175,8 +184,8 @@ def antijoin(main_keys, main_null, ref_keys, ref_null, workspace=None):
     n, nr = main_keys.numel(), ref_keys.numel()
     km = torch.empty(n, dtype=torch.uint8, device=dev)
     rr = torch.empty(n, dtype=torch.int64, device=dev)
-    need = lib.dyd_antijoin_workspace_bytes(nr)
-    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
+    need = lib.dyd_antijoin_fast_workspace_bytes(n, nr)
+    ws = workspace if workspace is not None and workspace.numel() >= lib.dyd_antijoin_workspace_bytes(nr) else _ws(need, dev)
     with torch.cuda.device(dev):
         _lib.check(lib.dyd_antijoin(_ptr(main_keys), _ptr(main_null), n, _ptr(ref_keys), _ptr(ref_null), nr,
                                     _ptr(km), _ptr(rr), _ptr(ws), ws.numel(), _stream(dev)), "dyd_antijoin")
