@@ -49,7 +49,7 @@ UNIT = "images/s"
 IMAGES_PER_GPU = 10_000_000
 SEED = 0
 MIN_BOXES, THR = 2, 0.7
-URL_SMS = 8                      # SMs the fused kernel leaves to the URL stream (tools/overlap_sweep.py)
+URL_SMS = 0                      # SMs the fused kernel leaves to a second (URL) stream; 0 = one stream (overlap is zero-sum here)
 
 
 def peaks():

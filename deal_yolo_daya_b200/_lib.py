@@ -34,14 +34,13 @@ PROTOTYPES = {
     "dyd_dedup": (_int, [_p, _p, _i64, _int, _p, _p, _p, _sz, _p]),
     "dyd_dedup_ids": (_int, [_p, _p, _i64, _int, _p, _p, _p, _sz, _p]),
     "dyd_shard_bucket": (_int, [_p, _p, _i64, _i64, _i32, _i64, _p, _p, _p, _p]),
-    "dyd_dedup_records": (_int, [_p, _i64, _int, _p, _p, _p, _sz, _i64, _p]),
+    "dyd_dedup_records": (_int, [_p, _i64, _int, _p, _p, _p, _sz, _p]),
     "dyd_shard_bucket_p2p": (_int, [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p]),
     "dyd_shard_unpack_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _i32, _p]),
     "dyd_shard_pack_reply_p2p": (_int, [_p, _p, _p, _i64, _i64, _i32, _p, _i32, _i32, _p]),
     "dyd_shard_pack_reply": (_int, [_p, _p, _p, _i64, _p, _i32, _p]),
     "dyd_shard_unpack": (_int, [_p, _i64, _i64, _i64, _p, _p, _i32, _p]),
-    "dyd_antijoin_records": (_int, [_p, _i64, _p, _i64, _p, _p, _p, _sz, _i32, _i64, _p]),
-    "dyd_antijoin_fast_workspace_bytes": (_sz, [_i64, _i64]),
+    "dyd_antijoin_records": (_int, [_p, _i64, _p, _i64, _p, _p, _p, _sz, _i32, _p]),
     "dyd_bbox_iou_fused_ex": (_int, [_p, _p, _p, _i64, _i64, _i64, _f64, _p, _p, _p, _p, _p, _p, _sz, _i32, _p, _p]),
     "dyd_fused_cta_times": (_int, [_p, _i32]),
     "dyd_fused_tile_modes": (_int, [_p, _i64, _p, _p]),

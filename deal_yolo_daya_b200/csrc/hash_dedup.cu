@@ -552,277 +552,6 @@ static int dedup_table(const uint64_t* d_keys, const uint8_t* d_null, const int6
     return 0;
 }
 
-// =============================================================================== radix-partitioned K4 / K5
-// The large-input path of dedup, anti-join and the joint "URL filter" (dedup keep=first + anti-join in one pass).
-//
-//   scatter  one CTA per tile of 16 K records: partition index = top bits of the mixed key; the CTA counts its records per
-//            partition in shared memory, claims one run per partition with ONE global atomic and writes the 16-byte records
-//            {key, pos | id << 32} of a run next to each other -- a few million global atomics and 64-byte runs instead of
-//            one atomic and one isolated 16-byte store per record.  Partitions are fixed-capacity regions (4096 records,
-//            average fill <= 2731); an overflow (one key repeated thousands of times) raises a device flag and the gated
-//            global-table kernels redo the call on the device.
-//   resolve  one CTA per partition: an 8192-slot open-addressing table in shared memory (64-bit CAS for the key, native
-//            32-bit atomics for first / last row, count, smallest reference row), then every main record's answer is
-//            written at its position.  Random accesses never leave the SM.
-//
-// Row ids travel as 32 bits here, so the path is taken for tables below 2^32 - 1 rows (callers of the records form state
-// the bound); anything else keeps the older kernels above.
-constexpr int RP_CAP = 4096;                     // records per partition region
-constexpr int RP_SLOTS = 8192;                   // shared-memory table of one partition
-constexpr int RP_THREADS = 512;
-constexpr int RP_ITEMS = RP_CAP / RP_THREADS;    // records per thread of the resolve kernel
-constexpr int RP_AVG_MAX = 2731;                 // average fill that keeps an overflow ~25 sigma away
-constexpr int SC_THREADS = 512;
-constexpr int SC_ITEMS = 32;
-constexpr int SC_TILE = SC_THREADS * SC_ITEMS;   // records per scatter CTA
-constexpr int SC_MAX_NP = 8192;                  // partitions the scatter can count in shared memory
-constexpr unsigned RP_NONE = 0xFFFFFFFFu;
-enum { RP_FIRST = 0, RP_LAST = 1, RP_COUNT = 2, RP_ANTI = 3, RP_JOINT = 4 };
-
-struct RpLayout {
-    int log2_np;
-    size_t cursors, flag, kv, fallback, total;   // byte offsets from the workspace start
-};
-static inline RpLayout rp_layout(int64_t n_total, size_t fallback_bytes) {
-    RpLayout L{};
-    int k = 0;
-    while ((n_total >> k) > RP_AVG_MAX) ++k;
-    L.log2_np = k;
-    const uint64_t np = 1ULL << k;
-    size_t o = sizeof(TableHeader);
-    L.cursors = o; o += sizeof(unsigned) * np;
-    L.flag = o; o += 16;
-    o = (o + 255) & ~(size_t)255;
-    L.kv = o; o += sizeof(ulonglong2) * np * RP_CAP;
-    o = (o + 255) & ~(size_t)255;
-    L.fallback = o;
-    L.total = o + fallback_bytes;
-    return L;
-}
-static inline int64_t rp_min_rows() {
-    const char* m = getenv("DYD_DEDUP_PARTITION_MIN");
-    const long long lo = m ? atoll(m) : (1LL << 20);
-    return lo < 4096 ? 4096 : lo;
-}
-static inline bool rp_eligible(int64_t n_total, int64_t id_bound) {
-    const char* e = getenv("DYD_DEDUP_PARTITION");
-    if (e && atoi(e) == 0) return false;
-    return n_total >= rp_min_rows() && n_total < (1LL << 31) && id_bound > 0 && id_bound < (int64_t)RP_NONE && (n_total >> 16) <= RP_AVG_MAX;
-}
-
-struct RpSrc {                                   // one input of the scatter
-    const unsigned long long* data;              // KIND 0: keys; KIND 2: (key, id) records
-    const uint8_t* null;                         // KIND 0 only, may be NULL
-    int64_t n;
-    int64_t id_base;                             // KIND 0: id = id_base + row
-};
-struct RpOut {
-    uint8_t* keep; int64_t* rep;                 // dedup answers (NULL when not wanted)
-    uint8_t* keep2; int64_t* ref_row;            // anti-join answers (NULL when not wanted)
-};
-
-// AGG: block-aggregated cursors (np <= SC_MAX_NP); otherwise one global atomic per record.
-template <int KIND, bool AGG>
-__global__ void __launch_bounds__(SC_THREADS)
-rp_scatter_kernel(RpSrc src, bool is_ref, bool reset, int log2_np, TableHeader* hdr, unsigned* cursors, int* overflow,
-                  ulonglong2* __restrict__ kv, RpOut out) {
-    extern __shared__ unsigned s_hist[];                       // np counters, then the claimed bases
-    const unsigned np = 1u << log2_np;
-    const int pshift = 64 - log2_np;
-    const int64_t tile0 = (int64_t)blockIdx.x * SC_TILE;
-    if (AGG) {
-        for (unsigned p = threadIdx.x; p < np; p += SC_THREADS) s_hist[p] = 0;
-        __syncthreads();
-    }
-    unsigned short lr[SC_ITEMS];                               // rank of the record inside (this CTA, its partition)
-    unsigned gslot[AGG ? 1 : SC_ITEMS];
-#pragma unroll
-    for (int j = 0; j < SC_ITEMS; ++j) {
-        const int64_t r = tile0 + (int64_t)j * SC_THREADS + threadIdx.x;
-        lr[j] = 0xFFFF;
-        bool live = r < src.n;
-        unsigned long long key = 0;
-        if (KIND == 0) {
-            const bool isnull = live && src.null != nullptr && src.null[r] != 0;
-            if (!is_ref && out.rep != nullptr) {                // null statistics of the dedup (rows ascend with the lane)
-                const unsigned nm = __ballot_sync(FULL, isnull);
-                if (nm) {
-                    const int lane = threadIdx.x & 31;
-                    if (lane == __ffs(nm) - 1) { atomicMin(&hdr->null_first, (unsigned long long)r); atomicAdd(&hdr->null_count, (unsigned long long)__popc(nm)); }
-                    if (lane == 31 - __clz(nm)) atomicMax(&hdr->null_last, (long long)r);
-                }
-            }
-            if (isnull && !is_ref && out.ref_row != nullptr) { out.keep2[r] = 1; out.ref_row[r] = -1; }   // a NaN cell never matches
-            live = live && !isnull;
-            if (live) key = src.data[r];
-        } else if (live) {
-            const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(src.data)[r];
-            if ((long long)rec.y < 0) {                         // padding of a fixed-capacity exchange bucket: answered here
-                live = false;
-                if (!is_ref) {
-                    if (out.rep != nullptr) { out.rep[r] = -1; out.keep[r] = 0; }
-                    if (out.ref_row != nullptr) { out.ref_row[r] = -1; out.keep2[r] = 0; }
-                }
-            } else key = rec.x;
-        }
-        if (live) {
-            const unsigned p = log2_np == 0 ? 0u : (unsigned)((norm_key(key) * GOLD) >> pshift);
-            if (AGG) lr[j] = (unsigned short)atomicAdd(&s_hist[p], 1u);
-            else { gslot[AGG ? 0 : j] = atomicAdd(&cursors[p], 1u); lr[j] = 0; }
-        }
-    }
-    if (AGG) {
-        __syncthreads();
-        for (unsigned p = threadIdx.x; p < np; p += SC_THREADS) {
-            const unsigned c = s_hist[p];
-            if (c) s_hist[p] = atomicAdd(&cursors[p], c);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int j = 0; j < SC_ITEMS; ++j) {
-        if (lr[j] == 0xFFFF) continue;
-        const int64_t r = tile0 + (int64_t)j * SC_THREADS + threadIdx.x;
-        unsigned long long key, id;
-        if (KIND == 0) { key = src.data[r]; id = (unsigned long long)(src.id_base + r); }
-        else {
-            const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(src.data)[r];
-            key = rec.x; id = rec.y;
-            if (reset) const_cast<unsigned long long*>(src.data)[2 * r + 1] = ~0ULL;   // last reader: back to padding
-        }
-        key = norm_key(key);
-        const unsigned p = log2_np == 0 ? 0u : (unsigned)((key * GOLD) >> pshift);
-        const unsigned slot = AGG ? s_hist[p] + lr[j] : gslot[AGG ? 0 : j];
-        if (slot >= (unsigned)RP_CAP) { *overflow = 1; continue; }
-        const unsigned pos = is_ref ? RP_NONE : (unsigned)r;
-        kv[(size_t)p * RP_CAP + slot] = make_ulonglong2(key, (unsigned long long)pos | (id << 32));
-    }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(RP_THREADS)
-rp_resolve_kernel(const unsigned* __restrict__ cursors, const int* __restrict__ overflow, const ulonglong2* __restrict__ kv,
-                  int log2_np, RpOut out) {
-    extern __shared__ __align__(16) unsigned char rp_smem[];
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(rp_smem);
-    constexpr bool HAS_A = MODE != RP_ANTI, HAS_B = MODE >= RP_COUNT;
-    unsigned* sa = reinterpret_cast<unsigned*>(skey + RP_SLOTS);           // first / last main row
-    unsigned* sb = HAS_A ? sa + RP_SLOTS : sa;                             // count (RP_COUNT) or smallest reference row
-    if (*overflow) return;                                                 // the gated global-table kernels take over
-    const unsigned p = blockIdx.x;
-    const unsigned cnt = min(cursors[p], (unsigned)RP_CAP);
-    if (cnt == 0) return;
-    for (int i = threadIdx.x; i < RP_SLOTS; i += RP_THREADS) {
-        skey[i] = EMPTY;
-        if (HAS_A) sa[i] = MODE == RP_LAST ? 0u : RP_NONE;
-        if (HAS_B) sb[i] = MODE == RP_COUNT ? 0u : RP_NONE;
-    }
-    __syncthreads();
-    const ulonglong2* mine = kv + (size_t)p * RP_CAP;
-    ulonglong2 rec[RP_ITEMS];
-    unsigned short at[RP_ITEMS];
-#pragma unroll
-    for (int u = 0; u < RP_ITEMS; ++u) {
-        const unsigned i = threadIdx.x + u * RP_THREADS;
-        at[u] = 0xFFFF;
-        if (i >= cnt) continue;
-        rec[u] = mine[i];
-        const unsigned pos = (unsigned)rec[u].y, id = (unsigned)(rec[u].y >> 32);
-        const bool is_ref = pos == RP_NONE;
-        if (MODE == RP_ANTI && !is_ref) continue;                          // main records only probe
-        // the bits just below the partition bits pick the home slot
-        unsigned s = (unsigned)(((rec[u].x * GOLD) << log2_np) >> 51) & (RP_SLOTS - 1);
-        for (;;) {
-            const unsigned long long prev = atomicCAS(&skey[s], EMPTY, rec[u].x);
-            if (prev == EMPTY || prev == rec[u].x) break;
-            s = (s + 1) & (RP_SLOTS - 1);
-        }
-        if (is_ref) atomicMin(&sb[s], id);
-        else {
-            if (MODE == RP_LAST) atomicMax(&sa[s], id); else atomicMin(&sa[s], id);
-            if (MODE == RP_COUNT) atomicAdd(&sb[s], 1u);
-        }
-        at[u] = (unsigned short)s;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < RP_ITEMS; ++u) {
-        const unsigned i = threadIdx.x + u * RP_THREADS;
-        if (i >= cnt) continue;
-        const unsigned pos = (unsigned)rec[u].y, id = (unsigned)(rec[u].y >> 32);
-        if (pos == RP_NONE) continue;
-        if (MODE == RP_ANTI) {
-            unsigned s = (unsigned)(((rec[u].x * GOLD) << log2_np) >> 51) & (RP_SLOTS - 1);
-            unsigned rr = RP_NONE;
-            for (;;) {
-                const unsigned long long cur = skey[s];
-                if (cur == rec[u].x) { rr = sb[s]; break; }
-                if (cur == EMPTY) break;
-                s = (s + 1) & (RP_SLOTS - 1);
-            }
-            out.ref_row[pos] = rr == RP_NONE ? -1LL : (long long)rr;
-            out.keep2[pos] = rr == RP_NONE ? 1 : 0;
-            continue;
-        }
-        const unsigned s = at[u];
-        const unsigned rp = sa[s];
-        out.rep[pos] = (long long)rp;
-        out.keep[pos] = MODE == RP_COUNT ? (sb[s] == 1u) : (rp == id);
-        if (MODE == RP_JOINT) {
-            const unsigned rr = sb[s];
-            out.ref_row[pos] = rr == RP_NONE ? -1LL : (long long)rr;
-            out.keep2[pos] = rr == RP_NONE ? 1 : 0;
-        }
-    }
-}
-
-template <int KIND>
-static int rp_scatter(const RpSrc& src, bool is_ref, bool reset, const RpLayout& L, char* base, const RpOut& out, cudaStream_t s) {
-    if (src.n == 0) return 0;
-    TableHeader* hdr = reinterpret_cast<TableHeader*>(base);
-    unsigned* cursors = reinterpret_cast<unsigned*>(base + L.cursors);
-    int* overflow = reinterpret_cast<int*>(base + L.flag);
-    ulonglong2* kv = reinterpret_cast<ulonglong2*>(base + L.kv);
-    const unsigned grid = (unsigned)((src.n + SC_TILE - 1) / SC_TILE);
-    const unsigned np = 1u << L.log2_np;
-    if (np <= (unsigned)SC_MAX_NP)
-        rp_scatter_kernel<KIND, true><<<grid, SC_THREADS, sizeof(unsigned) * np, s>>>(src, is_ref, reset, L.log2_np, hdr, cursors, overflow, kv, out);
-    else
-        rp_scatter_kernel<KIND, false><<<grid, SC_THREADS, 0, s>>>(src, is_ref, reset, L.log2_np, hdr, cursors, overflow, kv, out);
-    return launch_check("rp_scatter_kernel");
-}
-
-template <int MODE>
-static int rp_resolve_launch(const RpLayout& L, char* base, const RpOut& out, cudaStream_t s) {
-    const size_t smem = RP_SLOTS * (sizeof(unsigned long long) + sizeof(unsigned) * ((MODE != RP_ANTI ? 1 : 0) + (MODE >= RP_COUNT ? 1 : 0)));
-    DYD_CUDA(cudaFuncSetAttribute(rp_resolve_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rp_resolve_kernel<MODE><<<1u << L.log2_np, RP_THREADS, smem, s>>>(reinterpret_cast<const unsigned*>(base + L.cursors),
-                                                                       reinterpret_cast<const int*>(base + L.flag),
-                                                                       reinterpret_cast<const ulonglong2*>(base + L.kv), L.log2_np, out);
-    return launch_check("rp_resolve_kernel");
-}
-
-// scatter (main, then reference) + resolve; returns the device overflow flag through *flag for the caller's gated fallback
-template <int KIND>
-static int rp_run(int mode, const RpSrc& main, const RpSrc* ref, bool reset_ref, const RpLayout& L, void* ws, const RpOut& out,
-                  int** flag, cudaStream_t s) {
-    char* base = reinterpret_cast<char*>(ws);
-    TableHeader* hdr = reinterpret_cast<TableHeader*>(base);
-    DYD_CUDA(cudaMemsetAsync(base, 0xFF, sizeof(TableHeader), s));
-    DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
-    DYD_CUDA(cudaMemsetAsync(base + L.cursors, 0, L.kv - L.cursors, s));                 // cursors + overflow flag
-    *flag = reinterpret_cast<int*>(base + L.flag);
-    if (ref != nullptr) if (int rc = rp_scatter<KIND>(*ref, true, reset_ref, L, base, out, s)) return rc;
-    if (int rc = rp_scatter<KIND>(main, false, false, L, base, out, s)) return rc;
-    switch (mode) {
-        case RP_FIRST: return rp_resolve_launch<RP_FIRST>(L, base, out, s);
-        case RP_LAST: return rp_resolve_launch<RP_LAST>(L, base, out, s);
-        case RP_COUNT: return rp_resolve_launch<RP_COUNT>(L, base, out, s);
-        case RP_ANTI: return rp_resolve_launch<RP_ANTI>(L, base, out, s);
-        default: return rp_resolve_launch<RP_JOINT>(L, base, out, s);
-    }
-}
-
 static inline size_t dedup_table_bytes(int64_t n) {
     const uint64_t cap = table_capacity(n);
     return sizeof(TableHeader) + cap * sizeof(Slot) + cap * sizeof(unsigned);
@@ -830,7 +559,7 @@ static inline size_t dedup_table_bytes(int64_t n) {
 
 template <int KIND>
 static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64_t* d_row_id, int64_t n, int keep_mode,
-                      uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream, int64_t id_bound = 0) {
+                      uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
     DYD_REQUIRE(n >= 0 && n < (1LL << 40), DYD_E_ARG, "bad row count");
     DYD_REQUIRE(keep_mode >= 0 && keep_mode <= 2, DYD_E_ARG, "keep_mode must be 0 (first), 1 (last) or 2 (False)");
     if (n == 0) return 0;
@@ -838,25 +567,6 @@ static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64
     DYD_REQUIRE(((uintptr_t)ws & 15) == 0, DYD_E_ALIGN, "workspace must be 16-byte aligned");
     DYD_REQUIRE(ws_bytes >= dyd_dedup_workspace_bytes(n), DYD_E_WORKSPACE, "workspace too small");
     cudaStream_t s = as_stream(stream);
-    if (KIND == 0) id_bound = n;
-    if (KIND != 1 && rp_eligible(n, id_bound)) {
-        const RpLayout L = rp_layout(n, dedup_table_bytes(n));
-        if (ws_bytes >= L.total) {
-            const RpSrc main{reinterpret_cast<const unsigned long long*>(d_keys), d_null, n, 0};
-            const RpOut out{d_keep, d_rep, nullptr, nullptr};
-            int* flag = nullptr;
-            if (int rc = rp_run<KIND>(keep_mode, main, nullptr, false, L, ws, out, &flag, s)) return rc;
-            char* base = reinterpret_cast<char*>(ws);
-            TableHeader* hdr = reinterpret_cast<TableHeader*>(base);
-            if (KIND == 0 && d_null != nullptr) {           // null cells: their answer needs the finished null statistics
-                dedup_leftover_kernel<KIND><<<grid_for(n), HT_THREADS, url_pad(), s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, d_row_id, n,
-                                                                                      keep_mode, hdr, flag, d_keep, d_rep);
-                if (int rc = launch_check("dedup_leftover_kernel")) return rc;
-            }
-            // a partition overflowed (one key repeated thousands of times): the same call falls back on the device
-            return dedup_table<KIND>(d_keys, d_null, d_row_id, n, keep_mode, d_keep, d_rep, base + L.fallback, flag, hdr, s);
-        }
-    }
     if (!use_partitions(n)) return dedup_table<KIND>(d_keys, d_null, d_row_id, n, keep_mode, d_keep, d_rep, ws, nullptr, nullptr, s);
 
     const PartLayout L = part_layout(n, KIND != 0);
@@ -904,9 +614,7 @@ extern "C" int dyd_hash_strings(const int64_t* d_off, const uint8_t* d_bytes, in
 
 extern "C" size_t dyd_dedup_workspace_bytes(int64_t n) {
     const size_t table = dedup_table_bytes(n);
-    size_t need = use_partitions(n) ? part_layout(n, true).total : table;
-    if (rp_eligible(n, n)) need = std::max(need, rp_layout(n, table).total);
-    return need;
+    return use_partitions(n) ? part_layout(n, true).total : table;
 }
 
 extern "C" int dyd_dedup(const uint64_t* d_keys, const uint8_t* d_null, int64_t n, int keep_mode,
@@ -920,8 +628,8 @@ extern "C" int dyd_dedup_ids(const uint64_t* d_keys, const int64_t* d_row_id, in
 }
 
 extern "C" int dyd_dedup_records(const int64_t* d_records, int64_t m, int keep_mode,
-                                 uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, int64_t id_bound, void* stream) {
-    return dedup_impl<2>(reinterpret_cast<const uint64_t*>(d_records), nullptr, nullptr, m, keep_mode, d_keep, d_rep, ws, ws_bytes, stream, id_bound);
+                                 uint8_t* d_keep, int64_t* d_rep, void* ws, size_t ws_bytes, void* stream) {
+    return dedup_impl<2>(reinterpret_cast<const uint64_t*>(d_records), nullptr, nullptr, m, keep_mode, d_keep, d_rep, ws, ws_bytes, stream);
 }
 
 extern "C" int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
@@ -994,22 +702,25 @@ extern "C" int dyd_shard_unpack(const int64_t* d_reply, int64_t m, int64_t row_b
     return launch_check("shard_unpack_kernel");
 }
 
+static inline uint64_t antijoin_capacity(int64_t n);
 extern "C" size_t dyd_antijoin_workspace_bytes(int64_t n_ref) {
-    return table_capacity(n_ref < 0 ? 0 : n_ref) * sizeof(Slot);
+    return antijoin_capacity(n_ref < 0 ? 0 : n_ref) * sizeof(Slot);
 }
 
-__global__ void __launch_bounds__(HT_THREADS) reset_record_ids_kernel(unsigned long long* records, int64_t m) {
-    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
-    if (r < m) records[2 * r + 1] = ~0ULL;
+// The anti-join table is sized for a load factor <= 2/3 (the dedup table, whose every lookup is a hit after an insert, for
+// <= 1/2): for 5 M reference keys that is 128 MB instead of 256 MB to clear, build and probe.
+static inline uint64_t antijoin_capacity(int64_t n) {
+    uint64_t cap = 1024;
+    while (cap * 2 < (uint64_t)(n > 0 ? n : 0) * 3) cap <<= 1;
+    return cap;
 }
-
-static inline size_t antijoin_table_bytes(int64_t n_ref) { return table_capacity(n_ref) * sizeof(Slot); }
+static inline size_t antijoin_table_bytes(int64_t n_ref) { return antijoin_capacity(n_ref) * sizeof(Slot); }
 
 // the global-table anti-join; gate == nullptr: unconditional, else only if *gate != 0
 template <int KIND>
 static int antijoin_table(uint64_t* d_ref, const uint8_t* d_ref_null, int64_t n_ref, const uint64_t* d_main, const uint8_t* d_main_null,
                           int64_t n_main, uint8_t* d_keep, int64_t* d_ref_row, void* ws, bool reset_ref, const int* gate, cudaStream_t s) {
-    const uint64_t cap = table_capacity(n_ref);
+    const uint64_t cap = antijoin_capacity(n_ref);
     const int shift = 64 - log2u(cap);
     Slot* tab = reinterpret_cast<Slot*>(ws);
     if (gate == nullptr) DYD_CUDA(cudaMemsetAsync(ws, 0xFF, cap * sizeof(Slot), s));
@@ -1030,8 +741,7 @@ static int antijoin_table(uint64_t* d_ref, const uint8_t* d_ref_null, int64_t n_
 
 template <int KIND>
 static int antijoin_impl(uint64_t* d_ref, const uint8_t* d_ref_null, int64_t n_ref, const uint64_t* d_main, const uint8_t* d_main_null,
-                         int64_t n_main, uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, bool reset_ref, void* stream,
-                         int64_t id_bound = 0) {
+                         int64_t n_main, uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, bool reset_ref, void* stream) {
     DYD_REQUIRE(n_main >= 0 && n_ref >= 0, DYD_E_ARG, "negative count");
     if (n_main == 0 && !(KIND == 2 && reset_ref)) return 0;
     DYD_REQUIRE((n_main == 0 || (d_main && d_keep && d_ref_row)) && ws && (n_ref == 0 || d_ref), DYD_E_ARG, "null pointer");
@@ -1039,34 +749,7 @@ static int antijoin_impl(uint64_t* d_ref, const uint8_t* d_ref_null, int64_t n_r
     DYD_REQUIRE(KIND == 0 || ((((uintptr_t)d_ref | (uintptr_t)d_main) & 15) == 0), DYD_E_ALIGN, "records must be 16-byte aligned");
     DYD_REQUIRE(ws_bytes >= dyd_antijoin_workspace_bytes(n_ref), DYD_E_WORKSPACE, "workspace too small");
     cudaStream_t s = as_stream(stream);
-    if (KIND == 0) id_bound = std::max(n_main, n_ref);
-    if (n_main > 0 && rp_eligible(n_main + n_ref, id_bound)) {
-        const RpLayout L = rp_layout(n_main + n_ref, antijoin_table_bytes(n_ref));
-        if (ws_bytes >= L.total) {
-            const RpSrc main{reinterpret_cast<const unsigned long long*>(d_main), d_main_null, n_main, 0};
-            const RpSrc ref{reinterpret_cast<const unsigned long long*>(d_ref), d_ref_null, n_ref, 0};
-            const RpOut out{nullptr, nullptr, d_keep, d_ref_row};
-            int* flag = nullptr;
-            // (the reference records are reset only after the gated fallback, which may have to read them again)
-            if (int rc = rp_run<KIND>(RP_ANTI, main, &ref, false, L, ws, out, &flag, s)) return rc;
-            if (int rc = antijoin_table<KIND>(d_ref, d_ref_null, n_ref, d_main, d_main_null, n_main, d_keep, d_ref_row,
-                                              reinterpret_cast<char*>(ws) + L.fallback, false, flag, s)) return rc;
-            if (KIND == 2 && reset_ref && n_ref > 0) {
-                reset_record_ids_kernel<<<grid_for(n_ref), HT_THREADS, url_pad(), s>>>(reinterpret_cast<unsigned long long*>(d_ref), n_ref);
-                return launch_check("reset_record_ids_kernel");
-            }
-            return 0;
-        }
-    }
     return antijoin_table<KIND>(d_ref, d_ref_null, n_ref, d_main, d_main_null, n_main, d_keep, d_ref_row, ws, reset_ref, nullptr, s);
-}
-
-extern "C" size_t dyd_antijoin_fast_workspace_bytes(int64_t n_main, int64_t n_ref) {
-    if (n_main < 0) n_main = 0;
-    if (n_ref < 0) n_ref = 0;
-    const size_t table = antijoin_table_bytes(n_ref);
-    if (!rp_eligible(n_main + n_ref, std::max<int64_t>(std::max(n_main, n_ref), 1))) return table;
-    return rp_layout(n_main + n_ref, table).total;
 }
 
 extern "C" int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
@@ -1077,8 +760,7 @@ extern "C" int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_n
 }
 
 extern "C" int dyd_antijoin_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main,
-                                    uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, int32_t reset_ref, int64_t id_bound,
-                                    void* stream) {
+                                    uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, int32_t reset_ref, void* stream) {
     return antijoin_impl<2>(reinterpret_cast<uint64_t*>(d_ref_records), nullptr, m_ref, reinterpret_cast<const uint64_t*>(d_main_records), nullptr,
-                            m_main, d_keep, d_ref_row, ws, ws_bytes, reset_ref != 0, stream, id_bound);
+                            m_main, d_keep, d_ref_row, ws, ws_bytes, reset_ref != 0, stream);
 }

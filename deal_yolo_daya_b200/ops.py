@@ -184,8 +184,8 @@ def antijoin(main_keys, main_null, ref_keys, ref_null, workspace=None):
     n, nr = main_keys.numel(), ref_keys.numel()
     km = torch.empty(n, dtype=torch.uint8, device=dev)
     rr = torch.empty(n, dtype=torch.int64, device=dev)
-    need = lib.dyd_antijoin_fast_workspace_bytes(n, nr)
-    ws = workspace if workspace is not None and workspace.numel() >= lib.dyd_antijoin_workspace_bytes(nr) else _ws(need, dev)
+    need = lib.dyd_antijoin_workspace_bytes(nr)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
     with torch.cuda.device(dev):
         _lib.check(lib.dyd_antijoin(_ptr(main_keys), _ptr(main_null), n, _ptr(ref_keys), _ptr(ref_null), nr,
                                     _ptr(km), _ptr(rr), _ptr(ws), ws.numel(), _stream(dev)), "dyd_antijoin")

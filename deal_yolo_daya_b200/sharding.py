@@ -101,12 +101,6 @@ def dedup_global(keys: torch.Tensor, null: torch.Tensor | None, row_base: int, k
     return keep_out, rep_out
 
 
-def row_base_bound(row_base: int, n_local: int, world: int) -> int:
-    """Upper bound of the global row ids when every rank holds n_local rows (rank r starts at r * n_local); a caller with
-    another layout passes rows in [0, bound) anyway or the kernels take their 64-bit path."""
-    return max(row_base + n_local, world * n_local)
-
-
 def _want_p2p(world, device):
     import os
     return (os.environ.get("DYD_EXCHANGE", "p2p") == "p2p" and world > 1 and dist.is_initialized()
@@ -241,7 +235,7 @@ class DedupExchange:
                                                 _ptr(self.cursors), _ptr(self.overflow), s), "dyd_shard_bucket")
                 dist.all_to_all_single(self.recv, self.send, group=group)
             _lib.check(lib.dyd_dedup_records(_ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_r), _ptr(self.rep_r),
-                                             _ptr(self.ws), self.ws.numel(), row_base_bound(row_base, self.n, self.world), s), "dyd_dedup_records")
+                                             _ptr(self.ws), self.ws.numel(), s), "dyd_dedup_records")
             if self.transport == "p2p":
                 self._reply_p2p(s)
             else:
@@ -306,7 +300,7 @@ class AntiJoinExchange(DedupExchange):
             self.cursors_ref = torch.empty(world, dtype=torch.uint64, device=device)
 
     def _workspace_bytes(self, m):
-        return self.lib.dyd_antijoin_fast_workspace_bytes(m, self.world * self.cap_ref)
+        return self.lib.dyd_antijoin_workspace_bytes(self.world * self.cap_ref)
 
     def run(self, main_keys, row_base: int, ref_keys, ref_row_base: int, group=None, check_overflow=True,
             main_null=None, ref_null=None):
@@ -329,8 +323,7 @@ class AntiJoinExchange(DedupExchange):
                                                 _ptr(self.send), _ptr(self.cursors), _ptr(self.overflow[:1]), s), "dyd_shard_bucket")
                 dist.all_to_all_single(self.recv, self.send, group=group)
             _lib.check(lib.dyd_antijoin_records(_ptr(self.recv_ref), m_ref, _ptr(self.recv), m, _ptr(self.keep_r), _ptr(self.rep_r),
-                                                _ptr(self.ws), self.ws.numel(), 1 if self.transport == "p2p" else 0,
-                                                max(row_base_bound(row_base, self.n, self.world), row_base_bound(ref_row_base, self.n_ref, self.world)), s),
+                                                _ptr(self.ws), self.ws.numel(), 1 if self.transport == "p2p" else 0, s),
                        "dyd_antijoin_records")
             if main_null is not None:                         # rows that never travel: a NaN cell never matches
                 self.keep.fill_(1); self.rep.fill_(-1)

@@ -137,10 +137,8 @@ int dyd_dedup_ids(const uint64_t* d_keys, const int64_t* d_row_id, int64_t n, in
  * owner; _unpack places them at rows id - row_base on the origin.                              */
 int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
                      int64_t cap, int64_t* d_records, uint64_t* d_cursors, int32_t* d_overflow, void* stream);
-/* id_bound: an upper bound of the record ids (global row ids), 0 = unknown.  Below 2^32 - 1 the radix-partitioned path
- * (32-bit rows in shared-memory tables) is taken for large inputs.                                        */
 int dyd_dedup_records(const int64_t* d_records, int64_t m, int keep_mode, uint8_t* d_keep, int64_t* d_rep,
-                      void* d_workspace, size_t workspace_bytes, int64_t id_bound, void* stream);   /* Peer-memory forms of the exchange steps (NVLink P2P, buffers mapped into every rank, e.g. by
+                      void* d_workspace, size_t workspace_bytes, void* stream);   /* Peer-memory forms of the exchange steps (NVLink P2P, buffers mapped into every rank, e.g. by
  * torch.distributed._symmetric_memory): the scatter writes each record straight into region `my_rank` of
  * its owner's receive buffer (and notes locally, in d_sent_row[world*cap], which row went into which
  * slot); the owner writes each 8-byte answer (rep | keep << 62, -1 for padding) straight into region
@@ -170,9 +168,6 @@ int dyd_shard_unpack(const int64_t* d_reply, int64_t m, int64_t row_base, int64_
  * set(ref.dropna()); null main rows are always kept.  d_ref_row[r] = first
  * reference row holding the key (-1 when kept), for collision verification.     */
 size_t dyd_antijoin_workspace_bytes(int64_t n_ref);
-/* Workspace that lets large inputs take the radix-partitioned path (both tables scattered into shared-memory sized
- * partitions, build + probe inside the SM); with only dyd_antijoin_workspace_bytes() the global table is used.  */
-size_t dyd_antijoin_fast_workspace_bytes(int64_t n_main, int64_t n_ref);
 int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
                  const uint64_t* d_ref_keys, const uint8_t* d_ref_null, int64_t n_ref,
                  uint8_t* d_keep, int64_t* d_ref_row,
@@ -181,11 +176,10 @@ int dyd_antijoin(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_
 /* Sharded form (owner side of the exchange): both tables arrive as (key, id) records in fixed-capacity buckets
  * (id < 0 = padding).  d_keep / d_ref_row are indexed by main record; d_ref_row = smallest reference id holding the
  * key (global reference row), -1 when kept; padding records get keep 0.  reset_ref != 0 turns the reference
- * records back into padding after they were read.  id_bound as for dyd_dedup_records.  Workspace:
- * dyd_antijoin_workspace_bytes(m_ref), or dyd_antijoin_fast_workspace_bytes(m_main, m_ref).              */
+ * records back into padding after they were read.  Workspace: dyd_antijoin_workspace_bytes(m_ref).      */
 int dyd_antijoin_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main,
                          uint8_t* d_keep, int64_t* d_ref_row, void* d_workspace, size_t workspace_bytes,
-                         int32_t reset_ref, int64_t id_bound, void* stream);
+                         int32_t reset_ref, void* stream);
 
 /* ---------------------------------------------------------------- K3 ------
  * Object-name rewrite through a lookup table, processor.py:582-602 with the

@@ -197,9 +197,8 @@ def test_hash_strings(cuda_device):
 
 @pytest.fixture
 def small_partitions(monkeypatch):
-    """The partitioned dedup / anti-join paths normally start at 1 M rows (radix path) and 2 M rows (older small-partition
-    kernels, still used for 64-bit row ids); let 32 K-row (64 K-row) inputs take them."""
-    monkeypatch.setenv("DYD_DEDUP_PARTITION_MIN", "32768")
+    """The partitioned dedup path normally starts at 2 M rows; let 64 K-row inputs take it."""
+    monkeypatch.setenv("DYD_DEDUP_PARTITION_MIN", "65536")
 
 
 @pytest.mark.parametrize("keep", ["first", "last", False])
@@ -271,35 +270,19 @@ def test_dedup_with_row_ids_partitioned(cuda_device, small_partitions, keep):
 
 
 @pytest.mark.parametrize("n,nr", [(4000, 0), (4000, 900), (100000, 60000), (300000, 0), (250000, 170000)])
-def test_antijoin(cuda_device, small_partitions, n, nr):
-    """Small inputs use the global table, the larger ones the radix-partitioned path (threshold lowered by the fixture)."""
+def test_antijoin(cuda_device, n, nr):
     d = cuda_device
     rng = np.random.RandomState(n + nr)
     mk = rng.randint(0, 120000, size=n).astype(np.uint64)
     rk = rng.randint(0, 120000, size=nr).astype(np.uint64)
-    if n > 1000:
-        mk[7] = rk[min(3, nr - 1)] = np.uint64(0xFFFFFFFFFFFFFFFF) if nr else mk[7]   # the EMPTY sentinel as a real key
+    if nr:
+        mk[7] = rk[3] = np.uint64(0xFFFFFFFFFFFFFFFF)                        # the EMPTY sentinel as a real key
     mn = (rng.rand(n) < 0.01).astype(np.uint8); rn = (rng.rand(nr) < 0.05).astype(np.uint8)
     want_keep, want_rr = oracle_c.antijoin(mk, mn, rk, rn)
     keep, rr = ops.antijoin(dev(mk, d), dev(mn, d), dev(rk, d), dev(rn, d))
     assert_bits(host(keep), want_keep); assert_bits(host(rr), want_rr)
     keep, rr = ops.antijoin(dev(mk, d), None, dev(rk, d), None)
     want_keep, want_rr = oracle_c.antijoin(mk, np.zeros(n, np.uint8), rk, np.zeros(nr, np.uint8))
-    assert_bits(host(keep), want_keep); assert_bits(host(rr), want_rr)
-
-
-def test_antijoin_partition_overflow_falls_back_on_device(cuda_device, small_partitions):
-    """One reference key repeated thousands of times overflows its partition: the gated global-table kernels answer."""
-    d = cuda_device
-    rng = np.random.RandomState(3)
-    n, nr = 200000, 120000
-    mk = rng.randint(0, 2 ** 62, size=n, dtype=np.int64).astype(np.uint64)
-    rk = rng.randint(0, 2 ** 62, size=nr, dtype=np.int64).astype(np.uint64)
-    rk[rng.choice(nr, size=7000, replace=False)] = np.uint64(0x0123456789ABCDEF)
-    mk[rng.choice(n, size=900, replace=False)] = np.uint64(0x0123456789ABCDEF)
-    mk[rng.choice(n, size=30000)] = rk[rng.choice(nr, size=30000)]
-    want_keep, want_rr = oracle_c.antijoin(mk, np.zeros(n, np.uint8), rk, np.zeros(nr, np.uint8))
-    keep, rr = ops.antijoin(dev(mk, d), None, dev(rk, d), None)
     assert_bits(host(keep), want_keep); assert_bits(host(rr), want_rr)
 
 
@@ -453,7 +436,7 @@ def test_exchange_kernels_single_rank_roundtrip(cuda_device, small_partitions):
         k = dev(keys, d); s = _stream(d)
         _lib.check(lib.dyd_shard_bucket(_ptr(k), None, 1000, n, world, cap, _ptr(send), _ptr(cursors), _ptr(overflow), s), "bucket")
         assert int(overflow.item()) == 0 and int(cursors.cpu().numpy().astype(np.int64).sum()) == n
-        _lib.check(lib.dyd_dedup_records(_ptr(send), m, ops.KEEP_MODES[keep], _ptr(keep_r), _ptr(rep_r), _ptr(ws), ws.numel(), 0, s), "records")
+        _lib.check(lib.dyd_dedup_records(_ptr(send), m, ops.KEEP_MODES[keep], _ptr(keep_r), _ptr(rep_r), _ptr(ws), ws.numel(), s), "records")
         _lib.check(lib.dyd_shard_pack_reply(_ptr(send), _ptr(keep_r), _ptr(rep_r), m, _ptr(reply), 0, s), "pack")
         _lib.check(lib.dyd_shard_unpack(_ptr(reply), m, 1000, n, _ptr(out_keep), _ptr(out_rep), 0, s), "unpack")
         assert_bits(host(out_keep), want_keep, f"keep {keep}"); assert_bits(host(out_rep), want_rep, f"rep {keep}")
@@ -468,7 +451,7 @@ def test_exchange_kernels_single_rank_roundtrip(cuda_device, small_partitions):
         ws1 = t(lib.dyd_dedup_workspace_bytes(cap1), dt=torch.uint8)
         for _ in range(2):
             _lib.check(lib.dyd_shard_bucket_p2p(_ptr(k), None, 1000, n, 1, 0, cap1, _ptr(peers_recv), _ptr(sent), _ptr(cur1), _ptr(overflow), s), "bucket_p2p")
-            _lib.check(lib.dyd_dedup_records(_ptr(recv), cap1, ops.KEEP_MODES[keep], _ptr(kr1), _ptr(rr1), _ptr(ws1), ws1.numel(), 1000 + n, s), "records")
+            _lib.check(lib.dyd_dedup_records(_ptr(recv), cap1, ops.KEEP_MODES[keep], _ptr(kr1), _ptr(rr1), _ptr(ws1), ws1.numel(), s), "records")
             _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(recv), _ptr(kr1), _ptr(rr1), cap1, cap1, 0, _ptr(peers_back), 0, 1, s), "pack_p2p")
             out_keep.fill_(7); out_rep.fill_(-7)
             _lib.check(lib.dyd_shard_unpack_p2p(_ptr(back), _ptr(sent), _ptr(cur1), 1, cap1, n, _ptr(out_keep), _ptr(out_rep), 0, s), "unpack_p2p")
@@ -479,8 +462,7 @@ def test_exchange_kernels_single_rank_roundtrip(cuda_device, small_partitions):
     assert int(overflow.item()) == 1
 
 
-@pytest.mark.parametrize("id_bound", [0, 1 << 20])
-def test_antijoin_records_roundtrip(cuda_device, small_partitions, id_bound):
+def test_antijoin_records_roundtrip(cuda_device):
     """Sharded anti-join on one GPU: both tables bucketed into 4 fixed-capacity regions of (key, id) records, the owner-side
     table step on records (dyd_antijoin_records), answers packed in anti-join mode and unpacked -- equals the plain anti-join
     with global reference rows; the reference records are reset to padding by the build kernel."""
@@ -500,12 +482,12 @@ def test_antijoin_records_roundtrip(cuda_device, small_partitions, id_bound):
     send, sendr, reply = t(2 * m), t(2 * mr), t(2 * m)
     cursors, overflow = t(world, dt=torch.uint64), t(2, dt=torch.int32)
     keep_r, row_r = t(m, dt=torch.uint8), t(m)
-    ws = t(lib.dyd_antijoin_fast_workspace_bytes(m, mr) if id_bound else lib.dyd_antijoin_workspace_bytes(mr), dt=torch.uint8)   # bound known: radix path
+    ws = t(lib.dyd_antijoin_workspace_bytes(mr), dt=torch.uint8)
     s = _stream(d)
     _lib.check(lib.dyd_shard_bucket(_ptr(dev(ref, d)), _ptr(dev(rnull, d)), 500, nr, world, capr, _ptr(sendr), _ptr(cursors), _ptr(overflow[1:]), s), "bucket ref")
     _lib.check(lib.dyd_shard_bucket(_ptr(dev(keys, d)), _ptr(dev(mnull, d)), 9000, n, world, cap, _ptr(send), _ptr(cursors), _ptr(overflow[:1]), s), "bucket main")
     assert overflow.cpu().tolist() == [0, 0]
-    _lib.check(lib.dyd_antijoin_records(_ptr(sendr), mr, _ptr(send), m, _ptr(keep_r), _ptr(row_r), _ptr(ws), ws.numel(), 1, id_bound, s), "antijoin_records")
+    _lib.check(lib.dyd_antijoin_records(_ptr(sendr), mr, _ptr(send), m, _ptr(keep_r), _ptr(row_r), _ptr(ws), ws.numel(), 1, s), "antijoin_records")
     assert bool((sendr.view(-1, 2)[:, 1] == -1).all()), "build kernel must reset the reference records"
     _lib.check(lib.dyd_shard_pack_reply(_ptr(send), _ptr(keep_r), _ptr(row_r), m, _ptr(reply), 1, s), "pack")
     out_keep = torch.ones(n, dtype=torch.uint8, device=d); out_row = torch.full((n,), -1, dtype=torch.int64, device=d)   # NaN rows never travel
