@@ -381,8 +381,7 @@ def main():
     ev_f0, ev_f1, ev_u0, ev_u1, ev_a0 = mk(), mk(), mk(), mk(), mk()
     state = {}
     if world > 1:
-        xd = sharding.DedupExchange(n_img, world, dev)
-        xa = sharding.AntiJoinExchange(n_img, n_ref, world, dev)
+        xj = sharding.UrlFilterExchange(n_img, n_ref, world, dev)       # dedup + anti-join in one exchange
     else:
         dws = torch.empty(max(lib.dyd_dedup_workspace_bytes(n_img), lib.dyd_antijoin_workspace_bytes(n_ref)), dtype=torch.uint8, device=dev)
 
@@ -393,14 +392,13 @@ def main():
         rkeys = ops.hash_strings(roff, rdata)
         if world == 1:
             state["keep"], state["rep"] = ops.dedup(keys, None, "first", workspace=dws)
-        else:
-            state["keep"], state["rep"] = xd.run(keys, first, "first", check_overflow=False)
-        if i is not None:
-            ev_a0[i].record()
-        if world == 1:
+            if i is not None:
+                ev_a0[i].record()
             state["keep_ref"], state["ref_row"] = ops.antijoin(keys, None, rkeys, None, workspace=dws)
         else:
-            state["keep_ref"], state["ref_row"] = xa.run(keys, first, rkeys, ref_first, check_overflow=False)
+            if i is not None:
+                ev_a0[i].record()
+            state["keep"], state["rep"], state["keep_ref"], state["ref_row"] = xj.run(keys, first, rkeys, ref_first, "first", check_overflow=False)
         if i is not None:
             ev_u1[i].record()
         state["keys"] = keys
@@ -464,7 +462,7 @@ def main():
     # ---------------- results + verification against the url-id ground truth (after the timed region) ----------------
     overflowed = 0
     if world > 1:
-        fl = torch.cat([xd.overflow, xa.overflow]).max().reshape(1).clone()
+        fl = xj.overflow.max().reshape(1).clone()
         dist.all_reduce(fl, op=dist.ReduceOp.MAX)
         overflowed = int(fl.item())
     assert overflowed == 0, "exchange bucket overflow: rerun with exact-size splits"
@@ -490,7 +488,7 @@ def main():
                "rows_dropped_by_either_global": dropped_either, "exchange_verified": verified,
                "verified_how": "keep / rep of the sharded dedup and keep / ref_row of the sharded anti-join of the LAST timed step compared bit for bit, on "
                                "every rank, with a torch sort-based ground truth over the all-gathered integer url ids (deal_yolo_daya_b200/verify.py)",
-               "exchange_transport": (xd.transport if world > 1 else "none (1 GPU)")}
+               "exchange_transport": (xj.transport + ", dedup + anti-join in one exchange (sharding.UrlFilterExchange)" if world > 1 else "none (1 GPU)")}
     assert verified, f"sharded dedup / anti-join differs from the url-id ground truth: {ok}"
 
     # ---------------- end to end through the host-buffer entry points (H2D + D2H inside the timed region) ----------------
@@ -613,7 +611,7 @@ def main():
         "gpu_launches": launches,
         "gpu_launches_how": "dyd_launch_count() before / after the timed region: every kernel launch of libdyd.so increments it",
         "streams": {"overlap": overlap, "fused_ctas": max_ctas or 148, "url_stream_sms": args.url_sms,
-                    "fused_ms": fused_ms, "url_chain_ms": url_ms_max, "antijoin_ms": anti_ms_max, "fused_cta_times_last_launch": cta_times,
+                    "fused_ms": fused_ms, "url_chain_ms": url_ms_max, ("antijoin_ms" if world == 1 else "joint_exchange_ms"): anti_ms_max, "fused_cta_times_last_launch": cta_times,
                     "note": "per-step CUDA-event times on each stream (max over ranks for the URL chain); a step ends when both streams are done"},
         "roofline": {"bound": "hbm", "kernel": "fused_tma_kernel (+ tile_desc pre-pass and crowd worklist kernel, timed together)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

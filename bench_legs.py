@@ -121,7 +121,7 @@ def c5_leg(dev, rank, world, t, peak, seed=42, ratios=(0.8, 0.1, 0.1)):
     hist = torch.zeros(n_cat * 3, dtype=torch.int64, device=dev)
     hist.scatter_add_(0, own_cat * 3 + split_own.long(), torch.ones_like(own_cat))
     possum = torch.zeros(n_cat, dtype=torch.float64, device=dev)
-    possum.scatter_add_(0, own_cat, (pos_own - cat_off_g[:-1][own_cat]).double())
+    possum.scatter_add_(0, own_cat, pos_own.double())          # pos = shuffled position inside the category
     tot = local_counts.clone()
     if world > 1:
         dist.all_reduce(hist); dist.all_reduce(possum); dist.all_reduce(tot)

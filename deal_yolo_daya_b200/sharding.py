@@ -424,6 +424,87 @@ def split_category_bases(local_counts, group=None):
     return base, cat_off
 
 
+class UrlFilterExchange(AntiJoinExchange):
+    """Steps 2 + 3 in ONE exchange: the main (key, row) records that travel to their owners for the anti-join are the
+    same records the dedup needs, so the owner runs both table steps on what it received and sends two 8-byte answers
+    per record back.  Compared with `DedupExchange` followed by `AntiJoinExchange` this saves a scatter of the main table
+    over NVLink and a barrier pair per step; results are identical (tests/test_gpu_multi.py)."""
+
+    def __init__(self, n_main_local: int, n_ref_local: int, world: int, device, slack: float = 1.10, group=None):
+        super().__init__(n_main_local, n_ref_local, world, device, slack, group)
+        m = world * self.cap
+        self.keep_dr = torch.empty(m, dtype=torch.uint8, device=device)
+        self.rep_dr = torch.empty(m, dtype=torch.int64, device=device)
+        self.ws_d = torch.empty(self.lib.dyd_dedup_workspace_bytes(m), dtype=torch.uint8, device=device)
+        self.keep_d = torch.empty(n_main_local, dtype=torch.uint8, device=device)
+        self.rep_d = torch.empty(n_main_local, dtype=torch.int64, device=device)
+        if self.transport == "p2p":
+            import torch.distributed._symmetric_memory as symm
+            grp = group if group is not None else dist.group.WORLD
+            self.back_d = symm.empty(m, dtype=torch.int64, device=device)
+            self.h_back_d = symm.rendezvous(self.back_d, grp)
+            self.peer_back_d = torch.tensor(list(self.h_back_d.buffer_ptrs), dtype=torch.int64, device=device)
+            self.back_d.fill_(-1)
+            torch.cuda.synchronize(device)
+            self.h_back_d.barrier(channel=0)
+        else:
+            self.reply_d = torch.empty(2 * m, dtype=torch.int64, device=device)
+            self.back_d = torch.empty(2 * m, dtype=torch.int64, device=device)
+
+    def run(self, main_keys, row_base: int, ref_keys, ref_row_base: int, keep="first", group=None, check_overflow=True,
+            main_null=None, ref_null=None):
+        """Returns (keep, rep, keep_ref, ref_row) for this rank's main rows."""
+        from . import _lib
+        from .ops import KEEP_MODES, _ptr, _stream
+        lib, dev = self.lib, self.dev
+        m, m_ref = self.world * self.cap, self.world * self.cap_ref
+        assert main_keys.numel() == self.n and ref_keys.numel() == self.n_ref
+        p2p = self.transport == "p2p"
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            if p2p:
+                self._scatter_p2p(self.ref, ref_keys, ref_null, ref_row_base, self.overflow[1:], s)
+                self._scatter_p2p(self.main, main_keys, main_null, row_base, self.overflow[:1], s)
+                self.main.h.barrier(channel=1)                    # both tables' records have landed
+            else:
+                _lib.check(lib.dyd_shard_bucket(_ptr(ref_keys), _ptr(ref_null), ref_row_base, self.n_ref, self.world, self.cap_ref,
+                                                _ptr(self.send_ref), _ptr(self.cursors_ref), _ptr(self.overflow[1:]), s), "dyd_shard_bucket")
+                dist.all_to_all_single(self.recv_ref, self.send_ref, group=group)
+                _lib.check(lib.dyd_shard_bucket(_ptr(main_keys), _ptr(main_null), row_base, self.n, self.world, self.cap,
+                                                _ptr(self.send), _ptr(self.cursors), _ptr(self.overflow[:1]), s), "dyd_shard_bucket")
+                dist.all_to_all_single(self.recv, self.send, group=group)
+            _lib.check(lib.dyd_dedup_records(_ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_dr), _ptr(self.rep_dr),
+                                             _ptr(self.ws_d), self.ws_d.numel(), s), "dyd_dedup_records")
+            _lib.check(lib.dyd_antijoin_records(_ptr(self.recv_ref), m_ref, _ptr(self.recv), m, _ptr(self.keep_r), _ptr(self.rep_r),
+                                                _ptr(self.ws), self.ws.numel(), 1 if p2p else 0, s), "dyd_antijoin_records")
+            if main_null is not None:                         # rows that never travel: a NaN cell never matches
+                self.keep.fill_(1); self.rep.fill_(-1)
+            if p2p:
+                _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(self.recv), _ptr(self.keep_dr), _ptr(self.rep_dr), m, self.cap, self.rank,
+                                                        _ptr(self.peer_back_d), 0, 0, s), "dyd_shard_pack_reply_p2p")
+                _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, self.cap, self.rank,
+                                                        _ptr(self.peer_back), 1, 1, s), "dyd_shard_pack_reply_p2p")
+                self.h_back.barrier(channel=0)                # all answers have landed
+                _lib.check(lib.dyd_shard_unpack_p2p(_ptr(self.back_d), _ptr(self.main.sent_row), _ptr(self.cursors), self.world, self.cap,
+                                                    self.n, _ptr(self.keep_d), _ptr(self.rep_d), 0, s), "dyd_shard_unpack_p2p")
+                _lib.check(lib.dyd_shard_unpack_p2p(_ptr(self.back), _ptr(self.main.sent_row), _ptr(self.cursors), self.world, self.cap,
+                                                    self.n, _ptr(self.keep), _ptr(self.rep), 1, s), "dyd_shard_unpack_p2p")
+            else:
+                _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_dr), _ptr(self.rep_dr), m, _ptr(self.reply_d), 0, s),
+                           "dyd_shard_pack_reply")
+                dist.all_to_all_single(self.back_d, self.reply_d, group=group)
+                _lib.check(lib.dyd_shard_unpack(_ptr(self.back_d), m, row_base, self.n, _ptr(self.keep_d), _ptr(self.rep_d), 0, s),
+                           "dyd_shard_unpack")
+                self._reply_nccl(row_base, group, s)
+            if main_null is not None:
+                _resolve_null_group(self.keep_d, self.rep_d, main_null, row_base, keep, group)
+        if check_overflow and self._overflowed(group):
+            k, r = dedup_global(main_keys, main_null, row_base, keep, group)
+            k2, r2 = antijoin_global(main_keys, main_null, ref_keys, ref_null, ref_row_base, group)
+            return k, r, k2, r2
+        return self.keep_d, self.rep_d, self.keep, self.rep
+
+
 class ShardedUrlFilter:
     """Steps 2 + 3 (dedup by `source`, then the reference filter; processor.py:140-144, 194-199) for a row-sharded
     table whose `source` columns live in HOST memory on every rank -- the N-GPU form of dyd_dedup_host /
@@ -441,8 +522,7 @@ class ShardedUrlFilter:
         self.d_roff = torch.empty(n_ref_local + 1, dtype=torch.int64, device=d)
         self.d_rdata = torch.empty(max_ref_bytes + 8, dtype=torch.uint8, device=d)
         if world > 1:
-            self.dedup = DedupExchange(n_local, world, d, group=group)
-            self.anti = AntiJoinExchange(n_local, n_ref_local, world, d, group=group)
+            self.xchg = UrlFilterExchange(n_local, n_ref_local, world, d, group=group)
         else:
             self.ws = torch.empty(max(self.lib.dyd_dedup_workspace_bytes(n_local), self.lib.dyd_antijoin_workspace_bytes(n_ref_local)),
                                   dtype=torch.uint8, device=d)
@@ -464,8 +544,7 @@ class ShardedUrlFilter:
             keys = ops.hash_strings(self.d_off, self.d_data[:nb])
             rkeys = ops.hash_strings(self.d_roff, self.d_rdata[:nrb])
             if self.world > 1:
-                k, r = self.dedup.run(keys, row_base, keep, group=self.group)
-                k2, r2 = self.anti.run(keys, row_base, rkeys, ref_row_base, group=self.group)
+                k, r, k2, r2 = self.xchg.run(keys, row_base, rkeys, ref_row_base, keep, group=self.group)
             else:
                 k, r = ops.dedup(keys, None, keep, workspace=self.ws)
                 k2, r2 = ops.antijoin(keys, None, rkeys, None, workspace=self.ws)

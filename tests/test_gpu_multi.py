@@ -22,4 +22,5 @@ def test_peer_memory_exchange_equals_nccl_exchange():
     assert "p2p == nccl: True  p2p == exact-size path: True  dedup == url-id ground truth: True" in out.stdout, out.stdout[-2000:]
     assert "antijoin p2p == nccl: True  antijoin p2p == exact-size path: True  antijoin == url-id ground truth: True" in out.stdout, \
         out.stdout[-2000:]
+    assert "joint exchange == separate exchanges (both transports): True" in out.stdout, out.stdout[-2000:]
     assert "requested p2p: using p2p" in out.stdout, out.stdout[-2000:]

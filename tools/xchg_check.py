@@ -18,7 +18,7 @@ ref_id, roff, rdata = synth_device.make_urls(0, rank * n_ref, n_ref, dev, n_main
 rkeys = ops.hash_strings(roff, rdata)
 null = (torch.arange(n, device=dev) % 997 == 5).to(torch.uint8)          # a few NaN cells on every rank
 rnull = (torch.arange(n_ref, device=dev) % 1013 == 7).to(torch.uint8)
-res, ares = {}, {}
+res, ares, jres = {}, {}, {}
 
 
 def timed(fn, label):
@@ -54,6 +54,13 @@ for transport in ("nccl", "p2p"):
     ares[(transport, "nulls")] = (k.clone(), r.clone())
     timed(lambda: y.run(keys, rank * n, rkeys, rank * n_ref, check_overflow=False), f"antijoin {y.transport}")
     del y
+    z = sharding.UrlFilterExchange(n, n_ref, world, dev)
+    for rep in range(2):
+        for keep in ("first", "last", False):
+            jres[(transport, keep, rep)] = [x.clone() for x in z.run(keys, rank * n, rkeys, rank * n_ref, keep)]
+    jres[(transport, "nulls")] = [x.clone() for x in z.run(keys, rank * n, rkeys, rank * n_ref, "first", main_null=null, ref_null=rnull)]
+    timed(lambda: z.run(keys, rank * n, rkeys, rank * n_ref, "first", check_overflow=False), f"joint {z.transport}")
+    del z
 
 
 def eq(a, b):
@@ -75,10 +82,19 @@ kk, rr = sharding.antijoin_global(keys, null, rkeys, rnull, rank * n_ref)
 a_exact = a_exact and eq((kk, rr), ares[("p2p", "nulls")])
 ek, er = expected_antijoin(url_id, ref_id, rank * n_ref)
 a_truth = eq((ek, er), ares[("p2p", 1)])
-flags = torch.tensor([int(same), int(same_exact), int(truth), int(a_same), int(a_exact), int(a_truth)], device=dev)
+j_ok = True
+for transport in ("nccl", "p2p"):
+    for rep in (0, 1):
+        for keep in ("first", "last", False):
+            j = jres[(transport, keep, rep)]
+            j_ok = j_ok and eq(j[:2], res[("p2p", keep, 1)]) and eq(j[2:], ares[("p2p", 1)])
+    j = jres[(transport, "nulls")]
+    j_ok = j_ok and eq(j[:2], res[("p2p", "nulls")]) and eq(j[2:], ares[("p2p", "nulls")])
+flags = torch.tensor([int(same), int(same_exact), int(truth), int(a_same), int(a_exact), int(a_truth), int(j_ok)], device=dev)
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
     f = [bool(v) for v in flags.tolist()]
     print("p2p == nccl:", f[0], " p2p == exact-size path:", f[1], " dedup == url-id ground truth:", f[2], flush=True)
     print("antijoin p2p == nccl:", f[3], " antijoin p2p == exact-size path:", f[4], " antijoin == url-id ground truth:", f[5], flush=True)
+    print("joint exchange == separate exchanges (both transports):", f[6], flush=True)
 dist.destroy_process_group()
