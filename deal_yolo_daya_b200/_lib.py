@@ -49,6 +49,7 @@ PROTOTYPES = {
     "dyd_antijoin": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "dyd_label_lut": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
     "dyd_label_hist": (_int, [_p, _i64, _i32, _p, _p]),
+    "dyd_label_presence": (_int, [_p, _p, _i64, _i32, _p, _p, _p]),
     "dyd_split_workspace_bytes": (_sz, [_i64, _i32]),
     "dyd_split_count": (_int, [_p, _i64, _p, _p, _i32, _i32, _p, _p, _sz, _p]),
     "dyd_split_fill": (_int, [_p, _i64, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),

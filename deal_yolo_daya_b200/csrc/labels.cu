@@ -308,6 +308,32 @@ yolo_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts,
     }
 }
 
+// ------------------------------------------------------------------------------- per-image label presence
+// summarize_yolo_label_counts (processor.py:1113-1131): a label counts once per image that holds it ("图片数量") and once
+// per box ("标注框数量").  A block owns IMG_PER_CTA consecutive images; one thread per object finds its image by bisection
+// and adds to the image histogram iff no earlier object of the same image carries the same label (images hold tens of
+// boxes, so the backward scan is short and L1-resident).  Ids outside [0, n_vocab) are ignored.
+__global__ void __launch_bounds__(LB_THREADS)
+label_presence_kernel(const int64_t* __restrict__ img_off, const int32_t* __restrict__ label_id, int64_t n_img, int32_t n_vocab,
+                      unsigned long long* __restrict__ img_hist, unsigned long long* __restrict__ box_hist) {
+    __shared__ long long soff[IMG_PER_CTA + 1];
+    const int64_t i0 = blockIdx.x * (int64_t)IMG_PER_CTA;
+    const int n_here = (int)min((int64_t)IMG_PER_CTA, n_img - i0);
+    for (int k = threadIdx.x; k <= n_here; k += LB_THREADS) soff[k] = img_off[i0 + k];
+    __syncthreads();
+    const int64_t q0 = soff[0], q1 = soff[n_here];
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += LB_THREADS) {
+        const int32_t v = label_id[q];
+        if (v < 0 || v >= n_vocab) continue;
+        int lo = 0, hi = n_here;                   // last image whose first object is <= q (skips empty images)
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (soff[mid] <= q) lo = mid; else hi = mid; }
+        bool first = true;
+        for (int64_t e = soff[lo]; e < q && first; ++e) first = label_id[e] != v;
+        atomicAdd(&box_hist[v], 1ULL);
+        if (first) atomicAdd(&img_hist[v], 1ULL);
+    }
+}
+
 static inline int64_t n_chunks_of(int64_t n_img) { return (n_img + IMG_PER_WARP - 1) / IMG_PER_WARP; }
 
 }  // namespace dyd
@@ -343,6 +369,23 @@ extern "C" int dyd_label_hist(const int32_t* d_label_id, int64_t n_box, int32_t 
     if (grid < NUM_SMS * 2) grid = NUM_SMS * 2;
     label_hist_kernel<<<(unsigned)grid, LB_THREADS, 0, s>>>(d_label_id, n_box, n_vocab, reinterpret_cast<unsigned long long*>(d_hist));
     return launch_check("label_hist_kernel");
+}
+
+extern "C" int dyd_label_presence(const int64_t* d_img_off, const int32_t* d_label_id, int64_t n_img, int32_t n_vocab,
+                                  uint64_t* d_img_hist, uint64_t* d_box_hist, void* stream) {
+    DYD_REQUIRE(n_img >= 0 && n_vocab >= 0, DYD_E_ARG, "negative count");
+    if (n_vocab == 0) return 0;
+    DYD_REQUIRE(d_img_hist && d_box_hist, DYD_E_ARG, "null pointer");
+    cudaStream_t s = as_stream(stream);
+    DYD_CUDA(cudaMemsetAsync(d_img_hist, 0, sizeof(uint64_t) * n_vocab, s));
+    DYD_CUDA(cudaMemsetAsync(d_box_hist, 0, sizeof(uint64_t) * n_vocab, s));
+    if (n_img == 0) return 0;
+    DYD_REQUIRE(d_img_off && d_label_id, DYD_E_ARG, "null pointer");
+    const int64_t grid = (n_img + IMG_PER_CTA - 1) / IMG_PER_CTA;
+    label_presence_kernel<<<(unsigned)grid, LB_THREADS, 0, s>>>(d_img_off, d_label_id, n_img, n_vocab,
+                                                               reinterpret_cast<unsigned long long*>(d_img_hist),
+                                                               reinterpret_cast<unsigned long long*>(d_box_hist));
+    return launch_check("label_presence_kernel");
 }
 
 extern "C" size_t dyd_split_workspace_bytes(int64_t n_img, int32_t n_cat) {

@@ -282,9 +282,10 @@ def _csv_column(col):
     return None
 
 
-def to_csv(df, path, encoding="utf-8-sig") -> None:
-    """``df.to_csv(path, index=False, encoding=encoding)``, byte-identical, body rows written by
-    csrc/ingest.cpp (multi-threaded).  Falls back to pandas for frames it does not cover."""
+def to_csv(df, path, encoding="utf-8-sig", mode="w", header=True) -> None:
+    """``df.to_csv(path, index=False, encoding=encoding, mode=mode, header=header)``, byte-identical, body rows written
+    by csrc/ingest.cpp (multi-threaded).  Falls back to pandas for frames it does not cover.  In append mode no BOM is
+    written (Python's TextIOWrapper skips it when the file position is not 0, which is what pandas relies on)."""
     import csv
     import io
     enc = (encoding or "utf-8").lower().replace("_", "-")
@@ -294,7 +295,7 @@ def to_csv(df, path, encoding="utf-8-sig") -> None:
         if any(c is None for c in cols):
             cols = None
     if cols is None:
-        df.to_csv(path, index=False, encoding=encoding)
+        df.to_csv(path, index=False, encoding=encoding, mode=mode, header=header)
         return
     lib = _lib.load()
     n, nc = len(df), len(cols)
@@ -309,10 +310,12 @@ def to_csv(df, path, encoding="utf-8-sig") -> None:
     _lib.check(lib.dyd_csv_write(*a, _p(body), _threads()), "dyd_csv_write(write)")
     head = io.StringIO()
     csv.writer(head, lineterminator="\n", quoting=csv.QUOTE_MINIMAL).writerow([str(c) for c in df.columns])
-    with open(path, "wb") as f:
-        if enc == "utf-8-sig":
+    append = mode == "a"
+    with open(path, "ab" if append else "wb") as f:
+        if enc == "utf-8-sig" and not (append and f.tell() != 0):
             f.write(b"\xef\xbb\xbf")
-        f.write(head.getvalue().encode("utf-8"))
+        if header:
+            f.write(head.getvalue().encode("utf-8"))
         f.write(body.tobytes() if body.size < (1 << 20) else memoryview(body))
 
 
@@ -372,17 +375,25 @@ def _na_table():
     return np.frombuffer(b"".join(vals) or b"\0", dtype=np.uint8), off, len(vals)
 
 
-def read_csv(path, encoding="utf-8", **kwargs):
+class NotNative(Exception):
+    """read_csv(..., _strict_native=True): the input is outside what the native reader restates."""
+
+
+def read_csv(path, encoding="utf-8", _strict_native=False, _window_rows=None, **kwargs):
     """``pd.read_csv(path, encoding=encoding, **kwargs)`` -- same frame, text columns tokenised by
     csrc/csv_read.cpp.  Anything the native reader does not cover (other encodings or keyword
     arguments, an unusual dialect, ragged rows, pandas without the Arrow ``str`` dtype, small files)
-    is read by pandas itself."""
+    is read by pandas itself -- or, with ``_strict_native``, reported with NotNative so that the caller
+    can apply its own reading rules (the merge step reads with ``errors="ignore"`` in chunks of ``_window_rows`` rows,
+    each inferred on its own: a longer file is then measured per such chunk)."""
     import io
     import pandas as pd
     enc = (encoding or "utf-8").lower().replace("_", "-")
     extra = {k: v for k, v in kwargs.items() if not (k == "parse_dates" and v is False)}
 
     def fallback():
+        if _strict_native:
+            raise NotNative(str(path))
         _READ_STATS["pandas"] += 1
         return pd.read_csv(path, encoding=encoding, **kwargs)
 
@@ -413,6 +424,10 @@ def read_csv(path, encoding="utf-8", **kwargs):
         if len(names) != n_cols:
             return fallback()
         window = _buffer_lines(n_cols)
+        if _window_rows is not None and n_rows > _window_rows:
+            if _window_rows > window:
+                return fallback()              # the caller's chunks would be cut again by pandas' own buffer: not restated
+            window = int(_window_rows)
         col_bytes = np.zeros(n_cols, np.int64); col_nulls = np.zeros(n_cols, np.int64)
         col_text = np.zeros(n_cols, np.uint8); col_utf8 = np.zeros(n_cols, np.uint8)
         _lib.check(lib.dyd_csv_measure(h, window, _p(col_bytes), _p(col_nulls), _p(col_text), _p(col_utf8), _threads()),

@@ -228,6 +228,18 @@ def label_hist(label_id, n_vocab):
     return hist
 
 
+def label_presence(img_off, label_id, n_vocab):
+    """(img_hist, box_hist) uint64[n_vocab]: images holding each id at least once / objects per id (processor.py:1113-1131)."""
+    _need_cuda(img_off, label_id)
+    lib = _lib.load()
+    dev = img_off.device
+    hists = torch.empty(2, max(n_vocab, 1), dtype=torch.uint64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_label_presence(_ptr(_chk(img_off, torch.int64, "img_off")), _ptr(_chk(label_id, torch.int32, "label_id")),
+                                          img_off.numel() - 1, n_vocab, _ptr(hists[0]), _ptr(hists[1]), _stream(dev)), "dyd_label_presence")
+    return hists[0, :n_vocab], hists[1, :n_vocab]
+
+
 def split_expand(img_off, label_id, cat_of_label, n_cat):
     """Category expansion (processor.py:751-775).  Returns (exp_img, exp_box, exp_cat, cat_off)."""
     _need_cuda(img_off, label_id, cat_of_label)

@@ -106,6 +106,23 @@ class CudaKernels:
         s, p = ops.split_assign(self._up(cat_off, d), self._up(perm, d), self._up(n_train, d), self._up(n_val, d))
         return s.cpu().numpy(), p.cpu().numpy()
 
+    def yolo(self, img_off, pts, img_wh):
+        """(cxcywh float64[4*n_box], ok uint8[n_box]) of processor.py:1045-1052 for boxes grouped by row."""
+        from . import ops
+        d = self._dev()
+        out, ok = ops.yolo_normalise(self._up(img_off, d), self._up(pts, d), None, self._up(img_wh, d))
+        return out.cpu().numpy(), ok.cpu().numpy()
+
+    def label_presence(self, img_off, label_id, n_vocab):
+        from . import ops
+        d = self._dev()
+        ih, bh = ops.label_presence(self._up(img_off, d), self._up(label_id, d), n_vocab)
+        return ih.cpu().numpy().astype(np.int64), bh.cpu().numpy().astype(np.int64)
+
+    def hist(self, ids, n_vocab):
+        from . import ops
+        return ops.label_hist(self._up(ids, self._dev()), n_vocab).cpu().numpy().astype(np.int64)
+
 
 KERNELS = CudaKernels()
 
@@ -564,3 +581,11 @@ def split_dataset_by_rules(
     res["split_counts"].to_excel(split_counts_path, index=False)
     return {"output_dir": output_dir, "category_files": category_files, "unclassified": unclassified_path,
             "split_counts": split_counts_path, "summary": res["summary"]}
+
+
+# =============================================================================================
+# the callers either side of the path: merge in front, dataset writer + summaries behind
+# reference: processor.py:26-109, 833-891, 893-1087, 1089-1163
+# =============================================================================================
+from .dataset import (generate_yolo_datasets_from_excels, merge_all_csv_in_folder, summarize_unclassified,  # noqa: E402,F401
+                      summarize_yolo_label_counts)

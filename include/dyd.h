@@ -197,6 +197,12 @@ int dyd_label_lut(const int64_t* d_img_off, const int32_t* d_label_id, int64_t n
  * with the host's token tables this gives the unmatched-label counts of processor.py:591-593. */
 int dyd_label_hist(const int32_t* d_label_id, int64_t n_box, int32_t n_vocab, uint64_t* d_hist, void* stream);
 
+/* Per-image label presence + per-box counts of summarize_yolo_label_counts (processor.py:1113-1131): d_img_hist[v] =
+ * images holding at least one object with id v ("图片数量"), d_box_hist[v] = objects with id v ("标注框数量"); both
+ * uint64[n_vocab], zeroed by the call; ids outside [0, n_vocab) are ignored.                              */
+int dyd_label_presence(const int64_t* d_img_off, const int32_t* d_label_id, int64_t n_img, int32_t n_vocab,
+                       uint64_t* d_img_hist, uint64_t* d_box_hist, void* stream);
+
 /* ---------------------------------------------------------------- K6 ------
  * label -> category expansion of processor.py:751-775: one expanded row per
  * object whose label has a category, stably grouped by category (encounter

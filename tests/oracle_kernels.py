@@ -43,3 +43,33 @@ class OracleKernels:
             r = np.arange(b - a)
             split[a + p] = np.where(r < n_train[c], 0, np.where(r < n_train[c] + n_val[c], 1, 2))
         return split, pos
+
+    def yolo(self, img_off, pts, img_wh):
+        img_off = np.asarray(img_off); pts = np.asarray(pts, np.float64).reshape(-1, 4); wh = np.asarray(img_wh, np.float64).reshape(-1, 2)
+        out = np.zeros((len(pts), 4), np.float64); ok = np.zeros(len(pts), np.uint8)
+        for i in range(len(img_off) - 1):
+            for q in range(int(img_off[i]), int(img_off[i + 1])):
+                r = oracle_np.yolo_norm(tuple(pts[q]), wh[i, 0], wh[i, 1])
+                if r is not None:
+                    out[q] = r; ok[q] = 1
+                else:                              # the kernel still writes the arithmetic; only `ok` is observable
+                    x1, y1, x2, y2 = pts[q]
+                    with np.errstate(all="ignore"):
+                        out[q] = ((x1 + x2) / 2 / wh[i, 0], (y1 + y2) / 2 / wh[i, 1], max(x2 - x1, 0.0) / wh[i, 0], max(y2 - y1, 0.0) / wh[i, 1])
+        return out.reshape(-1), ok
+
+    def label_presence(self, img_off, label_id, n_vocab):
+        ih = np.zeros(n_vocab, np.int64); bh = np.zeros(n_vocab, np.int64)
+        lid = np.asarray(label_id)
+        for i in range(len(img_off) - 1):
+            seg = lid[int(img_off[i]):int(img_off[i + 1])]
+            seg = seg[(seg >= 0) & (seg < n_vocab)]
+            for v in seg:
+                bh[v] += 1
+            for v in set(seg.tolist()):
+                ih[v] += 1
+        return ih, bh
+
+    def hist(self, ids, n_vocab):
+        ids = np.asarray(ids)
+        return np.bincount(ids[(ids >= 0) & (ids < n_vocab)], minlength=n_vocab).astype(np.int64)

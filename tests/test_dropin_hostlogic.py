@@ -38,6 +38,24 @@ def test_split():
     C.check_split()
 
 
+def test_signatures_equal_the_reference():
+    from tests import dataset_checks as D
+    D.check_signatures()
+
+
+@pytest.mark.parametrize("native_min", ["0", None])
+def test_merge(tmp_path, monkeypatch, native_min):
+    from tests import dataset_checks as D
+    if native_min is not None:
+        monkeypatch.setenv("DYD_CSV_NATIVE_MIN_BYTES", native_min)     # the small inputs take the native reader
+    D.check_merge(tmp_path)
+
+
+def test_yolo_writer_and_summaries(tmp_path):
+    from tests import dataset_checks as D
+    D.check_yolo_and_summaries(tmp_path)
+
+
 def test_product_refuses_to_run_without_cuda(monkeypatch):
     """Without the oracle facade and without a GPU the drop-in must fail loudly, not fall back."""
     import torch

@@ -50,3 +50,18 @@ def test_remap():
 
 def test_split():
     C.check_split()
+
+
+def test_signatures_equal_the_reference():
+    from tests import dataset_checks as D
+    D.check_signatures()
+
+
+def test_merge(tmp_path):
+    from tests import dataset_checks as D
+    D.check_merge(tmp_path)
+
+
+def test_yolo_writer_and_summaries(tmp_path):
+    from tests import dataset_checks as D
+    D.check_yolo_and_summaries(tmp_path)

@@ -493,3 +493,17 @@ def test_antijoin_records_roundtrip(cuda_device):
     out_keep = torch.ones(n, dtype=torch.uint8, device=d); out_row = torch.full((n,), -1, dtype=torch.int64, device=d)   # NaN rows never travel
     _lib.check(lib.dyd_shard_unpack(_ptr(reply), m, 9000, n, _ptr(out_keep), _ptr(out_row), 1, s), "unpack")
     assert_bits(host(out_keep), want_keep, "keep"); assert_bits(host(out_row), want_row, "ref_row")
+
+
+def test_label_presence(cuda_device):
+    """Per-image label presence + per-box counts (summarize_yolo_label_counts) against a plain count on the numpy twin."""
+    from tests.oracle_kernels import OracleKernels
+    d = cuda_device
+    t = synth.make_table(31, 0, 3000)
+    lid = t.label_id.copy()
+    lid[::17] = -1; lid[5::23] = 200                        # ids outside the vocabulary are ignored
+    ih, bh = ops.label_presence(dev(t.img_off, d), dev(lid, d), synth.N_LABELS)
+    wi, wb = OracleKernels().label_presence(t.img_off, lid, synth.N_LABELS)
+    assert_bits(host(ih).astype(np.int64), wi, "image counts"); assert_bits(host(bh).astype(np.int64), wb, "box counts")
+    ih, bh = ops.label_presence(dev(np.zeros(1, np.int64), d), dev(np.zeros(0, np.int32), d), 4)
+    assert host(ih).sum() == 0 and host(bh).sum() == 0
