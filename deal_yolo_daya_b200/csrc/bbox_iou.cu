@@ -152,24 +152,41 @@ iou_tile_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ 
 
 // ------------------------------------------------------------------------------- K2 (block per crowded image)
 // Processes the worklist: computes the valid prefix, writes count and high.
-__global__ void __launch_bounds__(CTA_THREADS)
+//
+// Pairing: box s meets s+1 .. s+(n-1)/2 (mod n); for even n the antipodal pair is taken by the lower half only -- every
+// unordered pair exactly once, no pair table.  Register tiling: a thread owns CROWD_R = 4 CONSECUTIVE boxes and walks the
+// partners t = s0+1, s0+2, ... once; each partner (two 16-byte shared loads) is tested against all four own boxes, so the
+// shared-memory traffic per pair is a quarter of the one-box-per-thread form and the loop is bound by the four fp64
+// compares of the overlap pre-test (processor.py:329-333 reduces to them when no coordinate is NaN).  Boxes sit in shared
+// memory de-interleaved by 4 (position (j & 3) * 256 + j / 4), which makes the lanes' stride-4 partner reads consecutive.
+// Pairs that pass the pre-test (a fraction of a per cent) are queued and get the full IoU arithmetic from all threads after
+// every chunk of 32 partners -- dense warps instead of one diverged lane -- and the block leaves as soon as one hits.
+constexpr int CROWD_THREADS = 128;
+constexpr int CROWD_R = 4;
+constexpr int CROWD_CHUNK = 32;
+constexpr int CROWD_QCAP = 2048;
+__device__ __forceinline__ int crowd_pos(int j) { return ((j & 3) * (CROWD_SMEM_BOXES / 4)) | (j >> 2); }
+
+__global__ void __launch_bounds__(CROWD_THREADS)
 iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
                  int64_t min_boxes, double thr, uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
-    __shared__ double sx1[CROWD_SMEM_BOXES], sy1[CROWD_SMEM_BOXES], sx2[CROWD_SMEM_BOXES], sy2[CROWD_SMEM_BOXES];
-    __shared__ int found, has_nan;
+    __shared__ double2 slo[CROWD_SMEM_BOXES], shi[CROWD_SMEM_BOXES];       // (x1, y1) / (x2, y2), de-interleaved by 4
+    __shared__ unsigned queue[CROWD_QCAP];
+    __shared__ int found, has_nan, qn;
     __shared__ long long first_bad;
     const unsigned long long n_list = reinterpret_cast<CrowdList*>(ws)->count;
     const int* ids = crowd_ids(ws);
     const bool zero_hits = 0.0 >= thr;
+    const int tid = threadIdx.x;
     for (unsigned long long e = blockIdx.x; e < n_list; e += gridDim.x) {
         const int64_t img = ids[e];
         const int64_t q0 = img_off[img], n_all = img_off[img + 1] - q0;
         __syncthreads();                              // previous image fully consumed
-        if (threadIdx.x == 0) { found = 0; has_nan = 0; first_bad = n_all; }
+        if (tid == 0) { found = 0; has_nan = 0; qn = 0; first_bad = n_all; }
         __syncthreads();
         if (valid != nullptr) {
             long long mine = n_all;
-            for (int64_t j = threadIdx.x; j < n_all; j += CTA_THREADS)
+            for (int64_t j = tid; j < n_all; j += CROWD_THREADS)
                 if (valid[q0 + j] == 0) { mine = j; break; }
             if (mine < n_all) atomicMin(&first_bad, mine);
         }
@@ -180,40 +197,112 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
         const double2* src = reinterpret_cast<const double2*>(pts + 4 * q0);
         const bool in_smem = n <= CROWD_SMEM_BOXES;
         if (want && in_smem) {
-            for (int j = threadIdx.x; j < n; j += CTA_THREADS) {
+            for (int j = tid; j < n; j += CROWD_THREADS) {
                 double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
                 Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
-                sx1[j] = bx.x1; sy1[j] = bx.y1; sx2[j] = bx.x2; sy2[j] = bx.y2;
+                slo[crowd_pos(j)] = make_double2(bx.x1, bx.y1); shi[crowd_pos(j)] = make_double2(bx.x2, bx.y2);
                 if (bx.x1 != bx.x1 || bx.y1 != bx.y1 || bx.x2 != bx.x2 || bx.y2 != bx.y2) has_nan = 1;
             }
         }
         __syncthreads();
-        if (want) {
-            // circular half-range pairing: box s meets s+1 .. s+(n-1)/2 (mod n); for even n the
-            // antipodal pair is taken by the lower half only.  Covers every unordered pair once.
-            // Without NaN coordinates four cross comparisons are a superset of the exact overlap test
-            // (processor.py:329-333); only surviving pairs pay for the full IoU arithmetic.
-            const int half = (n - 1) / 2;
-            const bool even = (n & 1) == 0;
-            const bool cheap = in_smem && !has_nan && !zero_hits;
-            for (int s = threadIdx.x; s < n; s += CTA_THREADS) {
-                Box a;
-                if (in_smem) a = Box{sx1[s], sy1[s], sx2[s], sy2[s]};
-                else { double2 p1 = ldg_f64x2(src + 2 * s), p2 = ldg_f64x2(src + 2 * s + 1); a = box_from_points(p1.x, p1.y, p2.x, p2.y); }
+        const int half = (n - 1) / 2;
+        const bool even = (n & 1) == 0;
+        if (want && in_smem && !has_nan && !zero_hits) {
+            // ---- register-tiled pre-test + queued exact test
+            const int D = half + CROWD_R;                              // last partner distance any own box can need
+            for (int base = 0; base < n; base += CROWD_THREADS * CROWD_R) {
+                const int s0 = base + tid * CROWD_R;
+                double2 alo[CROWD_R], ahi[CROWD_R];
+                int dmax[CROWD_R];
+#pragma unroll
+                for (int k = 0; k < CROWD_R; ++k) {
+                    const int row = s0 + k;
+                    if (row < n) { alo[k] = slo[crowd_pos(row)]; ahi[k] = shi[crowd_pos(row)]; dmax[k] = half + ((even && row < n / 2) ? 1 : 0); }
+                    else { alo[k] = make_double2(pos_inf(), pos_inf()); ahi[k] = make_double2(neg_inf(), neg_inf()); dmax[k] = 0; }   // meets nothing
+                }
+                const bool active = s0 < n;
+                // one partner against the four own boxes; `rule` applies the pairing rule (needed at the two ends of the walk)
+                auto meet = [&](int t, int d, bool rule) {
+                    const double2 blo = slo[crowd_pos(t)], bhi = shi[crowd_pos(t)];
+                    bool ov[CROWD_R];
+#pragma unroll
+                    for (int k = 0; k < CROWD_R; ++k)
+                        ov[k] = ahi[k].x > blo.x && bhi.x > alo[k].x && ahi[k].y > blo.y && bhi.y > alo[k].y;
+                    if (ov[0] | ov[1] | ov[2] | ov[3]) {              // rare (a per cent of the partners): queue the survivors
+                        unsigned m = 0;
+#pragma unroll
+                        for (int k = 0; k < CROWD_R; ++k)
+                            if (ov[k] && (!rule || (d - k >= 1 && d - k <= dmax[k]))) m |= 1u << k;
+                        if (m) {
+                            unsigned slot = (unsigned)atomicAdd(&qn, __popc(m));
+                            for (; m; m &= m - 1, ++slot) {
+                                const int k = __ffs(m) - 1;
+                                if (slot < (unsigned)CROWD_QCAP) queue[slot] = ((unsigned)(s0 + k) << 16) | (unsigned)t;
+                                else if (iou_hits_cold(Box{slo[crowd_pos(s0 + k)].x, slo[crowd_pos(s0 + k)].y, shi[crowd_pos(s0 + k)].x, shi[crowd_pos(s0 + k)].y},
+                                                       Box{blo.x, blo.y, bhi.x, bhi.y}, thr, false)) found = 1;
+                            }
+                        }
+                    }
+                };
+                for (int d0 = 1; d0 <= D; d0 += CROWD_CHUNK) {
+                    const int d1 = min(d0 + CROWD_CHUNK - 1, D);
+                    if (active) {
+                        // Pass 1, branch-free: walk the chunk's partners and note in a bit mask which of them overlap ANY own
+                        // box (pairing rule not applied yet).  Pass 2 revisits the noted partners -- about one in sixty --
+                        // applies the rule and queues the surviving pairs.  Keeping the rare work out of the walk keeps the
+                        // warps converged: the walk is 2 shared loads + 16 fp64 compares per partner.
+                        unsigned pend = 0;
+                        int t = s0 + d0;
+                        while (t >= n) t -= n;
+                        const int t_first = t;
+#pragma unroll 4
+                        for (int d = d0; d <= d1; ++d) {
+                            const double2 blo = slo[crowd_pos(t)], bhi = shi[crowd_pos(t)];
+                            bool any = false;
+#pragma unroll
+                            for (int k = 0; k < CROWD_R; ++k)
+                                any |= ahi[k].x > blo.x && bhi.x > alo[k].x && ahi[k].y > blo.y && bhi.y > alo[k].y;
+                            pend |= any ? (1u << (d - d0)) : 0u;
+                            ++t; if (t >= n) t -= n;
+                        }
+                        for (; pend; pend &= pend - 1) {
+                            const int b = __ffs(pend) - 1;
+                            int tt = t_first + b;
+                            while (tt >= n) tt -= n;
+                            meet(tt, d0 + b, true);
+                        }
+                    }
+                    __syncthreads();
+                    const int nq = min(qn, CROWD_QCAP);
+                    for (int i = tid; i < nq; i += CROWD_THREADS) {
+                        const unsigned ent = queue[i];
+                        const int a = crowd_pos((int)(ent >> 16)), b = crowd_pos((int)(ent & 0xffffu));
+                        if (iou_hits(Box{slo[a].x, slo[a].y, shi[a].x, shi[a].y}, Box{slo[b].x, slo[b].y, shi[b].x, shi[b].y}, thr, false)) found = 1;
+                    }
+                    __syncthreads();
+                    const bool done = found != 0;
+                    if (tid == 0) qn = 0;
+                    __syncthreads();
+                    if (done) break;
+                }
+                if (found) break;                                      // uniform: read after the barrier above
+            }
+        } else if (want) {
+            // ---- generic form: NaN coordinates (exact selects in the reference's argument order), thr <= 0, or an image
+            //      too large for shared memory (direct loads)
+            auto load = [&](int j) {
+                if (in_smem) { const int pj = crowd_pos(j); return Box{slo[pj].x, slo[pj].y, shi[pj].x, shi[pj].y}; }
+                double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
+                return box_from_points(p1.x, p1.y, p2.x, p2.y);
+            };
+            for (int s = tid; s < n; s += CROWD_THREADS) {
+                const Box a = load(s);
                 const int dmax = half + ((even && s < n / 2) ? 1 : 0);
                 bool mine = false;
                 int t = s;
                 for (int d = 1; d <= dmax && !mine; ++d) {
                     ++t; if (t >= n) t -= n;
-                    if (cheap) {
-                        if (a.x2 > sx1[t] && sx2[t] > a.x1 && a.y2 > sy1[t] && sy2[t] > a.y1)
-                            mine = iou_hits(a, Box{sx1[t], sy1[t], sx2[t], sy2[t]}, thr, zero_hits);
-                    } else {
-                        Box b;
-                        if (in_smem) b = Box{sx1[t], sy1[t], sx2[t], sy2[t]};
-                        else { double2 p1 = ldg_f64x2(src + 2 * t), p2 = ldg_f64x2(src + 2 * t + 1); b = box_from_points(p1.x, p1.y, p2.x, p2.y); }
-                        mine = iou_hits(a, b, thr, zero_hits);
-                    }
+                    mine = iou_hits(a, load(t), thr, zero_hits);
                     if ((d & 31) == 0 && *(volatile int*)&found) break;
                 }
                 if (mine) found = 1;
@@ -221,7 +310,7 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) { high[img] = found ? 1 : 0; count[img] = n; }
+        if (tid == 0) { high[img] = found ? 1 : 0; count[img] = n; }
     }
 }
 
@@ -282,7 +371,7 @@ fused_warp_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict
     }
 }
 
-static inline int crowd_grid() { return NUM_SMS * 4; }
+static inline int crowd_grid() { return NUM_SMS * 5; }    // 41 KB of shared memory per block: five blocks per SM
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -291,7 +380,7 @@ static int env_int(const char* name, int dflt) {
 
 int launch_crowd(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid, int64_t min_boxes,
                  double thr, uint8_t* d_high, int32_t* d_count, void* ws, cudaStream_t s) {
-    iou_crowd_kernel<<<crowd_grid(), CTA_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, ws);
+    iou_crowd_kernel<<<crowd_grid(), CROWD_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, ws);
     return launch_check("iou_crowd_kernel");
 }
 
