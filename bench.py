@@ -208,13 +208,15 @@ def dropin_files_throughput(n_rows: int, device: int):
     filter), the same chain and file contract the reference arm runs."""
     import contextlib
     import io
-    from deal_yolo_daya_b200 import processor as P, synth
+    from deal_yolo_daya_b200 import processor as P, synth, tablecache
     os.environ["DYD_DEVICE"] = str(device)
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
         merged, ref = _write_sample(td, SEED, 0, n_rows)
         best, steps = float("inf"), None
         for _ in range(3):
+            tablecache.clear()                      # every pass starts cold: the first step really reads and parses merged.csv
+            P.PHASES.clear()
             with contextlib.redirect_stdout(io.StringIO()):
                 t0 = time.perf_counter()
                 P.deduplicate_csv_by_source(str(merged), str(td / "dedup.csv"))
@@ -228,7 +230,7 @@ def dropin_files_throughput(n_rows: int, device: int):
             if t4 - t0 < best:
                 best = t4 - t0
                 steps = {"dedup_s": t1 - t0, "ref_filter_s": t2 - t1, "replace_ptlist_s": t3 - t2, "iou_filter_s": t4 - t3,
-                         "phases": dict(getattr(P, "PHASES", {}))}
+                         "phases": {k: round(v, 4) for k, v in P.PHASES.items()}, "table_cache": dict(tablecache.STATS)}
         # steps 5.5 / 6 on what the chain left over (informational; not part of `value`)
         try:
             from deal_yolo_daya_b200 import labels as L
@@ -318,6 +320,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=IMAGES_PER_GPU, help="images per GPU")
     ap.add_argument("--url-sms", type=int, default=URL_SMS, help="SMs left to the URL stream by the fused kernel (0: one stream, no overlap)")
+    ap.add_argument("--coresident", action="store_true", help="URL chain on a second stream next to ALL 148 fused CTAs (its CTAs share the SMs "
+                    "with the persistent ones; needs a fused kernel built with room in shared memory, DESIGN.md §5.1)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = --steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -366,8 +370,8 @@ def main():
     buf = ops.FusedBuffers(n_img, n_poly, dev)
     fused_bytes = 16 * n_vert + 8 * (n_poly + 1) + 33 * n_poly + 8 * (n_img + 1) + 5 * n_img
     url_bytes = int(udata.numel() + rdata.numel()) + 16 * (n_img + n_ref) + 18 * n_img + 8 * n_ref + 17 * n_img   # K0 (both) + K4 + K5
-    overlap = args.url_sms > 0
-    max_ctas = 148 - args.url_sms if overlap else 0
+    overlap = args.url_sms > 0 or args.coresident
+    max_ctas = 148 - args.url_sms if args.url_sms > 0 else 0
     # The polygon stream has the higher priority: when the pre-pass ends its persistent CTAs are placed first and the URL
     # stream's kernels, released by the same event, fill the SMs that are left (and all of them once the fused kernel is done).
     s_poly = torch.cuda.Stream(dev, priority=-1) if overlap else torch.cuda.current_stream(dev)
@@ -639,7 +643,10 @@ def main():
             vd, dsteps = dropin_files_throughput(20_000, local)
             line["dropin_files"] = {"value": vd, "unit": UNIT, "rows": 20_000, "seconds": dsteps,
                                     "note": "this repo's processor.py step functions on CSV files, one process (native CSV reader/writer, native JSON "
-                                            "ingest/egress, CUDA kernels); value = rows / (dedup + reference filter + ptList->bbox + IoU filter seconds); "
+                                            "ingest/egress, CUDA kernels; every output file written synchronously; a step finds the frame the previous step "
+                                            "wrote in the process-level table cache instead of parsing the file again, the cache is emptied before every "
+                                            "pass so the first step reads merged.csv from disk); value = rows / (dedup + reference filter + ptList->bbox + "
+                                            "IoU filter seconds); seconds.phases = where the time went, summed over the four steps; "
                                             "seconds.labels = label remap + split of the rows that remain (not in value); "
                                             "the like-for-like figure against cpu_baseline (same files, same chain)"}
         except Exception as e:  # noqa: BLE001

@@ -79,6 +79,8 @@ PROTOTYPES = {
     "dyd_csv_measure": (_int, [_p, _i64, _p, _p, _p, _p, _i32]),
     "dyd_csv_fill": (_int, [_p, _i32, _p, _p, _p, _p, _i32]),
     "dyd_csv_close": (None, [_p]),
+    "dyd_csv_roundtrip_check": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _i32, _i32, _i32]),
+    "dyd_csv_write_file": (_int, [C.c_char_p, _i32, _p, _i64, _p, _p, _p, _p, _i32, _p, _i64, _int, _p]),
 }
 
 # libdyd_synth.so (include/dyd_synth.h): the synthetic-table generator of bench.py / the GPU tests, not product code
@@ -110,7 +112,7 @@ def load() -> C.CDLL:
                 raise DydError(
                     f"{LIB_PATH} is missing: the CUDA hot path is not built. "
                     "Run `python -m deal_yolo_daya_b200.build` (needs nvcc); there is no CPU fallback.")
-            lib = C.CDLL(str(LIB_PATH))
+            lib = C.CDLL(str(LIB_PATH), use_errno=True)
             for name, (res, args) in PROTOTYPES.items():
                 fn = getattr(lib, name)          # AttributeError = header / library out of sync
                 fn.restype = res

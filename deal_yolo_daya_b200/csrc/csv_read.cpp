@@ -19,6 +19,7 @@
 // scanned under both hypotheses for its first byte (outside / inside a quoted field) and the chunks
 // are stitched left to right, which fixes the true hypothesis of each.
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -386,3 +387,42 @@ extern "C" int dyd_csv_fill(void* handle, int32_t n_sel, const int32_t* cols, in
 }
 
 extern "C" void dyd_csv_close(void* handle) { delete (Csv*)handle; }
+
+// Would pd.read_csv give back this text column after DataFrame.to_csv wrote it?  (deal_yolo_daya_b200/tablecache.py keeps
+// the frame a step wrote so that the next step does not parse the file again; that is only sound for columns that survive
+// the round trip.)  Yes iff no valid cell is empty or one of pandas' NA strings (it would come back as NaN), no cell holds
+// a NUL byte, and every dtype-inference window of `window` rows holds a cell that is certainly text (the column then stays
+// a string column in every chunk).  valid = one byte per row (NULL: all valid); check_cells = 0 skips the per-cell part
+// for columns whose cells are known to come from this reader.  Returns 1 / 0, or DYD_E_ARG.
+extern "C" int dyd_csv_roundtrip_check(const int64_t* off, const uint8_t* data, const uint8_t* valid, int64_t n_rows, int64_t window,
+                                       const uint8_t* na_bytes, const int64_t* na_off, int32_t n_na, int32_t check_cells, int32_t threads) {
+    if (!off || n_rows < 0 || window <= 0 || (n_rows > 0 && !data && off[n_rows] > off[0]) || n_na < 0 || (n_na > 0 && (!na_bytes || !na_off))) return DYD_E_ARG;
+    if (n_rows == 0) return 0;
+    Csv c;
+    for (int32_t k = 0; k < n_na; ++k) c.na.emplace_back((const char*)na_bytes + na_off[k], (size_t)(na_off[k + 1] - na_off[k]));
+    const int64_t n_win = (n_rows + window - 1) / window;
+    int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<std::vector<uint8_t>> t_win((size_t)T);
+    std::atomic<int> bad{0};
+    parallel_ranges(n_rows, T, 4096, [&](int64_t ra, int64_t rb, int t) {
+        auto& win = t_win[(size_t)t];
+        win.assign((size_t)n_win, 0);
+        for (int64_t r = ra; r < rb; ++r) {
+            if (valid && !valid[r]) continue;
+            const uint8_t* s = data + off[r];
+            const int64_t len = off[r + 1] - off[r];
+            uint8_t& text = win[(size_t)(r / window)];
+            if (!text && certainly_text(s, len)) text = 1;
+            if (check_cells) {
+                if (c.is_na(s, len) || memchr(s, 0, (size_t)len)) { bad.store(1); return; }
+            } else if (text) {
+                r = std::min(rb, (r / window + 1) * window) - 1;        // this window is settled: on to the next one
+            }
+        }
+    });
+    std::vector<uint8_t> win_ok((size_t)n_win, 0);
+    for (const auto& win : t_win) for (size_t w = 0; w < win.size(); ++w) win_ok[w] |= win[w];
+    if (bad.load()) return 0;
+    for (int64_t w = 0; w < n_win; ++w) if (!win_ok[(size_t)w]) return 0;
+    return 1;
+}

@@ -16,8 +16,15 @@
 // Canonical form is verified, not assumed: separators, string escapes, and every number literal
 // must equal CPython's repr of its parsed value (shortest round-trip digits, repr's fixed/exponent
 // switch at 1e16 / 1e-4, ".0" suffix), computed here with std::to_chars / std::from_chars.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <charconv>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdint>
@@ -28,6 +35,7 @@
 #include <vector>
 
 #include "../../include/dyd.h"
+#include "simd_text.hpp"
 
 namespace {
 
@@ -923,7 +931,7 @@ inline size_t csv_field_len(const CsvCol& c, int64_t r) {
             if (c.valid && !c.valid[r]) return 0;
             const uint8_t* s = c.data + c.off[r]; const int64_t n = c.off[r + 1] - c.off[r];
             size_t q = 0; bool need = false;
-            for (int64_t i = 0; i < n; ++i) { const uint8_t ch = s[i]; if (ch == '"') { ++q; need = true; } else if (ch == ',' || ch == '\n' || ch == '\r') need = true; }
+            dyd_simd::csv_scan(s, n, q, need);
             return (size_t)n + (need ? q + 2 : 0);
         }
         case 1: {
@@ -936,16 +944,17 @@ inline size_t csv_field_len(const CsvCol& c, int64_t r) {
         default: return c.data[r] ? 4 : 5;
     }
 }
-inline char* csv_field_write(char* o, const CsvCol& c, int64_t r) {
+// `slack`: 64 writable bytes follow whatever this call produces (lets the quote-doubling copy use wide stores)
+inline char* csv_field_write(char* o, const CsvCol& c, int64_t r, bool slack = false) {
     switch (c.kind) {
         case 0: {
             if (c.valid && !c.valid[r]) return o;
             const uint8_t* s = c.data + c.off[r]; const int64_t n = c.off[r + 1] - c.off[r];
-            bool need = false;
-            for (int64_t i = 0; i < n && !need; ++i) { const uint8_t ch = s[i]; need = ch == '"' || ch == ',' || ch == '\n' || ch == '\r'; }
+            size_t q = 0; bool need = false;
+            dyd_simd::csv_scan(s, n, q, need);
             if (!need) { memcpy(o, s, (size_t)n); return o + n; }
             *o++ = '"';
-            for (int64_t i = 0; i < n; ++i) { if (s[i] == '"') *o++ = '"'; *o++ = (char)s[i]; }
+            o = q ? dyd_simd::csv_double_quotes(o, s, n, slack) : (char*)memcpy(o, s, (size_t)n) + n;
             *o++ = '"';
             return o;
         }
@@ -992,6 +1001,157 @@ extern "C" int dyd_csv_write(const int32_t* kinds, const int64_t* const* offs, c
             *o++ = '\n';
         }
     });
+    return 0;
+}
+
+// ---- to_csv straight into the file --------------------------------------------------------------------
+// DataFrame.to_csv(path, index=False) of selected rows without materialising either the selected frame or the
+// whole body: worker threads format blocks of rows into their own buffers (quote doubling with wide stores),
+// the calling thread writes finished blocks in order with write(2) -- formatting and the page-cache copy overlap,
+// and a buffered write to one file does not scale over threads anyway (the inode lock serialises it).
+namespace {
+
+struct OutBuf {
+    char* p = nullptr; size_t cap = 0, len = 0;
+    ~OutBuf() { free(p); }
+    inline char* room(size_t need) {                  // `need` bytes + 64 of slack behind them
+        if (cap - len < need + 64) {
+            size_t nc = std::max(cap * 2, len + need + 64 + (1u << 16));
+            char* np = (char*)realloc(p, nc);
+            if (!np) throw std::bad_alloc();
+            p = np; cap = nc;
+        }
+        return p + len;
+    }
+    void release() { free(p); p = nullptr; cap = len = 0; }
+};
+
+inline void csv_format_rows(const std::vector<CsvCol>& cols, const int64_t* rows, int64_t a, int64_t b, OutBuf& out) {
+    const int nc = (int)cols.size();
+    for (int64_t k = a; k < b; ++k) {
+        const int64_t r = rows ? rows[k] : k;
+        for (int c = 0; c < nc; ++c) {
+            const CsvCol& col = cols[(size_t)c];
+            size_t worst = 48;                                                   // number / bool + separator
+            if (col.kind == 0) worst = 2 * (size_t)(col.off[r + 1] - col.off[r]) + 4;
+            char* o = out.room(worst);
+            char* const o0 = o;
+            if (c) *o++ = ',';
+            o = csv_field_write(o, col, r, true);
+            out.len += (size_t)(o - o0);
+        }
+        *out.room(1) = '\n'; ++out.len;
+    }
+}
+
+inline bool write_all(int fd, const char* p, size_t n) {
+    while (n) {
+        const ssize_t w = ::write(fd, p, n);
+        if (w < 0) { if (errno == EINTR) continue; return false; }
+        p += w; n -= (size_t)w;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" int dyd_csv_write_file(const char* path, int32_t append, const uint8_t* prefix, int64_t prefix_len,
+                                  const int32_t* kinds, const int64_t* const* offs, const uint8_t* const* datas,
+                                  const uint8_t* const* valids, int32_t n_cols, const int64_t* rows, int64_t n_sel,
+                                  int n_threads, int64_t* bytes_written) {
+    if (!path || !kinds || !datas || n_cols < 2 || n_sel < 0 || prefix_len < 0 || (prefix_len > 0 && !prefix)) return DYD_E_ARG;
+    std::vector<CsvCol> cols((size_t)n_cols);
+    double str_bytes = 0;
+    for (int c = 0; c < n_cols; ++c) {
+        cols[(size_t)c] = CsvCol{kinds[c], offs ? offs[c] : nullptr, datas[c], valids ? valids[c] : nullptr};
+        if (kinds[c] < 0 || kinds[c] > 3 || !datas[c] || (kinds[c] == 0 && !cols[(size_t)c].off)) return DYD_E_ARG;
+    }
+    // rows per block: about 2 MB of output, estimated from a sample of the selected rows
+    {
+        const int64_t step = std::max<int64_t>(1, n_sel / 64);
+        int64_t cnt = 0;
+        for (int64_t k = 0; k < n_sel; k += step, ++cnt) {
+            const int64_t r = rows ? rows[k] : k;
+            for (const CsvCol& c : cols) str_bytes += c.kind == 0 ? (double)(c.off[r + 1] - c.off[r]) + 1 : 12;
+        }
+        if (cnt) str_bytes /= (double)cnt;
+    }
+    const int64_t block_rows = std::max<int64_t>(16, (int64_t)((2 << 20) / std::max(str_bytes, 1.0)));
+    const int64_t nb = (n_sel + block_rows - 1) / block_rows;
+    const int fd = ::open(path, O_WRONLY | O_CREAT | O_CLOEXEC | (append ? O_APPEND : O_TRUNC), 0666);
+    if (fd < 0) return DYD_E_IO;
+    int64_t total = 0;
+    bool ok = prefix_len == 0 || write_all(fd, (const char*)prefix, (size_t)prefix_len);
+    total += prefix_len;
+    int T = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::min<int64_t>(T, nb);
+    try {
+        if (ok && nb > 0 && T <= 1) {
+            OutBuf buf;
+            for (int64_t b = 0; b < nb && ok; ++b) {
+                buf.len = 0;
+                csv_format_rows(cols, rows, b * block_rows, std::min(n_sel, (b + 1) * block_rows), buf);
+                ok = write_all(fd, buf.p, buf.len);
+                total += (int64_t)buf.len;
+            }
+        } else if (ok && nb > 0) {
+            std::vector<OutBuf> slot((size_t)nb);
+            std::vector<uint8_t> ready((size_t)nb, 0);
+            std::mutex mu;
+            std::condition_variable cv;
+            std::atomic<int64_t> next{0};
+            int64_t written = 0;
+            bool failed = false;
+            const int64_t window = 2 * (int64_t)T + 2;                  // blocks in flight: bounds the memory held
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; ++t)
+                th.emplace_back([&] {
+                    for (;;) {
+                        const int64_t b = next.fetch_add(1);
+                        if (b >= nb) return;
+                        {
+                            std::unique_lock<std::mutex> lk(mu);
+                            cv.wait(lk, [&] { return failed || b < written + window; });
+                            if (failed) return;
+                        }
+                        bool good = true;
+                        try { csv_format_rows(cols, rows, b * block_rows, std::min(n_sel, (b + 1) * block_rows), slot[(size_t)b]); }
+                        catch (const std::bad_alloc&) { good = false; }
+                        {
+                            std::lock_guard<std::mutex> lk(mu);
+                            if (!good) failed = true;
+                            ready[(size_t)b] = 1;
+                        }
+                        cv.notify_all();
+                    }
+                });
+            for (int64_t b = 0; b < nb; ++b) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return failed || ready[(size_t)b]; });
+                    if (failed) break;
+                }
+                const bool w = write_all(fd, slot[(size_t)b].p, slot[(size_t)b].len);
+                total += (int64_t)slot[(size_t)b].len;
+                slot[(size_t)b].release();
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!w) failed = true;
+                    written = b + 1;
+                }
+                cv.notify_all();
+                if (!w) break;
+            }
+            for (auto& t : th) t.join();
+            ok = !failed;
+        }
+    } catch (const std::bad_alloc&) {
+        ok = false;
+    }
+    const int saved = errno;
+    if (::close(fd) != 0) ok = false;
+    if (!ok) { errno = saved; return DYD_E_IO; }
+    if (bytes_written) *bytes_written = total;
     return 0;
 }
 

@@ -267,8 +267,12 @@ def _csv_column(col):
         a = np.ascontiguousarray(col.to_numpy()).astype(np.uint8)
         return 3, None, a, None, a
     if isinstance(dt, pd.StringDtype) or dt == object:
+        pa_arr = getattr(getattr(col, "array", None), "_pa_array", None)          # Arrow-backed column: its own buffers
         try:
-            arr = pa.array(col, type=pa.large_string(), from_pandas=True)      # raises on non-str objects
+            if pa_arr is not None and str(pa_arr.type) == "large_string":
+                arr = pa_arr.chunk(0) if pa_arr.num_chunks == 1 else pa_arr.combine_chunks()
+            else:
+                arr = pa.array(col, type=pa.large_string(), from_pandas=True)  # raises on non-str objects
         except Exception:  # noqa: BLE001
             return None
         if arr.offset != 0:
@@ -282,41 +286,86 @@ def _csv_column(col):
     return None
 
 
-def to_csv(df, path, encoding="utf-8-sig", mode="w", header=True) -> None:
-    """``df.to_csv(path, index=False, encoding=encoding, mode=mode, header=header)``, byte-identical, body rows written
-    by csrc/ingest.cpp (multi-threaded).  Falls back to pandas for frames it does not cover.  In append mode no BOM is
-    written (Python's TextIOWrapper skips it when the file position is not 0, which is what pandas relies on)."""
+def to_csv(df, path, encoding="utf-8-sig", mode="w", header=True, rows=None) -> bool:
+    """``df.to_csv(path, index=False, encoding=encoding, mode=mode, header=header)``, byte-identical, written by
+    csrc/ingest.cpp straight into the file (worker threads format blocks of rows, the calling thread writes them in
+    order).  ``rows`` (int64 row positions, in output order) writes ``df.iloc[rows]`` without building that frame.
+    Falls back to pandas for frames the native writer does not cover; returns True when the native writer wrote the
+    file.  In append mode no BOM is written (Python's TextIOWrapper skips it when the file position is not 0, which is
+    what pandas relies on)."""
     import csv
     import io
     enc = (encoding or "utf-8").lower().replace("_", "-")
     cols = None
-    if enabled() and df.shape[1] >= 2 and enc in ("utf-8", "utf-8-sig", "utf8") and df.columns.is_unique:
+    if enabled() and df.shape[1] >= 2 and enc in ("utf-8", "utf-8-sig", "utf8") and df.columns.is_unique and isinstance(path, (str, os.PathLike)):
         cols = [_csv_column(df[c]) for c in df.columns]
         if any(c is None for c in cols):
             cols = None
     if cols is None:
-        df.to_csv(path, index=False, encoding=encoding, mode=mode, header=header)
-        return
+        (df if rows is None else df.iloc[rows]).to_csv(path, index=False, encoding=encoding, mode=mode, header=header)
+        return False
     lib = _lib.load()
-    n, nc = len(df), len(cols)
+    nc = len(cols)
     kinds = (C.c_int32 * nc)(*[c[0] for c in cols])
     offs = (C.c_void_p * nc)(*[c[1].ctypes.data if c[1] is not None else None for c in cols])
     datas = (C.c_void_p * nc)(*[c[2].ctypes.data for c in cols])
     valids = (C.c_void_p * nc)(*[c[3].ctypes.data if c[3] is not None else None for c in cols])
-    row_off = np.empty(n + 1, np.int64)
-    a = (kinds, offs, datas, valids, nc, n, _p(row_off))
-    _lib.check(lib.dyd_csv_write(*a, None, _threads()), "dyd_csv_write(size)")
-    body = np.empty(int(row_off[-1]), np.uint8)
-    _lib.check(lib.dyd_csv_write(*a, _p(body), _threads()), "dyd_csv_write(write)")
-    head = io.StringIO()
-    csv.writer(head, lineterminator="\n", quoting=csv.QUOTE_MINIMAL).writerow([str(c) for c in df.columns])
+    if rows is not None:
+        rows = np.ascontiguousarray(rows, np.int64)
+        if rows.size and (int(rows.min()) < 0 or int(rows.max()) >= len(df)):
+            raise IndexError("to_csv: row position out of range")
+    n_sel = len(df) if rows is None else int(rows.size)
     append = mode == "a"
-    with open(path, "ab" if append else "wb") as f:
-        if enc == "utf-8-sig" and not (append and f.tell() != 0):
-            f.write(b"\xef\xbb\xbf")
-        if header:
-            f.write(head.getvalue().encode("utf-8"))
-        f.write(body.tobytes() if body.size < (1 << 20) else memoryview(body))
+    prefix = b""
+    if enc == "utf-8-sig" and not (append and os.path.exists(path) and os.path.getsize(path) != 0):
+        prefix += b"\xef\xbb\xbf"
+    if header:
+        head = io.StringIO()
+        csv.writer(head, lineterminator="\n", quoting=csv.QUOTE_MINIMAL).writerow([str(c) for c in df.columns])
+        prefix += head.getvalue().encode("utf-8")
+    if mode not in ("w", "a"):
+        raise ValueError(f"to_csv: unsupported mode {mode!r}")
+    written = C.c_int64()
+    rc = lib.dyd_csv_write_file(os.fsencode(path), 1 if append else 0, prefix, len(prefix), kinds, offs, datas, valids, nc,
+                                _p(rows) if rows is not None else None, n_sel, _threads(), C.byref(written))
+    if rc == -4:                                   # DYD_E_IO: the same exception open() / write() would have raised
+        err = C.get_errno()
+        raise OSError(err, os.strerror(err) if err else "write failed", os.fspath(path))
+    _lib.check(rc, "dyd_csv_write_file")
+    return True
+
+
+def roundtrip_safe(df, check_cells=True) -> bool:
+    """True when ``pd.read_csv(file, encoding="utf-8-sig")`` of the file ``to_csv(df, file)`` writes returns `df` again
+    (RangeIndex assumed): what tablecache needs to know before it hands the written frame to the next step."""
+    import pandas as pd
+    n, nc = df.shape
+    if n == 0 or nc < 2 or not df.columns.is_unique or not _pandas_infers_arrow_str():
+        return False
+    for name in df.columns:
+        if not isinstance(name, str) or not name or name != name.strip() or any(ch in name for ch in '\r\n\0'):
+            return False
+    lib = _lib.load()
+    na_bytes, na_off, n_na = _na_table()
+    window = _buffer_lines(nc)
+    for name in df.columns:
+        col = df[name]
+        dt = col.dtype
+        if dt == np.float64 or dt == np.int64 or dt == np.bool_:
+            continue
+        if not (isinstance(dt, pd.StringDtype) and dt.storage == "pyarrow" and str(dt) == "str"):
+            return False
+        got = _csv_column(col)
+        if got is None or got[0] != 0:
+            return False
+        _, off, data, valid, _keep = got
+        rc = lib.dyd_csv_roundtrip_check(_p(off), _p(data), _p(valid), n, window, _p(na_bytes), _p(na_off), n_na,
+                                         1 if check_cells else 0, _threads())
+        if rc != 1:
+            if rc < 0:
+                _lib.check(rc, "dyd_csv_roundtrip_check")
+            return False
+    return True
 
 
 def yolo_label_texts(img_off, class_id, cxcywh, ok):

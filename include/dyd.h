@@ -42,6 +42,7 @@ extern "C" {
 #define DYD_E_ARG (-1)           /* null pointer / negative count / bad enum */
 #define DYD_E_ALIGN (-2)         /* pointer not aligned as required */
 #define DYD_E_WORKSPACE (-3)     /* workspace too small */
+#define DYD_E_IO (-4)            /* a file could not be opened / written (errno holds the reason) */
 
 int dyd_version(void);
 /* Number of CUDA kernels this library has launched in the calling process so far (statistic; bench.py reports the
@@ -320,6 +321,15 @@ int dyd_egress_ptlist(const dyd_ingest* h, const uint8_t* text, const int64_t* o
 int dyd_csv_write(const int32_t* kinds, const int64_t* const* offs, const uint8_t* const* datas,
                   const uint8_t* const* valids, int32_t n_cols, int64_t n_rows, int64_t* row_off,
                   uint8_t* out, int n_threads);
+/* DataFrame.to_csv(path, index=False) of the selected rows straight into the file (processor.py:158, 213, 310-313,
+ * 402-407): `prefix` = BOM + header line (written first), rows = int64[n_sel] row numbers in output order (NULL: rows
+ * 0..n_sel-1), columns as for dyd_csv_write.  Worker threads format blocks of rows while the calling thread writes the
+ * finished blocks in order; neither the selected frame nor the whole body is materialised.  append != 0 opens with
+ * O_APPEND instead of truncating.  Returns DYD_E_IO (errno set) when the file cannot be opened or written.        */
+int dyd_csv_write_file(const char* path, int32_t append, const uint8_t* prefix, int64_t prefix_len,
+                       const int32_t* kinds, const int64_t* const* offs, const uint8_t* const* datas,
+                       const uint8_t* const* valids, int32_t n_cols, const int64_t* rows, int64_t n_sel,
+                       int n_threads, int64_t* bytes_written);
 int dyd_py_float_repr(double v, char* out40);     /* CPython repr(float); used by the canonical-form check */
 
 /* YOLO label text of processor.py:1045-1052 from dyd_yolo_normalise's output: per image the lines
@@ -346,6 +356,11 @@ int dyd_csv_measure(void* handle, int64_t window, int64_t* col_bytes, int64_t* c
 int dyd_csv_fill(void* handle, int32_t n_sel, const int32_t* cols, int64_t* const* off_out, uint8_t* const* data_out,
                  uint8_t* const* bitmap_out, int32_t threads);
 void dyd_csv_close(void* handle);
+/* 1 iff pd.read_csv would return this text column (Arrow large_string buffers; valid = one byte per row or NULL)
+ * unchanged after DataFrame.to_csv wrote it: no valid cell empty / an NA string / holding NUL, and every window of
+ * `window` rows holds a cell that is certainly text.  check_cells = 0: only the window rule (cells known clean).   */
+int dyd_csv_roundtrip_check(const int64_t* off, const uint8_t* data, const uint8_t* valid, int64_t n_rows, int64_t window,
+                            const uint8_t* na_bytes, const int64_t* na_off, int32_t n_na, int32_t check_cells, int32_t threads);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,11 @@ class OracleKernels:
     def bbox(self, poly_off, xy):
         return oracle_c.bbox_fold(poly_off, xy)
 
+    def bbox_fused(self, img_off, poly_off, xy, min_boxes, thr):
+        pts, valid, arg = oracle_c.bbox_fold(poly_off, xy)
+        high, count = oracle_c.iou_filter(img_off, pts, valid, min_boxes, thr)
+        return pts, valid, arg, high, count
+
     def iou(self, img_off, pts, valid, min_boxes, thr):
         return oracle_c.iou_filter(img_off, pts, valid, min_boxes, thr)
 

@@ -18,6 +18,7 @@ n = int(args[0]) if args else 20000
 if "--oracle" in sys.argv:
     from tests.oracle_kernels import OracleKernels
     P.KERNELS = OracleKernels()
+cold = "--cold" in sys.argv
 if "--nocache" in sys.argv:
     os.environ["DYD_TABLE_CACHE"] = "0"
 sys.path.insert(0, str(ROOT))
@@ -31,8 +32,11 @@ with tempfile.TemporaryDirectory(dir=os.environ.get("DYD_TMP")) as td:
              ("ref_filter", lambda: P.remove_duplicates_between_csv(str(td / "dedup.csv"), str(ref), str(td / "filtered.csv"))),
              ("replace", lambda: P.process_csv_replace_ptlist(str(td / "filtered.csv"), str(td / "rep.csv"), str(td / "exc.csv"))),
              ("iou", lambda: P.filter_by_box_count_and_iou(str(td / "rep.csv"), str(td / "hi.csv"), str(td / "other.csv"), 2, 0.7))]
+    from deal_yolo_daya_b200 import tablecache
     for rep in range(3):
         tot = 0.0
+        if cold:
+            tablecache.clear()
         for name, fn in steps:
             if hasattr(P, "PHASES"):
                 P.PHASES.clear()
