@@ -79,6 +79,7 @@ PROTOTYPES = {
     "dyd_csv_measure": (_int, [_p, _i64, _p, _p, _p, _p, _i32]),
     "dyd_csv_fill": (_int, [_p, _i32, _p, _p, _p, _p, _i32]),
     "dyd_csv_close": (None, [_p]),
+    "dyd_read_file": (_int, [C.c_char_p, _p, _i64, _i32]),
     "dyd_csv_roundtrip_check": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _i32, _i32, _i32]),
     "dyd_csv_write_file": (_int, [C.c_char_p, _i32, _p, _i64, _p, _p, _p, _p, _i32, _p, _i64, _int, _p]),
 }

@@ -18,8 +18,14 @@
 // Parallel tokenisation: the input is cut at line feeds into one chunk per thread; a chunk is
 // scanned under both hypotheses for its first byte (outside / inside a quoted field) and the chunks
 // are stitched left to right, which fixes the true hypothesis of each.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
+#include <chrono>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -27,10 +33,11 @@
 #include <vector>
 
 #include "../../include/dyd.h"
+#include "simd_text.hpp"
 
 namespace {
 
-enum : int32_t { FLAG_UNSUPPORTED = 1, FLAG_EMPTY = 2 };
+enum : int32_t { FLAG_UNSUPPORTED = 1, FLAG_EMPTY = 2, FLAG_WIDE = 4 };
 
 template <typename F>
 void parallel_ranges(int64_t n, int n_threads, int64_t grain, F f) {
@@ -176,6 +183,10 @@ struct Csv {
     // measure()
     std::vector<std::vector<int64_t>> off;       // per column: n_rows + 1 offsets of the unescaped cell text
     std::vector<std::vector<uint8_t>> isna;      // per column: 1 = missing
+    // wide (AVX-512) tokenizer: end position and quote count of every field, row-major [n_rows * n_cols]
+    bool fast = false;
+    std::vector<int64_t> fend;
+    std::vector<uint32_t> fquotes;
 
     bool is_na(const uint8_t* s, int64_t len) const {
         if (len == 0) return true;
@@ -184,6 +195,259 @@ struct Csv {
         return false;
     }
 };
+
+
+// ---- wide tokenizer ------------------------------------------------------------------------------
+// Same records and fields as the state machine above for the files it accepts, found with 64-byte compares:
+// quote parity by carry-less multiplication (a byte is inside a quoted field iff an odd number of quotes precede or
+// sit on it), separators = commas / line feeds outside quotes.  That shortcut is only the pandas tokenizer when
+// quotes appear nowhere but around whole fields and doubled inside them, so the scan CHECKS that: every opening
+// quote follows a separator, the start of the data or a closing quote (""), every closing quote is followed by a
+// separator, a quote or the end of the data; no '\r', no NUL.  Any other file makes the scan give up and
+// dyd_csv_open falls back to the byte-wise scanner (which knows `ab"c` and `"ab"c`).
+#define DYD_TOK __attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi2,bmi2,popcnt,pclmul")))
+
+struct FastChunk {
+    int64_t quotes = 0;          // pass 1
+    bool bad = false;
+    std::vector<int64_t> sep;    // pass 2: separator positions, line feeds flagged in bit 62
+    std::vector<uint32_t> sepq;  // quotes between the previous separator (or the chunk start) and this one
+    uint32_t tail_quotes = 0;    // quotes after the last separator of the chunk
+    bool first_open_needs_prev = false;   // the chunk's first byte is an opening quote: the previous byte decides
+    bool last_close_needs_next = false;   // the chunk's last byte is a closing quote: the next byte decides
+};
+constexpr int64_t LF_FLAG = 1LL << 62;
+
+DYD_TOK inline uint64_t prefix_xor(uint64_t q) {
+    const __m128i r = _mm_clmulepi64_si128(_mm_set_epi64x(0, (long long)q), _mm_set1_epi8((char)0xFF), 0);
+    return (uint64_t)_mm_cvtsi128_si64(r);
+}
+
+DYD_TOK void fast_pass1(const uint8_t* d, int64_t a, int64_t b, FastChunk& out) {
+    const __m512i vq = _mm512_set1_epi8('"'), vr = _mm512_set1_epi8('\r'), vz = _mm512_setzero_si512();
+    int64_t q = 0; uint64_t bad = 0;
+    int64_t i = a;
+    for (; i + 64 <= b; i += 64) {
+        const __m512i v = _mm512_loadu_si512(d + i);
+        q += _mm_popcnt_u64(_mm512_cmpeq_epi8_mask(v, vq));
+        bad |= _mm512_cmpeq_epi8_mask(v, vr) | _mm512_cmpeq_epi8_mask(v, vz);
+    }
+    if (i < b) {
+        const __mmask64 m = (~0ULL) >> (64 - (b - i));
+        const __m512i v = _mm512_maskz_loadu_epi8(m, d + i);
+        q += _mm_popcnt_u64(_mm512_cmpeq_epi8_mask(v, vq));
+        bad |= (_mm512_cmpeq_epi8_mask(v, vr) | _mm512_cmpeq_epi8_mask(v, vz)) & m;
+    }
+    out.quotes = q; out.bad = bad != 0;
+}
+
+// [a, b): a is a multiple of 64 relative to `base` is NOT required; `inside` = state before byte a
+DYD_TOK void fast_pass2(const uint8_t* d, int64_t a, int64_t b, int64_t n, int64_t data_start, bool inside, FastChunk& out) {
+    const __m512i vq = _mm512_set1_epi8('"'), vc = _mm512_set1_epi8(','), vn = _mm512_set1_epi8('\n');
+    uint64_t carry = inside ? ~0ULL : 0ULL;       // parity before the block, spread over all bits
+    uint64_t prev_allow = 0;                      // bit 0: the byte before this block allows an opening quote
+    bool have_prev = false;                       // false for the first block of the chunk (decided by the caller)
+    uint64_t pend_close = 0;                      // the previous block's last byte was a closing quote
+    uint32_t run_q = 0;                           // quotes since the last separator
+    out.sep.reserve((size_t)((b - a) / 2048 + 16));
+    out.sepq.reserve((size_t)((b - a) / 2048 + 16));
+    for (int64_t i = a; i < b; i += 64) {
+        const int64_t len = std::min<int64_t>(64, b - i);
+        const __mmask64 m = len == 64 ? ~0ULL : ((~0ULL) >> (64 - len));
+        const __m512i v = _mm512_maskz_loadu_epi8(m, d + i);
+        const uint64_t q = _mm512_cmpeq_epi8_mask(v, vq) & m;
+        const uint64_t cm = _mm512_cmpeq_epi8_mask(v, vc) & m, lf = _mm512_cmpeq_epi8_mask(v, vn) & m;
+        const uint64_t P = prefix_xor(q) ^ carry;               // bit k: inside a quoted field after byte k
+        const uint64_t S = (cm | lf) & ~P;                       // separators
+        const uint64_t O = q & P, C = q & ~P;                   // opening / closing quotes
+        // a closing quote needs a separator, a quote or the end of the data behind it
+        const uint64_t follow = cm | lf | q;
+        if (pend_close && !(follow & 1)) { out.bad = true; return; }
+        uint64_t need_next = C & ~(follow >> 1);
+        pend_close = 0;
+        if (need_next & (1ULL << (len - 1))) { need_next &= ~(1ULL << (len - 1)); pend_close = 1; }
+        if (need_next) { out.bad = true; return; }
+        // an opening quote needs a separator, the start of the data or a closing quote in front of it
+        const uint64_t allow = ((S | C) << 1) | (have_prev ? prev_allow : 0);
+        uint64_t bad_open = O & ~allow;
+        if (!have_prev && (bad_open & 1)) {                    // first byte of the chunk: the caller checks the byte before it
+            bad_open &= ~1ULL;
+            if (i == data_start) { /* start of the data: allowed */ } else out.first_open_needs_prev = true;
+        }
+        if (bad_open) { out.bad = true; return; }
+        prev_allow = ((S | C) >> (len - 1)) & 1;
+        have_prev = true;
+        // separators out, with the quotes seen since the previous one
+        uint64_t s = S;
+        uint64_t done = 0;                                       // bits below the current separator
+        while (s) {
+            const int k = __builtin_ctzll(s);
+            const uint64_t below = (k == 63) ? ~0ULL : ((1ULL << (k + 1)) - 1);
+            run_q += (uint32_t)_mm_popcnt_u64(q & below & ~done);
+            out.sep.push_back((i + k) | (((lf >> k) & 1) ? LF_FLAG : 0));
+            out.sepq.push_back(run_q);
+            run_q = 0;
+            done = below;
+            s &= s - 1;
+        }
+        run_q += (uint32_t)_mm_popcnt_u64(q & ~done);
+        carry = (uint64_t)0 - ((P >> (len - 1)) & 1);
+    }
+    out.tail_quotes = run_q;
+    out.last_close_needs_next = pend_close != 0;
+    (void)n;
+}
+
+// unescaped copy of the inside of a quoted field: every second quote of a run of quotes is dropped
+DYD_TOK inline uint8_t* unescape_wide(uint8_t* o, const uint8_t* s, int64_t n) {
+    const __m512i vq = _mm512_set1_epi8('"');
+    const uint64_t EVEN = 0x5555555555555555ULL;
+    uint64_t pending = 0;                                        // the previous block ended on the first quote of a pair
+    for (int64_t i = 0; i < n; i += 64) {
+        const int64_t len = std::min<int64_t>(64, n - i);
+        const __mmask64 m = len == 64 ? ~0ULL : ((~0ULL) >> (64 - len));
+        const __m512i v = _mm512_maskz_loadu_epi8(m, s + i);
+        uint64_t q = _mm512_cmpeq_epi8_mask(v, vq) & m;
+        uint64_t drop = 0;
+        if (pending) { drop = q & 1; q &= ~1ULL; }
+        if (q) {
+            const uint64_t starts = q & ~(q << 1);
+            const uint64_t se = starts & EVEN;
+            const uint64_t re = q & ~(q + se);                   // runs that start on an even position
+            const uint64_t ro = q & ~re;
+            drop |= (re & ~EVEN) | (ro & EVEN);
+        }
+        const uint64_t last = 1ULL << (len - 1);
+        pending = ((q | (drop & 1)) & last) && !(drop & last);
+        const uint64_t keep = m & ~drop;
+        const int cnt = (int)_mm_popcnt_u64(keep);
+        _mm512_mask_storeu_epi8(o, cnt == 64 ? ~0ULL : ((1ULL << cnt) - 1), _mm512_maskz_compress_epi8(keep, v));
+        o += cnt;
+    }
+    return o;
+}
+
+inline uint8_t* unescape_scalar(uint8_t* o, const uint8_t* s, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) { *o++ = s[i]; if (s[i] == '"') ++i; }
+    return o;
+}
+
+DYD_TOK inline bool any_high_bit(const uint8_t* s, int64_t n) {
+    int64_t i = 0;
+    uint64_t acc = 0;
+    for (; i + 64 <= n; i += 64) acc |= _mm512_movepi8_mask(_mm512_loadu_si512(s + i));
+    if (i < n) acc |= _mm512_movepi8_mask(_mm512_maskz_loadu_epi8((~0ULL) >> (64 - (n - i)), s + i));
+    return acc != 0;
+}
+
+inline bool fast_any_high_bit(const uint8_t* s, int64_t n) { return any_high_bit(s, n); }
+inline void fast_unescape(uint8_t* o, const uint8_t* s, int64_t n) { unescape_wide(o, s, n); }
+
+// Fills header / rows / field table of `c`; false = not a file for this scanner (nothing in `c` is touched then).
+static double tnow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+bool fast_tokenize(Csv* c, int64_t start, int threads) {
+    const bool timing = getenv("DYD_CSV_TIMING") != nullptr;
+    double t0 = tnow();
+    auto lap = [&](const char* what) { if (timing) { double t1 = tnow(); fprintf(stderr, "  csv wide %-10s %.4f s\n", what, t1 - t0); t0 = t1; } };
+    if (!dyd_simd::wide() || !__builtin_cpu_supports("pclmul")) return false;
+    if (const char* e = getenv("DYD_CSV_WIDE")) if (*e == '0') return false;       // tests compare the two scanners
+    const uint8_t* d = c->d;
+    const int64_t n = c->n;
+    if (n - start < 1) return false;
+    int64_t chunk_min = 1 << 20;
+    if (const char* e = getenv("DYD_CSV_CHUNK_MIN")) chunk_min = std::max<int64_t>(1, atoll(e));   // tests: many chunks on small inputs
+    int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::min<int64_t>(T, std::max<int64_t>(1, (n - start) / chunk_min));
+    std::vector<int64_t> cut((size_t)T + 1);
+    for (int t = 0; t <= T; ++t) cut[(size_t)t] = t == T ? n : start + (n - start) / T * t;
+    std::vector<FastChunk> ch((size_t)T);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) th.emplace_back([&, t] { fast_pass1(d, cut[(size_t)t], cut[(size_t)t + 1], ch[(size_t)t]); });
+        for (auto& x : th) x.join();
+    }
+    lap("pass1");
+    std::vector<uint8_t> inside((size_t)T + 1, 0);
+    for (int t = 0; t < T; ++t) { if (ch[(size_t)t].bad) return false; inside[(size_t)t + 1] = inside[(size_t)t] ^ (uint8_t)(ch[(size_t)t].quotes & 1); }
+    if (inside[(size_t)T]) return false;                         // the data ends inside a quoted field
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] { fast_pass2(d, cut[(size_t)t], cut[(size_t)t + 1], n, start, inside[(size_t)t] != 0, ch[(size_t)t]); });
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < T; ++t) {
+        const FastChunk& k = ch[(size_t)t];
+        if (k.bad) return false;
+        const int64_t a = cut[(size_t)t], b = cut[(size_t)t + 1];
+        if (k.first_open_needs_prev) {                           // d[a] opens a field: d[a-1] must be a separator outside quotes or a closing quote
+            const uint8_t pb = d[a - 1];
+            const bool sep_before = (pb == ',' || pb == '\n') && !inside[(size_t)t];
+            const bool close_before = pb == '"' && !inside[(size_t)t];     // state before a is "outside": that quote closed a field
+            if (!sep_before && !close_before) return false;
+        }
+        if (k.last_close_needs_next && b < n) { const uint8_t nb = d[b]; if (nb != ',' && nb != '\n' && nb != '"') return false; }
+    }
+    lap("pass2");
+    // lines -> records
+    struct Line { int64_t begin, end; int64_t first_sep; int32_t n_sep; };          // n_sep = commas in the line
+    std::vector<int64_t> sep; std::vector<uint32_t> sepq;
+    {
+        size_t total = 0;
+        for (auto& k : ch) total += k.sep.size();
+        sep.reserve(total + 1); sepq.reserve(total + 1);
+        uint32_t carry_q = 0;
+        for (auto& k : ch) {
+            for (size_t i = 0; i < k.sep.size(); ++i) { sep.push_back(k.sep[i]); sepq.push_back(k.sepq[i] + (i == 0 ? carry_q : 0)); }
+            carry_q = k.sep.empty() ? carry_q + k.tail_quotes : k.tail_quotes;
+            std::vector<int64_t>().swap(k.sep); std::vector<uint32_t>().swap(k.sepq);
+        }
+        int64_t after_last_lf = start;                           // first byte behind the last record-terminating line feed
+        for (size_t i = sep.size(); i-- > 0;) if (sep[i] & LF_FLAG) { after_last_lf = (sep[i] & ~LF_FLAG) + 1; break; }
+        if (after_last_lf < n) { sep.push_back(n | LF_FLAG); sepq.push_back(carry_q); }   // the end of the data ends the last record
+    }
+    lap("merge");
+    std::vector<Line> lines;
+    {
+        int64_t begin = start; int64_t first = 0; int32_t commas = 0;
+        for (size_t i = 0; i < sep.size(); ++i) {
+            if (sep[i] & LF_FLAG) {
+                const int64_t e = sep[i] & ~LF_FLAG;
+                lines.push_back(Line{begin, e, first, commas});
+                begin = e + 1; first = (int64_t)i + 1; commas = 0;
+            } else ++commas;
+        }
+    }
+    int64_t hdr = -1;
+    std::vector<uint8_t> keep(lines.size());
+    for (size_t k = 0; k < lines.size(); ++k) {
+        keep[k] = lines[k].end > lines[k].begin && !is_blank(d + lines[k].begin, d + lines[k].end);
+        if (keep[k] && hdr < 0) hdr = (int64_t)k;
+    }
+    if (hdr < 0) return false;
+    const int32_t nc = lines[(size_t)hdr].n_sep + 1;
+    size_t nr = 0;
+    for (size_t k = (size_t)hdr + 1; k < lines.size(); ++k) if (keep[k]) { if (lines[k].n_sep + 1 != nc) return false; ++nr; }
+    if (nr == 0) return false;
+    c->header_begin = lines[(size_t)hdr].begin; c->header_end = lines[(size_t)hdr].end;
+    c->n_cols = nc;
+    c->row_begin.resize(nr); c->row_end.resize(nr);
+    c->fend.resize(nr * (size_t)nc); c->fquotes.resize(nr * (size_t)nc);
+    size_t r = 0;
+    for (size_t k = (size_t)hdr + 1; k < lines.size(); ++k) {
+        if (!keep[k]) continue;
+        c->row_begin[r] = lines[k].begin; c->row_end[r] = lines[k].end;
+        for (int32_t j = 0; j < nc; ++j) {
+            c->fend[r * (size_t)nc + (size_t)j] = sep[(size_t)lines[k].first_sep + (size_t)j] & ~LF_FLAG;
+            c->fquotes[r * (size_t)nc + (size_t)j] = sepq[(size_t)lines[k].first_sep + (size_t)j];
+        }
+        ++r;
+    }
+    lap("rows");
+    c->fast = true;
+    c->flags |= FLAG_WIDE;
+    return true;
+}
 
 }  // namespace
 
@@ -196,6 +460,8 @@ extern "C" int dyd_csv_open(const uint8_t* data, int64_t n, const uint8_t* na_by
     *handle = c;
     const uint8_t* d = data;
     int64_t start = (n >= 3 && d[0] == 0xEF && d[1] == 0xBB && d[2] == 0xBF) ? 3 : 0;
+
+    if (fast_tokenize(c, start, threads)) return 0;
 
     // ---- phase A: chunk boundaries right after a '\n', two hypotheses per chunk, stitch
     int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
@@ -292,6 +558,33 @@ extern "C" int dyd_csv_measure(void* handle, int64_t window, int64_t* col_bytes,
     // per thread: one flag per (column, window) and per column, merged after the join
     std::vector<std::vector<uint8_t>> t_text((size_t)T), t_bad((size_t)T);
     const uint8_t* d = c->d;
+    if (c->fast) {
+        parallel_ranges(nr, T, 2048, [&](int64_t ra, int64_t rb, int t) {
+            auto& text = t_text[t];
+            auto& bad = t_bad[t];
+            text.assign((size_t)(nc * n_win), 0);
+            bad.assign((size_t)nc, 0);
+            uint8_t small[32];
+            for (int64_t r = ra; r < rb; ++r) {
+                const int64_t w = r / window;
+                int64_t b = c->row_begin[r];
+                for (int f = 0; f < nc; ++f) {
+                    const int64_t e = c->fend[(size_t)r * nc + f];
+                    const uint32_t nq = c->fquotes[(size_t)r * nc + f];
+                    const uint8_t* s = d + b;
+                    int64_t len = e - b;
+                    if (nq) { ++s; len = len - 2 - (int64_t)(nq - 2) / 2; }       // quoted: drop the outer quotes, "" counts once
+                    c->off[f][r + 1] = len;
+                    const uint8_t* content = s;
+                    if (nq > 2 && len <= 9) { unescape_scalar(small, s, e - b - 2); content = small; }
+                    if (c->is_na(content, len)) c->isna[f][r] = 1;
+                    else if (certainly_text(content, len)) text[(size_t)(f * n_win + w)] = 1;
+                    if (len && fast_any_high_bit(d + b, e - b) && !utf8_ok(d + b, e - b)) bad[f] = 1;
+                    b = e + 1;
+                }
+            }
+        });
+    } else
     parallel_ranges(nr, T, 2048, [&](int64_t ra, int64_t rb, int t) {
         auto& text = t_text[t];
         auto& bad = t_bad[t];
@@ -356,6 +649,25 @@ extern "C" int dyd_csv_fill(void* handle, int32_t n_sel, const int32_t* cols, in
         memcpy(off_out[k], c->off[cols[k]].data(), sizeof(int64_t) * (size_t)(nr + 1));
     }
     const uint8_t* d = c->d;
+    if (c->fast) {
+        const int nc = c->n_cols;
+        parallel_ranges(nr, threads, 512, [&](int64_t a, int64_t b, int) {
+            for (int64_t r = a; r < b; ++r) {
+                int64_t fb = c->row_begin[r];
+                for (int f = 0; f < nc; ++f) {
+                    const int64_t e = c->fend[(size_t)r * nc + f];
+                    const int k = slot[f];
+                    if (k >= 0 && !c->isna[f][r]) {
+                        const uint32_t nq = c->fquotes[(size_t)r * nc + f];
+                        uint8_t* o = data_out[k] + c->off[f][r];
+                        if (nq <= 2) memcpy(o, d + fb + (nq ? 1 : 0), (size_t)(e - fb - (nq ? 2 : 0)));
+                        else fast_unescape(o, d + fb + 1, e - fb - 2);
+                    }
+                    fb = e + 1;
+                }
+            }
+        });
+    } else
     parallel_ranges(nr, threads, 2048, [&](int64_t a, int64_t b, int) {
         for (int64_t r = a; r < b; ++r) {
             int64_t pos = 0;
@@ -387,6 +699,26 @@ extern "C" int dyd_csv_fill(void* handle, int32_t n_sel, const int32_t* cols, in
 }
 
 extern "C" void dyd_csv_close(void* handle) { delete (Csv*)handle; }
+
+// The first n bytes of a file into `out`, several threads each reading its own range with pread(2) (the copy out of
+// the page cache and the first touch of `out` both spread over the cores).  DYD_E_IO (errno set) on failure / short file.
+extern "C" int dyd_read_file(const char* path, uint8_t* out, int64_t n, int32_t threads) {
+    if (!path || n < 0 || (n > 0 && !out)) return DYD_E_ARG;
+    const int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return DYD_E_IO;
+    std::atomic<int> err{0};
+    parallel_ranges(n, threads, 4 << 20, [&](int64_t a, int64_t b, int) {
+        while (a < b && !err.load(std::memory_order_relaxed)) {
+            const ssize_t r = ::pread(fd, out + a, (size_t)std::min<int64_t>(b - a, 8 << 20), (off_t)a);
+            if (r < 0) { if (errno == EINTR) continue; err.store(errno); return; }
+            if (r == 0) { err.store(EIO); return; }               // the file is shorter than the caller was told
+            a += r;
+        }
+    });
+    ::close(fd);
+    if (err.load()) { errno = err.load(); return DYD_E_IO; }
+    return 0;
+}
 
 // Would pd.read_csv give back this text column after DataFrame.to_csv wrote it?  (deal_yolo_daya_b200/tablecache.py keeps
 // the frame a step wrote so that the next step does not parse the file again; that is only sound for columns that survive

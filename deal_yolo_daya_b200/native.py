@@ -387,7 +387,7 @@ def yolo_label_texts(img_off, class_id, cxcywh, ok):
 # ------------------------------------------------------------------------------------------------
 # CSV ingest: pd.read_csv(path, encoding="utf-8[-sig]") with the text columns tokenised natively
 # ------------------------------------------------------------------------------------------------
-_READ_STATS = {"native": 0, "pandas": 0, "delegated_columns": 0}
+_READ_STATS = {"native": 0, "pandas": 0, "delegated_columns": 0, "wide": 0}
 _STR_PROBE = None
 
 
@@ -456,7 +456,11 @@ def read_csv(path, encoding="utf-8", _strict_native=False, _window_rows=None, **
         return fallback()
     import pyarrow as pa
     lib = _lib.load()
-    data = np.fromfile(path, dtype=np.uint8)
+    data = np.empty(size, np.uint8)
+    rc = lib.dyd_read_file(os.fsencode(path), _p(data), size, _threads())
+    if rc == -4:
+        return fallback()                      # unreadable / changed while reading: pandas raises what it raises
+    _lib.check(rc, "dyd_read_file")
     na_bytes, na_off, n_na = _na_table()
     h = C.c_void_p()
     _lib.check(lib.dyd_csv_open(_p(data), data.size, _p(na_bytes), _p(na_off), n_na, _threads(), C.byref(h)), "dyd_csv_open")
@@ -528,4 +532,5 @@ def read_csv(path, encoding="utf-8", _strict_native=False, _window_rows=None, **
     df = pd.DataFrame({i: columns[i] for i in range(n_cols)}, copy=False)
     df.columns = names
     _READ_STATS["native"] += 1
+    _READ_STATS["wide"] += 1 if fl.value & 4 else 0
     return df

@@ -348,6 +348,8 @@ int dyd_yolo_format(const int64_t* img_off, const int32_t* class_id, const doubl
 int dyd_csv_open(const uint8_t* data, int64_t n, const uint8_t* na_bytes, const int64_t* na_off, int32_t n_na,
                  int32_t threads, void** handle);
 int dyd_csv_info(void* handle, int64_t* n_rows, int32_t* n_cols, int64_t* header_begin, int64_t* header_end, int32_t* flags);
+/* flags: bit 0 = outside the restated dialect (pandas reads the file), bit 1 = no record at all, bit 2 = the file was
+ * tokenised by the AVX-512 scanner (statistic).                                                             */
 /* window = rows per dtype-inference chunk of pandas' low-memory reader.  Per column: unescaped bytes,
  * missing cells, 1 iff every window holds a cell that is certainly text, 1 iff valid UTF-8.         */
 int dyd_csv_measure(void* handle, int64_t window, int64_t* col_bytes, int64_t* col_nulls, uint8_t* col_text,
@@ -356,6 +358,8 @@ int dyd_csv_measure(void* handle, int64_t window, int64_t* col_bytes, int64_t* c
 int dyd_csv_fill(void* handle, int32_t n_sel, const int32_t* cols, int64_t* const* off_out, uint8_t* const* data_out,
                  uint8_t* const* bitmap_out, int32_t threads);
 void dyd_csv_close(void* handle);
+/* Reads the first n bytes of the file into h_out with several threads (pread); DYD_E_IO + errno on failure.     */
+int dyd_read_file(const char* path, uint8_t* h_out, int64_t n, int32_t threads);
 /* 1 iff pd.read_csv would return this text column (Arrow large_string buffers; valid = one byte per row or NULL)
  * unchanged after DataFrame.to_csv wrote it: no valid cell empty / an NA string / holding NUL, and every window of
  * `window` rows holds a cell that is certainly text.  check_cells = 0: only the window rule (cells known clean).   */

@@ -191,3 +191,58 @@ def test_parallel_stitch_with_quoted_newlines(tmp_path, monkeypatch):
     text = "\n".join(rows) + "\n"
     assert len(text) > 8 * (1 << 20)
     assert _both(tmp_path, text) is True
+
+
+def test_wide_scanner_equals_bytewise_scanner_and_pandas(tmp_path, monkeypatch):
+    """The AVX-512 tokenizer (quote parity by carry-less multiply) against the byte-wise state machine and against pandas on
+    texts long enough to cross many 64-byte blocks and several chunks, with quotes, doubled quotes, separators and line feeds
+    at every alignment; texts it must decline (quotes inside unquoted fields, text behind a closing quote, CR) included."""
+    from deal_yolo_daya_b200 import simd_available
+    if not simd_available():
+        pytest.skip("host CPU without AVX-512 VBMI2: only the byte-wise scanner exists here")
+    rng = random.Random(77)
+    pieces = ["a", "bb", "http://x/1.jpg", '{"k": [1, 2.5], "name": "v"}', "标注", "é", "x" * 61, "y" * 64, "z" * 130, '"', '""', '"""', ",", "\n", " ",
+              '{"objects": [{"name": "' + "q" * 50 + '", "p": [{"x": 1.5, "y": 2}]}]}']
+    wide_before = native._READ_STATS["wide"]
+    took_wide = declined = 0
+    for it in range(300):
+        ncols = rng.randint(2, 4)
+        rows = rng.randint(1, 30)
+        odd_file = rng.random() < 0.3               # some files hold cells the wide scanner must decline
+        lines = [",".join(f"c{j}" for j in range(ncols))]
+        for _ in range(rows):
+            cells = []
+            for _ in range(ncols):
+                cell = "".join(rng.choice(pieces) for _ in range(rng.randint(0, 5)))
+                mode = rng.random() if odd_file else 0.0
+                if mode < 0.93:                         # what csv.writer would write
+                    if any(ch in cell for ch in ',"\n'):
+                        cell = '"' + cell.replace('"', '""') + '"'
+                    elif rng.random() < 0.2:
+                        cell = '"' + cell + '"'
+                elif mode < 0.96:
+                    cell = cell.replace(",", ";").replace("\n", " ")           # raw: quotes inside an unquoted field
+                else:
+                    cell = '"' + cell.replace('"', '""') + '"' + rng.choice(["tail", " ", ""])   # text behind the closing quote
+                cells.append(cell)
+            lines.append(",".join(cells))
+        text = "\n".join(lines) + ("\n" if rng.random() < 0.8 else "")
+        if rng.random() < 0.05:
+            text = text.replace("\n", "\r\n")
+        if rng.random() < 0.2:
+            text = "﻿" + text
+        monkeypatch.setenv("DYD_CSV_CHUNK_MIN", str(rng.choice([1, 7, 64, 100, 1000, 1 << 20])))
+        before = native._READ_STATS["wide"]
+        monkeypatch.setenv("DYD_CSV_WIDE", "1")
+        took = _both(tmp_path, text, name="w.csv")
+        was_wide = native._READ_STATS["wide"] > before
+        a = native.read_csv(str(tmp_path / "w.csv"), encoding="utf-8-sig") if took else None
+        monkeypatch.setenv("DYD_CSV_WIDE", "0")
+        took2 = _both(tmp_path, text, name="w.csv")
+        if took and took2:
+            b = native.read_csv(str(tmp_path / "w.csv"), encoding="utf-8-sig")
+            pd.testing.assert_frame_equal(a, b)
+        took_wide += was_wide
+        declined += (took2 and not was_wide)
+    assert took_wide > 150 and declined > 20, (took_wide, declined)
+    assert native._READ_STATS["wide"] > wide_before
