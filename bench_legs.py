@@ -110,12 +110,12 @@ def c5_leg(dev, rank, world, t, peak, seed=42, ratios=(0.8, 0.1, 0.1)):
     s_perm = time.perf_counter() - a
     n_train = torch.tensor([int(x * ratios[0]) for x in n_c], dtype=torch.int64, device=dev)
     n_val = torch.tensor([int(x * ratios[1]) for x in n_c], dtype=torch.int64, device=dev)
-    ms_assign = _time(lambda: st.__setitem__("sp", ops.split_assign(cat_off_g, perm, n_train, n_val)), 3)
-    split_g, pos_g = st["sp"]
-    # own rows of category c sit at global positions base[c] .. base[c] + local_counts[c]
-    own = torch.cat([torch.arange(int(base[c].item()), int(base[c].item()) + int(local_counts[c].item()), device=dev) for c in range(n_cat)])
+    # own rows of category c are rows base[c] - cat_off_g[c] .. of that category; every rank sweeps the global permutation once
+    # and keeps the answers of its own rows (dyd_split_assign_range)
+    own_lo = (base - cat_off_g[:-1]).contiguous()
+    ms_assign = _time(lambda: st.__setitem__("sp", ops.split_assign_range(cat_off_g, perm, n_train, n_val, own_lo, local_counts, st["co"][:-1].contiguous())), 3)
+    split_own, pos_own = st["sp"]
     own_cat = st["ec"].long()
-    split_own, pos_own = split_g[own], pos_g[own]
     # ---- verification
     checks = {}
     hist = torch.zeros(n_cat * 3, dtype=torch.int64, device=dev)

@@ -38,6 +38,8 @@ PROTOTYPES = {
     "dyd_shard_bucket_p2p": (_int, [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p]),
     "dyd_shard_unpack_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _i32, _p]),
     "dyd_shard_pack_reply_p2p": (_int, [_p, _p, _p, _i64, _i64, _i32, _p, _i32, _i32, _p]),
+    "dyd_shard_pack_reply2_p2p": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _i32, _p]),
+    "dyd_shard_unpack2_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
     "dyd_shard_pack_reply": (_int, [_p, _p, _p, _i64, _p, _i32, _p]),
     "dyd_shard_unpack": (_int, [_p, _i64, _i64, _i64, _p, _p, _i32, _p]),
     "dyd_antijoin_records": (_int, [_p, _i64, _p, _i64, _p, _p, _p, _sz, _i32, _p]),
@@ -54,6 +56,7 @@ PROTOTYPES = {
     "dyd_split_count": (_int, [_p, _i64, _p, _p, _i32, _i32, _p, _p, _sz, _p]),
     "dyd_split_fill": (_int, [_p, _i64, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "dyd_split_assign": (_int, [_p, _i32, _p, _i64, _p, _p, _p, _p, _p]),
+    "dyd_split_assign_range": (_int, [_p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dyd_yolo_normalise": (_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
     "dyd_bbox_iou_host": (_int, [_p, _p, _p, _i64, _i64, _f64, _p, _p, _p, _p, _p, _i64]),
     "dyd_dedup_host": (_int, [_p, _p, _p, _i64, _int, _p, _p]),

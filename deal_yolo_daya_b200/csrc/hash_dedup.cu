@@ -467,6 +467,93 @@ shard_unpack_p2p_kernel(const long long* __restrict__ reply, const unsigned* __r
     rep[row] = (mode == 1 && k) ? -1 : (v & ((1LL << 62) - 1));
 }
 
+// Staged form of the same scatter (world <= P2P_MAX_WORLD): a block takes ST_PER_BLOCK records, counting-sorts them by
+// owner in shared memory, claims one run of slots per owner and writes each run with consecutive threads -> consecutive
+// 16-byte stores, i.e. full-width NVLink packets instead of the 16 .. 64-byte pieces of the per-thread form.
+constexpr int ST_THREADS = 512;
+constexpr int ST_PER_THREAD = 4;
+constexpr int ST_PER_BLOCK = ST_THREADS * ST_PER_THREAD;
+__global__ void __launch_bounds__(ST_THREADS)
+shard_bucket_staged_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t row_base,
+                           int64_t n, int world, int me, int64_t cap, long long* const* __restrict__ peer_records,
+                           unsigned* __restrict__ sent_row, unsigned long long* cursors, int* overflow) {
+    __shared__ unsigned long long skey[ST_PER_BLOCK];
+    __shared__ unsigned srow[ST_PER_BLOCK];
+    __shared__ unsigned scnt[P2P_MAX_WORLD], soff[P2P_MAX_WORLD + 1];
+    __shared__ unsigned long long sbase[P2P_MAX_WORLD];
+    const int64_t r0 = blockIdx.x * (int64_t)ST_PER_BLOCK;
+    if (threadIdx.x < world) scnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long key[ST_PER_THREAD];
+    int own[ST_PER_THREAD];
+    unsigned rank[ST_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < ST_PER_THREAD; ++u) {
+        const int64_t r = r0 + u * ST_THREADS + threadIdx.x;
+        const bool live = r < n && (null == nullptr || null[r] == 0);
+        key[u] = live ? keys[r] : 0ULL;
+        own[u] = live ? owner_of(key[u], world) : -1;
+        rank[u] = live ? atomicAdd(&scnt[own[u]], 1u) : 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned acc = 0; for (int o = 0; o < world; ++o) { soff[o] = acc; acc += scnt[o]; } soff[world] = acc; }
+    if (threadIdx.x < world && scnt[threadIdx.x]) sbase[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long)scnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < ST_PER_THREAD; ++u) {
+        if (own[u] < 0) continue;
+        const unsigned at = soff[own[u]] + rank[u];
+        skey[at] = key[u];
+        srow[at] = (unsigned)(u * ST_THREADS + threadIdx.x);                 // row inside the block
+    }
+    __syncthreads();
+    const unsigned total = soff[world];
+    for (unsigned p = threadIdx.x; p < total; p += ST_THREADS) {
+        int o = 0;
+        while (soff[o + 1] <= p) ++o;                                     // world <= 64: a short walk, the same for neighbouring threads
+        const unsigned long long slot = sbase[o] + (p - soff[o]);
+        if (slot >= (unsigned long long)cap) { *overflow = 1; continue; }
+        const int64_t r = r0 + srow[p];
+        longlong2* rec = reinterpret_cast<longlong2*>(peer_records[o]) + ((int64_t)me * cap + (int64_t)slot);
+        *rec = make_longlong2((long long)skey[p], row_base + r);
+        if (sent_row != nullptr) sent_row[(int64_t)o * cap + (int64_t)slot] = (unsigned)r;
+    }
+}
+
+// Both answers of the joint exchange (sharding.UrlFilterExchange) in one 16-byte store per record: word 0 = dedup
+// (rep | keep << 62), word 1 = anti-join (kept ? 1 << 62 : first matching reference row); padding records answer (-1, -1).
+__global__ void __launch_bounds__(HT_THREADS)
+shard_pack_reply2_p2p_kernel(long long* __restrict__ records, const uint8_t* __restrict__ keep_d, const int64_t* __restrict__ rep_d,
+                             const uint8_t* __restrict__ keep_a, const int64_t* __restrict__ rep_a, int64_t m, int64_t cap, int me,
+                             long long* const* __restrict__ peer_reply, bool reset) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= m) return;
+    const int src = (int)(r / cap);
+    const int64_t slot = r - (int64_t)src * cap;
+    const long long id = records[2 * r + 1];
+    if (reset && id >= 0) records[2 * r + 1] = -1;
+    reinterpret_cast<longlong2*>(peer_reply[src])[(int64_t)me * cap + slot] =
+        make_longlong2(reply_word(0, id, keep_d[r], rep_d[r]), reply_word(1, id, keep_a[r], rep_a[r]));
+}
+__global__ void __launch_bounds__(HT_THREADS)
+shard_unpack2_p2p_kernel(const longlong2* __restrict__ reply, const unsigned* __restrict__ sent_row,
+                         const unsigned long long* __restrict__ cursors, int world, int64_t cap, int64_t n,
+                         uint8_t* __restrict__ keep_d, int64_t* __restrict__ rep_d, uint8_t* __restrict__ keep_a, int64_t* __restrict__ rep_a) {
+    const int64_t t = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (t >= (int64_t)world * cap) return;
+    const int own = (int)(t / cap);
+    const int64_t slot = t - (int64_t)own * cap;
+    if ((unsigned long long)slot >= cursors[own]) return;           // never filled
+    const longlong2 v = reply[t];
+    const int64_t row = sent_row[t];
+    if (v.x < 0 || row >= n) return;
+    keep_d[row] = (uint8_t)((v.x >> 62) & 1);
+    rep_d[row] = v.x & ((1LL << 62) - 1);
+    const uint8_t k = (uint8_t)((v.y >> 62) & 1);
+    keep_a[row] = k;
+    rep_a[row] = k ? -1 : (v.y & ((1LL << 62) - 1));
+}
+
 // owner side: (id, rep | keep << 62) per received record
 __global__ void __launch_bounds__(HT_THREADS)
 shard_pack_reply_kernel(const long long* __restrict__ records, const uint8_t* __restrict__ keep,
@@ -656,6 +743,13 @@ extern "C" int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_nul
     DYD_CUDA(cudaMemsetAsync(d_cursors, 0, sizeof(uint64_t) * world, s));
     DYD_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
     if (n == 0) return 0;
+    const char* e = getenv("DYD_SCATTER_STAGED");
+    if (world <= P2P_MAX_WORLD && !(e && atoi(e) == 0)) {
+        shard_bucket_staged_kernel<<<(unsigned)((n + ST_PER_BLOCK - 1) / ST_PER_BLOCK), ST_THREADS, 0, s>>>(
+            reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n, world, my_rank, cap,
+            reinterpret_cast<long long* const*>(d_peer_records), d_sent_row, reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
+        return launch_check("shard_bucket_staged_kernel");
+    }
     shard_bucket_p2p_kernel<<<grid_for(n), HT_THREADS, url_pad(), s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
                                                               world, my_rank, cap, reinterpret_cast<long long* const*>(d_peer_records),
                                                               d_sent_row, reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
@@ -681,6 +775,31 @@ extern "C" int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_se
     shard_unpack_p2p_kernel<<<grid_for((int64_t)world * cap), HT_THREADS, url_pad(), as_stream(stream)>>>(
         reinterpret_cast<const long long*>(d_reply), d_sent_row, reinterpret_cast<const unsigned long long*>(d_cursors), world, cap, n, d_keep, d_rep, mode);
     return launch_check("shard_unpack_p2p_kernel");
+}
+
+extern "C" int dyd_shard_pack_reply2_p2p(int64_t* d_records, const uint8_t* d_keep_dedup, const int64_t* d_rep_dedup,
+                                         const uint8_t* d_keep_anti, const int64_t* d_ref_row, int64_t m, int64_t cap, int32_t my_rank,
+                                         int64_t* const* d_peer_reply2, int32_t reset_records, void* stream) {
+    DYD_REQUIRE(m >= 0 && cap > 0 && my_rank >= 0 && m % cap == 0, DYD_E_ARG, "bad arguments");
+    if (m == 0) return 0;
+    DYD_REQUIRE(d_records && d_keep_dedup && d_rep_dedup && d_keep_anti && d_ref_row && d_peer_reply2, DYD_E_ARG, "null pointer");
+    shard_pack_reply2_p2p_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<long long*>(d_records), d_keep_dedup, d_rep_dedup,
+                                                                                   d_keep_anti, d_ref_row, m, cap, my_rank,
+                                                                                   reinterpret_cast<long long* const*>(d_peer_reply2), reset_records != 0);
+    return launch_check("shard_pack_reply2_p2p_kernel");
+}
+
+extern "C" int dyd_shard_unpack2_p2p(const int64_t* d_reply2, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
+                                     int64_t cap, int64_t n, uint8_t* d_keep_dedup, int64_t* d_rep_dedup, uint8_t* d_keep_anti,
+                                     int64_t* d_ref_row, void* stream) {
+    DYD_REQUIRE(world >= 1 && cap >= 0 && n >= 0, DYD_E_ARG, "bad arguments");
+    if (cap == 0 || n == 0) return 0;
+    DYD_REQUIRE(d_reply2 && d_sent_row && d_cursors && d_keep_dedup && d_rep_dedup && d_keep_anti && d_ref_row, DYD_E_ARG, "null pointer");
+    DYD_REQUIRE(((uintptr_t)d_reply2 & 15) == 0, DYD_E_ALIGN, "reply buffer must be 16-byte aligned");
+    shard_unpack2_p2p_kernel<<<grid_for((int64_t)world * cap), HT_THREADS, 0, as_stream(stream)>>>(
+        reinterpret_cast<const longlong2*>(d_reply2), d_sent_row, reinterpret_cast<const unsigned long long*>(d_cursors), world, cap, n,
+        d_keep_dedup, d_rep_dedup, d_keep_anti, d_ref_row);
+    return launch_check("shard_unpack2_p2p_kernel");
 }
 
 extern "C" int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,

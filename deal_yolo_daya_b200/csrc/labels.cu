@@ -276,6 +276,37 @@ split_assign_kernel(const int64_t* __restrict__ cat_off, int32_t n_cat, const in
     pos[base + j] = rp;
 }
 
+// Sharded form: the permutation covers the GLOBAL category-grouped table, this rank owns, per category c, the rows
+// own_lo[c] .. own_lo[c] + own_cnt[c] of the category (sharding.split_category_bases) and keeps them at local_off[c] .. in
+// its own arrays.  Every rank sweeps the whole permutation (coalesced 16-byte loads) and keeps what lands in its ranges.
+__global__ void __launch_bounds__(LB_THREADS)
+split_assign_range_kernel(const int64_t* __restrict__ cat_off, int32_t n_cat, const int64_t* __restrict__ perm, int64_t n_exp,
+                          const int64_t* __restrict__ n_train, const int64_t* __restrict__ n_val,
+                          const int64_t* __restrict__ own_lo, const int64_t* __restrict__ own_cnt, const int64_t* __restrict__ local_off,
+                          uint8_t* __restrict__ split, int64_t* __restrict__ pos) {
+    const int64_t r0 = (blockIdx.x * (int64_t)LB_THREADS + threadIdx.x) * 2;   // two shuffled positions per thread
+    if (r0 >= n_exp) return;
+    long long j2[2];
+    if (r0 + 1 < n_exp) { const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(perm + r0)); j2[0] = v.x; j2[1] = v.y; }
+    else { j2[0] = perm[r0]; j2[1] = -1; }
+    int lo = 0, hi = n_cat;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (cat_off[mid] <= r0) lo = mid; else hi = mid; }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int64_t r = r0 + u;
+        if (r >= n_exp) break;
+        while (lo + 1 < n_cat && cat_off[lo + 1] <= r) ++lo;             // the second position may start the next category
+        const int64_t rp = r - cat_off[lo];
+        const int64_t k = j2[u] - own_lo[lo];
+        if (k >= 0 && k < own_cnt[lo]) {
+            const int64_t ntr = n_train[lo], nva = n_val[lo];
+            const int64_t at = local_off[lo] + k;
+            split[at] = rp < ntr ? 0 : (rp < ntr + nva ? 1 : 2);
+            pos[at] = rp;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- YOLO normalisation
 // processor.py:1045-1052.  A block owns IMG_PER_CTA consecutive images = one contiguous object range:
 // the image offsets and sizes go to shared memory, then one thread per object streams its corner
@@ -446,6 +477,20 @@ extern "C" int dyd_split_assign(const int64_t* d_cat_off, int32_t n_cat, const i
     const int64_t grid = (n_exp + LB_THREADS - 1) / LB_THREADS;
     split_assign_kernel<<<(unsigned)grid, LB_THREADS, 0, as_stream(stream)>>>(d_cat_off, n_cat, d_perm, n_exp, d_n_train, d_n_val, d_split, d_pos);
     return launch_check("split_assign_kernel");
+}
+
+extern "C" int dyd_split_assign_range(const int64_t* d_cat_off, int32_t n_cat, const int64_t* d_perm, int64_t n_exp,
+                                      const int64_t* d_n_train, const int64_t* d_n_val, const int64_t* d_own_lo,
+                                      const int64_t* d_own_cnt, const int64_t* d_local_off, uint8_t* d_split, int64_t* d_pos, void* stream) {
+    DYD_REQUIRE(n_exp >= 0 && n_cat >= 0, DYD_E_ARG, "negative count");
+    if (n_exp == 0) return 0;
+    DYD_REQUIRE(d_cat_off && d_perm && d_n_train && d_n_val && d_own_lo && d_own_cnt && d_local_off && d_split && d_pos && n_cat > 0, DYD_E_ARG,
+                "null pointer");
+    DYD_REQUIRE(((uintptr_t)d_perm & 15) == 0, DYD_E_ALIGN, "perm must be 16-byte aligned");
+    const int64_t grid = ((n_exp + 1) / 2 + LB_THREADS - 1) / LB_THREADS;
+    split_assign_range_kernel<<<(unsigned)grid, LB_THREADS, 0, as_stream(stream)>>>(d_cat_off, n_cat, d_perm, n_exp, d_n_train, d_n_val, d_own_lo,
+                                                                                   d_own_cnt, d_local_off, d_split, d_pos);
+    return launch_check("split_assign_range_kernel");
 }
 
 extern "C" int dyd_yolo_normalise(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid,

@@ -279,6 +279,25 @@ def split_assign(cat_off, perm, n_train, n_val):
     return split, pos
 
 
+def split_assign_range(cat_off, perm, n_train, n_val, own_lo, own_cnt, local_off):
+    """Sharded split_assign: split id + shuffled position of THIS rank's expanded rows (category c: rows own_lo[c] ..
+    own_lo[c] + own_cnt[c] of the global category, kept at local_off[c] .. in the outputs) from the global permutation."""
+    _need_cuda(cat_off, perm, n_train, n_val, own_lo, own_cnt, local_off)
+    lib = _lib.load()
+    dev = cat_off.device
+    n_cat = cat_off.numel() - 1
+    n_local = int((own_cnt.sum()).item())
+    split = torch.empty(n_local, dtype=torch.uint8, device=dev)
+    pos = torch.empty(n_local, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_split_assign_range(_ptr(_chk(cat_off, torch.int64, "cat_off")), n_cat, _ptr(_chk(perm, torch.int64, "perm")), perm.numel(),
+                                              _ptr(_chk(n_train, torch.int64, "n_train")), _ptr(_chk(n_val, torch.int64, "n_val")),
+                                              _ptr(_chk(own_lo, torch.int64, "own_lo")), _ptr(_chk(own_cnt, torch.int64, "own_cnt")),
+                                              _ptr(_chk(local_off, torch.int64, "local_off")), _ptr(split), _ptr(pos), _stream(dev)),
+                   "dyd_split_assign_range")
+    return split, pos
+
+
 def yolo_normalise(img_off, pts, valid, img_wh):
     """cx, cy, w, h per box (processor.py:1045-1052).  Returns (cxcywh float64[4*n_box], ok uint8)."""
     _need_cuda(img_off, pts, valid, img_wh)

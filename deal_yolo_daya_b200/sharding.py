@@ -441,12 +441,12 @@ class UrlFilterExchange(AntiJoinExchange):
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
             grp = group if group is not None else dist.group.WORLD
-            self.back_d = symm.empty(m, dtype=torch.int64, device=device)
-            self.h_back_d = symm.rendezvous(self.back_d, grp)
-            self.peer_back_d = torch.tensor(list(self.h_back_d.buffer_ptrs), dtype=torch.int64, device=device)
-            self.back_d.fill_(-1)
+            self.back2 = symm.empty(2 * m, dtype=torch.int64, device=device)     # (dedup answer, anti-join answer) per slot
+            self.h_back2 = symm.rendezvous(self.back2, grp)
+            self.peer_back2 = torch.tensor(list(self.h_back2.buffer_ptrs), dtype=torch.int64, device=device)
+            self.back2.fill_(-1)
             torch.cuda.synchronize(device)
-            self.h_back_d.barrier(channel=0)
+            self.h_back2.barrier(channel=0)
         else:
             self.reply_d = torch.empty(2 * m, dtype=torch.int64, device=device)
             self.back_d = torch.empty(2 * m, dtype=torch.int64, device=device)
@@ -480,15 +480,13 @@ class UrlFilterExchange(AntiJoinExchange):
             if main_null is not None:                         # rows that never travel: a NaN cell never matches
                 self.keep.fill_(1); self.rep.fill_(-1)
             if p2p:
-                _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(self.recv), _ptr(self.keep_dr), _ptr(self.rep_dr), m, self.cap, self.rank,
-                                                        _ptr(self.peer_back_d), 0, 0, s), "dyd_shard_pack_reply_p2p")
-                _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(self.recv), _ptr(self.keep_r), _ptr(self.rep_r), m, self.cap, self.rank,
-                                                        _ptr(self.peer_back), 1, 1, s), "dyd_shard_pack_reply_p2p")
-                self.h_back.barrier(channel=0)                # all answers have landed
-                _lib.check(lib.dyd_shard_unpack_p2p(_ptr(self.back_d), _ptr(self.main.sent_row), _ptr(self.cursors), self.world, self.cap,
-                                                    self.n, _ptr(self.keep_d), _ptr(self.rep_d), 0, s), "dyd_shard_unpack_p2p")
-                _lib.check(lib.dyd_shard_unpack_p2p(_ptr(self.back), _ptr(self.main.sent_row), _ptr(self.cursors), self.world, self.cap,
-                                                    self.n, _ptr(self.keep), _ptr(self.rep), 1, s), "dyd_shard_unpack_p2p")
+                # both answers of a record leave in one 16-byte store; the pack kernel, the last reader of the records, resets them
+                _lib.check(lib.dyd_shard_pack_reply2_p2p(_ptr(self.recv), _ptr(self.keep_dr), _ptr(self.rep_dr), _ptr(self.keep_r), _ptr(self.rep_r),
+                                                         m, self.cap, self.rank, _ptr(self.peer_back2), 1, s), "dyd_shard_pack_reply2_p2p")
+                self.h_back2.barrier(channel=0)               # all answers have landed
+                _lib.check(lib.dyd_shard_unpack2_p2p(_ptr(self.back2), _ptr(self.main.sent_row), _ptr(self.cursors), self.world, self.cap,
+                                                     self.n, _ptr(self.keep_d), _ptr(self.rep_d), _ptr(self.keep), _ptr(self.rep), s),
+                           "dyd_shard_unpack2_p2p")
             else:
                 _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_dr), _ptr(self.rep_dr), m, _ptr(self.reply_d), 0, s),
                            "dyd_shard_pack_reply")

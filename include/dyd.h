@@ -158,6 +158,15 @@ int dyd_shard_pack_reply_p2p(int64_t* d_records, const uint8_t* d_keep, const in
                              int32_t my_rank, int64_t* const* d_peer_reply, int32_t mode, int32_t reset_records, void* stream);
 int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
                          int64_t cap, int64_t n, uint8_t* d_keep, int64_t* d_rep, int32_t mode, void* stream);
+/* Joint exchange (dedup + anti-join answers of the same main records, sharding.UrlFilterExchange): both 8-byte answers
+ * travel as ONE 16-byte store into region `my_rank` of the origin's reply buffer (int64[2 * world * cap], 16-byte
+ * aligned); _unpack2 places them into the four result columns.                                            */
+int dyd_shard_pack_reply2_p2p(int64_t* d_records, const uint8_t* d_keep_dedup, const int64_t* d_rep_dedup,
+                              const uint8_t* d_keep_anti, const int64_t* d_ref_row, int64_t m, int64_t cap, int32_t my_rank,
+                              int64_t* const* d_peer_reply2, int32_t reset_records, void* stream);
+int dyd_shard_unpack2_p2p(const int64_t* d_reply2, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
+                          int64_t cap, int64_t n, uint8_t* d_keep_dedup, int64_t* d_rep_dedup, uint8_t* d_keep_anti,
+                          int64_t* d_ref_row, void* stream);
 /* NCCL-transport forms: (id, answer) pairs */
 int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,
                          int64_t* d_reply, int32_t mode, void* stream);
@@ -228,6 +237,14 @@ int dyd_split_fill(const int64_t* d_img_off, int64_t n_img, const int32_t* d_lab
 int dyd_split_assign(const int64_t* d_cat_off, int32_t n_cat, const int64_t* d_perm, int64_t n_exp,
                      const int64_t* d_n_train, const int64_t* d_n_val,
                      uint8_t* d_split, int64_t* d_pos, void* stream);
+
+/* Sharded form (rows partitioned by image over the ranks): d_cat_off / d_perm / n_exp describe the GLOBAL
+ * category-grouped table; this rank owns rows d_own_lo[c] .. d_own_lo[c] + d_own_cnt[c] of category c (positions inside
+ * the category; sharding.split_category_bases) and receives their split id and shuffled position at
+ * d_local_off[c] + k of its own d_split / d_pos.  Every rank sweeps the whole permutation once.            */
+int dyd_split_assign_range(const int64_t* d_cat_off, int32_t n_cat, const int64_t* d_perm, int64_t n_exp,
+                           const int64_t* d_n_train, const int64_t* d_n_val, const int64_t* d_own_lo,
+                           const int64_t* d_own_cnt, const int64_t* d_local_off, uint8_t* d_split, int64_t* d_pos, void* stream);
 
 /* ------------------------------------------------------------ YOLO (f-3) ---
  * cx, cy, w, h of processor.py:1045-1052 for every box: ((x1+x2)/2)/W etc., fp64,

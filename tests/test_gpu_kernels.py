@@ -350,6 +350,18 @@ def test_split_expand_and_assign(cuda_device, n_img, n_cat):
     if len(perm):
         split, pos = ops.split_assign(coff, dev(perm, d), dev(ntr, d), dev(nva, d))
         assert_bits(host(split), want_split); assert_bits(host(pos), want_pos)
+        # sharded form: three pretend ranks own consecutive slices of every category and together reproduce the single-table answer
+        cuts = [np.array([int(n * f) for n in sizes], np.int64) for f in (0.0, 0.3, 0.85, 1.0)]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            cnt = hi - lo
+            loc = np.zeros(n_cat, np.int64); loc[1:] = np.cumsum(cnt)[:-1]
+            if cnt.sum() == 0:
+                continue
+            s2, p2 = ops.split_assign_range(coff, dev(perm, d), dev(ntr, d), dev(nva, d), dev(lo, d), dev(cnt, d), dev(loc, d))
+            s2, p2 = host(s2), host(p2)
+            for c in range(n_cat):
+                a = int(woff[c] + lo[c])
+                assert_bits(s2[loc[c]:loc[c] + cnt[c]], want_split[a:a + cnt[c]]); assert_bits(p2[loc[c]:loc[c] + cnt[c]], want_pos[a:a + cnt[c]])
 
 
 def test_yolo_normalise(cuda_device):

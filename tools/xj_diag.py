@@ -14,8 +14,8 @@ _, roff, rdata = synth_device.make_urls(0, rank * n_ref, n_ref, dev, n_main_for_
 x = sharding.UrlFilterExchange(n, n_ref, world, dev)
 assert x.transport == "p2p", getattr(x, "p2p_error", "")
 lib = x.lib; m = world * x.cap; m_ref = world * x.cap_ref; s = _stream(dev)
-names = ["hash_main", "hash_ref", "scatter_ref", "scatter_main", "barrier_1", "dedup_records", "antijoin_records", "pack_dedup", "pack_anti",
-         "barrier_2", "unpack_dedup", "unpack_anti"]
+names = ["hash_main", "hash_ref", "scatter_ref", "scatter_main", "barrier_1", "dedup_records", "antijoin_records", "pack_both",
+         "barrier_2", "unpack_both"]
 acc = {k: 0.0 for k in names}
 def ev(): return torch.cuda.Event(enable_timing=True)
 R = 12
@@ -30,11 +30,9 @@ for it in range(R):
     e[i].record(); i += 1; x.main.h.barrier(channel=1)
     e[i].record(); i += 1; _lib.check(lib.dyd_dedup_records(_ptr(x.recv), m, 0, _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.ws_d), x.ws_d.numel(), s), "d")
     e[i].record(); i += 1; _lib.check(lib.dyd_antijoin_records(_ptr(x.recv_ref), m_ref, _ptr(x.recv), m, _ptr(x.keep_r), _ptr(x.rep_r), _ptr(x.ws), x.ws.numel(), 1, s), "a")
-    e[i].record(); i += 1; _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(x.recv), _ptr(x.keep_dr), _ptr(x.rep_dr), m, x.cap, rank, _ptr(x.peer_back_d), 0, 0, s), "p")
-    e[i].record(); i += 1; _lib.check(lib.dyd_shard_pack_reply_p2p(_ptr(x.recv), _ptr(x.keep_r), _ptr(x.rep_r), m, x.cap, rank, _ptr(x.peer_back), 1, 1, s), "p")
-    e[i].record(); i += 1; x.h_back.barrier(channel=0)
-    e[i].record(); i += 1; _lib.check(lib.dyd_shard_unpack_p2p(_ptr(x.back_d), _ptr(x.main.sent_row), _ptr(x.cursors), world, x.cap, n, _ptr(x.keep_d), _ptr(x.rep_d), 0, s), "u")
-    e[i].record(); i += 1; _lib.check(lib.dyd_shard_unpack_p2p(_ptr(x.back), _ptr(x.main.sent_row), _ptr(x.cursors), world, x.cap, n, _ptr(x.keep), _ptr(x.rep), 1, s), "u")
+    e[i].record(); i += 1; _lib.check(lib.dyd_shard_pack_reply2_p2p(_ptr(x.recv), _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.keep_r), _ptr(x.rep_r), m, x.cap, rank, _ptr(x.peer_back2), 1, s), "p")
+    e[i].record(); i += 1; x.h_back2.barrier(channel=0)
+    e[i].record(); i += 1; _lib.check(lib.dyd_shard_unpack2_p2p(_ptr(x.back2), _ptr(x.main.sent_row), _ptr(x.cursors), world, x.cap, n, _ptr(x.keep_d), _ptr(x.rep_d), _ptr(x.keep), _ptr(x.rep), s), "u")
     e[i].record(); torch.cuda.synchronize()
     if it >= 4:
         for j, k in enumerate(names): acc[k] += e[j].elapsed_time(e[j + 1]) / (R - 4)
