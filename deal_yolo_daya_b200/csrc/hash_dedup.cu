@@ -153,9 +153,15 @@ dedup_lookup_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
 }
 
 // ------------------------------------------------------------------------------- K4, partitioned
+#ifndef DYD_PT_THREADS
+#define DYD_PT_THREADS 256
+#endif
+#ifndef DYD_PT_FILL
+#define DYD_PT_FILL 128                          // average records per partition in [FILL, 2 * FILL)
+#endif
 constexpr int PT_SLOTS = 1024;                   // shared-memory table of one partition
-constexpr int PT_THREADS = 256;
-constexpr int PT_MAX_PER_THREAD = 2;             // partition capacity < PT_THREADS * PT_MAX_PER_THREAD
+constexpr int PT_THREADS = DYD_PT_THREADS;
+constexpr int PT_MAX_PER_THREAD = 512 / PT_THREADS;   // partition capacity < PT_THREADS * PT_MAX_PER_THREAD = 512
 constexpr unsigned long long GOLD = 0x9E3779B97F4A7C15ULL;
 
 struct PartLayout {                              // carved out of the caller's workspace
@@ -166,7 +172,7 @@ struct PartLayout {                              // carved out of the caller's w
 static inline PartLayout part_layout(int64_t n, bool with_r) {
     PartLayout L{};
     int k = 0;
-    while ((128LL << (k + 1)) <= n) ++k;         // 2^k partitions, average fill in [128, 256)
+    while (((long long)DYD_PT_FILL << (k + 1)) <= n) ++k;   // 2^k partitions, average fill in [FILL, 2 * FILL)
     L.log2_np = k;
     const uint64_t np = 1ULL << k;
     L.pcap = (unsigned)((2 * (uint64_t)n) / np);
@@ -199,10 +205,17 @@ __global__ void __launch_bounds__(HT_THREADS)
 dedup_partition_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null,
                        const int64_t* __restrict__ row_id, int64_t n, TableHeader* hdr, unsigned* cursors, int* overflow,
                        ulonglong2* __restrict__ kv, unsigned* __restrict__ rr, int pshift, unsigned pcap,
-                       uint8_t* __restrict__ keep, int64_t* __restrict__ rep) {
+                       uint8_t* __restrict__ keep, int64_t* __restrict__ rep,
+                       uint8_t* __restrict__ keep2 = nullptr, int64_t* __restrict__ ref2 = nullptr) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     const bool live = r < n;
     constexpr bool IDS = KIND != 0;
+    // joint form (dyd_url_filter): the anti-join answer of a row no reference key meets, written here with coalesced stores;
+    // the resolve kernel rewrites only the rows it finds in the reference set.  Bucket padding answers 0 / -1.
+    if (live && keep2 != nullptr) {
+        keep2[r] = (KIND == 2 && (long long)keys[2 * r + 1] < 0) || (KIND == 1 && row_id[r] < 0) ? 0 : 1;
+        ref2[r] = -1;
+    }
     const bool isnull = live && !IDS && null != nullptr && null[r] != 0;
     const unsigned nm = __ballot_sync(FULL, isnull);
     if (nm) {                                          // rows ascend with the lane: aggregate per warp
@@ -220,6 +233,9 @@ dedup_partition_kernel(const unsigned long long* __restrict__ keys, const uint8_
     const size_t at = (size_t)p * pcap + slot;
     kv[at] = make_ulonglong2(key, (unsigned long long)id);
     if (IDS) rr[at] = (unsigned)r;
+    // the answer of a row that turns out to be its group's survivor, written here with coalesced stores: the resolve
+    // kernel then only touches the rows it drops (a few percent) instead of scattering 9 bytes to every row
+    rep[r] = id; keep[r] = 1;
 }
 
 // One CTA per partition: shared-memory table, then keep / rep of every record of the partition.
@@ -272,9 +288,11 @@ dedup_resolve_kernel(const unsigned* __restrict__ cursors, const int* __restrict
         if (at[u] < 0) continue;
         const unsigned i = threadIdx.x + u * PT_THREADS;
         const long long rp = (long long)(SRowT)srow[at[u]];
+        const bool kept = MODE == 2 ? (scnt[at[u]] == 1u) : (rp == (long long)id[u]);
+        if (kept && rp == (long long)id[u]) continue;                  // already answered by the partition kernel
         const size_t out = KIND == 0 ? (size_t)id[u] : (size_t)rr[(size_t)p * pcap + i];
         rep[out] = rp;
-        keep[out] = MODE == 2 ? (scnt[at[u]] == 1u) : (rp == (long long)id[u]);
+        keep[out] = kept ? 1 : 0;
     }
 }
 
@@ -687,6 +705,112 @@ static int dedup_impl(const uint64_t* d_keys, const uint8_t* d_null, const int64
     return dedup_table<KIND>(d_keys, d_null, d_row_id, n, keep_mode, d_keep, d_rep, base + L.fallback, overflow, hdr, s);
 }
 
+
+// ------------------------------------------------------------------------------- K4 + K5 joint, partitioned
+// Steps 2 and 3 of the pipeline ask two questions about the same `source` key of every main row: which row represents its
+// group (dedup, processor.py:140-144) and does the reference set hold it (anti-join, :194-199).  Both tables are scattered
+// into the same key partitions; one CTA per partition then builds ONE shared-memory table holding, per distinct key, the
+// first / last main row and the smallest reference row, and answers both questions for its main records.  Compared with
+// the partitioned dedup followed by the global-table anti-join this drops the 128 MB table (fill, 5 M two-atomic inserts,
+// 10 M random probes): 0.44 + 0.48 ms -> see DESIGN.md §4.
+template <int KIND>
+__global__ void __launch_bounds__(HT_THREADS)
+ref_partition_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t n, unsigned* cursors,
+                     int* overflow, ulonglong2* __restrict__ kv, int pshift, unsigned pcap) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r >= n) return;
+    unsigned long long key, id;
+    if (KIND == 0) {
+        if (null != nullptr && null[r] != 0) return;                 // ref.dropna()
+        key = norm_key(keys[r]); id = (unsigned long long)r;
+    } else {
+        const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(keys)[r];
+        if ((long long)rec.y < 0) return;
+        key = norm_key(rec.x); id = rec.y;
+    }
+    const unsigned p = pshift >= 64 ? 0u : (unsigned)((key * GOLD) >> pshift);
+    const unsigned slot = atomicAdd(&cursors[p], 1u);
+    if (slot >= pcap) { *overflow = 1; return; }
+    kv[(size_t)p * pcap + slot] = make_ulonglong2(key, id);
+}
+
+// (key, id) records whose id is set back to padding once the step has read them (peer-memory exchange buffers)
+__global__ void __launch_bounds__(HT_THREADS)
+reset_records_kernel(unsigned long long* __restrict__ records, int64_t m) {
+    const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
+    if (r < m) records[2 * r + 1] = ~0ULL;
+}
+
+template <int KIND, int MODE, bool ROW32>
+__global__ void __launch_bounds__(PT_THREADS)
+joint_resolve_kernel(const unsigned* __restrict__ cur_m, const unsigned* __restrict__ cur_r, const int* __restrict__ overflow,
+                     const ulonglong2* __restrict__ kv_m, const unsigned* __restrict__ rr_m, const ulonglong2* __restrict__ kv_r,
+                     int pshift, unsigned pcap_m, unsigned pcap_r,
+                     uint8_t* __restrict__ keep, int64_t* __restrict__ rep, uint8_t* __restrict__ keep2, int64_t* __restrict__ ref2) {
+    using RowT = typename std::conditional<ROW32, unsigned, unsigned long long>::type;
+    using SRowT = typename std::conditional<ROW32, int, long long>::type;
+    __shared__ unsigned long long skey[PT_SLOTS];
+    __shared__ RowT srow[PT_SLOTS];                    // first (min) or last (max) main row of the key
+    __shared__ RowT sref[PT_SLOTS];                    // smallest reference row of the key, all ones = the reference set lacks it
+    __shared__ unsigned scnt[MODE == 2 ? PT_SLOTS : 1];
+    if (*overflow) return;                             // the gated global-table kernels take over
+    const unsigned p = blockIdx.x;
+    const unsigned cm = min(cur_m[p], pcap_m), cr = min(cur_r[p], pcap_r);
+    if (cm == 0) return;                               // no main record asks anything here
+    for (int i = threadIdx.x; i < PT_SLOTS; i += PT_THREADS) {
+        skey[i] = EMPTY; srow[i] = (RowT)~(RowT)0; sref[i] = (RowT)~(RowT)0;
+        if (MODE == 2) scnt[i] = 0;
+    }
+    __syncthreads();
+    const ulonglong2* refs = kv_r + (size_t)p * pcap_r;
+    for (unsigned i = threadIdx.x; i < cr; i += PT_THREADS) {
+        const ulonglong2 rec = refs[i];
+        unsigned s = (unsigned)(((rec.x * GOLD) << (64 - pshift)) >> 54) & (PT_SLOTS - 1);
+        for (;;) {
+            const unsigned long long prev = atomicCAS(&skey[s], EMPTY, rec.x);
+            if (prev == EMPTY || prev == rec.x) break;
+            s = (s + 1) & (PT_SLOTS - 1);
+        }
+        atomicMin(&sref[s], (RowT)rec.y);
+    }
+    const ulonglong2* mine = kv_m + (size_t)p * pcap_m;
+    unsigned long long id[PT_MAX_PER_THREAD];
+    int at[PT_MAX_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PT_MAX_PER_THREAD; ++u) {
+        const unsigned i = threadIdx.x + u * PT_THREADS;
+        at[u] = -1;
+        if (i < cm) {
+            const ulonglong2 rec = mine[i];
+            id[u] = rec.y;
+            unsigned s = (unsigned)(((rec.x * GOLD) << (64 - pshift)) >> 54) & (PT_SLOTS - 1);
+            for (;;) {
+                const unsigned long long prev = atomicCAS(&skey[s], EMPTY, rec.x);
+                if (prev == EMPTY || prev == rec.x) break;
+                s = (s + 1) & (PT_SLOTS - 1);
+            }
+            if (MODE == 1) atomicMax(reinterpret_cast<SRowT*>(&srow[s]), (SRowT)rec.y);
+            else atomicMin(&srow[s], (RowT)rec.y);
+            if (MODE == 2) atomicAdd(&scnt[s], 1u);
+            at[u] = (int)s;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PT_MAX_PER_THREAD; ++u) {
+        if (at[u] < 0) continue;
+        const unsigned i = threadIdx.x + u * PT_THREADS;
+        const long long rp = (long long)(SRowT)srow[at[u]];
+        const bool kept = MODE == 2 ? (scnt[at[u]] == 1u) : (rp == (long long)id[u]);
+        const RowT hit = sref[at[u]];
+        const bool in_ref = hit != (RowT)~(RowT)0;
+        if (kept && rp == (long long)id[u] && !in_ref) continue;       // both answers were written by the partition kernel
+        const size_t out = KIND == 0 ? (size_t)id[u] : (size_t)rr_m[(size_t)p * pcap_m + i];
+        if (!(kept && rp == (long long)id[u])) { rep[out] = rp; keep[out] = kept ? 1 : 0; }
+        if (in_ref) { keep2[out] = 0; ref2[out] = (long long)hit; }
+    }
+}
+
 }  // namespace dyd
 
 using namespace dyd;
@@ -882,4 +1006,122 @@ extern "C" int dyd_antijoin_records(int64_t* d_ref_records, int64_t m_ref, const
                                     uint8_t* d_keep, int64_t* d_ref_row, void* ws, size_t ws_bytes, int32_t reset_ref, void* stream) {
     return antijoin_impl<2>(reinterpret_cast<uint64_t*>(d_ref_records), nullptr, m_ref, reinterpret_cast<const uint64_t*>(d_main_records), nullptr,
                             m_main, d_keep, d_ref_row, ws, ws_bytes, reset_ref != 0, stream);
+}
+
+
+// ------------------------------------------------------------------------------- K4 + K5 joint: host side
+extern "C" size_t dyd_url_filter_workspace_bytes(int64_t n_main, int64_t n_ref);
+struct JointLayout {
+    int log2_np;
+    unsigned pcap_m, pcap_r;
+    size_t cur_m, cur_r, flag, kv_m, rr_m, kv_r, fb_dedup, fb_anti, total;
+};
+static inline JointLayout joint_layout(int64_t n_main, int64_t n_ref, bool with_r) {
+    JointLayout L{};
+    int k = 0;
+    while (((192LL << k) < n_main || (96LL << k) < n_ref) && k < 30) ++k;      // main fill < 192, reference fill < 96 on average
+    L.log2_np = k;
+    const uint64_t np = 1ULL << k;
+    L.pcap_m = (unsigned)std::min<uint64_t>(PT_THREADS * PT_MAX_PER_THREAD - 1, 2 * ((uint64_t)n_main / np) + 32);
+    L.pcap_r = (unsigned)std::min<uint64_t>(255, 2 * ((uint64_t)n_ref / np) + 32);
+    size_t o = sizeof(TableHeader);
+    L.cur_m = o; o += sizeof(unsigned) * np;
+    L.cur_r = o; o += sizeof(unsigned) * np;
+    L.flag = o; o += 16;
+    o = (o + 15) & ~(size_t)15;
+    L.kv_m = o; o += sizeof(ulonglong2) * np * L.pcap_m;
+    L.kv_r = o; o += sizeof(ulonglong2) * np * L.pcap_r;
+    L.rr_m = o; o += with_r ? sizeof(unsigned) * np * L.pcap_m : 0;
+    o = (o + 255) & ~(size_t)255;
+    L.fb_dedup = o; o += dedup_table_bytes(n_main);
+    o = (o + 255) & ~(size_t)255;
+    L.fb_anti = o; o += antijoin_table_bytes(n_ref);
+    L.total = o;
+    return L;
+}
+
+// dedup + anti-join of the same main keys; KIND 0: key arrays with null flags, KIND 2: (key, id) records of the exchange
+template <int KIND>
+static int url_filter_impl(const uint64_t* d_main, const uint8_t* d_main_null, int64_t n_main, uint64_t* d_ref, const uint8_t* d_ref_null,
+                           int64_t n_ref, int keep_mode, uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep2, int64_t* d_ref2,
+                           void* ws, size_t ws_bytes, bool reset_ref, void* stream) {
+    DYD_REQUIRE(n_main >= 0 && n_ref >= 0 && n_main < (1LL << 40) && n_ref < (1LL << 40), DYD_E_ARG, "bad row count");
+    DYD_REQUIRE(keep_mode >= 0 && keep_mode <= 2, DYD_E_ARG, "keep_mode must be 0 (first), 1 (last) or 2 (False)");
+    cudaStream_t s = as_stream(stream);
+    if (n_main > 0) {
+        DYD_REQUIRE(d_main && d_keep && d_rep && d_keep2 && d_ref2 && ws && (n_ref == 0 || d_ref), DYD_E_ARG, "null pointer");
+        DYD_REQUIRE(((uintptr_t)ws & 15) == 0, DYD_E_ALIGN, "workspace must be 16-byte aligned");
+        DYD_REQUIRE(ws_bytes >= dyd_url_filter_workspace_bytes(n_main, n_ref), DYD_E_WORKSPACE, "workspace too small");
+        char* base = reinterpret_cast<char*>(ws);
+        if (!use_partitions(n_main) || n_ref >= (1LL << 32) - 1) {
+            // small tables: the two single-question kernels one after the other (their tables sit in L2)
+            if (int rc = dedup_impl<KIND>(d_main, d_main_null, nullptr, n_main, keep_mode, d_keep, d_rep, ws, dyd_dedup_workspace_bytes(n_main), stream)) return rc;
+            char* aws = base + ((dyd_dedup_workspace_bytes(n_main) + 255) & ~(size_t)255);
+            if (int rc = antijoin_table<KIND>(d_ref, d_ref_null, n_ref, d_main, d_main_null, n_main, d_keep2, d_ref2, aws, false, nullptr, s)) return rc;
+        } else {
+            const JointLayout L = joint_layout(n_main, n_ref, KIND != 0);
+            TableHeader* hdr = reinterpret_cast<TableHeader*>(base);
+            unsigned* cur_m = reinterpret_cast<unsigned*>(base + L.cur_m);
+            unsigned* cur_r = reinterpret_cast<unsigned*>(base + L.cur_r);
+            int* overflow = reinterpret_cast<int*>(base + L.flag);
+            ulonglong2* kv_m = reinterpret_cast<ulonglong2*>(base + L.kv_m);
+            ulonglong2* kv_r = reinterpret_cast<ulonglong2*>(base + L.kv_r);
+            unsigned* rr_m = reinterpret_cast<unsigned*>(base + L.rr_m);
+            const unsigned long long* m64 = reinterpret_cast<const unsigned long long*>(d_main);
+            DYD_CUDA(cudaMemsetAsync(base, 0xFF, sizeof(TableHeader), s));
+            DYD_CUDA(cudaMemsetAsync(&hdr->null_count, 0, sizeof(unsigned long long), s));
+            DYD_CUDA(cudaMemsetAsync(cur_m, 0, L.kv_m - L.cur_m, s));                  // both cursor arrays + overflow flag
+            const int pshift = 64 - L.log2_np;
+            if (n_ref > 0) {
+                ref_partition_kernel<KIND><<<grid_for(n_ref), HT_THREADS, 0, s>>>(reinterpret_cast<const unsigned long long*>(d_ref), d_ref_null, n_ref,
+                                                                                  cur_r, overflow, kv_r, pshift, L.pcap_r);
+                if (int rc = launch_check("ref_partition_kernel")) return rc;
+            }
+            dedup_partition_kernel<KIND><<<grid_for(n_main), HT_THREADS, 0, s>>>(m64, d_main_null, nullptr, n_main, hdr, cur_m, overflow, kv_m, rr_m, pshift,
+                                                                               L.pcap_m, d_keep, d_rep, d_keep2, d_ref2);
+            if (int rc = launch_check("dedup_partition_kernel")) return rc;
+            const unsigned np = 1u << L.log2_np;
+            constexpr bool R32 = KIND == 0;            // main rows < 2^31 and reference rows < 2^32 - 1 on this path
+#define DYD_JOINT(MODE) joint_resolve_kernel<KIND, MODE, R32><<<np, PT_THREADS, 0, s>>>(cur_m, cur_r, overflow, kv_m, rr_m, kv_r, pshift, L.pcap_m, \
+                                                                                        L.pcap_r, d_keep, d_rep, d_keep2, d_ref2)
+            if (keep_mode == 0) DYD_JOINT(0); else if (keep_mode == 1) DYD_JOINT(1); else DYD_JOINT(2);
+#undef DYD_JOINT
+            if (int rc = launch_check("joint_resolve_kernel")) return rc;
+            if (KIND == 0 && d_main_null != nullptr) {
+                dedup_leftover_kernel<KIND><<<grid_for(n_main), HT_THREADS, 0, s>>>(m64, d_main_null, nullptr, n_main, keep_mode, hdr, overflow, d_keep, d_rep);
+                if (int rc = launch_check("dedup_leftover_kernel")) return rc;
+            }
+            // a partition overflowed (one key repeated hundreds of times): both questions are asked again of the global tables
+            if (int rc = dedup_table<KIND>(d_main, d_main_null, nullptr, n_main, keep_mode, d_keep, d_rep, base + L.fb_dedup, overflow, hdr, s)) return rc;
+            if (int rc = antijoin_table<KIND>(d_ref, d_ref_null, n_ref, d_main, d_main_null, n_main, d_keep2, d_ref2, base + L.fb_anti, false, overflow, s)) return rc;
+        }
+    }
+    if (KIND == 2 && reset_ref && n_ref > 0) {
+        reset_records_kernel<<<grid_for(n_ref), HT_THREADS, 0, s>>>(reinterpret_cast<unsigned long long*>(d_ref), n_ref);
+        if (int rc = launch_check("reset_records_kernel")) return rc;
+    }
+    return 0;
+}
+
+extern "C" size_t dyd_url_filter_workspace_bytes(int64_t n_main, int64_t n_ref) {
+    if (n_main < 0) n_main = 0;
+    if (n_ref < 0) n_ref = 0;
+    const size_t separate = ((dyd_dedup_workspace_bytes(n_main) + 255) & ~(size_t)255) + antijoin_table_bytes(n_ref);
+    if (!use_partitions(n_main) || n_ref >= (1LL << 32) - 1) return separate;
+    return std::max(separate, joint_layout(n_main, n_ref, true).total);
+}
+
+extern "C" int dyd_url_filter(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
+                              const uint64_t* d_ref_keys, const uint8_t* d_ref_null, int64_t n_ref, int keep_mode,
+                              uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep_ref, int64_t* d_ref_row,
+                              void* ws, size_t ws_bytes, void* stream) {
+    return url_filter_impl<0>(d_main_keys, d_main_null, n_main, const_cast<uint64_t*>(d_ref_keys), d_ref_null, n_ref, keep_mode, d_keep, d_rep,
+                              d_keep_ref, d_ref_row, ws, ws_bytes, false, stream);
+}
+
+extern "C" int dyd_url_filter_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main, int keep_mode,
+                                      uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep_ref, int64_t* d_ref_row,
+                                      void* ws, size_t ws_bytes, int32_t reset_ref, void* stream) {
+    return url_filter_impl<2>(reinterpret_cast<const uint64_t*>(d_main_records), nullptr, m_main, reinterpret_cast<uint64_t*>(d_ref_records), nullptr,
+                              m_ref, keep_mode, d_keep, d_rep, d_keep_ref, d_ref_row, ws, ws_bytes, reset_ref != 0, stream);
 }

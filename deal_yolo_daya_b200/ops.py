@@ -192,6 +192,24 @@ def antijoin(main_keys, main_null, ref_keys, ref_null, workspace=None):
     return km, rr
 
 
+def url_filter(main_keys, main_null, ref_keys, ref_null, keep="first", workspace=None):
+    """Steps 2 + 3 on the same main keys in one call: (keep, rep) of `dedup` and (keep_ref, ref_row) of `antijoin`."""
+    _need_cuda(main_keys, main_null, ref_keys, ref_null)
+    lib = _lib.load()
+    main_keys = _chk(main_keys, torch.uint64, "main_keys"); ref_keys = _chk(ref_keys, torch.uint64, "ref_keys")
+    main_null = _chk(main_null, torch.uint8, "main_null"); ref_null = _chk(ref_null, torch.uint8, "ref_null")
+    dev = main_keys.device
+    n, nr = main_keys.numel(), ref_keys.numel()
+    km = torch.empty(n, dtype=torch.uint8, device=dev); rep = torch.empty(n, dtype=torch.int64, device=dev)
+    ka = torch.empty(n, dtype=torch.uint8, device=dev); rr = torch.empty(n, dtype=torch.int64, device=dev)
+    need = lib.dyd_url_filter_workspace_bytes(n, nr)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dyd_url_filter(_ptr(main_keys), _ptr(main_null), n, _ptr(ref_keys), _ptr(ref_null), nr, KEEP_MODES[keep],
+                                      _ptr(km), _ptr(rep), _ptr(ka), _ptr(rr), _ptr(ws), ws.numel(), _stream(dev)), "dyd_url_filter")
+    return km, rep, ka, rr
+
+
 # ------------------------------------------------------------------ K3 / K6 / YOLO
 COUNTER_NAMES = ("total_objects", "missing_name_objects", "total_labels", "replaced_labels",
                  "replaced_objects", "replaced_rows")

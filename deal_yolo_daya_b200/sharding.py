@@ -435,7 +435,7 @@ class UrlFilterExchange(AntiJoinExchange):
         m = world * self.cap
         self.keep_dr = torch.empty(m, dtype=torch.uint8, device=device)
         self.rep_dr = torch.empty(m, dtype=torch.int64, device=device)
-        self.ws_d = torch.empty(self.lib.dyd_dedup_workspace_bytes(m), dtype=torch.uint8, device=device)
+        self.ws_d = torch.empty(self.lib.dyd_url_filter_workspace_bytes(m, world * self.cap_ref), dtype=torch.uint8, device=device)
         self.keep_d = torch.empty(n_main_local, dtype=torch.uint8, device=device)
         self.rep_d = torch.empty(n_main_local, dtype=torch.int64, device=device)
         if self.transport == "p2p":
@@ -473,10 +473,10 @@ class UrlFilterExchange(AntiJoinExchange):
                 _lib.check(lib.dyd_shard_bucket(_ptr(main_keys), _ptr(main_null), row_base, self.n, self.world, self.cap,
                                                 _ptr(self.send), _ptr(self.cursors), _ptr(self.overflow[:1]), s), "dyd_shard_bucket")
                 dist.all_to_all_single(self.recv, self.send, group=group)
-            _lib.check(lib.dyd_dedup_records(_ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_dr), _ptr(self.rep_dr),
-                                             _ptr(self.ws_d), self.ws_d.numel(), s), "dyd_dedup_records")
-            _lib.check(lib.dyd_antijoin_records(_ptr(self.recv_ref), m_ref, _ptr(self.recv), m, _ptr(self.keep_r), _ptr(self.rep_r),
-                                                _ptr(self.ws), self.ws.numel(), 1 if p2p else 0, s), "dyd_antijoin_records")
+            # owner side: both questions about every received main record from one shared-memory table per key partition
+            _lib.check(lib.dyd_url_filter_records(_ptr(self.recv_ref), m_ref, _ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_dr), _ptr(self.rep_dr),
+                                                  _ptr(self.keep_r), _ptr(self.rep_r), _ptr(self.ws_d), self.ws_d.numel(), 1 if p2p else 0, s),
+                       "dyd_url_filter_records")
             if main_null is not None:                         # rows that never travel: a NaN cell never matches
                 self.keep.fill_(1); self.rep.fill_(-1)
             if p2p:
@@ -522,8 +522,7 @@ class ShardedUrlFilter:
         if world > 1:
             self.xchg = UrlFilterExchange(n_local, n_ref_local, world, d, group=group)
         else:
-            self.ws = torch.empty(max(self.lib.dyd_dedup_workspace_bytes(n_local), self.lib.dyd_antijoin_workspace_bytes(n_ref_local)),
-                                  dtype=torch.uint8, device=d)
+            self.ws = torch.empty(self.lib.dyd_url_filter_workspace_bytes(n_local, n_ref_local), dtype=torch.uint8, device=d)
         pin = lambda n, dt: torch.empty(n, dtype=dt, pin_memory=True)   # noqa: E731
         self.h_keep, self.h_rep = pin(n_local, torch.uint8), pin(n_local, torch.int64)
         self.h_keep_ref, self.h_ref_row = pin(n_local, torch.uint8), pin(n_local, torch.int64)
@@ -544,8 +543,7 @@ class ShardedUrlFilter:
             if self.world > 1:
                 k, r, k2, r2 = self.xchg.run(keys, row_base, rkeys, ref_row_base, keep, group=self.group)
             else:
-                k, r = ops.dedup(keys, None, keep, workspace=self.ws)
-                k2, r2 = ops.antijoin(keys, None, rkeys, None, workspace=self.ws)
+                k, r, k2, r2 = ops.url_filter(keys, None, rkeys, None, keep, workspace=self.ws)
             self.h_keep.copy_(k, non_blocking=True); self.h_rep.copy_(r, non_blocking=True)
             self.h_keep_ref.copy_(k2, non_blocking=True); self.h_ref_row.copy_(r2, non_blocking=True)
             torch.cuda.current_stream(self.dev).synchronize()

@@ -191,6 +191,20 @@ int dyd_antijoin_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d
                          uint8_t* d_keep, int64_t* d_ref_row, void* d_workspace, size_t workspace_bytes,
                          int32_t reset_ref, void* stream);
 
+/* ------------------------------------------------------------ K4 + K5 ------
+ * Steps 2 and 3 on the same main `source` keys in one call (processor.py:140-144 and :194-199): the outputs are exactly
+ * those of dyd_dedup (d_keep / d_rep) and dyd_antijoin (d_keep_ref / d_ref_row).  Large tables are scattered into common key
+ * partitions and one shared-memory table per partition answers both questions; small ones run the two kernels above.
+ * _records: the sharded form on (key, id) records of the exchange (dyd_dedup_records + dyd_antijoin_records).        */
+size_t dyd_url_filter_workspace_bytes(int64_t n_main, int64_t n_ref);
+int dyd_url_filter(const uint64_t* d_main_keys, const uint8_t* d_main_null, int64_t n_main,
+                   const uint64_t* d_ref_keys, const uint8_t* d_ref_null, int64_t n_ref, int keep_mode,
+                   uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep_ref, int64_t* d_ref_row,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+int dyd_url_filter_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main, int keep_mode,
+                           uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep_ref, int64_t* d_ref_row,
+                           void* d_workspace, size_t workspace_bytes, int32_t reset_ref, void* stream);
+
 /* ---------------------------------------------------------------- K3 ------
  * Object-name rewrite through a lookup table, processor.py:582-602 with the
  * string rules of utils.py:659-679 folded into three per-vocabulary tables built

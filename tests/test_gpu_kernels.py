@@ -286,6 +286,65 @@ def test_antijoin(cuda_device, n, nr):
     assert_bits(host(keep), want_keep); assert_bits(host(rr), want_rr)
 
 
+@pytest.mark.parametrize("keep", ["first", "last", False])
+@pytest.mark.parametrize("n,nr,hot", [(3000, 1200, 0), (200000, 90000, 0), (300000, 0, 0), (250000, 170000, 5000), (120000, 400000, 0)])
+def test_url_filter_joint_equals_dedup_plus_antijoin(cuda_device, small_partitions, keep, n, nr, hot):
+    """dyd_url_filter (one shared-memory table per key partition answering both questions) against the oracle's dedup and
+    anti-join: null cells on both sides, the EMPTY sentinel as a key, duplicate reference keys (smallest row wins), a key
+    repeated thousands of times (partition overflow -> both gated global-table fallbacks inside the same call)."""
+    d = cuda_device
+    rng = np.random.RandomState(n + nr + hot)
+    mk = rng.randint(0, 150000, size=n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    rk = rng.randint(100000, 260000, size=nr).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    if nr:
+        mk[7] = rk[3] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    if hot:
+        mk[rng.choice(n, size=hot, replace=False)] = np.uint64(0x1234567890ABCDEF)
+        rk[rng.choice(nr, size=300, replace=False)] = np.uint64(0x1234567890ABCDEF)
+    mn = (rng.rand(n) < 0.01).astype(np.uint8); rn = (rng.rand(nr) < 0.05).astype(np.uint8)
+    for main_null, ref_null in ((mn, rn), (None, None)):
+        zm = main_null if main_null is not None else np.zeros(n, np.uint8)
+        zr = ref_null if ref_null is not None else np.zeros(nr, np.uint8)
+        want_keep, want_rep = oracle_c.dedup(mk, zm, keep)
+        want_ka, want_rr = oracle_c.antijoin(mk, zm, rk, zr)
+        km, rep, ka, rr = ops.url_filter(dev(mk, d), None if main_null is None else dev(main_null, d), dev(rk, d),
+                                         None if ref_null is None else dev(ref_null, d), keep)
+        assert_bits(host(km), want_keep, "keep"); assert_bits(host(rep), want_rep, "rep")
+        assert_bits(host(ka), want_ka, "keep_ref"); assert_bits(host(rr), want_rr, "ref_row")
+
+
+def test_url_filter_records_equals_separate_record_kernels(cuda_device, small_partitions):
+    """The sharded form on (key, id) records with bucket padding: same four answers as dyd_dedup_records followed by
+    dyd_antijoin_records; reference records are padding afterwards when asked."""
+    from deal_yolo_daya_b200 import _lib
+    from deal_yolo_daya_b200.ops import _ptr, _stream
+    lib = _lib.load(); d = cuda_device
+    rng = np.random.RandomState(5)
+    m, mr = 180000, 90000
+    rec = np.empty((m, 2), np.int64); ref = np.empty((mr, 2), np.int64)
+    rec[:, 0] = (rng.randint(0, 70000, size=m).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)).view(np.int64)
+    rec[:, 1] = rng.permutation(m).astype(np.int64) * 7 + (1 << 34)
+    ref[:, 0] = (rng.randint(50000, 120000, size=mr).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)).view(np.int64)
+    ref[:, 1] = rng.permutation(mr).astype(np.int64) * 3 + (1 << 35)
+    rec[rng.choice(m, 9000, replace=False), 1] = -1; ref[rng.choice(mr, 4000, replace=False), 1] = -1          # bucket padding
+    s = _stream(d)
+    t = lambda n, dt=torch.int64: torch.empty(n, dtype=dt, device=d)   # noqa: E731
+    for keep in ("first", "last", False):
+        mode = ops.KEEP_MODES[keep]
+        drec, dref = dev(rec.reshape(-1), d), dev(ref.reshape(-1), d)
+        k1, r1, k2, r2 = t(m, torch.uint8), t(m), t(m, torch.uint8), t(m)
+        ws_d = t(lib.dyd_dedup_workspace_bytes(m), torch.uint8); ws_a = t(lib.dyd_antijoin_workspace_bytes(mr), torch.uint8)
+        _lib.check(lib.dyd_dedup_records(_ptr(drec), m, mode, _ptr(k1), _ptr(r1), _ptr(ws_d), ws_d.numel(), s), "dedup_records")
+        _lib.check(lib.dyd_antijoin_records(_ptr(dref), mr, _ptr(drec), m, _ptr(k2), _ptr(r2), _ptr(ws_a), ws_a.numel(), 0, s), "antijoin_records")
+        j = [t(m, torch.uint8), t(m), t(m, torch.uint8), t(m)]
+        ws = t(lib.dyd_url_filter_workspace_bytes(m, mr), torch.uint8)
+        _lib.check(lib.dyd_url_filter_records(_ptr(dref), mr, _ptr(drec), m, mode, _ptr(j[0]), _ptr(j[1]), _ptr(j[2]), _ptr(j[3]), _ptr(ws), ws.numel(), 1, s),
+                   "url_filter_records")
+        assert_bits(host(j[0]), host(k1), f"keep {keep}"); assert_bits(host(j[1]), host(r1), f"rep {keep}")
+        assert_bits(host(j[2]), host(k2), f"keep_ref {keep}"); assert_bits(host(j[3]), host(r2), f"ref_row {keep}")
+        assert bool((dref.view(-1, 2)[:, 1] == -1).all()), "reference records must be padding after the call"
+
+
 def test_url_pipeline_device(cuda_device):
     """Device-generated URL bytes -> hash -> dedup equals the oracle on the numpy twin's URLs."""
     d = cuda_device

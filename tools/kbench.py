@@ -105,6 +105,9 @@ def main():
             rkeys = ops.hash_strings(roff, rdata)
             ms, best = time_ms(lambda: ops.antijoin(keys, None, rkeys, None, workspace=ws), args.reps)
             report("K5 antijoin (ref = n/2)", ms, best, 8 * (n_img // 2) + 17 * n_img, n_img, "rows")
+            ws2 = torch.empty(_lib.load().dyd_url_filter_workspace_bytes(n_img, n_img // 2), dtype=torch.uint8, device=dev)
+            ms, best = time_ms(lambda: ops.url_filter(keys, None, rkeys, None, "first", workspace=ws2), args.reps)
+            report("K4+K5 joint url filter", ms, best, 8 * (n_img // 2) + 8 * n_img + 18 * n_img, n_img, "rows")
     if "crowd" in which:
         nc = max(1000, args.images // 400)
         io, pts = synth_device.make_crowd(0, 0, nc, device=dev)
