@@ -580,7 +580,9 @@ static void parse_box_row(const char* text, size_t len, RowOut& out) {
                                             ps.need(ps.p < ps.end);
                                             if (*ps.p == '{' || *ps.p == '[' || *ps.p == '"') Parser::fail();   // non-numeric coordinate: slow lane
                                             Span sp; double val; bool exact; Kind kd = ps.scalar(&sp, &val, &exact);
-                                            if (!exact) Parser::fail();                     // int beyond 2^53: CPython big-int arithmetic
+                                            // CPython computes IoU of int coordinates in exact big-int arithmetic; fp64 is the same only while
+                                            // every product stays below 2^53, i.e. for |int| <= 2^25: larger ones take the CPython lane
+                                            if (!exact || (kd == K_INT && std::fabs(val) > 33554432.0)) Parser::fail();
                                             const int idx = slot * 2 + (isy ? 1 : 0);
                                             has[idx] = true; c[idx] = val; isnull[idx] = kd == K_NULL;
                                         } else ps.skip();

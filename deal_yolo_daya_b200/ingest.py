@@ -30,13 +30,18 @@ from . import _hostlane
 _EXACT = 2 ** 53
 
 
-def _dev_ok(v) -> bool:
+def _dev_ok(v, int_bound=_EXACT) -> bool:
     t = type(v)
     if t is float:
         return True
     if t is int or t is bool:
-        return -_EXACT <= v <= _EXACT
+        return -int_bound <= v <= int_bound
     return False
+
+
+# Step 5 does arithmetic on the coordinates.  CPython's is exact for ints; fp64 gives the same quotient only while every
+# difference, product and sum is exactly representable, which |int| <= 2^25 guarantees (products <= 2^52, their sum <= 2^53).
+_IOU_INT = 2 ** 25
 
 
 @dataclass
@@ -134,7 +139,7 @@ def parse_boxes(cells) -> BoxBatch:
                     vals = (p["x"], p["y"], q["x"], q["y"])
                     if vals[0] is None and vals[1] is None and vals[2] is None and vals[3] is None:
                         raise TypeError("null bbox")       # min(None, None) raises (processor.py:359)
-                    if not all(_dev_ok(v) for v in vals):
+                    if not all(_dev_ok(v, _IOU_INT) for v in vals):
                         exotic = True
                         break
                     row_pts.extend(vals); row_valid.append(1)

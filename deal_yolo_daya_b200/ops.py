@@ -258,9 +258,25 @@ def label_presence(img_off, label_id, n_vocab):
     return hists[0, :n_vocab], hists[1, :n_vocab]
 
 
+MAX_CAT_PER_PASS = 256          # dyd_split_count / _fill keep their per-category counters in shared memory
+
+
 def split_expand(img_off, label_id, cat_of_label, n_cat):
-    """Category expansion (processor.py:751-775).  Returns (exp_img, exp_box, exp_cat, cat_off)."""
+    """Category expansion (processor.py:751-775).  Returns (exp_img, exp_box, exp_cat, cat_off).
+    More than 256 categories (a rules table in two_column mode can hold any number; the reference has no limit) are
+    expanded in blocks of 256: the rows of a block's categories with the other labels masked out, blocks in category order."""
     _need_cuda(img_off, label_id, cat_of_label)
+    if n_cat > MAX_CAT_PER_PASS:
+        parts, offs, base = [], [], 0
+        for c0 in range(0, n_cat, MAX_CAT_PER_PASS):
+            c1 = min(n_cat, c0 + MAX_CAT_PER_PASS)
+            sub = torch.where((cat_of_label >= c0) & (cat_of_label < c1), cat_of_label - c0, torch.full_like(cat_of_label, -1))
+            ei, eb, ec, co = split_expand(img_off, label_id, sub.contiguous(), c1 - c0)
+            parts.append((ei, eb, ec + c0))
+            offs.append(co[:-1] + base)
+            base += int(co[-1].item())
+        offs.append(torch.tensor([base], dtype=torch.int64, device=img_off.device))
+        return (torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), torch.cat([p[2] for p in parts]), torch.cat(offs))
     lib = _lib.load()
     dev = img_off.device
     n_img = img_off.numel() - 1

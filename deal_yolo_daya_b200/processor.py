@@ -234,7 +234,7 @@ STATS = {"hostlane_objects": 0, "hostlane_rows": 0, "hash_collisions": 0, "nativ
 # =============================================================================================
 # step 2: dedup by source                                            reference: processor.py:111-164
 # =============================================================================================
-def _source_buffers(col):
+def _source_buffers(col, normalise_zero=False):
     """`source` column -> (off int64[n+1], data uint8[], null uint8[n], values or None).  An Arrow-backed text column
     goes to the kernels as its own buffers (no Python string per row); anything else is packed from its values with
     str() like the reference's astype(str) (`values` is then the list the collision repair compares)."""
@@ -246,6 +246,8 @@ def _source_buffers(col):
             data = np.zeros(1, np.uint8)
         return off, data, (is_text == 0).astype(np.uint8), None, keep
     vals = col.tolist()
+    if normalise_zero and col.dtype == np.float64:
+        vals = (col.to_numpy() + 0.0).tolist()         # drop_duplicates compares values: -0.0 and 0.0 are one group
     off, data, null = ingest.pack_strings(vals)
     return off, data, null, vals, None
 
@@ -274,7 +276,7 @@ def dedup_keep_mask(col, keep="first") -> np.ndarray:
     row checked against the row that caused the drop (a 64-bit hash collision regroups on the strings)."""
     STATS["hash_collisions"] = 0
     t0 = time.perf_counter()
-    off, data, null, vals, _keepalive = _source_buffers(col)
+    off, data, null, vals, _keepalive = _source_buffers(col, normalise_zero=True)
     t1 = _phase("ingest", t0)
     km, rep = KERNELS.dedup(off, data, null, keep)
     t1 = time.perf_counter()
@@ -493,7 +495,10 @@ def replace_ptlist_cells(cells, side=None):
             # one pass over the vertices: corner points with their vertex indices AND the IoU flags of the likely step 5
             mb, thr = IOU_SPECULATION
             pts, valid, arg, high, count = KERNELS.bbox_fused(ing.img_off, ing.poly_off, ing.xy, mb, thr)
-            fused = {"img_off": ing.img_off.copy(), "pts": pts, "valid": valid, "flags": {(int(mb), float(thr)): high.astype(bool)}}
+            # step 5 may reuse these boxes only where fp64 arithmetic equals CPython's on the JSON numbers: an int coordinate
+            # beyond 2^25 is computed exactly there (ingest._IOU_INT); such tables are parsed again by step 5's own lanes
+            if not pts.size or float(np.nanmax(np.abs(np.where(np.isfinite(pts), pts, 0.0)))) <= float(ingest._IOU_INT):
+                fused = {"img_off": ing.img_off.copy(), "pts": pts, "valid": valid, "flags": {(int(mb), float(thr)): high.astype(bool)}}
         elif ing.n_obj:
             _, valid, arg = KERNELS.bbox(ing.poly_off, ing.xy)
         else:

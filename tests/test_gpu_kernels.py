@@ -389,13 +389,16 @@ def test_label_lut(cuda_device):
     assert np.array_equal(w2, want_new[:t.img_off[199]])
 
 
-@pytest.mark.parametrize("n_img,n_cat", [(1, 1), (300, 4), (70000, 20), (5000, 256), (60000, 16), (40000, 3), (9000, 1)])
+@pytest.mark.parametrize("n_img,n_cat", [(1, 1), (300, 4), (70000, 20), (5000, 256), (60000, 16), (40000, 3), (9000, 1), (6000, 257), (8000, 700)])
 def test_split_expand_and_assign(cuda_device, n_img, n_cat):
     d = cuda_device
     t = synth.make_table(n_cat, 0, n_img)
     lab = t.label_id.copy(); lab[::53] = -1
     rng = np.random.RandomState(n_cat)
     cat = rng.randint(-1, n_cat, synth.N_LABELS).astype(np.int32)
+    if n_cat > 256:                                      # more categories than one pass holds: a wide label vocabulary
+        lab = (lab.astype(np.int64) * 37 + np.arange(len(lab)) % 1500).astype(np.int32) % 1500; lab[::53] = -1
+        cat = rng.randint(-1, n_cat, 1500).astype(np.int32)
     wi, wb, wc, woff = oracle_c.split_expand(t.img_off, lab, cat, n_cat)
     ei, eb, ec, coff = ops.split_expand(dev(t.img_off, d), dev(lab, d), dev(cat, d), n_cat)
     assert_bits(host(coff), woff); assert_bits(host(ei), wi); assert_bits(host(eb), wb); assert_bits(host(ec), wc)

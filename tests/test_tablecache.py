@@ -219,3 +219,56 @@ def test_wide_and_scalar_writers_agree(tmp_path):
     b = tmp_path / "p.csv"
     df.to_csv(b, index=False, encoding="utf-8-sig")
     assert b.read_bytes() == outs[0]
+
+
+def test_float_source_column_groups_signed_zeros_like_pandas():
+    df = pd.DataFrame({"source": [0.0, -0.0, 1.5, float("nan"), float("nan"), 1.5, -0.0], "v": list("abcdefg")})
+    for keep in ("first", "last", False):
+        want = df.drop_duplicates(subset=["source"], keep=keep, ignore_index=True)
+        pd.testing.assert_frame_equal(P.deduplicate_df(df, keep), want)
+
+
+def test_int_coordinates_beyond_2_pow_25_are_computed_like_cpython(tmp_path):
+    """CPython's IoU on int coordinates is exact big-int arithmetic; fp64 agrees only up to |int| <= 2^25.  Rows beyond that
+    bound take the CPython lane in step 5 (native parser and Python parser alike), and step 4 does not hand its fp64 boxes over."""
+    import json
+    big = 2 ** 27
+
+    def cell(boxes):
+        return json.dumps({"width": 10, "height": 10, "objects": [
+            {"name": "a", "polygon": {"ptList": [{"x": b[0], "y": b[1]}, {"x": b[2], "y": b[1]}, {"x": b[2], "y": b[3]}, {"x": b[0], "y": b[3]}]}} for b in boxes]})
+    rows = [cell([(0, 0, big + 3, big + 1), (1, 0, big + 3, big + 1)]),           # IoU just below / above thresholds only exact arithmetic separates
+            cell([(0, 0, 100, 100), (0, 0, 100, 70)]),
+            cell([(0.5, 0.5, 10.5, 10.5), (0.5, 0.5, 10.5, 9.5)])]
+    df = pd.DataFrame({P.COL_SRC: [f"u{i}" for i in range(len(rows))], P.COL_ANN: rows})
+    src = tmp_path / "in.csv"
+    df.to_csv(src, index=False, encoding="utf-8-sig")
+    quiet(P.process_csv_replace_ptlist, str(src), str(tmp_path / "rep.csv"), str(tmp_path / "exc.csv"))
+    ent = tablecache.get(tmp_path / "rep.csv")
+    assert ent is not None and "boxes" not in ent.extras, "fp64 boxes of a table with huge int coordinates must not be reused"
+    rep = pd.read_csv(tmp_path / "rep.csv", encoding="utf-8-sig")
+
+    def reference_mask(cells, mb, thr):          # processor.py:328-376 restated on Python objects (exact int arithmetic)
+        out = []
+        for c in cells:
+            bx = []
+            for o in json.loads(c)["objects"]:
+                p, q = o["polygon"]["ptList"]
+                bx.append((min(p["x"], q["x"]), min(p["y"], q["y"]), max(p["x"], q["x"]), max(p["y"], q["y"])))
+            hit = False
+            for i in range(len(bx)):
+                for j in range(i + 1, len(bx)):
+                    a, b = bx[i], bx[j]
+                    iw = max(0, min(a[2], b[2]) - max(a[0], b[0])); ih = max(0, min(a[3], b[3]) - max(a[1], b[1]))
+                    inter = iw * ih
+                    if inter == 0:
+                        continue
+                    union = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+                    hit = hit or (union != 0 and inter / union >= thr)
+            out.append(len(bx) >= mb and hit)
+        return np.array(out)
+    exact = ((big + 2) * (big + 1)) / ((big + 3) * (big + 1))
+    for thr in (0.7, exact, float(np.nextafter(exact, 1.0)), float(np.nextafter(exact, 0.0))):
+        want = reference_mask(rep[P.COL_NEW], 2, thr)
+        assert np.array_equal(P.high_iou_mask(rep[P.COL_NEW], 2, thr), want), thr
+        assert P.STATS["slow_rows"] >= 1

@@ -77,6 +77,50 @@ int main(int argc, char** argv) {
         for (int j = 0; j < ncol; ++j) { cols[j] = j; datas[j].resize((size_t)cb[j] + 1); maps[j].resize((size_t)(nr + 7) / 8); po[j] = offs[j].data(); pd[j] = datas[j].data(); pm[j] = maps[j].data(); }
         dyd_csv_fill(hc, ncol, cols.data(), po.data(), pd.data(), pm.data(), 4);
         checks += nr * ncol;
+        // round-trip verdict of every column, then the straight-to-file writer (all rows, a row selection) and the wide tokenizer
+        // on what it wrote: the cells must come back unchanged
+        for (int j = 0; j < ncol; ++j) checks += dyd_csv_roundtrip_check(po[j], pd[j], nullptr, nr, 5, (const uint8_t*)nas, na_off.data(), 3, 1, 4) >= 0;
+        if (ncol >= 2) {
+            std::vector<int32_t> kinds(ncol, 0);
+            std::vector<const int64_t*> co(ncol); std::vector<const uint8_t*> cd(ncol), cv(ncol, nullptr);
+            std::vector<std::vector<uint8_t>> vbytes(ncol);
+            for (int j = 0; j < ncol; ++j) {
+                co[j] = po[j]; cd[j] = pd[j];
+                vbytes[j].resize((size_t)nr);
+                for (int64_t r = 0; r < nr; ++r) vbytes[j][(size_t)r] = (maps[j][(size_t)r / 8] >> (r % 8)) & 1;
+                cv[j] = vbytes[j].data();
+            }
+            std::string hdr = "\xef\xbb\xbf";
+            for (int j = 0; j < ncol; ++j) { hdr += (j ? ",c" : "c") + std::to_string(j); }
+            hdr += "\n";
+            std::vector<int64_t> rows;
+            for (int64_t r = nr - 1; r >= 0; r -= 3) rows.push_back(r);
+            int64_t wrote = 0;
+            const char* out_path = "/tmp/dyd_asan_out.csv";
+            if (dyd_csv_write_file(out_path, 0, (const uint8_t*)hdr.data(), (int64_t)hdr.size(), kinds.data(), co.data(), cd.data(), cv.data(), ncol, rows.data(),
+                                   (int64_t)rows.size(), 3, &wrote)) { printf("write (rows) failed\n"); return 1; }
+            if (dyd_csv_write_file(out_path, 0, (const uint8_t*)hdr.data(), (int64_t)hdr.size(), kinds.data(), co.data(), cd.data(), cv.data(), ncol, nullptr, nr, 3,
+                                   &wrote)) { printf("write failed\n"); return 1; }
+            std::vector<uint8_t> back((size_t)wrote);
+            if (dyd_read_file(out_path, back.data(), wrote, 3)) { printf("read back failed\n"); return 1; }
+            void* h2 = nullptr;
+            dyd_csv_open(back.data(), wrote, (const uint8_t*)nas, na_off.data(), 3, 3, &h2);
+            int64_t nr2; int32_t nc2, fl2; dyd_csv_info(h2, &nr2, &nc2, &hb, &he, &fl2);
+            if (!(fl2 & 1) && nr2 > 0) {
+                std::vector<int64_t> cb2(nc2), cn2(nc2); std::vector<uint8_t> ct2(nc2), cu2(nc2);
+                dyd_csv_measure(h2, 7, cb2.data(), cn2.data(), ct2.data(), cu2.data(), 3);
+                std::vector<std::vector<int64_t>> o2(nc2, std::vector<int64_t>(nr2 + 1)); std::vector<std::vector<uint8_t>> d2(nc2), m2(nc2);
+                std::vector<int32_t> c2(nc2); std::vector<int64_t*> p2(nc2); std::vector<uint8_t*> q2(nc2), r2(nc2);
+                for (int j = 0; j < nc2; ++j) { c2[j] = j; d2[j].resize((size_t)std::max<int64_t>(cb2[j], 1)); m2[j].resize((size_t)(nr2 + 7) / 8); p2[j] = o2[j].data(); q2[j] = d2[j].data(); r2[j] = m2[j].data(); }
+                dyd_csv_fill(h2, nc2, c2.data(), p2.data(), q2.data(), r2.data(), 3);
+                // rows whose every cell is missing are blank lines in the file and vanish on the way back: compare only when none did
+                if (nr2 == nr && nc2 == ncol)
+                    for (int j = 0; j < ncol; ++j)
+                        if (cb2[j] != cb[j] || memcmp(d2[j].data(), datas[j].data(), (size_t)cb[j]) != 0) { printf("round trip changed column %d (flags %d)\n", j, fl2); return 1; }
+                checks += nr2 + (fl2 & 4);
+            }
+            dyd_csv_close(h2);
+        }
     }
     dyd_csv_close(hc);
     printf("ok %ld\n", checks);
