@@ -38,8 +38,9 @@ PROTOTYPES = {
     "dyd_shard_bucket_p2p": (_int, [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p]),
     "dyd_shard_unpack_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _i32, _p]),
     "dyd_shard_pack_reply_p2p": (_int, [_p, _p, _p, _i64, _i64, _i32, _p, _i32, _i32, _p]),
-    "dyd_shard_pack_reply2_p2p": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _i32, _p]),
-    "dyd_shard_unpack2_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
+    "dyd_shard_bucket_p2p_defaults": (_int, [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "dyd_shard_pack_reply2_p2p": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _i32, _i32, _p]),
+    "dyd_shard_unpack2_p2p": (_int, [_p, _p, _p, _i32, _i64, _i64, _p, _p, _p, _p, _i32, _p]),
     "dyd_shard_pack_reply": (_int, [_p, _p, _p, _i64, _p, _i32, _p]),
     "dyd_shard_unpack": (_int, [_p, _i64, _i64, _i64, _p, _p, _i32, _p]),
     "dyd_url_filter_workspace_bytes": (_sz, [_i64, _i64]),

@@ -494,7 +494,9 @@ constexpr int ST_PER_BLOCK = ST_THREADS * ST_PER_THREAD;
 __global__ void __launch_bounds__(ST_THREADS)
 shard_bucket_staged_kernel(const unsigned long long* __restrict__ keys, const uint8_t* __restrict__ null, int64_t row_base,
                            int64_t n, int world, int me, int64_t cap, long long* const* __restrict__ peer_records,
-                           unsigned* __restrict__ sent_row, unsigned long long* cursors, int* overflow) {
+                           unsigned* __restrict__ sent_row, unsigned long long* cursors, int* overflow,
+                           uint8_t* __restrict__ def_keep_d, int64_t* __restrict__ def_rep_d, uint8_t* __restrict__ def_keep_a,
+                           int64_t* __restrict__ def_ref_row) {
     __shared__ unsigned long long skey[ST_PER_BLOCK];
     __shared__ unsigned srow[ST_PER_BLOCK];
     __shared__ unsigned scnt[P2P_MAX_WORLD], soff[P2P_MAX_WORLD + 1];
@@ -512,6 +514,9 @@ shard_bucket_staged_kernel(const unsigned long long* __restrict__ keys, const ui
         key[u] = live ? keys[r] : 0ULL;
         own[u] = live ? owner_of(key[u], world) : -1;
         rank[u] = live ? atomicAdd(&scnt[own[u]], 1u) : 0u;
+        // sparse replies (sharding.UrlFilterExchange): the answer of a row that survives both questions is written here,
+        // coalesced; the owners then send back -- and the unpack kernel scatters -- only the few per cent that differ
+        if (def_keep_d != nullptr && r < n) { def_keep_d[r] = 1; def_rep_d[r] = row_base + r; def_keep_a[r] = 1; def_ref_row[r] = -1; }
     }
     __syncthreads();
     if (threadIdx.x == 0) { unsigned acc = 0; for (int o = 0; o < world; ++o) { soff[o] = acc; acc += scnt[o]; } soff[world] = acc; }
@@ -543,28 +548,33 @@ shard_bucket_staged_kernel(const unsigned long long* __restrict__ keys, const ui
 __global__ void __launch_bounds__(HT_THREADS)
 shard_pack_reply2_p2p_kernel(long long* __restrict__ records, const uint8_t* __restrict__ keep_d, const int64_t* __restrict__ rep_d,
                              const uint8_t* __restrict__ keep_a, const int64_t* __restrict__ rep_a, int64_t m, int64_t cap, int me,
-                             long long* const* __restrict__ peer_reply, bool reset) {
+                             long long* const* __restrict__ peer_reply, bool reset, bool sparse) {
     const int64_t r = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (r >= m) return;
     const int src = (int)(r / cap);
     const int64_t slot = r - (int64_t)src * cap;
     const long long id = records[2 * r + 1];
     if (reset && id >= 0) records[2 * r + 1] = -1;
+    // sparse: the origin already holds "kept by both" for every row and its reply buffer says "no answer" everywhere
+    if (sparse && (id < 0 || (keep_d[r] != 0 && rep_d[r] == id && keep_a[r] != 0))) return;
     reinterpret_cast<longlong2*>(peer_reply[src])[(int64_t)me * cap + slot] =
         make_longlong2(reply_word(0, id, keep_d[r], rep_d[r]), reply_word(1, id, keep_a[r], rep_a[r]));
 }
 __global__ void __launch_bounds__(HT_THREADS)
-shard_unpack2_p2p_kernel(const longlong2* __restrict__ reply, const unsigned* __restrict__ sent_row,
+shard_unpack2_p2p_kernel(longlong2* __restrict__ reply, const unsigned* __restrict__ sent_row,
                          const unsigned long long* __restrict__ cursors, int world, int64_t cap, int64_t n,
-                         uint8_t* __restrict__ keep_d, int64_t* __restrict__ rep_d, uint8_t* __restrict__ keep_a, int64_t* __restrict__ rep_a) {
+                         uint8_t* __restrict__ keep_d, int64_t* __restrict__ rep_d, uint8_t* __restrict__ keep_a, int64_t* __restrict__ rep_a,
+                         bool sparse) {
     const int64_t t = blockIdx.x * (int64_t)HT_THREADS + threadIdx.x;
     if (t >= (int64_t)world * cap) return;
     const int own = (int)(t / cap);
     const int64_t slot = t - (int64_t)own * cap;
     if ((unsigned long long)slot >= cursors[own]) return;           // never filled
     const longlong2 v = reply[t];
+    if (v.x < 0) return;                                            // padding, or (sparse) nothing to change
+    if (sparse) reply[t] = make_longlong2(-1, -1);                  // last reader: the slot says "no answer" again for the next step
     const int64_t row = sent_row[t];
-    if (v.x < 0 || row >= n) return;
+    if (row >= n) return;
     keep_d[row] = (uint8_t)((v.x >> 62) & 1);
     rep_d[row] = v.x & ((1LL << 62) - 1);
     const uint8_t k = (uint8_t)((v.y >> 62) & 1);
@@ -858,9 +868,29 @@ extern "C" int dyd_shard_bucket(const uint64_t* d_keys, const uint8_t* d_null, i
     return launch_check("shard_bucket_kernel");
 }
 
+static int shard_bucket_p2p_impl(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
+                                 int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
+                                 uint64_t* d_cursors, int32_t* d_overflow, uint8_t* d_def_keep_d, int64_t* d_def_rep_d,
+                                 uint8_t* d_def_keep_a, int64_t* d_def_ref_row, void* stream);
 extern "C" int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
                                     int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
                                     uint64_t* d_cursors, int32_t* d_overflow, void* stream) {
+    return shard_bucket_p2p_impl(d_keys, d_null, row_base, n, world, my_rank, cap, d_peer_records, d_sent_row, d_cursors, d_overflow,
+                                 nullptr, nullptr, nullptr, nullptr, stream);
+}
+extern "C" int dyd_shard_bucket_p2p_defaults(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
+                                             int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
+                                             uint64_t* d_cursors, int32_t* d_overflow, uint8_t* d_keep_dedup, int64_t* d_rep_dedup,
+                                             uint8_t* d_keep_anti, int64_t* d_ref_row, void* stream) {
+    DYD_REQUIRE(world <= P2P_MAX_WORLD, DYD_E_ARG, "the sparse-reply form needs world <= 64");
+    DYD_REQUIRE(d_keep_dedup && d_rep_dedup && d_keep_anti && d_ref_row, DYD_E_ARG, "null pointer");
+    return shard_bucket_p2p_impl(d_keys, d_null, row_base, n, world, my_rank, cap, d_peer_records, d_sent_row, d_cursors, d_overflow,
+                                 d_keep_dedup, d_rep_dedup, d_keep_anti, d_ref_row, stream);
+}
+static int shard_bucket_p2p_impl(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
+                                 int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
+                                 uint64_t* d_cursors, int32_t* d_overflow, uint8_t* d_def_keep_d, int64_t* d_def_rep_d,
+                                 uint8_t* d_def_keep_a, int64_t* d_def_ref_row, void* stream) {
     DYD_REQUIRE(n >= 0 && n < (1LL << 32) && world >= 1 && cap >= 0 && my_rank >= 0 && my_rank < world, DYD_E_ARG, "bad arguments");
     DYD_REQUIRE(d_peer_records && d_cursors && d_overflow && (n == 0 || d_keys), DYD_E_ARG, "null pointer");
     cudaStream_t s = as_stream(stream);
@@ -868,10 +898,11 @@ extern "C" int dyd_shard_bucket_p2p(const uint64_t* d_keys, const uint8_t* d_nul
     DYD_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), s));
     if (n == 0) return 0;
     const char* e = getenv("DYD_SCATTER_STAGED");
-    if (world <= P2P_MAX_WORLD && !(e && atoi(e) == 0)) {
+    if (world <= P2P_MAX_WORLD && (d_def_keep_d != nullptr || !(e && atoi(e) == 0))) {
         shard_bucket_staged_kernel<<<(unsigned)((n + ST_PER_BLOCK - 1) / ST_PER_BLOCK), ST_THREADS, 0, s>>>(
             reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n, world, my_rank, cap,
-            reinterpret_cast<long long* const*>(d_peer_records), d_sent_row, reinterpret_cast<unsigned long long*>(d_cursors), d_overflow);
+            reinterpret_cast<long long* const*>(d_peer_records), d_sent_row, reinterpret_cast<unsigned long long*>(d_cursors), d_overflow,
+            d_def_keep_d, d_def_rep_d, d_def_keep_a, d_def_ref_row);
         return launch_check("shard_bucket_staged_kernel");
     }
     shard_bucket_p2p_kernel<<<grid_for(n), HT_THREADS, url_pad(), s>>>(reinterpret_cast<const unsigned long long*>(d_keys), d_null, row_base, n,
@@ -903,26 +934,26 @@ extern "C" int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_se
 
 extern "C" int dyd_shard_pack_reply2_p2p(int64_t* d_records, const uint8_t* d_keep_dedup, const int64_t* d_rep_dedup,
                                          const uint8_t* d_keep_anti, const int64_t* d_ref_row, int64_t m, int64_t cap, int32_t my_rank,
-                                         int64_t* const* d_peer_reply2, int32_t reset_records, void* stream) {
+                                         int64_t* const* d_peer_reply2, int32_t reset_records, int32_t sparse, void* stream) {
     DYD_REQUIRE(m >= 0 && cap > 0 && my_rank >= 0 && m % cap == 0, DYD_E_ARG, "bad arguments");
     if (m == 0) return 0;
     DYD_REQUIRE(d_records && d_keep_dedup && d_rep_dedup && d_keep_anti && d_ref_row && d_peer_reply2, DYD_E_ARG, "null pointer");
     shard_pack_reply2_p2p_kernel<<<grid_for(m), HT_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<long long*>(d_records), d_keep_dedup, d_rep_dedup,
                                                                                    d_keep_anti, d_ref_row, m, cap, my_rank,
-                                                                                   reinterpret_cast<long long* const*>(d_peer_reply2), reset_records != 0);
+                                                                                   reinterpret_cast<long long* const*>(d_peer_reply2), reset_records != 0, sparse != 0);
     return launch_check("shard_pack_reply2_p2p_kernel");
 }
 
-extern "C" int dyd_shard_unpack2_p2p(const int64_t* d_reply2, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
+extern "C" int dyd_shard_unpack2_p2p(int64_t* d_reply2, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
                                      int64_t cap, int64_t n, uint8_t* d_keep_dedup, int64_t* d_rep_dedup, uint8_t* d_keep_anti,
-                                     int64_t* d_ref_row, void* stream) {
+                                     int64_t* d_ref_row, int32_t sparse, void* stream) {
     DYD_REQUIRE(world >= 1 && cap >= 0 && n >= 0, DYD_E_ARG, "bad arguments");
     if (cap == 0 || n == 0) return 0;
     DYD_REQUIRE(d_reply2 && d_sent_row && d_cursors && d_keep_dedup && d_rep_dedup && d_keep_anti && d_ref_row, DYD_E_ARG, "null pointer");
     DYD_REQUIRE(((uintptr_t)d_reply2 & 15) == 0, DYD_E_ALIGN, "reply buffer must be 16-byte aligned");
     shard_unpack2_p2p_kernel<<<grid_for((int64_t)world * cap), HT_THREADS, 0, as_stream(stream)>>>(
-        reinterpret_cast<const longlong2*>(d_reply2), d_sent_row, reinterpret_cast<const unsigned long long*>(d_cursors), world, cap, n,
-        d_keep_dedup, d_rep_dedup, d_keep_anti, d_ref_row);
+        reinterpret_cast<longlong2*>(d_reply2), d_sent_row, reinterpret_cast<const unsigned long long*>(d_cursors), world, cap, n,
+        d_keep_dedup, d_rep_dedup, d_keep_anti, d_ref_row, sparse != 0);
     return launch_check("shard_unpack2_p2p_kernel");
 }
 

@@ -462,9 +462,16 @@ class UrlFilterExchange(AntiJoinExchange):
         p2p = self.transport == "p2p"
         with torch.cuda.device(dev):
             s = _stream(dev)
+            sparse = p2p and self.world <= 64
             if p2p:
                 self._scatter_p2p(self.ref, ref_keys, ref_null, ref_row_base, self.overflow[1:], s)
-                self._scatter_p2p(self.main, main_keys, main_null, row_base, self.overflow[:1], s)
+                if sparse:        # the scatter also writes "kept by both" for every row; only other answers travel back
+                    _lib.check(lib.dyd_shard_bucket_p2p_defaults(_ptr(main_keys), _ptr(main_null), row_base, self.n, self.world, self.rank, self.main.cap,
+                                                                 _ptr(self.main.peers), _ptr(self.main.sent_row), _ptr(self.main.cursors),
+                                                                 _ptr(self.overflow[:1]), _ptr(self.keep_d), _ptr(self.rep_d), _ptr(self.keep),
+                                                                 _ptr(self.rep), s), "dyd_shard_bucket_p2p_defaults")
+                else:
+                    self._scatter_p2p(self.main, main_keys, main_null, row_base, self.overflow[:1], s)
                 self.main.h.barrier(channel=1)                    # both tables' records have landed
             else:
                 _lib.check(lib.dyd_shard_bucket(_ptr(ref_keys), _ptr(ref_null), ref_row_base, self.n_ref, self.world, self.cap_ref,
@@ -477,16 +484,17 @@ class UrlFilterExchange(AntiJoinExchange):
             _lib.check(lib.dyd_url_filter_records(_ptr(self.recv_ref), m_ref, _ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_dr), _ptr(self.rep_dr),
                                                   _ptr(self.keep_r), _ptr(self.rep_r), _ptr(self.ws_d), self.ws_d.numel(), 1 if p2p else 0, s),
                        "dyd_url_filter_records")
-            if main_null is not None:                         # rows that never travel: a NaN cell never matches
+            if main_null is not None and not sparse:          # rows that never travel: a NaN cell never matches
                 self.keep.fill_(1); self.rep.fill_(-1)
             if p2p:
                 # both answers of a record leave in one 16-byte store; the pack kernel, the last reader of the records, resets them
                 _lib.check(lib.dyd_shard_pack_reply2_p2p(_ptr(self.recv), _ptr(self.keep_dr), _ptr(self.rep_dr), _ptr(self.keep_r), _ptr(self.rep_r),
-                                                         m, self.cap, self.rank, _ptr(self.peer_back2), 1, s), "dyd_shard_pack_reply2_p2p")
+                                                         m, self.cap, self.rank, _ptr(self.peer_back2), 1, 1 if sparse else 0, s),
+                           "dyd_shard_pack_reply2_p2p")
                 self.h_back2.barrier(channel=0)               # all answers have landed
                 _lib.check(lib.dyd_shard_unpack2_p2p(_ptr(self.back2), _ptr(self.main.sent_row), _ptr(self.cursors), self.world, self.cap,
-                                                     self.n, _ptr(self.keep_d), _ptr(self.rep_d), _ptr(self.keep), _ptr(self.rep), s),
-                           "dyd_shard_unpack2_p2p")
+                                                     self.n, _ptr(self.keep_d), _ptr(self.rep_d), _ptr(self.keep), _ptr(self.rep),
+                                                     1 if sparse else 0, s), "dyd_shard_unpack2_p2p")
             else:
                 _lib.check(lib.dyd_shard_pack_reply(_ptr(self.recv), _ptr(self.keep_dr), _ptr(self.rep_dr), m, _ptr(self.reply_d), 0, s),
                            "dyd_shard_pack_reply")

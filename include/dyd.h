@@ -160,13 +160,21 @@ int dyd_shard_unpack_p2p(const int64_t* d_reply, const uint32_t* d_sent_row, con
                          int64_t cap, int64_t n, uint8_t* d_keep, int64_t* d_rep, int32_t mode, void* stream);
 /* Joint exchange (dedup + anti-join answers of the same main records, sharding.UrlFilterExchange): both 8-byte answers
  * travel as ONE 16-byte store into region `my_rank` of the origin's reply buffer (int64[2 * world * cap], 16-byte
- * aligned); _unpack2 places them into the four result columns.                                            */
+ * aligned); _unpack2 places them into the four result columns.
+ * Sparse replies (sparse != 0): _bucket_p2p_defaults, the scatter of the main table, also writes the answer "kept by both"
+ * (keep 1, rep = own global row, keep_ref 1, ref_row -1) for every row with coalesced stores; the origin's reply buffer holds
+ * -1 everywhere (filled once; _unpack2 resets the slots it reads); the owners then store only the answers that differ
+ * (a few per cent of the records cross NVLink on the way back) and _unpack2 scatters only those.                   */
+int dyd_shard_bucket_p2p_defaults(const uint64_t* d_keys, const uint8_t* d_null, int64_t row_base, int64_t n, int32_t world,
+                                  int32_t my_rank, int64_t cap, int64_t* const* d_peer_records, uint32_t* d_sent_row,
+                                  uint64_t* d_cursors, int32_t* d_overflow, uint8_t* d_keep_dedup, int64_t* d_rep_dedup,
+                                  uint8_t* d_keep_anti, int64_t* d_ref_row, void* stream);
 int dyd_shard_pack_reply2_p2p(int64_t* d_records, const uint8_t* d_keep_dedup, const int64_t* d_rep_dedup,
                               const uint8_t* d_keep_anti, const int64_t* d_ref_row, int64_t m, int64_t cap, int32_t my_rank,
-                              int64_t* const* d_peer_reply2, int32_t reset_records, void* stream);
-int dyd_shard_unpack2_p2p(const int64_t* d_reply2, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
+                              int64_t* const* d_peer_reply2, int32_t reset_records, int32_t sparse, void* stream);
+int dyd_shard_unpack2_p2p(int64_t* d_reply2, const uint32_t* d_sent_row, const uint64_t* d_cursors, int32_t world,
                           int64_t cap, int64_t n, uint8_t* d_keep_dedup, int64_t* d_rep_dedup, uint8_t* d_keep_anti,
-                          int64_t* d_ref_row, void* stream);
+                          int64_t* d_ref_row, int32_t sparse, void* stream);
 /* NCCL-transport forms: (id, answer) pairs */
 int dyd_shard_pack_reply(const int64_t* d_records, const uint8_t* d_keep, const int64_t* d_rep, int64_t m,
                          int64_t* d_reply, int32_t mode, void* stream);

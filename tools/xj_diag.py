@@ -14,7 +14,7 @@ _, roff, rdata = synth_device.make_urls(0, rank * n_ref, n_ref, dev, n_main_for_
 x = sharding.UrlFilterExchange(n, n_ref, world, dev)
 assert x.transport == "p2p", getattr(x, "p2p_error", "")
 lib = x.lib; m = world * x.cap; m_ref = world * x.cap_ref; s = _stream(dev)
-names = ["hash_main", "hash_ref", "scatter_ref", "scatter_main", "barrier_1", "dedup_records", "antijoin_records", "pack_both",
+names = ["hash_main", "hash_ref", "scatter_ref", "scatter_main", "barrier_1", "url_filter_records", "pack_both",
          "barrier_2", "unpack_both"]
 acc = {k: 0.0 for k in names}
 def ev(): return torch.cuda.Event(enable_timing=True)
@@ -26,13 +26,12 @@ for it in range(R):
     e[i].record(); i += 1; keys = ops.hash_strings(uoff, udata)
     e[i].record(); i += 1; rkeys = ops.hash_strings(roff, rdata)
     e[i].record(); i += 1; x._scatter_p2p(x.ref, rkeys, None, rank * n_ref, x.overflow[1:], s)
-    e[i].record(); i += 1; x._scatter_p2p(x.main, keys, None, rank * n, x.overflow[:1], s)
+    e[i].record(); i += 1; _lib.check(lib.dyd_shard_bucket_p2p_defaults(_ptr(keys), None, rank * n, n, world, rank, x.main.cap, _ptr(x.main.peers), _ptr(x.main.sent_row), _ptr(x.main.cursors), _ptr(x.overflow[:1]), _ptr(x.keep_d), _ptr(x.rep_d), _ptr(x.keep), _ptr(x.rep), s), "s")
     e[i].record(); i += 1; x.main.h.barrier(channel=1)
-    e[i].record(); i += 1; _lib.check(lib.dyd_dedup_records(_ptr(x.recv), m, 0, _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.ws_d), x.ws_d.numel(), s), "d")
-    e[i].record(); i += 1; _lib.check(lib.dyd_antijoin_records(_ptr(x.recv_ref), m_ref, _ptr(x.recv), m, _ptr(x.keep_r), _ptr(x.rep_r), _ptr(x.ws), x.ws.numel(), 1, s), "a")
-    e[i].record(); i += 1; _lib.check(lib.dyd_shard_pack_reply2_p2p(_ptr(x.recv), _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.keep_r), _ptr(x.rep_r), m, x.cap, rank, _ptr(x.peer_back2), 1, s), "p")
+    e[i].record(); i += 1; _lib.check(lib.dyd_url_filter_records(_ptr(x.recv_ref), m_ref, _ptr(x.recv), m, 0, _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.keep_r), _ptr(x.rep_r), _ptr(x.ws_d), x.ws_d.numel(), 1, s), "j")
+    e[i].record(); i += 1; _lib.check(lib.dyd_shard_pack_reply2_p2p(_ptr(x.recv), _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.keep_r), _ptr(x.rep_r), m, x.cap, rank, _ptr(x.peer_back2), 1, 1, s), "p")
     e[i].record(); i += 1; x.h_back2.barrier(channel=0)
-    e[i].record(); i += 1; _lib.check(lib.dyd_shard_unpack2_p2p(_ptr(x.back2), _ptr(x.main.sent_row), _ptr(x.cursors), world, x.cap, n, _ptr(x.keep_d), _ptr(x.rep_d), _ptr(x.keep), _ptr(x.rep), s), "u")
+    e[i].record(); i += 1; _lib.check(lib.dyd_shard_unpack2_p2p(_ptr(x.back2), _ptr(x.main.sent_row), _ptr(x.cursors), world, x.cap, n, _ptr(x.keep_d), _ptr(x.rep_d), _ptr(x.keep), _ptr(x.rep), 1, s), "u")
     e[i].record(); torch.cuda.synchronize()
     if it >= 4:
         for j, k in enumerate(names): acc[k] += e[j].elapsed_time(e[j + 1]) / (R - 4)
