@@ -599,12 +599,13 @@ def main():
             dist.destroy_process_group()
         return
 
-    traffic = None
+    traffic, traffic_source = None, None
     tp = ROOT / "profiles" / "roofline_traffic.json"
     if tp.exists():
         tj = json.loads(tp.read_text())
         if tj.get("images") == n_img:
             traffic = tj.get("dram_bytes_per_launch")
+            traffic_source = "not measured in this run (a run under ncu is never a bench value): " + str(tj.get("source"))
     achieved = fused_bytes / (fused_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
@@ -618,7 +619,7 @@ def main():
                     "fused_ms": fused_ms, "url_chain_ms": url_ms_max, ("url_filter_ms" if world == 1 else "joint_exchange_ms"): anti_ms_max, "fused_cta_times_last_launch": cta_times,
                     "note": "per-step CUDA-event times on each stream (max over ranks for the URL chain); a step ends when both streams are done"},
         "roofline": {"bound": "hbm", "kernel": "fused_tma_kernel (+ tile_desc pre-pass and crowd worklist kernel, timed together)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                      "peak_source": peak_kind, "algorithmic_bytes_per_launch": fused_bytes,
                      "bytes_per_image": fused_bytes / n_img, "ms_per_launch": fused_ms,
                      "concurrent": "timed while the URL stream runs beside it" if overlap else "timed alone"},

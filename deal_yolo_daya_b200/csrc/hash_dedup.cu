@@ -154,7 +154,7 @@ dedup_lookup_kernel(const unsigned long long* __restrict__ keys, const uint8_t* 
 
 // ------------------------------------------------------------------------------- K4, partitioned
 #ifndef DYD_PT_THREADS
-#define DYD_PT_THREADS 256
+#define DYD_PT_THREADS 128
 #endif
 #ifndef DYD_PT_FILL
 #define DYD_PT_FILL 128                          // average records per partition in [FILL, 2 * FILL)
@@ -1042,6 +1042,9 @@ extern "C" int dyd_antijoin_records(int64_t* d_ref_records, int64_t m_ref, const
 
 // ------------------------------------------------------------------------------- K4 + K5 joint: host side
 extern "C" size_t dyd_url_filter_workspace_bytes(int64_t n_main, int64_t n_ref);
+#ifndef DYD_JOINT_FILL
+#define DYD_JOINT_FILL 192
+#endif
 struct JointLayout {
     int log2_np;
     unsigned pcap_m, pcap_r;
@@ -1050,11 +1053,11 @@ struct JointLayout {
 static inline JointLayout joint_layout(int64_t n_main, int64_t n_ref, bool with_r) {
     JointLayout L{};
     int k = 0;
-    while (((192LL << k) < n_main || (96LL << k) < n_ref) && k < 30) ++k;      // main fill < 192, reference fill < 96 on average
+    while ((((long long)DYD_JOINT_FILL << k) < n_main || (((long long)DYD_JOINT_FILL / 2) << k) < n_ref) && k < 30) ++k;   // main fill < 192, reference fill < 96 on average
     L.log2_np = k;
     const uint64_t np = 1ULL << k;
     L.pcap_m = (unsigned)std::min<uint64_t>(PT_THREADS * PT_MAX_PER_THREAD - 1, 2 * ((uint64_t)n_main / np) + 32);
-    L.pcap_r = (unsigned)std::min<uint64_t>(255, 2 * ((uint64_t)n_ref / np) + 32);
+    L.pcap_r = (unsigned)std::min<uint64_t>(383, 2 * ((uint64_t)n_ref / np) + 32);      // pcap_m + pcap_r < PT_SLOTS
     size_t o = sizeof(TableHeader);
     L.cur_m = o; o += sizeof(unsigned) * np;
     L.cur_r = o; o += sizeof(unsigned) * np;

@@ -9,7 +9,9 @@ mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $out/${tag}_gpu.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest_gpu.log
 tail -3 $out/${tag}_pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > $out/${tag}_smoke.log 2>&1; tail -1 $out/${tag}_smoke.log
 timeout 900 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err; echo "bench exit $?"
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu --no-legs > $out/${tag}_bench_n1_steps20.json 2>> $out/${tag}_bench_n1.err; echo "bench 20+5 exit $?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference_arm.json 2> $out/${tag}_bench_ref.err; echo "ref arm exit $?"
 timeout 600 python tools/kbench.py --images 10000000 --reps 10 > $out/${tag}_kbench_10M.txt 2>&1; echo "kbench exit $?"
 # ncu: launch list of the bench step (no CPU legs), then full captures
