@@ -5,7 +5,7 @@ from pathlib import Path
 P = Path(__file__).resolve().parent.parent / "profiles"
 rows, base = [], None
 for n in (1, 2, 4, 8):
-    f = P / f"r2_bench_n{n}.json"
+    f = P / (f"r2_bench_n{n}.json" if n > 1 else "r2_bench_n1_steps20.json")
     if not f.exists():
         continue
     d = json.loads(f.read_text())
