@@ -68,7 +68,7 @@ def c4_leg(dev, rank, world, peak, n_img=1_000_000):
 
 
 def c5_leg(dev, rank, world, t, peak, seed=42, ratios=(0.8, 0.1, 0.1)):
-    from deal_yolo_daya_b200 import ops, sharding, synth
+    from deal_yolo_daya_b200 import native, ops, sharding, synth
     from oracle import oracle_c
     n_img, n_obj = t.n_img, t.n_poly
     n_lab, n_grp, n_cat = synth.N_LABELS, 20, 4
@@ -95,14 +95,14 @@ def c5_leg(dev, rank, world, t, peak, seed=42, ratios=(0.8, 0.1, 0.1)):
     ms_bases = (time.perf_counter() - a) * 1e3
     n_c = (cat_off_g[1:] - cat_off_g[:-1]).cpu().numpy()
     n_exp_g = int(cat_off_g[-1].item())
-    # host permutations (numpy MT19937, what DataFrame.sample(frac=1, random_state=seed) applies): category c is shuffled by
+    # host permutations (numpy's legacy MT19937 shuffle, what DataFrame.sample(frac=1, random_state=seed) applies; native.permutation): category c is shuffled by
     # rank c % world and broadcast, so the wall time is one category's, not the sum
     a = time.perf_counter()
     perm = torch.empty(n_exp_g, dtype=torch.int64, device=dev)
     for c in range(n_cat):
         seg = perm[int(cat_off_g[c].item()):int(cat_off_g[c + 1].item())]
         if c % world == rank:
-            seg.copy_(torch.from_numpy(np.random.RandomState(seed).permutation(int(n_c[c]))))
+            seg.copy_(torch.from_numpy(native.permutation(seed, int(n_c[c]))))
     if world > 1:
         for c in range(n_cat):
             dist.broadcast(perm[int(cat_off_g[c].item()):int(cat_off_g[c + 1].item())], src=c % world)
@@ -148,7 +148,7 @@ def c5_leg(dev, rank, world, t, peak, seed=42, ratios=(0.8, 0.1, 0.1)):
            "images_per_s_kernels": world * n_img / ((ms3 + ms6 + ms_assign) * 1e-3),
            "replaced_labels_rank0": int(cnt[3]), "checks": checks, "verified": bool(all(checks.values())),
            "note": "K3 label LUT 80->20 + K6 expand / global category offsets (NCCL all_gather) / assign on every rank's C2 table; the host permutation "
-                   "(numpy RandomState(42).permutation per category, reference semantics) is timed separately and is not in images_per_s_kernels"}
+                   "(np.random.RandomState(42).permutation per category, reference semantics, produced bit for bit by dyd_numpy_permutation) is timed separately and is not in images_per_s_kernels"}
     ok_t = torch.tensor([int(all(checks.values()))], device=dev)
     if world > 1:
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)

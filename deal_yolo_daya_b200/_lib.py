@@ -61,6 +61,7 @@ PROTOTYPES = {
     "dyd_split_fill": (_int, [_p, _i64, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "dyd_split_assign": (_int, [_p, _i32, _p, _i64, _p, _p, _p, _p, _p]),
     "dyd_split_assign_range": (_int, [_p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "dyd_numpy_permutation": (_int, [C.c_uint32, _i64, _p]),
     "dyd_yolo_normalise": (_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p]),
     "dyd_bbox_iou_host": (_int, [_p, _p, _p, _i64, _i64, _f64, _p, _p, _p, _p, _p, _i64]),
     "dyd_dedup_host": (_int, [_p, _p, _p, _i64, _int, _p, _p]),

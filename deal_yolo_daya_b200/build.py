@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libdyd.so"
 SYNTH_OUT = PKG / "libdyd_synth.so"          # synthetic-table generator (bench / tests), kept out of the product library
-SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "host_pipeline.cu", "ingest.cpp", "csv_read.cpp"]
+SOURCES = ["api.cu", "bbox_iou.cu", "bbox_tma.cu", "hash_dedup.cu", "labels.cu", "host_pipeline.cu", "ingest.cpp", "csv_read.cpp", "np_perm.cpp"]
 SYNTH_SOURCES = ["api.cu", "synth.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -459,7 +459,7 @@ def _split_native(df, l2c, json_columns, train_ratio, val_ratio, random_seed):
         sizes = np.diff(cat_off)
         n_train = np.array([int(k * train_ratio) for k in sizes], np.int64)
         n_val = np.array([int(k * val_ratio) for k in sizes], np.int64)
-        perms = [np.random.RandomState(random_seed).permutation(int(k)) for k in sizes]
+        perms = [native.permutation(random_seed, int(k)) for k in sizes]
         perm = np.concatenate(perms).astype(np.int64) if perms else np.zeros(0, np.int64)
         if len(perm):
             split_id, pos = _kernels().split_assign(cat_off, perm, n_train, n_val)
@@ -631,7 +631,8 @@ def split_df(df: pd.DataFrame, l2c: dict, json_columns=None,
     sizes = np.diff(cat_off)
     n_train = np.array([int(n * train_ratio) for n in sizes], np.int64)
     n_val = np.array([int(n * val_ratio) for n in sizes], np.int64)
-    perms = [np.random.RandomState(random_seed).permutation(int(n)) for n in sizes]
+    from . import native
+    perms = [native.permutation(random_seed, int(n)) for n in sizes]
     perm = np.concatenate(perms).astype(np.int64) if perms else np.zeros(0, np.int64)
     if len(perm):
         split_id, pos = _kernels().split_assign(cat_off, perm, n_train, n_val)

@@ -368,6 +368,17 @@ def roundtrip_safe(df, check_cells=True) -> bool:
     return True
 
 
+def permutation(seed, n: int) -> np.ndarray:
+    """``np.random.RandomState(seed).permutation(n)`` (the order ``DataFrame.sample(frac=1, random_state=seed)`` gives the rows,
+    processor.py:800), bit for bit, from csrc/np_perm.cpp; seeds numpy treats differently (not an int in 0 .. 2^32-1) and small
+    n go to numpy itself."""
+    if n < 4096 or n > 0xFFFFFFFF or not enabled() or isinstance(seed, bool) or not isinstance(seed, (int, np.integer)) or not 0 <= int(seed) <= 0xFFFFFFFF:
+        return np.random.RandomState(seed).permutation(n)
+    out = np.empty(n, np.int64)
+    _lib.check(_lib.load().dyd_numpy_permutation(int(seed), n, _p(out)), "dyd_numpy_permutation")
+    return out
+
+
 def yolo_label_texts(img_off, class_id, cxcywh, ok):
     """Label-file texts of processor.py:1045-1052 for every image: (text uint8[], off int64[n_img+1]).
     Inputs are host arrays: img_off int64[n_img+1], class_id int32[n_box], cxcywh float64[4*n_box]

@@ -268,6 +268,11 @@ int dyd_split_assign_range(const int64_t* d_cat_off, int32_t n_cat, const int64_
                            const int64_t* d_n_train, const int64_t* d_n_val, const int64_t* d_own_lo,
                            const int64_t* d_own_cnt, const int64_t* d_local_off, uint8_t* d_split, int64_t* d_pos, void* stream);
 
+/* np.random.RandomState(seed).permutation(n), bit for bit (host; what DataFrame.sample(frac=1, random_state=seed) of
+ * processor.py:800 / :1003 applies): MT19937 + numpy's legacy masked-rejection shuffle, with the swap targets drawn a
+ * block ahead and prefetched.  h_out int64[n].  Integer seeds 0 .. 2^32-1 (what the reference passes).               */
+int dyd_numpy_permutation(uint32_t seed, int64_t n, int64_t* h_out);
+
 /* ------------------------------------------------------------ YOLO (f-3) ---
  * cx, cy, w, h of processor.py:1045-1052 for every box: ((x1+x2)/2)/W etc., fp64,
  * same operation order; ok[q] = 0 where bw <= 0 or bh <= 0 or the box is invalid. */

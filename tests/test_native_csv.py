@@ -79,3 +79,17 @@ def test_yolo_label_text_matches_python_formatting():
         want = "\n".join(f"{cls[q]} {vals[4*q]:.6f} {vals[4*q+1]:.6f} {vals[4*q+2]:.6f} {vals[4*q+3]:.6f}"
                          for q in range(img_off[i], img_off[i + 1]) if ok[q])
         assert bytes(text[off[i]:off[i + 1]]).decode() == want
+
+
+def test_native_permutation_is_numpys_legacy_permutation():
+    """dyd_numpy_permutation == np.random.RandomState(seed).permutation(n), bit for bit (the order DataFrame.sample(frac=1,
+    random_state=seed) gives the rows of a category, processor.py:800); other seeds and small n are numpy's own."""
+    for seed in (0, 1, 42, 2024, 2 ** 32 - 1):
+        for n in (4096, 4097, 65535, 65536, 65537, 300001, (1 << 20) + 3):
+            assert np.array_equal(native.permutation(seed, n), np.random.RandomState(seed).permutation(n)), (seed, n)
+    for seed in (42, np.int64(7), None.__class__ and 5):
+        assert np.array_equal(native.permutation(seed, 100), np.random.RandomState(seed).permutation(100))
+    df = pd.DataFrame({"a": np.arange(50000)})
+    assert np.array_equal(df.sample(frac=1, random_state=42)["a"].to_numpy(), native.permutation(42, 50000))
+    with pytest.raises((ValueError, TypeError)):
+        native.permutation(-1, 10)
