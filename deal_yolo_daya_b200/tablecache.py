@@ -3,7 +3,7 @@
 The reference's steps talk to each other through CSV files (processor.py:158 -> :181, :213 -> :235, :310 -> :379):
 every step re-reads what the previous one wrote.  The drop-in keeps the file contract -- every output file is
 written, synchronously, byte for byte -- and additionally remembers, per path, the frame ``pd.read_csv`` WOULD
-return for the file it just wrote or read, keyed by (absolute path, size, mtime_ns, inode).  A later ``_read_csv``
+return for the file it just wrote or read, keyed by (absolute path, size, mtime_ns, inode, a hash of the file's first and last 4 KB).  A later ``_read_csv``
 of the same, unchanged file gets that frame back (a shallow copy: pandas >= 3 is copy-on-write, so callers cannot
 alter the cached columns).  A file changed by anyone else has another size / mtime and is read from disk.
 
@@ -46,11 +46,21 @@ def _limit() -> int:
 
 
 def _key(path):
+    """(absolute path, size, mtime_ns, inode, hash of the first and last 4 KB).  The content probe costs two small reads and
+    closes the one gap stat() leaves: a same-size rewrite by somebody else inside one tick of the file system's clock."""
     try:
-        st = os.stat(path)
+        with open(path, "rb") as f:
+            st = os.fstat(f.fileno())
+            head = f.read(4096)
+            tail = b""
+            if st.st_size > 8192:
+                f.seek(st.st_size - 4096)
+                tail = f.read(4096)
+            elif st.st_size > 4096:
+                tail = f.read()
     except OSError:
         return None
-    return (os.path.abspath(os.fspath(path)), st.st_size, st.st_mtime_ns, st.st_ino)
+    return (os.path.abspath(os.fspath(path)), st.st_size, st.st_mtime_ns, st.st_ino, hash(head), hash(tail))
 
 
 def _frame_bytes(df) -> int:
