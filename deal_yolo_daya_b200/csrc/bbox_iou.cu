@@ -153,25 +153,216 @@ iou_tile_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ 
 // ------------------------------------------------------------------------------- K2 (block per crowded image)
 // Processes the worklist: computes the valid prefix, writes count and high.
 //
-// Pairing: box s meets s+1 .. s+(n-1)/2 (mod n); for even n the antipodal pair is taken by the lower half only -- every
-// unordered pair exactly once, no pair table.  Register tiling: a thread owns CROWD_R = 4 CONSECUTIVE boxes and walks the
+// Two forms.  Up to CROWD_SWEEP_MAX (512) boxes -- every image of config C4 -- the BINNED form below (crowd_sweep): only pairs
+// that can overlap in x are met.  Larger images (up to 1024 boxes in shared memory) take the ALL-PAIRS form (crowd_tiled):
+// box s meets s+1 .. s+(n-1)/2 (mod n); for even n the antipodal pair is taken by the lower half only -- every unordered pair
+// exactly once, no pair table.  Register tiling: a thread owns 4 CONSECUTIVE boxes and walks the
 // partners t = s0+1, s0+2, ... once; each partner (two 16-byte shared loads) is tested against all four own boxes, so the
 // shared-memory traffic per pair is a quarter of the one-box-per-thread form and the loop is bound by the four fp64
 // compares of the overlap pre-test (processor.py:329-333 reduces to them when no coordinate is NaN).  Boxes sit in shared
 // memory de-interleaved by 4 (position (j & 3) * 256 + j / 4), which makes the lanes' stride-4 partner reads consecutive.
 // Pairs that pass the pre-test (a fraction of a per cent) are queued and get the full IoU arithmetic from all threads after
 // every chunk of 32 partners -- dense warps instead of one diverged lane -- and the block leaves as soon as one hits.
+// (Tile widths of 2 and 3 for smaller images were measured and change nothing: idle lanes are filled by the other resident
+// blocks.)  Images beyond shared memory, NaN coordinates and thr <= 0 take the generic loop at the end of the kernel.
 constexpr int CROWD_THREADS = 128;
 constexpr int CROWD_R = 4;
 constexpr int CROWD_CHUNK = 32;
 constexpr int CROWD_QCAP = 2048;
-__device__ __forceinline__ int crowd_pos(int j) { return ((j & 3) * (CROWD_SMEM_BOXES / 4)) | (j >> 2); }
+// all-pairs form: position (j % 4) * 256 + j / 4; binned form (R = 1): boxes in their own order
+template <int R> __device__ __forceinline__ int crowd_pos_t(int j) { return (j % R) * (R == 4 ? CROWD_SMEM_BOXES / 4 : CROWD_THREADS) + j / R; }
+__device__ __forceinline__ int crowd_pos(int j, int R) { return R == 4 ? crowd_pos_t<4>(j) : j; }
+constexpr int CROWD_SWEEP_MAX = CROWD_SMEM_BOXES / 2;
+
+// Binned form of the same question for images of at most CROWD_SWEEP_MAX boxes.  A pair can only reach a positive IoU if
+// the boxes overlap in x, so the block buckets the boxes by x1 into CROWD_BINS bins with a counting sort in shared memory
+// (bin = a monotone function of x1 between the image's smallest and largest x1), copies them in bin order into the upper
+// half of the arrays, and every thread meets only the boxes behind its own up to the last bin its [x1, x2] touches.  Each
+// unordered pair is taken from the side of the box that sits first in that array; the comparisons are the reference's own
+// (processor.py:329-333), applied to a few per cent of the n(n-1)/2 pairs on crowd images.  Survivors of the pre-test are
+// queued with their ORIGINAL box numbers and get the full IoU arithmetic from all threads, in the reference's argument order.
+constexpr int CROWD_BINS = 64;
+__device__ __forceinline__ int crowd_bin(double x, double mn, double scale) {
+    double t = (x - mn) * scale;                              // monotone in x; scale == 0 puts every box into bin 0
+    t = t < 0.0 ? 0.0 : t;
+    t = t > (double)(CROWD_BINS - 1) ? (double)(CROWD_BINS - 1) : t;
+    return (int)t;
+}
+__device__ __forceinline__ void crowd_sweep(double2* __restrict__ slo, double2* __restrict__ shi, int* __restrict__ sint,
+                                            unsigned short* __restrict__ sidx, unsigned* __restrict__ queue, int& found, int& qn,
+                                            int n, double thr, int tid) {
+    // sint (the queue's memory, free until the walk starts): [0, 64) bin counts, [64, 129) bin offsets, [160, 168) min / max exchange
+    int* cnt = sint;
+    int* off = sint + CROWD_BINS;
+    double* red = reinterpret_cast<double*>(sint + 160);
+    double mn = pos_inf(), mx = neg_inf();
+    for (int j = tid; j < n; j += CROWD_THREADS) { const double x = slo[j].x; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double a = __shfl_xor_sync(FULL, mn, o), b = __shfl_xor_sync(FULL, mx, o);
+        mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+    }
+    if (tid < CROWD_BINS) cnt[tid] = 0;
+    if ((tid & 31) == 0) { red[2 * (tid >> 5)] = mn; red[2 * (tid >> 5) + 1] = mx; }
+    __syncthreads();
+    mn = red[0]; mx = red[1];
+    for (int w = 1; w < CROWD_THREADS / 32; ++w) { const double a = red[2 * w], b = red[2 * w + 1]; mn = a < mn ? a : mn; mx = b > mx ? b : mx; }
+    double scale = (double)CROWD_BINS / (mx - mn);
+    if (!(scale > 0.0) || !(scale < 1.0e300) || !(mn > -1.0e300)) scale = 0.0;      // one x1 value, or infinities: a single bin
+    if (scale == 0.0) mn = 0.0;
+    int mybin[CROWD_SWEEP_MAX / CROWD_THREADS], myrank[CROWD_SWEEP_MAX / CROWD_THREADS];
+#pragma unroll
+    for (int u = 0; u < CROWD_SWEEP_MAX / CROWD_THREADS; ++u) {
+        const int j = tid + u * CROWD_THREADS;
+        if (j < n) { mybin[u] = scale == 0.0 ? 0 : crowd_bin(slo[j].x, mn, scale); myrank[u] = atomicAdd(&cnt[mybin[u]], 1); }
+    }
+    __syncthreads();
+    if (tid < 32) {                                            // exclusive scan of the 64 counts by one warp
+        const int c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
+        int x = c0 + c1;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (tid >= o) x += y; }
+        off[2 * tid] = x - c0 - c1; off[2 * tid + 1] = x - c1;
+        if (tid == 31) off[CROWD_BINS] = x;
+    }
+    __syncthreads();
+    double2* qlo = slo + CROWD_SWEEP_MAX;
+    double2* qhi = shi + CROWD_SWEEP_MAX;
+#pragma unroll
+    for (int u = 0; u < CROWD_SWEEP_MAX / CROWD_THREADS; ++u) {
+        const int j = tid + u * CROWD_THREADS;
+        if (j < n) { const int p = off[mybin[u]] + myrank[u]; qlo[p] = slo[j]; qhi[p] = shi[j]; sidx[p] = (unsigned short)j; }
+    }
+    __syncthreads();
+    // the bin offsets are needed during the walk, the queue starts behind them
+    unsigned* q = queue + 192;
+    constexpr int QCAP = CROWD_QCAP - 192;
+    for (int base = 0; base < n; base += CROWD_THREADS) {
+        const int i = base + tid;
+        if (i < n) {
+            const double2 alo = qlo[i], ahi = qhi[i];
+            const int b1 = scale == 0.0 ? 0 : crowd_bin(ahi.x, mn, scale);
+            const int p1 = off[b1 + 1];
+            // The pair {a, b} belongs to the box that sits first in the binned array: a box behind a sits in a's bin or a later
+            // one, and if the two overlap in x its x1 is below a.x2, i.e. its bin is at most b1 -- so the boxes at positions
+            // i+1 .. p1-1 are all the partners a has to meet, and nobody is met twice.
+            for (int p = i + 1; p < p1; ++p) {
+                const double2 blo = qlo[p], bhi = qhi[p];
+                if (ahi.x > blo.x && bhi.x > alo.x && ahi.y > blo.y && bhi.y > alo.y) {
+                    const unsigned oi = sidx[i], oj = sidx[p];
+                    const unsigned lo = min(oi, oj), hi = max(oi, oj);
+                    const unsigned slot = (unsigned)atomicAdd(&qn, 1);
+                    if (slot < (unsigned)QCAP) q[slot] = (lo << 16) | hi;
+                    else if (iou_hits_cold(Box{slo[lo].x, slo[lo].y, shi[lo].x, shi[lo].y}, Box{slo[hi].x, slo[hi].y, shi[hi].x, shi[hi].y}, thr, false)) found = 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int nq = min(qn, QCAP);
+        for (int k = tid; k < nq; k += CROWD_THREADS) {
+            const unsigned ent = q[k];
+            const int a = (int)(ent >> 16), b = (int)(ent & 0xffffu);
+            if (iou_hits(Box{slo[a].x, slo[a].y, shi[a].x, shi[a].y}, Box{slo[b].x, slo[b].y, shi[b].x, shi[b].y}, thr, false)) found = 1;
+        }
+        __syncthreads();
+        const bool done = found != 0;
+        if (tid == 0) qn = 0;
+        __syncthreads();
+        if (done) break;
+    }
+}
+
+// The register-tiled pre-test + queued exact test of one image whose boxes are in shared memory (layout of tile width R).
+template <int R>
+__device__ __forceinline__ void crowd_tiled(const double2* __restrict__ slo, const double2* __restrict__ shi, unsigned* __restrict__ queue,
+                                            int& found, int& qn, int n, int half, bool even, double thr, int tid) {
+    const int D = half + R;                              // last partner distance any own box can need
+    for (int base = 0; base < n; base += CROWD_THREADS * R) {
+        const int s0 = base + tid * R;
+        double2 alo[R], ahi[R];
+        int dmax[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int row = s0 + k;
+            if (row < n) { alo[k] = slo[crowd_pos_t<R>(row)]; ahi[k] = shi[crowd_pos_t<R>(row)]; dmax[k] = half + ((even && row < n / 2) ? 1 : 0); }
+            else { alo[k] = make_double2(pos_inf(), pos_inf()); ahi[k] = make_double2(neg_inf(), neg_inf()); dmax[k] = 0; }   // meets nothing
+        }
+        const bool active = s0 < n;
+        // one partner against the four own boxes; `rule` applies the pairing rule (needed at the two ends of the walk)
+        auto meet = [&](int t, int d, bool rule) {
+            const double2 blo = slo[crowd_pos_t<R>(t)], bhi = shi[crowd_pos_t<R>(t)];
+            bool ov[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                ov[k] = ahi[k].x > blo.x && bhi.x > alo[k].x && ahi[k].y > blo.y && bhi.y > alo[k].y;
+            bool some = false;
+#pragma unroll
+            for (int k = 0; k < R; ++k) some |= ov[k];
+            if (some) {                                       // rare (a per cent of the partners): queue the survivors
+                unsigned m = 0;
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    if (ov[k] && (!rule || (d - k >= 1 && d - k <= dmax[k]))) m |= 1u << k;
+                if (m) {
+                    unsigned slot = (unsigned)atomicAdd(&qn, __popc(m));
+                    for (; m; m &= m - 1, ++slot) {
+                        const int k = __ffs(m) - 1;
+                        if (slot < (unsigned)CROWD_QCAP) queue[slot] = ((unsigned)(s0 + k) << 16) | (unsigned)t;
+                        else if (iou_hits_cold(Box{slo[crowd_pos_t<R>(s0 + k)].x, slo[crowd_pos_t<R>(s0 + k)].y, shi[crowd_pos_t<R>(s0 + k)].x, shi[crowd_pos_t<R>(s0 + k)].y},
+                                               Box{blo.x, blo.y, bhi.x, bhi.y}, thr, false)) found = 1;
+                    }
+                }
+            }
+        };
+        for (int d0 = 1; d0 <= D; d0 += CROWD_CHUNK) {
+            const int d1 = min(d0 + CROWD_CHUNK - 1, D);
+            if (active) {
+                // Pass 1, branch-free: walk the chunk's partners and note in a bit mask which of them overlap ANY own
+                // box (pairing rule not applied yet).  Pass 2 revisits the noted partners -- about one in sixty --
+                // applies the rule and queues the surviving pairs.  Keeping the rare work out of the walk keeps the
+                // warps converged: the walk is 2 shared loads + 16 fp64 compares per partner.
+                unsigned pend = 0;
+                int t = s0 + d0;
+                while (t >= n) t -= n;
+                const int t_first = t;
+#pragma unroll 4
+                for (int d = d0; d <= d1; ++d) {
+                    const double2 blo = slo[crowd_pos_t<R>(t)], bhi = shi[crowd_pos_t<R>(t)];
+                    bool any = false;
+#pragma unroll
+                    for (int k = 0; k < R; ++k)
+                        any |= ahi[k].x > blo.x && bhi.x > alo[k].x && ahi[k].y > blo.y && bhi.y > alo[k].y;
+                    pend |= any ? (1u << (d - d0)) : 0u;
+                    ++t; if (t >= n) t -= n;
+                }
+                for (; pend; pend &= pend - 1) {
+                    const int b = __ffs(pend) - 1;
+                    int tt = t_first + b;
+                    while (tt >= n) tt -= n;
+                    meet(tt, d0 + b, true);
+                }
+            }
+            __syncthreads();
+            const int nq = min(qn, CROWD_QCAP);
+            for (int i = tid; i < nq; i += CROWD_THREADS) {
+                const unsigned ent = queue[i];
+                const int a = crowd_pos_t<R>((int)(ent >> 16)), b = crowd_pos_t<R>((int)(ent & 0xffffu));
+                if (iou_hits(Box{slo[a].x, slo[a].y, shi[a].x, shi[a].y}, Box{slo[b].x, slo[b].y, shi[b].x, shi[b].y}, thr, false)) found = 1;
+            }
+            __syncthreads();
+            const bool done = found != 0;
+            if (tid == 0) qn = 0;
+            __syncthreads();
+            if (done) break;
+        }
+        if (found) break;                                      // uniform: read after the barrier above
+    }
+}
 
 __global__ void __launch_bounds__(CROWD_THREADS)
 iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
                  int64_t min_boxes, double thr, uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
     __shared__ double2 slo[CROWD_SMEM_BOXES], shi[CROWD_SMEM_BOXES];       // (x1, y1) / (x2, y2), de-interleaved by 4
-    __shared__ unsigned queue[CROWD_QCAP];
+    __shared__ __align__(16) unsigned queue[CROWD_QCAP];
+    __shared__ unsigned short sidx[CROWD_SWEEP_MAX];                       // binned form: box numbers in bin order
     __shared__ int found, has_nan, qn;
     __shared__ long long first_bad;
     const unsigned long long n_list = reinterpret_cast<CrowdList*>(ws)->count;
@@ -196,11 +387,18 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
         const bool want = n64 >= min_boxes && n >= 2;
         const double2* src = reinterpret_cast<const double2*>(pts + 4 * q0);
         const bool in_smem = n <= CROWD_SMEM_BOXES;
+        // tile width: as many own boxes per thread as it takes to give every thread of the block work (2 .. 4); fewer own boxes
+        // per thread means more shared-memory reads per pair but no idle lanes (n = 350: 117 busy threads with R = 3, 88 with 4)
+        // up to CROWD_SWEEP_MAX boxes: sweep form (boxes in shared memory in their own order, a sorted copy in the upper half);
+        // above: the register-tiled all-pairs form (de-interleaved by 4)
+        const bool sweep = n <= CROWD_SWEEP_MAX;
+        const int R = sweep ? 1 : 4;
         if (want && in_smem) {
             for (int j = tid; j < n; j += CROWD_THREADS) {
                 double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
                 Box bx = box_from_points(p1.x, p1.y, p2.x, p2.y);
-                slo[crowd_pos(j)] = make_double2(bx.x1, bx.y1); shi[crowd_pos(j)] = make_double2(bx.x2, bx.y2);
+                slo[crowd_pos(j, R)] = make_double2(bx.x1, bx.y1); shi[crowd_pos(j, R)] = make_double2(bx.x2, bx.y2);
+
                 if (bx.x1 != bx.x1 || bx.y1 != bx.y1 || bx.x2 != bx.x2 || bx.y2 != bx.y2) has_nan = 1;
             }
         }
@@ -208,90 +406,13 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
         const int half = (n - 1) / 2;
         const bool even = (n & 1) == 0;
         if (want && in_smem && !has_nan && !zero_hits) {
-            // ---- register-tiled pre-test + queued exact test
-            const int D = half + CROWD_R;                              // last partner distance any own box can need
-            for (int base = 0; base < n; base += CROWD_THREADS * CROWD_R) {
-                const int s0 = base + tid * CROWD_R;
-                double2 alo[CROWD_R], ahi[CROWD_R];
-                int dmax[CROWD_R];
-#pragma unroll
-                for (int k = 0; k < CROWD_R; ++k) {
-                    const int row = s0 + k;
-                    if (row < n) { alo[k] = slo[crowd_pos(row)]; ahi[k] = shi[crowd_pos(row)]; dmax[k] = half + ((even && row < n / 2) ? 1 : 0); }
-                    else { alo[k] = make_double2(pos_inf(), pos_inf()); ahi[k] = make_double2(neg_inf(), neg_inf()); dmax[k] = 0; }   // meets nothing
-                }
-                const bool active = s0 < n;
-                // one partner against the four own boxes; `rule` applies the pairing rule (needed at the two ends of the walk)
-                auto meet = [&](int t, int d, bool rule) {
-                    const double2 blo = slo[crowd_pos(t)], bhi = shi[crowd_pos(t)];
-                    bool ov[CROWD_R];
-#pragma unroll
-                    for (int k = 0; k < CROWD_R; ++k)
-                        ov[k] = ahi[k].x > blo.x && bhi.x > alo[k].x && ahi[k].y > blo.y && bhi.y > alo[k].y;
-                    if (ov[0] | ov[1] | ov[2] | ov[3]) {              // rare (a per cent of the partners): queue the survivors
-                        unsigned m = 0;
-#pragma unroll
-                        for (int k = 0; k < CROWD_R; ++k)
-                            if (ov[k] && (!rule || (d - k >= 1 && d - k <= dmax[k]))) m |= 1u << k;
-                        if (m) {
-                            unsigned slot = (unsigned)atomicAdd(&qn, __popc(m));
-                            for (; m; m &= m - 1, ++slot) {
-                                const int k = __ffs(m) - 1;
-                                if (slot < (unsigned)CROWD_QCAP) queue[slot] = ((unsigned)(s0 + k) << 16) | (unsigned)t;
-                                else if (iou_hits_cold(Box{slo[crowd_pos(s0 + k)].x, slo[crowd_pos(s0 + k)].y, shi[crowd_pos(s0 + k)].x, shi[crowd_pos(s0 + k)].y},
-                                                       Box{blo.x, blo.y, bhi.x, bhi.y}, thr, false)) found = 1;
-                            }
-                        }
-                    }
-                };
-                for (int d0 = 1; d0 <= D; d0 += CROWD_CHUNK) {
-                    const int d1 = min(d0 + CROWD_CHUNK - 1, D);
-                    if (active) {
-                        // Pass 1, branch-free: walk the chunk's partners and note in a bit mask which of them overlap ANY own
-                        // box (pairing rule not applied yet).  Pass 2 revisits the noted partners -- about one in sixty --
-                        // applies the rule and queues the surviving pairs.  Keeping the rare work out of the walk keeps the
-                        // warps converged: the walk is 2 shared loads + 16 fp64 compares per partner.
-                        unsigned pend = 0;
-                        int t = s0 + d0;
-                        while (t >= n) t -= n;
-                        const int t_first = t;
-#pragma unroll 4
-                        for (int d = d0; d <= d1; ++d) {
-                            const double2 blo = slo[crowd_pos(t)], bhi = shi[crowd_pos(t)];
-                            bool any = false;
-#pragma unroll
-                            for (int k = 0; k < CROWD_R; ++k)
-                                any |= ahi[k].x > blo.x && bhi.x > alo[k].x && ahi[k].y > blo.y && bhi.y > alo[k].y;
-                            pend |= any ? (1u << (d - d0)) : 0u;
-                            ++t; if (t >= n) t -= n;
-                        }
-                        for (; pend; pend &= pend - 1) {
-                            const int b = __ffs(pend) - 1;
-                            int tt = t_first + b;
-                            while (tt >= n) tt -= n;
-                            meet(tt, d0 + b, true);
-                        }
-                    }
-                    __syncthreads();
-                    const int nq = min(qn, CROWD_QCAP);
-                    for (int i = tid; i < nq; i += CROWD_THREADS) {
-                        const unsigned ent = queue[i];
-                        const int a = crowd_pos((int)(ent >> 16)), b = crowd_pos((int)(ent & 0xffffu));
-                        if (iou_hits(Box{slo[a].x, slo[a].y, shi[a].x, shi[a].y}, Box{slo[b].x, slo[b].y, shi[b].x, shi[b].y}, thr, false)) found = 1;
-                    }
-                    __syncthreads();
-                    const bool done = found != 0;
-                    if (tid == 0) qn = 0;
-                    __syncthreads();
-                    if (done) break;
-                }
-                if (found) break;                                      // uniform: read after the barrier above
-            }
+            if (sweep) crowd_sweep(slo, shi, reinterpret_cast<int*>(queue), sidx, queue, found, qn, n, thr, tid);
+            else crowd_tiled<4>(slo, shi, queue, found, qn, n, half, even, thr, tid);
         } else if (want) {
             // ---- generic form: NaN coordinates (exact selects in the reference's argument order), thr <= 0, or an image
             //      too large for shared memory (direct loads)
             auto load = [&](int j) {
-                if (in_smem) { const int pj = crowd_pos(j); return Box{slo[pj].x, slo[pj].y, shi[pj].x, shi[pj].y}; }
+                if (in_smem) { const int pj = crowd_pos(j, R); return Box{slo[pj].x, slo[pj].y, shi[pj].x, shi[pj].y}; }
                 double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
                 return box_from_points(p1.x, p1.y, p2.x, p2.y);
             };
@@ -371,7 +492,17 @@ fused_warp_kernel(const int64_t* __restrict__ img_off, const int64_t* __restrict
     }
 }
 
-static inline int crowd_grid() { return NUM_SMS * 5; }    // 41 KB of shared memory per block: five blocks per SM
+// as many blocks as are resident at once (42 KB of shared memory per block: five per SM): the worklist is strided over the
+// grid, so a block that only starts when another one has finished would double the time
+static inline int crowd_grid() {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, iou_crowd_kernel, CROWD_THREADS, 0) != cudaSuccess || v < 1) v = 4;
+        per_sm = v;
+    }
+    return NUM_SMS * per_sm;
+}
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
