@@ -153,6 +153,38 @@ def test_iou_box_tables(cuda_device, lo, hi, n):
     assert_bits(host(high), want_high); assert_bits(host(count), want_count)
 
 
+def test_crowd_binned_form_edge_images(cuda_device):
+    """The binned form of the block-per-image kernel (33 .. 512 boxes) on images built to stress its counting sort: every box
+    with the same x1 (one bin), x1 spread over 1e300 (scale underflow), infinite coordinates, boxes that only touch (x2 == x1 of
+    the next: no overlap), exact duplicates far apart in box order, a hit only between the first and the last box."""
+    d = cuda_device
+    rng = np.random.RandomState(3)
+    imgs = []
+
+    def boxes(n, x1, w, y1=None, h=None):
+        y1 = rng.uniform(0, 1000, n) if y1 is None else y1
+        h = rng.uniform(5, 40, n) if h is None else h
+        return np.stack([x1, y1, x1 + w, y1 + h], axis=1)
+    n = 200
+    imgs.append(boxes(n, np.full(n, 7.0), rng.uniform(5, 40, n)))                                # one x1 value
+    imgs.append(boxes(n, rng.uniform(0, 1900, n) * 1e298, rng.uniform(5, 40, n) * 1e298))       # huge range
+    b = boxes(n, rng.uniform(0, 1900, n), rng.uniform(5, 40, n)); b[5, 0] = -np.inf; b[9, 2] = np.inf; imgs.append(b)
+    x = np.arange(n) * 10.0
+    imgs.append(boxes(n, x, np.full(n, 10.0), np.zeros(n), np.full(n, 10.0)))                    # a row of touching boxes
+    b = boxes(n, rng.uniform(0, 1900, n), rng.uniform(5, 40, n)); b[199] = b[0]; imgs.append(b)  # first == last
+    b = boxes(n, rng.uniform(0, 1900, n), rng.uniform(5, 40, n)); b[120] = b[17] + np.array([0.0, 0.0, 0.001, 0.0]); imgs.append(b)
+    imgs.append(boxes(40, rng.uniform(0, 50, 40), rng.uniform(5, 40, 40), rng.uniform(0, 50, 40)))   # everything overlaps: the queue fills
+    imgs.append(boxes(512, rng.uniform(0, 1900, 512), rng.uniform(5, 40, 512)))                  # the largest binned image
+    imgs.append(boxes(513, rng.uniform(0, 1900, 513), rng.uniform(5, 40, 513)))                  # the smallest all-pairs image
+    img_off = np.zeros(len(imgs) + 1, np.int64); np.cumsum([len(b) for b in imgs], out=img_off[1:])
+    pts = np.concatenate(imgs).reshape(-1).astype(np.float64)
+    for mb, thr in ((2, 0.7), (2, 0.98), (2, 1.0), (2, 1e-300), (300, 0.5)):
+        want_high, want_count = oracle_c.iou_filter(img_off, pts, None, mb, thr)
+        high, count = ops.iou_filter(dev(img_off, d), dev(pts, d), None, mb, thr)
+        assert_bits(host(high), want_high, f"high mb={mb} thr={thr}"); assert_bits(host(count), want_count, "count")
+    assert oracle_c.iou_filter(img_off, pts, None, 2, 0.98)[0][4] == 1
+
+
 def test_crowd_generator_and_worst_case(cuda_device):
     d = cuda_device
     io, pts = synth.make_crowd_boxes(3, 10, 40)
