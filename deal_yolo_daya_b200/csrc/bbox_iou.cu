@@ -188,88 +188,6 @@ __device__ __forceinline__ int crowd_bin(double x, double mn, double scale) {
     t = t > (double)(CROWD_BINS - 1) ? (double)(CROWD_BINS - 1) : t;
     return (int)t;
 }
-__device__ __forceinline__ void crowd_sweep(double2* __restrict__ slo, double2* __restrict__ shi, int* __restrict__ sint,
-                                            unsigned short* __restrict__ sidx, unsigned* __restrict__ queue, int& found, int& qn,
-                                            int n, double thr, int tid) {
-    // sint (the queue's memory, free until the walk starts): [0, 64) bin counts, [64, 129) bin offsets, [160, 168) min / max exchange
-    int* cnt = sint;
-    int* off = sint + CROWD_BINS;
-    double* red = reinterpret_cast<double*>(sint + 160);
-    double mn = pos_inf(), mx = neg_inf();
-    for (int j = tid; j < n; j += CROWD_THREADS) { const double x = slo[j].x; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }
-    for (int o = 16; o > 0; o >>= 1) {
-        const double a = __shfl_xor_sync(FULL, mn, o), b = __shfl_xor_sync(FULL, mx, o);
-        mn = a < mn ? a : mn; mx = b > mx ? b : mx;
-    }
-    if (tid < CROWD_BINS) cnt[tid] = 0;
-    if ((tid & 31) == 0) { red[2 * (tid >> 5)] = mn; red[2 * (tid >> 5) + 1] = mx; }
-    __syncthreads();
-    mn = red[0]; mx = red[1];
-    for (int w = 1; w < CROWD_THREADS / 32; ++w) { const double a = red[2 * w], b = red[2 * w + 1]; mn = a < mn ? a : mn; mx = b > mx ? b : mx; }
-    double scale = (double)CROWD_BINS / (mx - mn);
-    if (!(scale > 0.0) || !(scale < 1.0e300) || !(mn > -1.0e300)) scale = 0.0;      // one x1 value, or infinities: a single bin
-    if (scale == 0.0) mn = 0.0;
-    int mybin[CROWD_SWEEP_MAX / CROWD_THREADS], myrank[CROWD_SWEEP_MAX / CROWD_THREADS];
-#pragma unroll
-    for (int u = 0; u < CROWD_SWEEP_MAX / CROWD_THREADS; ++u) {
-        const int j = tid + u * CROWD_THREADS;
-        if (j < n) { mybin[u] = scale == 0.0 ? 0 : crowd_bin(slo[j].x, mn, scale); myrank[u] = atomicAdd(&cnt[mybin[u]], 1); }
-    }
-    __syncthreads();
-    if (tid < 32) {                                            // exclusive scan of the 64 counts by one warp
-        const int c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
-        int x = c0 + c1;
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (tid >= o) x += y; }
-        off[2 * tid] = x - c0 - c1; off[2 * tid + 1] = x - c1;
-        if (tid == 31) off[CROWD_BINS] = x;
-    }
-    __syncthreads();
-    double2* qlo = slo + CROWD_SWEEP_MAX;
-    double2* qhi = shi + CROWD_SWEEP_MAX;
-#pragma unroll
-    for (int u = 0; u < CROWD_SWEEP_MAX / CROWD_THREADS; ++u) {
-        const int j = tid + u * CROWD_THREADS;
-        if (j < n) { const int p = off[mybin[u]] + myrank[u]; qlo[p] = slo[j]; qhi[p] = shi[j]; sidx[p] = (unsigned short)j; }
-    }
-    __syncthreads();
-    // the bin offsets are needed during the walk, the queue starts behind them
-    unsigned* q = queue + 192;
-    constexpr int QCAP = CROWD_QCAP - 192;
-    for (int base = 0; base < n; base += CROWD_THREADS) {
-        const int i = base + tid;
-        if (i < n) {
-            const double2 alo = qlo[i], ahi = qhi[i];
-            const int b1 = scale == 0.0 ? 0 : crowd_bin(ahi.x, mn, scale);
-            const int p1 = off[b1 + 1];
-            // The pair {a, b} belongs to the box that sits first in the binned array: a box behind a sits in a's bin or a later
-            // one, and if the two overlap in x its x1 is below a.x2, i.e. its bin is at most b1 -- so the boxes at positions
-            // i+1 .. p1-1 are all the partners a has to meet, and nobody is met twice.
-            for (int p = i + 1; p < p1; ++p) {
-                const double2 blo = qlo[p], bhi = qhi[p];
-                if (ahi.x > blo.x && bhi.x > alo.x && ahi.y > blo.y && bhi.y > alo.y) {
-                    const unsigned oi = sidx[i], oj = sidx[p];
-                    const unsigned lo = min(oi, oj), hi = max(oi, oj);
-                    const unsigned slot = (unsigned)atomicAdd(&qn, 1);
-                    if (slot < (unsigned)QCAP) q[slot] = (lo << 16) | hi;
-                    else if (iou_hits_cold(Box{slo[lo].x, slo[lo].y, shi[lo].x, shi[lo].y}, Box{slo[hi].x, slo[hi].y, shi[hi].x, shi[hi].y}, thr, false)) found = 1;
-                }
-            }
-        }
-        __syncthreads();
-        const int nq = min(qn, QCAP);
-        for (int k = tid; k < nq; k += CROWD_THREADS) {
-            const unsigned ent = q[k];
-            const int a = (int)(ent >> 16), b = (int)(ent & 0xffffu);
-            if (iou_hits(Box{slo[a].x, slo[a].y, shi[a].x, shi[a].y}, Box{slo[b].x, slo[b].y, shi[b].x, shi[b].y}, thr, false)) found = 1;
-        }
-        __syncthreads();
-        const bool done = found != 0;
-        if (tid == 0) qn = 0;
-        __syncthreads();
-        if (done) break;
-    }
-}
-
 // The register-tiled pre-test + queued exact test of one image whose boxes are in shared memory (layout of tile width R).
 template <int R>
 __device__ __forceinline__ void crowd_tiled(const double2* __restrict__ slo, const double2* __restrict__ shi, unsigned* __restrict__ queue,
@@ -357,12 +275,165 @@ __device__ __forceinline__ void crowd_tiled(const double2* __restrict__ slo, con
     }
 }
 
+// The binned form as its own kernel: images of at most CROWD_SWEEP_MAX boxes.  A thread keeps its (at most four) boxes in
+// registers from the global load to the scatter into the binned array, so shared memory holds ONE copy of the boxes (25 KB per
+// block instead of the 42 KB of the kernel below, which keeps the 1024-box arrays of the all-pairs form): more resident blocks to
+// hide the per-image latencies behind.  Larger images are left to iou_crowd_kernel, which skips the ones handled here.
+constexpr int CROWD_OWN = CROWD_SWEEP_MAX / CROWD_THREADS;
+#ifndef DYD_CROWD_MIN_BLOCKS
+#define DYD_CROWD_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(CROWD_THREADS, DYD_CROWD_MIN_BLOCKS)
+iou_crowd_binned_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
+                        int64_t min_boxes, double thr, uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
+    __shared__ double2 qlo[CROWD_SWEEP_MAX], qhi[CROWD_SWEEP_MAX];        // (x1, y1) / (x2, y2) in bin order
+    __shared__ __align__(16) unsigned queue[CROWD_QCAP];                   // first 192 words: bin counts / offsets / min-max exchange
+    __shared__ unsigned short sidx[CROWD_SWEEP_MAX];                       // box number of every position
+    __shared__ int found, has_nan, qn;
+    __shared__ long long first_bad;
+    const unsigned long long n_list = reinterpret_cast<CrowdList*>(ws)->count;
+    const int* ids = crowd_ids(ws);
+    const bool zero_hits = 0.0 >= thr;
+    const int tid = threadIdx.x;
+    int* cnt = reinterpret_cast<int*>(queue);
+    int* off = cnt + CROWD_BINS;
+    double* red = reinterpret_cast<double*>(cnt + 160);
+    unsigned* q = queue + 192;
+    constexpr int QCAP = CROWD_QCAP - 192;
+    for (unsigned long long e = blockIdx.x; e < n_list; e += gridDim.x) {
+        const int64_t img = ids[e];
+        const int64_t q0 = img_off[img], n_all = img_off[img + 1] - q0;
+        __syncthreads();                              // previous image fully consumed
+        if (tid == 0) { found = 0; has_nan = 0; qn = 0; first_bad = n_all; }
+        if (tid < CROWD_BINS) cnt[tid] = 0;
+        __syncthreads();
+        if (valid != nullptr) {
+            long long mine = n_all;
+            for (int64_t j = tid; j < n_all; j += CROWD_THREADS)
+                if (valid[q0 + j] == 0) { mine = j; break; }
+            if (mine < n_all) atomicMin(&first_bad, mine);
+            __syncthreads();
+        }
+        const int64_t n64 = first_bad;
+        if (n64 > CROWD_SWEEP_MAX) continue;          // the all-pairs kernel's image (uniform over the block)
+        const int n = (int)n64;
+        const bool want = n64 >= min_boxes && n >= 2;
+        const double2* src = reinterpret_cast<const double2*>(pts + 4 * q0);
+        if (want) {
+            Box bx[CROWD_OWN];
+            double mn = pos_inf(), mx = neg_inf();
+            bool nan_here = false;
+#pragma unroll
+            for (int u = 0; u < CROWD_OWN; ++u) {
+                const int j = tid + u * CROWD_THREADS;
+                if (j < n) {
+                    const double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
+                    bx[u] = box_from_points(p1.x, p1.y, p2.x, p2.y);
+                    nan_here |= bx[u].x1 != bx[u].x1 || bx[u].y1 != bx[u].y1 || bx[u].x2 != bx[u].x2 || bx[u].y2 != bx[u].y2;
+                    mn = bx[u].x1 < mn ? bx[u].x1 : mn; mx = bx[u].x1 > mx ? bx[u].x1 : mx;
+                }
+            }
+            if (nan_here) has_nan = 1;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double a = __shfl_xor_sync(FULL, mn, o), b = __shfl_xor_sync(FULL, mx, o);
+                mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+            }
+            if ((tid & 31) == 0) { red[2 * (tid >> 5)] = mn; red[2 * (tid >> 5) + 1] = mx; }
+            __syncthreads();
+            if (!has_nan && !zero_hits) {
+                mn = red[0]; mx = red[1];
+                for (int w = 1; w < CROWD_THREADS / 32; ++w) { const double a = red[2 * w], b = red[2 * w + 1]; mn = a < mn ? a : mn; mx = b > mx ? b : mx; }
+                double scale = (double)CROWD_BINS / (mx - mn);
+                if (!(scale > 0.0) || !(scale < 1.0e300) || !(mn > -1.0e300)) scale = 0.0;      // one x1 value, or infinities: a single bin
+                if (scale == 0.0) mn = 0.0;
+                int mybin[CROWD_OWN], myrank[CROWD_OWN];
+#pragma unroll
+                for (int u = 0; u < CROWD_OWN; ++u) {
+                    const int j = tid + u * CROWD_THREADS;
+                    if (j < n) { mybin[u] = scale == 0.0 ? 0 : crowd_bin(bx[u].x1, mn, scale); myrank[u] = atomicAdd(&cnt[mybin[u]], 1); }
+                }
+                __syncthreads();
+                if (tid < 32) {                                            // exclusive scan of the 64 counts by one warp
+                    const int c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
+                    int x = c0 + c1;
+                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (tid >= o) x += y; }
+                    off[2 * tid] = x - c0 - c1; off[2 * tid + 1] = x - c1;
+                    if (tid == 31) off[CROWD_BINS] = x;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < CROWD_OWN; ++u) {
+                    const int j = tid + u * CROWD_THREADS;
+                    if (j < n) {
+                        const int p = off[mybin[u]] + myrank[u];
+                        qlo[p] = make_double2(bx[u].x1, bx[u].y1); qhi[p] = make_double2(bx[u].x2, bx[u].y2); sidx[p] = (unsigned short)j;
+                    }
+                }
+                __syncthreads();
+                for (int base = 0; base < n; base += CROWD_THREADS) {
+                    const int i = base + tid;
+                    if (i < n) {
+                        const double2 alo = qlo[i], ahi = qhi[i];
+                        const int b1 = scale == 0.0 ? 0 : crowd_bin(ahi.x, mn, scale);
+                        const int p1 = off[b1 + 1];
+                        // the boxes at positions i+1 .. p1-1 are all the partners box i has to meet (see crowd_sweep's comment)
+                        for (int p = i + 1; p < p1; ++p) {
+                            const double2 blo = qlo[p], bhi = qhi[p];
+                            if (ahi.x > blo.x && bhi.x > alo.x && ahi.y > blo.y && bhi.y > alo.y) {
+                                const bool i_first = sidx[i] < sidx[p];          // the reference meets the lower box number first
+                                const unsigned lo = i_first ? (unsigned)i : (unsigned)p, hi = i_first ? (unsigned)p : (unsigned)i;
+                                const unsigned slot = (unsigned)atomicAdd(&qn, 1);
+                                if (slot < (unsigned)QCAP) q[slot] = (lo << 16) | hi;
+                                else if (iou_hits_cold(Box{qlo[lo].x, qlo[lo].y, qhi[lo].x, qhi[lo].y}, Box{qlo[hi].x, qlo[hi].y, qhi[hi].x, qhi[hi].y}, thr, false)) found = 1;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const int nq = min(qn, QCAP);
+                    for (int k2 = tid; k2 < nq; k2 += CROWD_THREADS) {
+                        const unsigned ent = q[k2];
+                        const int a = (int)(ent >> 16), b = (int)(ent & 0xffffu);
+                        if (iou_hits(Box{qlo[a].x, qlo[a].y, qhi[a].x, qhi[a].y}, Box{qlo[b].x, qlo[b].y, qhi[b].x, qhi[b].y}, thr, false)) found = 1;
+                    }
+                    __syncthreads();
+                    const bool done = found != 0;
+                    if (tid == 0) qn = 0;
+                    __syncthreads();
+                    if (done) break;
+                }
+            } else {
+                // NaN coordinates (exact selects in the reference's argument order) or thr <= 0: the generic loop on direct loads
+                const int half = (n - 1) / 2;
+                const bool even = (n & 1) == 0;
+                auto load = [&](int j) {
+                    const double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
+                    return box_from_points(p1.x, p1.y, p2.x, p2.y);
+                };
+                for (int s2 = tid; s2 < n; s2 += CROWD_THREADS) {
+                    const Box a = load(s2);
+                    const int dmax = half + ((even && s2 < n / 2) ? 1 : 0);
+                    bool mine = false;
+                    int t = s2;
+                    for (int d = 1; d <= dmax && !mine; ++d) {
+                        ++t; if (t >= n) t -= n;
+                        mine = iou_hits(a, load(t), thr, zero_hits);
+                        if ((d & 31) == 0 && *(volatile int*)&found) break;
+                    }
+                    if (mine) found = 1;
+                    if (*(volatile int*)&found) break;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { high[img] = found ? 1 : 0; count[img] = n; }
+    }
+}
+
 __global__ void __launch_bounds__(CROWD_THREADS)
 iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__ pts, const uint8_t* __restrict__ valid,
                  int64_t min_boxes, double thr, uint8_t* __restrict__ high, int32_t* __restrict__ count, void* ws) {
     __shared__ double2 slo[CROWD_SMEM_BOXES], shi[CROWD_SMEM_BOXES];       // (x1, y1) / (x2, y2), de-interleaved by 4
     __shared__ __align__(16) unsigned queue[CROWD_QCAP];
-    __shared__ unsigned short sidx[CROWD_SWEEP_MAX];                       // binned form: box numbers in bin order
     __shared__ int found, has_nan, qn;
     __shared__ long long first_bad;
     const unsigned long long n_list = reinterpret_cast<CrowdList*>(ws)->count;
@@ -372,6 +443,7 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
     for (unsigned long long e = blockIdx.x; e < n_list; e += gridDim.x) {
         const int64_t img = ids[e];
         const int64_t q0 = img_off[img], n_all = img_off[img + 1] - q0;
+        if (valid == nullptr && n_all <= CROWD_SWEEP_MAX) continue;    // cheap skip of the binned kernel's images
         __syncthreads();                              // previous image fully consumed
         if (tid == 0) { found = 0; has_nan = 0; qn = 0; first_bad = n_all; }
         __syncthreads();
@@ -389,10 +461,8 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
         const bool in_smem = n <= CROWD_SMEM_BOXES;
         // tile width: as many own boxes per thread as it takes to give every thread of the block work (2 .. 4); fewer own boxes
         // per thread means more shared-memory reads per pair but no idle lanes (n = 350: 117 busy threads with R = 3, 88 with 4)
-        // up to CROWD_SWEEP_MAX boxes: sweep form (boxes in shared memory in their own order, a sorted copy in the upper half);
-        // above: the register-tiled all-pairs form (de-interleaved by 4)
-        const bool sweep = n <= CROWD_SWEEP_MAX;
-        const int R = sweep ? 1 : 4;
+        if (n64 <= CROWD_SWEEP_MAX) continue;         // iou_crowd_binned_kernel's image (uniform over the block)
+        const int R = 4;                              // register-tiled all-pairs form, boxes de-interleaved by 4
         if (want && in_smem) {
             for (int j = tid; j < n; j += CROWD_THREADS) {
                 double2 p1 = ldg_f64x2(src + 2 * j), p2 = ldg_f64x2(src + 2 * j + 1);
@@ -406,8 +476,7 @@ iou_crowd_kernel(const int64_t* __restrict__ img_off, const double* __restrict__
         const int half = (n - 1) / 2;
         const bool even = (n & 1) == 0;
         if (want && in_smem && !has_nan && !zero_hits) {
-            if (sweep) crowd_sweep(slo, shi, reinterpret_cast<int*>(queue), sidx, queue, found, qn, n, thr, tid);
-            else crowd_tiled<4>(slo, shi, queue, found, qn, n, half, even, thr, tid);
+            crowd_tiled<4>(slo, shi, queue, found, qn, n, half, even, thr, tid);
         } else if (want) {
             // ---- generic form: NaN coordinates (exact selects in the reference's argument order), thr <= 0, or an image
             //      too large for shared memory (direct loads)
@@ -504,6 +573,16 @@ static inline int crowd_grid() {
     return NUM_SMS * per_sm;
 }
 
+static inline int crowd_binned_grid() {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, iou_crowd_binned_kernel, CROWD_THREADS, 0) != cudaSuccess || v < 1) v = 4;
+        per_sm = v;
+    }
+    return NUM_SMS * per_sm;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -511,6 +590,8 @@ static int env_int(const char* name, int dflt) {
 
 int launch_crowd(const int64_t* d_img_off, const double* d_pts, const uint8_t* d_valid, int64_t min_boxes,
                  double thr, uint8_t* d_high, int32_t* d_count, void* ws, cudaStream_t s) {
+    iou_crowd_binned_kernel<<<crowd_binned_grid(), CROWD_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, ws);
+    if (int rc = launch_check("iou_crowd_binned_kernel")) return rc;
     iou_crowd_kernel<<<crowd_grid(), CROWD_THREADS, 0, s>>>(d_img_off, d_pts, d_valid, min_boxes, thr, d_high, d_count, ws);
     return launch_check("iou_crowd_kernel");
 }
