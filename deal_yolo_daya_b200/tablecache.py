@@ -118,7 +118,8 @@ def put(path, frame, extras=None, clean=True, lazy=None) -> None:
     k = _key(path)
     if k is None:
         return
-    nbytes = _frame_bytes(frame) if frame is not None else 0
+    # a lazy entry keeps its parent frame alive: charge it (conservatively, even where another entry shares the columns)
+    nbytes = _frame_bytes(frame) if frame is not None else (_frame_bytes(lazy[0]) if lazy is not None else 0)
     with _LOCK:
         for old in [o for o in _ENTRIES if o[0] == k[0]]:
             _BYTES -= _ENTRIES.pop(old).nbytes
