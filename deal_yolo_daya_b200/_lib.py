@@ -45,7 +45,7 @@ PROTOTYPES = {
     "dyd_shard_unpack": (_int, [_p, _i64, _i64, _i64, _p, _p, _i32, _p]),
     "dyd_url_filter_workspace_bytes": (_sz, [_i64, _i64]),
     "dyd_url_filter": (_int, [_p, _p, _i64, _p, _p, _i64, _int, _p, _p, _p, _p, _p, _sz, _p]),
-    "dyd_url_filter_records": (_int, [_p, _i64, _p, _i64, _int, _p, _p, _p, _p, _p, _sz, _i32, _p]),
+    "dyd_url_filter_records": (_int, [_p, _i64, _p, _i64, _int, _p, _p, _p, _p, _p, _sz, _i32, _i64, _p]),
     "dyd_antijoin_records": (_int, [_p, _i64, _p, _i64, _p, _p, _p, _sz, _i32, _p]),
     "dyd_bbox_iou_fused_ex": (_int, [_p, _p, _p, _i64, _i64, _i64, _f64, _p, _p, _p, _p, _p, _p, _sz, _i32, _p, _p]),
     "dyd_fused_cta_times": (_int, [_p, _i32]),

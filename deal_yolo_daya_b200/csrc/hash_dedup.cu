@@ -1078,7 +1078,7 @@ static inline JointLayout joint_layout(int64_t n_main, int64_t n_ref, bool with_
 template <int KIND>
 static int url_filter_impl(const uint64_t* d_main, const uint8_t* d_main_null, int64_t n_main, uint64_t* d_ref, const uint8_t* d_ref_null,
                            int64_t n_ref, int keep_mode, uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep2, int64_t* d_ref2,
-                           void* ws, size_t ws_bytes, bool reset_ref, void* stream) {
+                           void* ws, size_t ws_bytes, bool reset_ref, int64_t id_bound, void* stream) {
     DYD_REQUIRE(n_main >= 0 && n_ref >= 0 && n_main < (1LL << 40) && n_ref < (1LL << 40), DYD_E_ARG, "bad row count");
     DYD_REQUIRE(keep_mode >= 0 && keep_mode <= 2, DYD_E_ARG, "keep_mode must be 0 (first), 1 (last) or 2 (False)");
     cudaStream_t s = as_stream(stream);
@@ -1115,10 +1115,13 @@ static int url_filter_impl(const uint64_t* d_main, const uint8_t* d_main_null, i
                                                                                L.pcap_m, d_keep, d_rep, d_keep2, d_ref2);
             if (int rc = launch_check("dedup_partition_kernel")) return rc;
             const unsigned np = 1u << L.log2_np;
-            constexpr bool R32 = KIND == 0;            // main rows < 2^31 and reference rows < 2^32 - 1 on this path
-#define DYD_JOINT(MODE) joint_resolve_kernel<KIND, MODE, R32><<<np, PT_THREADS, 0, s>>>(cur_m, cur_r, overflow, kv_m, rr_m, kv_r, pshift, L.pcap_m, \
-                                                                                        L.pcap_r, d_keep, d_rep, d_keep2, d_ref2)
-            if (keep_mode == 0) DYD_JOINT(0); else if (keep_mode == 1) DYD_JOINT(1); else DYD_JOINT(2);
+            // 32-bit rows in the shared-memory tables (native shared atomics) when every id fits: always for key arrays (main rows
+            // < 2^31, reference rows < 2^32 - 1 on this path), for exchange records when the caller bounds the ids below 2^31
+            const bool r32 = KIND == 0 || (id_bound > 0 && id_bound < (1LL << 31));
+#define DYD_JOINT(MODE, R32) joint_resolve_kernel<KIND, MODE, R32><<<np, PT_THREADS, 0, s>>>(cur_m, cur_r, overflow, kv_m, rr_m, kv_r, pshift, L.pcap_m, \
+                                                                                             L.pcap_r, d_keep, d_rep, d_keep2, d_ref2)
+            if (r32) { if (keep_mode == 0) DYD_JOINT(0, true); else if (keep_mode == 1) DYD_JOINT(1, true); else DYD_JOINT(2, true); }
+            else if (KIND != 0) { if (keep_mode == 0) DYD_JOINT(0, false); else if (keep_mode == 1) DYD_JOINT(1, false); else DYD_JOINT(2, false); }
 #undef DYD_JOINT
             if (int rc = launch_check("joint_resolve_kernel")) return rc;
             if (KIND == 0 && d_main_null != nullptr) {
@@ -1150,12 +1153,12 @@ extern "C" int dyd_url_filter(const uint64_t* d_main_keys, const uint8_t* d_main
                               uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep_ref, int64_t* d_ref_row,
                               void* ws, size_t ws_bytes, void* stream) {
     return url_filter_impl<0>(d_main_keys, d_main_null, n_main, const_cast<uint64_t*>(d_ref_keys), d_ref_null, n_ref, keep_mode, d_keep, d_rep,
-                              d_keep_ref, d_ref_row, ws, ws_bytes, false, stream);
+                              d_keep_ref, d_ref_row, ws, ws_bytes, false, 0, stream);
 }
 
 extern "C" int dyd_url_filter_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main, int keep_mode,
                                       uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep_ref, int64_t* d_ref_row,
-                                      void* ws, size_t ws_bytes, int32_t reset_ref, void* stream) {
+                                      void* ws, size_t ws_bytes, int32_t reset_ref, int64_t id_bound, void* stream) {
     return url_filter_impl<2>(reinterpret_cast<const uint64_t*>(d_main_records), nullptr, m_main, reinterpret_cast<uint64_t*>(d_ref_records), nullptr,
-                              m_ref, keep_mode, d_keep, d_rep, d_keep_ref, d_ref_row, ws, ws_bytes, reset_ref != 0, stream);
+                              m_ref, keep_mode, d_keep, d_rep, d_keep_ref, d_ref_row, ws, ws_bytes, reset_ref != 0, id_bound, stream);
 }

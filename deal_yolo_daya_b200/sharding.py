@@ -438,6 +438,7 @@ class UrlFilterExchange(AntiJoinExchange):
         self.ws_d = torch.empty(self.lib.dyd_url_filter_workspace_bytes(m, world * self.cap_ref), dtype=torch.uint8, device=device)
         self.keep_d = torch.empty(n_main_local, dtype=torch.uint8, device=device)
         self.rep_d = torch.empty(n_main_local, dtype=torch.int64, device=device)
+        self._bounds = {}
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
             grp = group if group is not None else dist.group.WORLD
@@ -452,8 +453,16 @@ class UrlFilterExchange(AntiJoinExchange):
             self.back_d = torch.empty(2 * m, dtype=torch.int64, device=device)
 
     def run(self, main_keys, row_base: int, ref_keys, ref_row_base: int, keep="first", group=None, check_overflow=True,
-            main_null=None, ref_null=None):
-        """Returns (keep, rep, keep_ref, ref_row) for this rank's main rows."""
+            main_null=None, ref_null=None, id_bound=None):
+        """Returns (keep, rep, keep_ref, ref_row) for this rank's main rows.  ``id_bound``: an upper bound of every global row id
+        of either table over ALL ranks (default: the equal-shard layout, world * rows per rank)."""
+        if id_bound is None:                          # agreed on once per (row_base, ref_row_base): one small all-reduce, then cached
+            key = (row_base, ref_row_base)
+            if key not in self._bounds:
+                b = torch.tensor([max(row_base + self.n, ref_row_base + self.n_ref)], dtype=torch.int64, device=self.dev)
+                dist.all_reduce(b, op=dist.ReduceOp.MAX, group=group)
+                self._bounds[key] = int(b.item())
+            id_bound = self._bounds[key]
         from . import _lib
         from .ops import KEEP_MODES, _ptr, _stream
         lib, dev = self.lib, self.dev
@@ -482,7 +491,8 @@ class UrlFilterExchange(AntiJoinExchange):
                 dist.all_to_all_single(self.recv, self.send, group=group)
             # owner side: both questions about every received main record from one shared-memory table per key partition
             _lib.check(lib.dyd_url_filter_records(_ptr(self.recv_ref), m_ref, _ptr(self.recv), m, KEEP_MODES[keep], _ptr(self.keep_dr), _ptr(self.rep_dr),
-                                                  _ptr(self.keep_r), _ptr(self.rep_r), _ptr(self.ws_d), self.ws_d.numel(), 1 if p2p else 0, s),
+                                                  _ptr(self.keep_r), _ptr(self.rep_r), _ptr(self.ws_d), self.ws_d.numel(), 1 if p2p else 0,
+                                                  int(id_bound), s),
                        "dyd_url_filter_records")
             if main_null is not None and not sparse:          # rows that never travel: a NaN cell never matches
                 self.keep.fill_(1); self.rep.fill_(-1)

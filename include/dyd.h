@@ -211,7 +211,9 @@ int dyd_url_filter(const uint64_t* d_main_keys, const uint8_t* d_main_null, int6
                    void* d_workspace, size_t workspace_bytes, void* stream);
 int dyd_url_filter_records(int64_t* d_ref_records, int64_t m_ref, const int64_t* d_main_records, int64_t m_main, int keep_mode,
                            uint8_t* d_keep, int64_t* d_rep, uint8_t* d_keep_ref, int64_t* d_ref_row,
-                           void* d_workspace, size_t workspace_bytes, int32_t reset_ref, void* stream);
+                           void* d_workspace, size_t workspace_bytes, int32_t reset_ref, int64_t id_bound, void* stream);
+/* id_bound: every record id (main and reference) is below this value (0 = unknown); below 2^31 the shared-memory tables keep
+ * 32-bit rows (native shared atomics).                                                                      */
 
 /* ---------------------------------------------------------------- K3 ------
  * Object-name rewrite through a lookup table, processor.py:582-602 with the

@@ -361,7 +361,14 @@ def test_url_filter_records_equals_separate_record_kernels(cuda_device, small_pa
     rec[rng.choice(m, 9000, replace=False), 1] = -1; ref[rng.choice(mr, 4000, replace=False), 1] = -1          # bucket padding
     s = _stream(d)
     t = lambda n, dt=torch.int64: torch.empty(n, dtype=dt, device=d)   # noqa: E731
-    for keep in ("first", "last", False):
+    big_rec, big_ref = rec.copy(), ref.copy()
+    for keep, small_ids in (("first", False), ("last", False), (False, False), ("first", True), ("last", True), (False, True)):
+        rec, ref = big_rec.copy(), big_ref.copy()
+        id_bound = 0                                   # ids beyond 2^31: 64-bit rows in the shared-memory tables
+        if small_ids:                                  # ids below 2^31 and a bound that says so: the 32-bit form
+            rec[:, 1] = np.where(rec[:, 1] >= 0, (rec[:, 1] - (1 << 34)) // 7 * 5 + 11, -1)
+            ref[:, 1] = np.where(ref[:, 1] >= 0, (ref[:, 1] - (1 << 35)) // 3 * 9 + 4, -1)
+            id_bound = int(max(rec[:, 1].max(), ref[:, 1].max())) + 1
         mode = ops.KEEP_MODES[keep]
         drec, dref = dev(rec.reshape(-1), d), dev(ref.reshape(-1), d)
         k1, r1, k2, r2 = t(m, torch.uint8), t(m), t(m, torch.uint8), t(m)
@@ -370,7 +377,7 @@ def test_url_filter_records_equals_separate_record_kernels(cuda_device, small_pa
         _lib.check(lib.dyd_antijoin_records(_ptr(dref), mr, _ptr(drec), m, _ptr(k2), _ptr(r2), _ptr(ws_a), ws_a.numel(), 0, s), "antijoin_records")
         j = [t(m, torch.uint8), t(m), t(m, torch.uint8), t(m)]
         ws = t(lib.dyd_url_filter_workspace_bytes(m, mr), torch.uint8)
-        _lib.check(lib.dyd_url_filter_records(_ptr(dref), mr, _ptr(drec), m, mode, _ptr(j[0]), _ptr(j[1]), _ptr(j[2]), _ptr(j[3]), _ptr(ws), ws.numel(), 1, s),
+        _lib.check(lib.dyd_url_filter_records(_ptr(dref), mr, _ptr(drec), m, mode, _ptr(j[0]), _ptr(j[1]), _ptr(j[2]), _ptr(j[3]), _ptr(ws), ws.numel(), 1, id_bound, s),
                    "url_filter_records")
         assert_bits(host(j[0]), host(k1), f"keep {keep}"); assert_bits(host(j[1]), host(r1), f"rep {keep}")
         assert_bits(host(j[2]), host(k2), f"keep_ref {keep}"); assert_bits(host(j[3]), host(r2), f"ref_row {keep}")

@@ -28,7 +28,7 @@ for it in range(R):
     e[i].record(); i += 1; x._scatter_p2p(x.ref, rkeys, None, rank * n_ref, x.overflow[1:], s)
     e[i].record(); i += 1; _lib.check(lib.dyd_shard_bucket_p2p_defaults(_ptr(keys), None, rank * n, n, world, rank, x.main.cap, _ptr(x.main.peers), _ptr(x.main.sent_row), _ptr(x.main.cursors), _ptr(x.overflow[:1]), _ptr(x.keep_d), _ptr(x.rep_d), _ptr(x.keep), _ptr(x.rep), s), "s")
     e[i].record(); i += 1; x.main.h.barrier(channel=1)
-    e[i].record(); i += 1; _lib.check(lib.dyd_url_filter_records(_ptr(x.recv_ref), m_ref, _ptr(x.recv), m, 0, _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.keep_r), _ptr(x.rep_r), _ptr(x.ws_d), x.ws_d.numel(), 1, s), "j")
+    e[i].record(); i += 1; _lib.check(lib.dyd_url_filter_records(_ptr(x.recv_ref), m_ref, _ptr(x.recv), m, 0, _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.keep_r), _ptr(x.rep_r), _ptr(x.ws_d), x.ws_d.numel(), 1, world * n, s), "j")
     e[i].record(); i += 1; _lib.check(lib.dyd_shard_pack_reply2_p2p(_ptr(x.recv), _ptr(x.keep_dr), _ptr(x.rep_dr), _ptr(x.keep_r), _ptr(x.rep_r), m, x.cap, rank, _ptr(x.peer_back2), 1, 1, s), "p")
     e[i].record(); i += 1; x.h_back2.barrier(channel=0)
     e[i].record(); i += 1; _lib.check(lib.dyd_shard_unpack2_p2p(_ptr(x.back2), _ptr(x.main.sent_row), _ptr(x.cursors), world, x.cap, n, _ptr(x.keep_d), _ptr(x.rep_d), _ptr(x.keep), _ptr(x.rep), 1, s), "u")
